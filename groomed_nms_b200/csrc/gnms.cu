@@ -1,0 +1,1022 @@
+// GrooMeD-NMS forward / backward, get_groups and classical hard NMS for sm_100a.
+//
+// Reference semantics: lib/groomed_nms.py:10-129 (differentiable_nms), :208-270 (get_groups),
+// lib/nms/nms_kernel.cu:24-144 (+ cpu_nms.pyx, py_cpu_nms.py, nms_others.py:119-150).
+//
+// Pipeline per image (all on one stream, no host sync, no allocation):
+//   1. sort_kernel        one CTA: bitonic argsort of the scores (descending, stable by index) in shared memory;
+//                         writes order / rank / sorted scores (+ box records gathered into sorted order).
+//   2. mask_*_kernel      whole grid: the "suppression bitmask" in SORTED space,
+//                             mask[jw][l] bit r  <=>  box at sorted position j = 32*jw + r leaves the pool when
+//                                                     the box at sorted position l < j is picked as a leader,
+//                                                     i.e. !(overlap[j,l] <= thr)   (lib/groomed_nms.py:249-250)
+//                         either by streaming the N x N overlap matrix once (coalesced 16 B loads, HBM bound:
+//                         4*N^2 bytes) or by evaluating the overlaps on the fly from the box records (lower
+//                         triangle only, ALU bound, nothing N^2 touches HBM).  Also emits, per row word, whether
+//                         any box of the word has an earlier overlapper at all (-> the certain leaders L0).
+//   3. chain_kernel       one CTA: greedy leader election.  The certain leaders L0 are applied in parallel;
+//                         what is left unresolved is processed in windows of 64 candidates whose mask columns
+//                         are fetched together and resolved exactly, in score order, by one warp.  Then first
+//                         suppressor -> group, in-group rank (group_size cap), gather of iou[m,leader],
+//                         pruning function, rescore, clamp, threshold, valid / invalid index lists.
+//   4. backward_kernel    one CTA: analytic vector-Jacobian product.
+#include "common.cuh"
+
+#include <limits.h>
+
+namespace gnms {
+
+constexpr int kChainThreads = 1024;
+constexpr int kWin = 64;                 // candidates resolved per window
+constexpr int kMaskThreads = 256;
+
+// ------------------------------------------------------------------------------------------ workspace
+struct WsLayout {
+    size_t rank, sbox, mask, has_earlier, colflag, total;   // byte offsets inside one image's slice
+};
+__host__ __device__ inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+__host__ __device__ inline WsLayout ws_layout(int N) {
+    WsLayout L;
+    size_t nw = (size_t)((N + 31) / 32);
+    size_t off = 0;
+    L.rank = off;        off += align_up((size_t)N * 4);
+    L.sbox = off;        off += align_up((size_t)N * 8 * 4);
+    L.mask = off;        off += align_up(nw * (size_t)N * 4);
+    L.has_earlier = off; off += align_up(nw * 4);
+    L.colflag = off;     off += align_up((size_t)N);
+    L.total = off;
+    return L;
+}
+
+enum BoxSrc { kSrcMatrix = 0, kSrcBox2d = 1, kSrcBox3d = 2, kSrcBoxShift = 3 };
+
+// ------------------------------------------------------------------------------------------ 1. sort
+// boxes (optional): kSrcBox2d  float[N,4]; kSrcBox3d float[N,8] records; kSrcBoxShift float[N,5] dets.
+// scores come from `scores` (stride sstride floats; dets use column 4 with stride 5).
+__global__ void __launch_bounds__(kChainThreads)
+sort_kernel(const float* __restrict__ scores, int64_t sstride, int64_t score_img_stride, int N,
+            const int32_t* __restrict__ n_per_image, int32_t* __restrict__ order_out, float* __restrict__ ss_out,
+            char* __restrict__ ws, size_t ws_img_stride, const float* __restrict__ boxes, int box_src,
+            int64_t box_img_stride, float shift, int presorted) {
+    extern __shared__ unsigned long long keys[];
+    const int b = blockIdx.x;
+    const int n = n_per_image ? min(n_per_image[b], N) : N;
+    const WsLayout L = ws_layout(N);
+    char* w = ws + (size_t)b * ws_img_stride;
+    int32_t* rank = reinterpret_cast<int32_t*>(w + L.rank);
+    float* sbox = reinterpret_cast<float*>(w + L.sbox);
+    uint32_t* has_earlier = reinterpret_cast<uint32_t*>(w + L.has_earlier);
+    uint8_t* colflag = reinterpret_cast<uint8_t*>(w + L.colflag);
+    const float* sc = scores + (size_t)b * score_img_stride;
+    int32_t* order = order_out + (size_t)b * N;
+    float* ss = ss_out + (size_t)b * N;
+    const int tid = threadIdx.x;
+
+    int P = 1;
+    while (P < n) P <<= 1;
+    for (int i = tid; i < P; i += kChainThreads) {
+        unsigned long long k = ~0ull;
+        if (i < n) {
+            uint32_t hi = presorted ? (uint32_t)0 : desc_key(sc[(int64_t)i * sstride]);
+            k = ((unsigned long long)hi << 32) | (uint32_t)i;
+        }
+        keys[i] = k;
+    }
+    const int nw = (N + 31) / 32;
+    for (int i = tid; i < nw; i += kChainThreads) has_earlier[i] = 0u;
+    for (int i = tid; i < N; i += kChainThreads) colflag[i] = 0;
+    __syncthreads();
+    if (!presorted) {
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (P >> 1); t += kChainThreads) {
+                    int i = 2 * t - (t & (j - 1));
+                    int l = i + j;
+                    unsigned long long a = keys[i], c = keys[l];
+                    bool up = ((i & k) == 0);
+                    if ((a > c) == up) { keys[i] = c; keys[l] = a; }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    const float* bx = boxes ? boxes + (size_t)b * box_img_stride : nullptr;
+    for (int pos = tid; pos < N; pos += kChainThreads) {
+        if (pos < n) {
+            int idx = (int)(uint32_t)(keys[pos] & 0xffffffffull);
+            order[pos] = idx;
+            rank[idx] = pos;
+            ss[pos] = sc[(int64_t)idx * sstride];
+            if (box_src == kSrcBox2d) {
+                float4 v = __ldg(reinterpret_cast<const float4*>(bx) + idx);
+                Box2 q = make_box2(v);
+                float4* o = reinterpret_cast<float4*>(sbox + (size_t)pos * 8);
+                o[0] = v;
+                o[1] = make_float4(q.area, 0.f, 0.f, 0.f);
+            } else if (box_src == kSrcBox3d) {
+                const float4* src = reinterpret_cast<const float4*>(bx + (size_t)idx * 8);
+                float4* o = reinterpret_cast<float4*>(sbox + (size_t)pos * 8);
+                o[0] = __ldg(src);
+                o[1] = __ldg(src + 1);
+            } else if (box_src == kSrcBoxShift) {
+                const float* d = bx + (size_t)idx * 5;
+                BoxS q = make_boxs(d[0], d[1], d[2], d[3], shift);
+                float4* o = reinterpret_cast<float4*>(sbox + (size_t)pos * 8);
+                o[0] = make_float4(q.x1, q.y1, q.x2, q.y2);
+                o[1] = make_float4(q.area, 0.f, 0.f, 0.f);
+            }
+        } else {
+            order[pos] = -1;
+            ss[pos] = 0.f;
+        }
+    }
+    // live boxes beyond n (padding) never get a rank; give them one past the end so mask builders skip them
+    for (int i = n + tid; i < N; i += kChainThreads) {
+        if (n_per_image) rank[i] = INT_MAX;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ 2a. mask from a matrix
+// grid (ceil(N/1024), NW, batch), 256 threads; thread = 4 consecutive INPUT columns x the 32 rows of row word jw.
+template <bool kVec>
+__global__ void __launch_bounds__(kMaskThreads)
+mask_matrix_kernel(const float* __restrict__ iou, int64_t ld, int64_t img_stride, int N,
+                   const int32_t* __restrict__ n_per_image, const int32_t* __restrict__ order_all,
+                   char* __restrict__ ws, size_t ws_img_stride, float thr) {
+    __shared__ int32_t rows[32];
+    const int b = blockIdx.z;
+    const int n = n_per_image ? min(n_per_image[b], N) : N;
+    const int jw = blockIdx.y;
+    if (jw * 32 >= n) return;
+    const WsLayout L = ws_layout(N);
+    char* w = ws + (size_t)b * ws_img_stride;
+    const int32_t* rank = reinterpret_cast<const int32_t*>(w + L.rank);
+    uint32_t* mask = reinterpret_cast<uint32_t*>(w + L.mask);
+    uint32_t* has_earlier = reinterpret_cast<uint32_t*>(w + L.has_earlier);
+    uint8_t* colflag = reinterpret_cast<uint8_t*>(w + L.colflag);
+    const int32_t* order = order_all + (size_t)b * N;
+    const float* m = iou + (size_t)b * img_stride;
+    if (threadIdx.x < 32) {
+        int pos = jw * 32 + threadIdx.x;
+        rows[threadIdx.x] = pos < n ? order[pos] : -1;
+    }
+    __syncthreads();
+    const int c0 = (blockIdx.x * kMaskThreads + threadIdx.x) * 4;
+    uint32_t wd[4] = {0u, 0u, 0u, 0u};
+    int rk[4];
+    int rkmin = INT_MAX;
+    if (c0 < n) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            rk[k] = (c0 + k < n) ? rank[c0 + k] : INT_MAX;
+            rkmin = min(rkmin, rk[k]);
+        }
+    }
+    const int pos_last = min(jw * 32 + 31, n - 1);
+    if (c0 < n && rkmin < pos_last) {          // otherwise none of my columns precedes any row of this word
+        const bool full = kVec && (c0 + 4 <= N);
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            const int row = rows[r];
+            if (row < 0) break;
+            const int pos = jw * 32 + r;
+            const float* src = m + (int64_t)row * ld + c0;
+            float v[4];
+            if (full) {
+                float4 q = ld_cs_f4(src);
+                v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = (c0 + k < N) ? __ldcs(src + k) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t bit = (!(v[k] <= thr)) && (rk[k] < pos);
+                wd[k] |= bit << r;
+            }
+        }
+    }
+    uint32_t any = 0u;
+    if (c0 < n) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (c0 + k < n && (rk[k] >> 5) <= jw) {           // words above the diagonal are never read
+                mask[(size_t)jw * N + rk[k]] = wd[k];
+                if (wd[k]) colflag[rk[k]] = 1;
+            }
+            any |= wd[k];
+        }
+    }
+    any = __reduce_or_sync(0xffffffffu, any);
+    if ((threadIdx.x & 31) == 0 && any) atomicOr(&has_earlier[jw], any);
+}
+
+// ------------------------------------------------------------------------------------------ 2b. mask from boxes
+// grid (ceil(N/256), NW, batch), 256 threads; thread = one SORTED column l x the 32 rows of row word jw.  Only
+// tiles that touch the lower triangle (some l < some j) do any work.
+template <int kSrc, bool kGen, bool kAffine, int kCmp>
+__global__ void __launch_bounds__(kMaskThreads)
+mask_boxes_kernel(int N, const int32_t* __restrict__ n_per_image, char* __restrict__ ws, size_t ws_img_stride,
+                  float thr, float shift) {
+    __shared__ float4 rrec[32][2];
+    const int b = blockIdx.z;
+    const int n = n_per_image ? min(n_per_image[b], N) : N;
+    const int jw = blockIdx.y;
+    const int l0 = blockIdx.x * kMaskThreads;
+    if (jw * 32 >= n || l0 > jw * 32 + 31 || l0 >= n) return;
+    const WsLayout L = ws_layout(N);
+    char* w = ws + (size_t)b * ws_img_stride;
+    const float* sbox = reinterpret_cast<const float*>(w + L.sbox);
+    uint32_t* mask = reinterpret_cast<uint32_t*>(w + L.mask);
+    uint32_t* has_earlier = reinterpret_cast<uint32_t*>(w + L.has_earlier);
+    uint8_t* colflag = reinterpret_cast<uint8_t*>(w + L.colflag);
+    if (threadIdx.x < 64) {
+        int r = threadIdx.x >> 1, h = threadIdx.x & 1;
+        int pos = jw * 32 + r;
+        rrec[r][h] = pos < n ? reinterpret_cast<const float4*>(sbox + (size_t)pos * 8)[h] : make_float4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    const int l = l0 + threadIdx.x;
+    uint32_t wd = 0u;
+    if (l < n && l < jw * 32 + 31) {
+        const float4 c0 = reinterpret_cast<const float4*>(sbox + (size_t)l * 8)[0];
+        const float4 c1 = reinterpret_cast<const float4*>(sbox + (size_t)l * 8)[1];
+        const int rend = min(32, n - jw * 32);
+#pragma unroll 4
+        for (int r = 0; r < rend; ++r) {
+            const float4 a0 = rrec[r][0], a1 = rrec[r][1];
+            float v;
+            if (kSrc == kSrcBox3d) {
+                Rec3 ra = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                Rec3 rb = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                v = iou3<kGen, kAffine>(ra, rb, inter_bev3(ra, rb));
+            } else if (kSrc == kSrcBox2d) {
+                Box2 ra = {a0.x, a0.y, a0.z, a0.w, a1.x};
+                Box2 rb = {c0.x, c0.y, c0.z, c0.w, c1.x};
+                v = iou2(ra, rb);
+            } else {
+                BoxS ra = {a0.x, a0.y, a0.z, a0.w, a1.x};
+                BoxS rb = {c0.x, c0.y, c0.z, c0.w, c1.x};
+                v = iou_shift(rb, ra, shift);   // (kept box, candidate) order of lib/nms/py_cpu_nms.py:26-33
+            }
+            bool hit = (kCmp == GNMS_CMP_GT) ? (v > thr) : (kCmp == GNMS_CMP_GE) ? (v >= thr) : !(v <= thr);
+            uint32_t bit = hit && (l < jw * 32 + r);
+            wd |= bit << r;
+        }
+    }
+    if (l < n && (l >> 5) <= jw) {
+        mask[(size_t)jw * N + l] = wd;
+        if (wd) colflag[l] = 1;
+    }
+    uint32_t any = __reduce_or_sync(0xffffffffu, wd);
+    if ((threadIdx.x & 31) == 0 && any) atomicOr(&has_earlier[jw], any);
+}
+
+// ------------------------------------------------------------------------------------------ 3. chain
+struct ChainArgs {
+    int N, batch;
+    const int32_t* n_per_image;
+    char* ws;
+    size_t ws_img_stride;
+    // overlap source for the (member, leader) gather
+    int src;                       // BoxSrc
+    const float* iou;              // kSrcMatrix
+    int64_t ld, iou_img_stride;
+    int generalized, affine;       // kSrcBox3d
+    gnms_params p;
+    // outputs
+    int32_t* order;                // [batch,N] in (written by sort_kernel)
+    float* sorted_scores;          // [batch,N] in
+    float* prob;                   // [batch,N]
+    int64_t* valid_idx;
+    int64_t* invalid_idx;
+    int32_t* counts;               // [batch,2]
+    int32_t* lead;                 // saved
+    float* pval;
+    float* dpval;
+    float* pre;
+    int32_t* slot;                 // [batch,N] position of sorted pos in the sorted output (or NULL)
+    // get_groups / hard-nms outputs (optional)
+    int32_t* group_id;             // [N] by INPUT index
+    int32_t* group_rank;           // [N] by INPUT index
+    int32_t* n_groups;             // [1]
+    int32_t* keep;                 // hard NMS: kept input indices in score order
+    int32_t* n_keep;
+    int leaders_only;              // hard NMS: stop after leader election
+};
+
+__device__ __forceinline__ uint32_t valid_word(int w, int n) {
+    int lo = w * 32;
+    if (n >= lo + 32) return 0xffffffffu;
+    if (n <= lo) return 0u;
+    return (1u << (n - lo)) - 1u;
+}
+
+// warp 0 only: list the positions of the first `limit` set bits of bits[0..nw) into out[], return the count
+__device__ int warp_list_bits(const uint32_t* bits, int nw, int limit, int32_t* out) {
+    const int lane = threadIdx.x & 31;
+    int total = 0;
+    for (int base = 0; base < nw && total < limit; base += 32) {
+        int wi = base + lane;
+        uint32_t w = wi < nw ? bits[wi] : 0u;
+        int c = __popc(w);
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        int off = total + incl - c;
+        while (w && off < limit) {
+            int bpos = __ffs(w) - 1;
+            w &= w - 1;
+            out[off++] = wi * 32 + bpos;
+        }
+        total += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    return min(total, limit);
+}
+
+__global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
+    extern __shared__ unsigned char smem_raw[];
+    const int b = blockIdx.x;
+    const int N = A.N;
+    const int n = A.n_per_image ? min(A.n_per_image[b], N) : N;
+    const int NW = (N + 31) / 32;
+    const int nw = (n + 31) / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const WsLayout L = ws_layout(N);
+    char* w = A.ws + (size_t)b * A.ws_img_stride;
+    const uint32_t* mask = reinterpret_cast<const uint32_t*>(w + L.mask);
+    const uint32_t* has_earlier = reinterpret_cast<const uint32_t*>(w + L.has_earlier);
+    const uint8_t* colflag = reinterpret_cast<const uint8_t*>(w + L.colflag);
+    const float* sbox = reinterpret_cast<const float*>(w + L.sbox);
+    const int32_t* order = A.order + (size_t)b * N;
+    const float* ss = A.sorted_scores + (size_t)b * N;
+
+    // shared memory carve-up
+    uint32_t* removed = reinterpret_cast<uint32_t*>(smem_raw);            // NW
+    uint32_t* leader = removed + NW;                                      // NW
+    uint32_t* tmpbits = leader + NW;                                      // NW
+    int32_t* fsup = reinterpret_cast<int32_t*>(tmpbits + NW);             // N   (later: lead[])
+    int32_t* list = fsup + N;                                             // N   (leader / candidate lists, later grank)
+    uint32_t* wcol = reinterpret_cast<uint32_t*>(list + N);               // kWin * NW (later: sort keys)
+    __shared__ int s_cnt;
+
+    for (int i = tid; i < NW; i += kChainThreads) {
+        removed[i] = 0u;
+        leader[i] = (i < nw) ? (~has_earlier[i] & valid_word(i, n)) : 0u;
+    }
+    for (int i = tid; i < N; i += kChainThreads) fsup[i] = INT_MAX;
+    __syncthreads();
+
+    // ---- certain leaders L0 (no earlier overlapper at all): apply their columns in parallel
+    for (int i = tid; i < nw; i += kChainThreads) tmpbits[i] = leader[i];
+    __syncthreads();
+    if (warp == 0) {
+        int c = warp_list_bits(tmpbits, nw, N, list);
+        if (lane == 0) s_cnt = c;
+    }
+    __syncthreads();
+    {
+        const int cnt = s_cnt;
+        for (int k = warp; k < cnt; k += kChainThreads / 32) {
+            const int l = list[k];
+            if (!colflag[l]) continue;
+            for (int jw = (l >> 5) + lane; jw < nw; jw += 32) {
+                uint32_t m = mask[(size_t)jw * N + l];
+                if (m) {
+                    atomicOr(&removed[jw], m);
+                    while (m) {
+                        int bp = __ffs(m) - 1;
+                        m &= m - 1;
+                        atomicMin(&fsup[jw * 32 + bp], l);
+                    }
+                }
+            }
+        }
+    }
+    // ---- unresolved boxes: windows of kWin candidates, resolved exactly in score order by warp 0
+    while (true) {
+        __syncthreads();
+        for (int i = tid; i < nw; i += kChainThreads) tmpbits[i] = ~(leader[i] | removed[i]) & valid_word(i, n);
+        __syncthreads();
+        if (warp == 0) {
+            int c = warp_list_bits(tmpbits, nw, kWin, list);
+            if (lane == 0) s_cnt = c;
+        }
+        __syncthreads();
+        const int cnt = s_cnt;
+        if (cnt == 0) break;
+        for (int k = warp; k < cnt; k += kChainThreads / 32) {
+            const int l = list[k];
+            const bool has = colflag[l] != 0;
+            for (int jw = lane; jw < nw; jw += 32)
+                wcol[k * NW + jw] = (has && jw >= (l >> 5)) ? mask[(size_t)jw * N + l] : 0u;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int k = 0; k < cnt; ++k) {
+                const int l = list[k];
+                const uint32_t rem = (removed[l >> 5] >> (l & 31)) & 1u;
+                if (!rem) {
+                    if (lane == 0) leader[l >> 5] |= 1u << (l & 31);
+                    for (int jw = (l >> 5) + lane; jw < nw; jw += 32) {
+                        uint32_t m = wcol[k * NW + jw];
+                        if (m) {
+                            removed[jw] |= m;
+                            while (m) {
+                                int bp = __ffs(m) - 1;
+                                m &= m - 1;
+                                int q = jw * 32 + bp;
+                                fsup[q] = min(fsup[q], l);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- hard NMS: the leaders are the keep set
+    if (A.leaders_only) {
+        if (warp == 0) {
+            int c = warp_list_bits(leader, nw, N, list);
+            if (lane == 0) { s_cnt = c; A.n_keep[b] = c; }
+        }
+        __syncthreads();
+        for (int k = tid; k < s_cnt; k += kChainThreads) A.keep[(size_t)b * N + k] = order[list[k]];
+        return;
+    }
+
+    // ---- group of every box: leaders lead themselves, others follow their first suppressor; a NaN overlap with
+    //      the leader means the box left the pool without joining the group (lib/groomed_nms.py:249-250)
+    int32_t* lead = fsup;
+    float* pval = A.pval + (size_t)b * N;
+    float* dpval = A.dpval + (size_t)b * N;
+    const gnms_params P = A.p;
+    for (int pos = tid; pos < n; pos += kChainThreads) {
+        const bool isl = (leader[pos >> 5] >> (pos & 31)) & 1u;
+        int f = fsup[pos];
+        int ld_ = isl ? pos : (f != INT_MAX ? f : -1);
+        float pv = 0.f, dpv = 0.f;
+        if (!isl && ld_ >= 0) {
+            float v;
+            if (A.src == kSrcMatrix) {
+                v = A.iou[(size_t)b * A.iou_img_stride + (int64_t)order[pos] * A.ld + order[ld_]];
+            } else {
+                const float4* pa = reinterpret_cast<const float4*>(sbox + (size_t)pos * 8);
+                const float4* pb = reinterpret_cast<const float4*>(sbox + (size_t)ld_ * 8);
+                float4 a0 = pa[0], a1 = pa[1], c0 = pb[0], c1 = pb[1];
+                if (A.src == kSrcBox3d) {
+                    Rec3 ra = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    Rec3 rb = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                    float ib = inter_bev3(ra, rb);
+                    v = A.generalized ? (A.affine ? iou3<true, true>(ra, rb, ib) : iou3<true, false>(ra, rb, ib))
+                                      : (A.affine ? iou3<false, true>(ra, rb, ib) : iou3<false, false>(ra, rb, ib));
+                } else {
+                    Box2 ra = {a0.x, a0.y, a0.z, a0.w, a1.x};
+                    Box2 rb = {c0.x, c0.y, c0.z, c0.w, c1.x};
+                    v = iou2(ra, rb);
+                }
+            }
+            if (v != v) {
+                ld_ = -1;
+            } else {
+                pv = prune(v, P.pruning_method, P.nms_threshold, P.temperature);
+                dpv = prune_grad(v, pv, P.pruning_method, P.temperature);
+            }
+        }
+        lead[pos] = ld_;
+        pval[pos] = pv;
+        dpval[pos] = dpv;
+    }
+    __syncthreads();
+
+    // ---- in-group rank (0 = leader) and the group_size cap: only the first group_size+1 boxes stay (:254-255)
+    int32_t* grank = list;
+    for (int pos = tid; pos < n; pos += kChainThreads) grank[pos] = 0;
+    for (int i = tid; i < nw; i += kChainThreads) tmpbits[i] = leader[i];
+    __syncthreads();
+    {
+        // leaders enumerated straight from the bitset words: warp k takes words k, k+32, ...
+        for (int wi = warp; wi < nw; wi += kChainThreads / 32) {
+            uint32_t lw = tmpbits[wi];
+            while (lw) {
+                const int l = wi * 32 + __ffs(lw) - 1;
+                lw &= lw - 1;
+                if (!colflag[l]) continue;
+                int carry = 0;
+                for (int base = (l >> 5); base < nw; base += 32) {
+                    const int jw = base + lane;
+                    uint32_t m = jw < nw ? mask[(size_t)jw * N + l] : 0u;
+                    uint32_t memb = 0u;
+                    while (m) {
+                        int bp = __ffs(m) - 1;
+                        m &= m - 1;
+                        if (lead[jw * 32 + bp] == l) memb |= 1u << bp;
+                    }
+                    int c = __popc(memb), incl = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        int t = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += t;
+                    }
+                    int before = carry + incl - c;
+                    uint32_t mm = memb;
+                    while (mm) {
+                        int bp = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        int rk = 1 + before + __popc(memb & ((1u << bp) - 1u));
+                        grank[jw * 32 + bp] = rk;
+                    }
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int gs = P.group_size;
+    for (int pos = tid; pos < n; pos += kChainThreads) {
+        if (lead[pos] >= 0 && lead[pos] != pos && grank[pos] > gs) lead[pos] = -1;
+    }
+    __syncthreads();
+
+    // ---- get_groups outputs
+    if (A.group_id) {
+        // exclusive prefix of leader popcounts per word (NW <= 256 words: warp 0, 8 words per lane)
+        if (warp == 0) {
+            int run = 0;
+            for (int base = 0; base < nw; base += 32) {
+                int wi = base + lane;
+                int c = wi < nw ? __popc(leader[wi]) : 0, incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (wi < nw) tmpbits[wi] = run + incl - c;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) A.n_groups[b] = run;
+        }
+        __syncthreads();
+        for (int pos = tid; pos < n; pos += kChainThreads) {
+            int ld_ = lead[pos];
+            int gid = -1;
+            if (ld_ >= 0) gid = tmpbits[ld_ >> 5] + __popc(leader[ld_ >> 5] & ((1u << (ld_ & 31)) - 1u));
+            A.group_id[(size_t)b * N + order[pos]] = gid;
+            A.group_rank[(size_t)b * N + order[pos]] = ld_ >= 0 ? grank[pos] : -1;
+        }
+        if (!A.prob) return;
+        __syncthreads();
+    }
+
+    // ---- rescore (mode GROUP_MASK closed form: row of I - Phi has two non-zeros), clamp, threshold
+    float* pre_out = A.pre + (size_t)b * N;
+    int32_t* lead_out = A.lead + (size_t)b * N;
+    float* prob = A.prob + (size_t)b * N;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(wcol);
+    const float vthr = P.valid_box_prob_threshold;
+    // validity bitset in tmpbits via ballot (warp handles 32 consecutive positions)
+    for (int base = 0; base < nw * 32; base += kChainThreads) {
+        const int pos = base + tid;
+        float r = 0.f, rt = 0.f;
+        bool is_valid = false;
+        if (pos < n) {
+            const int ld_ = lead[pos];
+            float prev = 0.f;
+            if (ld_ == pos) prev = ss[pos];
+            else if (ld_ >= 0) prev = __fsub_rn(ss[pos], __fmul_rn(pval[pos], ss[ld_]));
+            r = fminf(fmaxf(prev, 0.f), 1.f);
+            rt = (r < vthr) ? 0.f : r;
+            is_valid = rt >= vthr;
+            pre_out[pos] = prev;
+            lead_out[pos] = ld_;
+            if (!P.sorted_output) prob[pos] = P.thresholded_output ? rt : r;
+            // stash the thresholded value for the sort below
+            reinterpret_cast<float*>(list)[pos] = rt;
+        }
+        uint32_t bal = __ballot_sync(0xffffffffu, is_valid);
+        if (lane == 0 && (pos >> 5) < nw) tmpbits[pos >> 5] = bal;
+    }
+    for (int pos = n + tid; pos < N; pos += kChainThreads) {
+        pre_out[pos] = 0.f;
+        lead_out[pos] = -1;
+        prob[pos] = 0.f;
+        pval[pos] = 0.f;
+        dpval[pos] = 0.f;
+        if (A.slot) A.slot[(size_t)b * N + pos] = pos;
+    }
+    __syncthreads();
+    // word prefix of valid counts -> tmp in `removed` (no longer needed)
+    uint32_t* vpref = removed;
+    if (warp == 0) {
+        int run = 0;
+        for (int base = 0; base < nw; base += 32) {
+            int wi = base + lane;
+            int c = wi < nw ? __popc(tmpbits[wi]) : 0, incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (wi < nw) vpref[wi] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) s_cnt = run;
+    }
+    __syncthreads();
+    const int V = s_cnt;
+    if (tid == 0) { A.counts[b * 2 + 0] = V; A.counts[b * 2 + 1] = n - V; }
+    int PV = 1;
+    while (PV < V) PV <<= 1;
+    for (int i = tid; i < PV; i += kChainThreads) keys[i] = ~0ull;
+    __syncthreads();
+    const float* rthr = reinterpret_cast<const float*>(list);
+    int64_t* invalid_idx = A.invalid_idx + (size_t)b * N;
+    int64_t* valid_idx = A.valid_idx + (size_t)b * N;
+    for (int pos = tid; pos < n; pos += kChainThreads) {
+        const uint32_t wv = tmpbits[pos >> 5];
+        const int before = vpref[pos >> 5] + __popc(wv & ((1u << (pos & 31)) - 1u));
+        if ((wv >> (pos & 31)) & 1u) {
+            keys[before] = ((unsigned long long)desc_key(rthr[pos]) << 32) | (uint32_t)pos;
+        } else {
+            const int irank = pos - before;
+            invalid_idx[irank] = order[pos];
+            if (A.slot) A.slot[(size_t)b * N + pos] = V + irank;
+            if (P.sorted_output) prob[V + irank] = 0.f;
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= PV; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (PV >> 1); t += kChainThreads) {
+                int i = 2 * t - (t & (j - 1));
+                int l = i + j;
+                unsigned long long a = keys[i], c = keys[l];
+                bool up = ((i & k) == 0);
+                if ((a > c) == up) { keys[i] = c; keys[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < V; i += kChainThreads) {
+        const int pos = (int)(uint32_t)(keys[i] & 0xffffffffull);
+        valid_idx[i] = order[pos];
+        if (A.slot) A.slot[(size_t)b * N + pos] = i;
+        if (P.sorted_output) prob[i] = rthr[pos];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ 4. backward (mode GROUP_MASK)
+struct BwdArgs {
+    int N, batch;
+    const int32_t* n_per_image;
+    gnms_params p;
+    const float* grad_prob;
+    const int32_t* order;
+    const float* sorted_scores;
+    const int32_t* lead;
+    const float* pval;
+    const float* dpval;
+    const float* pre;
+    const int32_t* slot;
+    float* grad_scores;
+    float* grad_iou;
+    int64_t ld_gi;
+};
+
+__global__ void __launch_bounds__(kChainThreads) backward_mask_kernel(BwdArgs A) {
+    extern __shared__ float ds[];
+    const int b = blockIdx.x, N = A.N, tid = threadIdx.x;
+    const int n = A.n_per_image ? min(A.n_per_image[b], N) : N;
+    const size_t o = (size_t)b * N;
+    const float vthr = A.p.valid_box_prob_threshold;
+    // g~ = g * 1[0 <= pre <= 1] * 1[in a group] (* 1[r >= valid_thr] when the returned vector is the thresholded one)
+    for (int pos = tid; pos < n; pos += kChainThreads) {
+        const float pre = A.pre[o + pos];
+        const int ld_ = A.lead[o + pos];
+        float g = A.p.sorted_output ? A.grad_prob[o + A.slot[o + pos]] : A.grad_prob[o + pos];
+        bool pass = (pre >= 0.f) && (pre <= 1.f) && (ld_ >= 0);
+        if (A.p.sorted_output || A.p.thresholded_output) {
+            float r = fminf(fmaxf(pre, 0.f), 1.f);
+            pass = pass && (r >= vthr);
+        }
+        ds[pos] = pass ? g : 0.f;
+    }
+    __syncthreads();
+    // leaders: ds_l = g~_l - sum_m p_ml g~_m ; members add into a separate shared-memory accumulator (fp32 atomics:
+    // the summation order inside one group is not fixed, results agree to ~1 ulp between runs).
+    float* acc = ds + N;
+    for (int pos = tid; pos < n; pos += kChainThreads) acc[pos] = 0.f;
+    __syncthreads();
+    for (int pos = tid; pos < n; pos += kChainThreads) {
+        const int ld_ = A.lead[o + pos];
+        if (ld_ >= 0 && ld_ != pos) {
+            const float gt = ds[pos];
+            if (gt != 0.f) {
+                atomicAdd(&acc[ld_], __fmul_rn(A.pval[o + pos], gt));
+                if (A.grad_iou) {
+                    const int64_t gi = (int64_t)b * N * A.ld_gi + (int64_t)A.order[o + pos] * A.ld_gi + A.order[o + ld_];
+                    A.grad_iou[gi] = __fmul_rn(-__fmul_rn(A.sorted_scores[o + ld_], gt), A.dpval[o + pos]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int pos = tid; pos < n; pos += kChainThreads)
+        A.grad_scores[o + A.order[o + pos]] = __fsub_rn(ds[pos], acc[pos]);
+    if (n < N) {
+        // padded boxes (n_per_image < N): their input slots get zero gradient
+        for (int i = tid; i < N; i += kChainThreads) {
+            // slots not covered by order[0..n) are exactly the padded inputs n..N-1 of this image
+            if (i >= n) A.grad_scores[o + i] = 0.f;
+        }
+    }
+}
+
+static size_t chain_smem_bytes(int N) {
+    size_t NW = (size_t)((N + 31) / 32);
+    size_t keys = (size_t)N * 8;            // sort keys alias the window columns
+    size_t win = (size_t)kWin * NW * 4;
+    size_t P = 1;
+    while ((int)P < N) P <<= 1;
+    keys = P * 8;
+    return 3 * NW * 4 + (size_t)N * 4 * 2 + (keys > win ? keys : win);
+}
+
+static int configure_once() {
+    static bool done_dev[64] = {false};
+    int dev = 0;
+    GNMS_CUDA_TRY(cudaGetDevice(&dev));
+    bool& done = done_dev[dev & 63];
+    if (done) return 0;
+    GNMS_CUDA_TRY(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    GNMS_CUDA_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)chain_smem_bytes(GNMS_MAX_BOXES)));
+    GNMS_CUDA_TRY(cudaFuncSetAttribute(backward_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    done = true;
+    return 0;
+}
+
+static size_t sort_smem_bytes(int N) {
+    size_t P = 1;
+    while ((int)P < N) P <<= 1;
+    return P * 8;
+}
+
+template <int kSrc, int kCmp>
+static void launch_mask_boxes(dim3 grid, cudaStream_t s, int generalized, int affine, int N, const int32_t* npi,
+                              char* ws, size_t stride, float thr, float shift) {
+    if (kSrc == kSrcBox3d) {
+        if (generalized) {
+            if (affine) mask_boxes_kernel<kSrcBox3d, true, true, kCmp><<<grid, kMaskThreads, 0, s>>>(N, npi, ws, stride, thr, shift);
+            else mask_boxes_kernel<kSrcBox3d, true, false, kCmp><<<grid, kMaskThreads, 0, s>>>(N, npi, ws, stride, thr, shift);
+        } else {
+            if (affine) mask_boxes_kernel<kSrcBox3d, false, true, kCmp><<<grid, kMaskThreads, 0, s>>>(N, npi, ws, stride, thr, shift);
+            else mask_boxes_kernel<kSrcBox3d, false, false, kCmp><<<grid, kMaskThreads, 0, s>>>(N, npi, ws, stride, thr, shift);
+        }
+    } else {
+        mask_boxes_kernel<kSrc, false, false, kCmp><<<grid, kMaskThreads, 0, s>>>(N, npi, ws, stride, thr, shift);
+    }
+}
+
+static int check_common(int N, int batch, const gnms_params* p) {
+    if (N < 0 || batch < 0 || !p) return GNMS_E_BADARG;
+    if (N > GNMS_MAX_BOXES) return GNMS_E_TOOLARGE;
+    if (p->pruning_method < 0 || p->pruning_method > 2 || p->mode < 0 || p->mode > 2 || p->group_size < 0)
+        return GNMS_E_BADARG;
+    return 0;
+}
+
+}  // namespace gnms
+
+using namespace gnms;
+
+extern "C" int gnms_version(void) { return GNMS_VERSION; }
+
+extern "C" const char* gnms_error_string(int rc) {
+    if (rc == 0) return "success";
+    if (rc > 0) return cudaGetErrorString((cudaError_t)rc);
+    switch (rc) {
+        case GNMS_E_BADARG: return "gnms: bad argument";
+        case GNMS_E_TOOLARGE: return "gnms: more boxes per image than GNMS_MAX_BOXES";
+        case GNMS_E_ALIGN: return "gnms: pointer not 16-byte aligned";
+        case GNMS_E_UNSUPPORTED: return "gnms: unsupported configuration";
+    }
+    return "gnms: unknown error";
+}
+
+// Layout: [batch image slices][slot int32[batch*N]][4 scratch arrays of N words (get_groups / hard NMS)]
+extern "C" size_t gnms_workspace_bytes(int N, int batch) {
+    if (N <= 0 || batch <= 0) return 256;
+    return ws_layout(N).total * (size_t)batch + align_up((size_t)batch * N * 4) + 4 * align_up((size_t)N * 4);
+}
+
+static int run_forward(const float* scores, int src, const float* iou, int64_t ld, const float* boxes,
+                       int generalized, int affine, int N, int batch, const int32_t* npi, const gnms_params* p,
+                       float* prob, int64_t* valid_idx, int64_t* invalid_idx, int32_t* counts, gnms_saved sv,
+                       int32_t* slot, void* workspace, cudaStream_t s) {
+    int rc = check_common(N, batch, p);
+    if (rc) return rc;
+    if (N == 0 || batch == 0) return 0;
+    if (p->mode != GNMS_MODE_GROUP_MASK) return GNMS_E_UNSUPPORTED;
+    if (!scores || !prob || !valid_idx || !invalid_idx || !counts || !workspace || !sv.order || !sv.sorted_scores ||
+        !sv.lead || !sv.pval || !sv.dpval || !sv.pre)
+        return GNMS_E_BADARG;
+    if (p->sorted_output && !slot) return GNMS_E_BADARG;
+    rc = configure_once();
+    if (rc) return rc;
+    const WsLayout L = ws_layout(N);
+    char* ws = reinterpret_cast<char*>(workspace);
+    const int NW = (N + 31) / 32;
+    int box_stride = src == kSrcBox2d ? 4 : 8;
+    sort_kernel<<<batch, kChainThreads, sort_smem_bytes(N), s>>>(
+        scores, 1, N, N, npi, sv.order, sv.sorted_scores, ws, L.total, src == kSrcMatrix ? nullptr : boxes, src,
+        (int64_t)N * box_stride, 0.f, 0);
+    GNMS_LAUNCH_CHECK();
+    if (src == kSrcMatrix) {
+        if (!iou || ld < N) return GNMS_E_BADARG;
+        dim3 grid(gnms_div_up(N, kMaskThreads * 4), NW, batch);
+        bool vec = ((reinterpret_cast<uintptr_t>(iou) & 15u) == 0) && (ld % 4 == 0) && (((int64_t)N * ld) % 4 == 0);
+        if (vec) mask_matrix_kernel<true><<<grid, kMaskThreads, 0, s>>>(iou, ld, (int64_t)N * ld, N, npi, sv.order, ws, L.total, p->nms_threshold);
+        else mask_matrix_kernel<false><<<grid, kMaskThreads, 0, s>>>(iou, ld, (int64_t)N * ld, N, npi, sv.order, ws, L.total, p->nms_threshold);
+    } else {
+        if (!boxes) return GNMS_E_BADARG;
+        dim3 grid(gnms_div_up(N, kMaskThreads), NW, batch);
+        if (src == kSrcBox3d) launch_mask_boxes<kSrcBox3d, GNMS_CMP_NLE>(grid, s, generalized, affine, N, npi, ws, L.total, p->nms_threshold, 0.f);
+        else launch_mask_boxes<kSrcBox2d, GNMS_CMP_NLE>(grid, s, 0, 0, N, npi, ws, L.total, p->nms_threshold, 0.f);
+    }
+    GNMS_LAUNCH_CHECK();
+    ChainArgs A = {};
+    A.N = N; A.batch = batch; A.n_per_image = npi; A.ws = ws; A.ws_img_stride = L.total;
+    A.src = src; A.iou = iou; A.ld = ld; A.iou_img_stride = (int64_t)N * ld;
+    A.generalized = generalized; A.affine = affine; A.p = *p;
+    A.order = sv.order; A.sorted_scores = sv.sorted_scores; A.prob = prob; A.valid_idx = valid_idx;
+    A.invalid_idx = invalid_idx; A.counts = counts; A.lead = sv.lead; A.pval = sv.pval; A.dpval = sv.dpval;
+    A.pre = sv.pre; A.slot = slot;
+    chain_kernel<<<batch, kChainThreads, chain_smem_bytes(N), s>>>(A);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
+
+// `slot` (position of every sorted box in the sorted output) lives at the tail of the pre-array contract: callers
+// that use sorted_output pass a [batch,N] int32 buffer through gnms_saved.dpval's neighbour -- to keep the ABI flat
+// it is carried in the workspace instead (first bytes after the per-image slices).
+static int32_t* slot_ptr(void* workspace, int N, int batch) {
+    return reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + ws_layout(N).total * (size_t)batch);
+}
+
+extern "C" int gnms_forward_f32(const float* scores, const float* iou, int64_t ld, int N, int batch,
+                                const int32_t* n_per_image, const gnms_params* p, float* prob, int64_t* valid_idx,
+                                int64_t* invalid_idx, int32_t* counts, gnms_saved saved, void* workspace,
+                                void* stream) {
+    return run_forward(scores, kSrcMatrix, iou, ld, nullptr, 0, 0, N, batch, n_per_image, p, prob, valid_idx,
+                       invalid_idx, counts, saved, workspace ? slot_ptr(workspace, N, batch) : nullptr, workspace,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int gnms_forward_boxes_f32(const float* scores, const float* boxes, int box_kind, int generalized,
+                                      int affine, int N, int batch, const int32_t* n_per_image, const gnms_params* p,
+                                      float* prob, int64_t* valid_idx, int64_t* invalid_idx, int32_t* counts,
+                                      gnms_saved saved, void* workspace, void* stream) {
+    if (box_kind != GNMS_BOX_2D && box_kind != GNMS_BOX_3D_REC) return GNMS_E_BADARG;
+    if (boxes && (reinterpret_cast<uintptr_t>(boxes) & 15u)) return GNMS_E_ALIGN;
+    return run_forward(scores, box_kind == GNMS_BOX_2D ? kSrcBox2d : kSrcBox3d, nullptr, 0, boxes, generalized, affine,
+                       N, batch, n_per_image, p, prob, valid_idx, invalid_idx, counts, saved,
+                       workspace ? slot_ptr(workspace, N, batch) : nullptr, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int gnms_backward_f32(const float* grad_prob, const float* prob, const float* iou, int64_t ld, int N,
+                                 int batch, const int32_t* n_per_image, const gnms_params* p, gnms_saved sv,
+                                 float* grad_scores, float* grad_iou, int64_t ld_gi, void* workspace, void* stream) {
+    (void)prob; (void)iou; (void)ld;
+    int rc = check_common(N, batch, p);
+    if (rc) return rc;
+    if (N == 0 || batch == 0) return 0;
+    if (p->mode != GNMS_MODE_GROUP_MASK) return GNMS_E_UNSUPPORTED;
+    if (!grad_prob || !grad_scores || !sv.order || !sv.sorted_scores || !sv.lead || !sv.pval || !sv.dpval || !sv.pre)
+        return GNMS_E_BADARG;
+    if (grad_iou && ld_gi < N) return GNMS_E_BADARG;
+    if (p->sorted_output && !workspace) return GNMS_E_BADARG;
+    rc = configure_once();
+    if (rc) return rc;
+    BwdArgs A = {};
+    A.N = N; A.batch = batch; A.n_per_image = n_per_image; A.p = *p; A.grad_prob = grad_prob; A.order = sv.order;
+    A.sorted_scores = sv.sorted_scores; A.lead = sv.lead; A.pval = sv.pval; A.dpval = sv.dpval; A.pre = sv.pre;
+    A.slot = workspace ? slot_ptr(workspace, N, batch) : nullptr;
+    A.grad_scores = grad_scores; A.grad_iou = grad_iou; A.ld_gi = ld_gi;
+    backward_mask_kernel<<<batch, kChainThreads, (size_t)N * 8, (cudaStream_t)stream>>>(A);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gnms_get_groups_f32(const float* scores, const float* iou, int64_t ld, int N, float group_threshold,
+                                   int group_size, int32_t* group_id, int32_t* group_rank, int32_t* n_groups,
+                                   void* workspace, void* stream) {
+    if (N < 0 || group_size < 0) return GNMS_E_BADARG;
+    if (N > GNMS_MAX_BOXES) return GNMS_E_TOOLARGE;
+    if (N == 0) return 0;
+    if (!scores || !iou || ld < N || !group_id || !group_rank || !n_groups || !workspace) return GNMS_E_BADARG;
+    int rc = configure_once();
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const WsLayout L = ws_layout(N);
+    char* ws = reinterpret_cast<char*>(workspace);
+    // order / sorted scores / pval / dpval scratch live after the image slice (+ the slot array)
+    char* extra = ws + L.total + align_up((size_t)N * 4);
+    int32_t* order = reinterpret_cast<int32_t*>(extra);
+    float* ss = reinterpret_cast<float*>(extra + align_up((size_t)N * 4));
+    float* pv = reinterpret_cast<float*>(extra + 2 * align_up((size_t)N * 4));
+    float* dpv = reinterpret_cast<float*>(extra + 3 * align_up((size_t)N * 4));
+    const int NW = (N + 31) / 32;
+    sort_kernel<<<1, kChainThreads, sort_smem_bytes(N), s>>>(scores, 1, N, N, nullptr, order, ss, ws, L.total, nullptr,
+                                                            kSrcMatrix, 0, 0.f, 0);
+    GNMS_LAUNCH_CHECK();
+    dim3 grid(gnms_div_up(N, kMaskThreads * 4), NW, 1);
+    bool vec = ((reinterpret_cast<uintptr_t>(iou) & 15u) == 0) && (ld % 4 == 0);
+    if (vec) mask_matrix_kernel<true><<<grid, kMaskThreads, 0, s>>>(iou, ld, 0, N, nullptr, order, ws, L.total, group_threshold);
+    else mask_matrix_kernel<false><<<grid, kMaskThreads, 0, s>>>(iou, ld, 0, N, nullptr, order, ws, L.total, group_threshold);
+    GNMS_LAUNCH_CHECK();
+    ChainArgs A = {};
+    A.N = N; A.batch = 1; A.ws = ws; A.ws_img_stride = L.total; A.src = kSrcMatrix; A.iou = iou; A.ld = ld;
+    A.p.nms_threshold = group_threshold; A.p.group_size = group_size; A.p.pruning_method = GNMS_PRUNE_LINEAR;
+    A.order = order; A.sorted_scores = ss; A.pval = pv; A.dpval = dpv;
+    A.group_id = group_id; A.group_rank = group_rank; A.n_groups = n_groups;
+    chain_kernel<<<1, kChainThreads, chain_smem_bytes(N), s>>>(A);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
+
+static int hard_nms_impl(const float* dets, int N, float thresh, float shift, int cmp, int32_t* keep,
+                         int32_t* n_keep, void* workspace, void* stream, int presorted) {
+    if (N < 0 || cmp < 0 || cmp > 2) return GNMS_E_BADARG;
+    if (N > GNMS_MAX_BOXES) return GNMS_E_TOOLARGE;
+    if (!n_keep) return GNMS_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (N == 0) return (int)cudaMemsetAsync(n_keep, 0, sizeof(int32_t), s);
+    if (!dets || !keep || !workspace) return GNMS_E_BADARG;
+    int rc = configure_once();
+    if (rc) return rc;
+    const WsLayout L = ws_layout(N);
+    char* ws = reinterpret_cast<char*>(workspace);
+    char* extra = ws + L.total + align_up((size_t)N * 4);
+    int32_t* order = reinterpret_cast<int32_t*>(extra);
+    float* ss = reinterpret_cast<float*>(extra + align_up((size_t)N * 4));
+    const int NW = (N + 31) / 32;
+    sort_kernel<<<1, kChainThreads, sort_smem_bytes(N), s>>>(dets + 4, 5, 0, N, nullptr, order, ss, ws, L.total, dets,
+                                                            kSrcBoxShift, 0, shift, presorted);
+    GNMS_LAUNCH_CHECK();
+    dim3 grid(gnms_div_up(N, kMaskThreads), NW, 1);
+    if (cmp == GNMS_CMP_GT) launch_mask_boxes<kSrcBoxShift, GNMS_CMP_GT>(grid, s, 0, 0, N, nullptr, ws, L.total, thresh, shift);
+    else if (cmp == GNMS_CMP_GE) launch_mask_boxes<kSrcBoxShift, GNMS_CMP_GE>(grid, s, 0, 0, N, nullptr, ws, L.total, thresh, shift);
+    else launch_mask_boxes<kSrcBoxShift, GNMS_CMP_NLE>(grid, s, 0, 0, N, nullptr, ws, L.total, thresh, shift);
+    GNMS_LAUNCH_CHECK();
+    ChainArgs A = {};
+    A.N = N; A.batch = 1; A.ws = ws; A.ws_img_stride = L.total; A.src = kSrcBoxShift;
+    A.order = order; A.sorted_scores = ss; A.keep = keep; A.n_keep = n_keep; A.leaders_only = 1;
+    chain_kernel<<<1, kChainThreads, chain_smem_bytes(N), s>>>(A);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gnms_hard_nms_f32(const float* dets, int N, float thresh, float shift, int cmp, int32_t* keep,
+                                 int32_t* n_keep, void* workspace, void* stream) {
+    return hard_nms_impl(dets, N, thresh, shift, cmp, keep, n_keep, workspace, stream, 0);
+}
+
+// Drop-in for `_nms` (lib/nms/gpu_nms.hpp:1-2, lib/nms/nms_kernel.cu:91-144): host pointers, boxes sorted by score.
+extern "C" int gnms_nms_host(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim,
+                             float nms_overlap_thresh, int device_id) {
+    if (!num_out || boxes_num < 0) return GNMS_E_BADARG;
+    if (boxes_num == 0) { *num_out = 0; return 0; }
+    if (!keep_out || !boxes_host || boxes_dim != 5) return GNMS_E_BADARG;
+    if (boxes_num > GNMS_MAX_BOXES) return GNMS_E_TOOLARGE;
+    int cur = 0;
+    GNMS_CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != device_id) GNMS_CUDA_TRY(cudaSetDevice(device_id));
+    const int N = boxes_num;
+    size_t wsb = gnms_workspace_bytes(N, 1);
+    size_t detb = align_up((size_t)N * 5 * 4), keepb = align_up((size_t)N * 4);
+    char* dev = nullptr;
+    int rc = (int)cudaMalloc(&dev, detb + keepb + 256 + wsb);
+    if (rc) return rc;
+    float* d_dets = reinterpret_cast<float*>(dev);
+    int32_t* d_keep = reinterpret_cast<int32_t*>(dev + detb);
+    int32_t* d_n = reinterpret_cast<int32_t*>(dev + detb + keepb);
+    void* d_ws = dev + detb + keepb + 256;
+    cudaStream_t s = 0;
+    rc = (int)cudaMemcpyAsync(d_dets, boxes_host, (size_t)N * 5 * 4, cudaMemcpyHostToDevice, s);
+    if (!rc) rc = hard_nms_impl(d_dets, N, nms_overlap_thresh, 1.0f, GNMS_CMP_GT, d_keep, d_n, d_ws, s, 1);
+    int nk = 0;
+    if (!rc) rc = (int)cudaMemcpyAsync(&nk, d_n, 4, cudaMemcpyDeviceToHost, s);
+    if (!rc) rc = (int)cudaStreamSynchronize(s);
+    if (!rc && nk > 0) rc = (int)cudaMemcpy(keep_out, d_keep, (size_t)nk * 4, cudaMemcpyDeviceToHost);
+    if (!rc) *num_out = nk;
+    cudaFree(dev);
+    if (cur != device_id) cudaSetDevice(cur);
+    return rc;
+}

@@ -1,0 +1,311 @@
+// Soft-NMS (lib/nms_others.py:6-116) and AP loss (lib/loss/aploss.py:14-97) for sm_100a.
+// Both are small, inherently sequential-over-rounds algorithms: one CTA per problem, block-wide reductions.
+#include "common.cuh"
+
+namespace gnms {
+
+constexpr int kT = 1024;
+
+__device__ __forceinline__ void block_argmax(double v, int idx, double* s_val, int* s_idx, double& out_v, int& out_i) {
+    // (value desc, index asc): the reference's `maxscore < boxes[pos,4]` scan keeps the FIRST maximum
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        double ov = __shfl_down_sync(0xffffffffu, v, d);
+        int oi = __shfl_down_sync(0xffffffffu, idx, d);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    if (lane == 0) { s_val[warp] = v; s_idx[warp] = idx; }
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < (kT / 32) ? s_val[lane] : -INFINITY;
+        idx = lane < (kT / 32) ? s_idx[lane] : INT_MAX;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            double ov = __shfl_down_sync(0xffffffffu, v, d);
+            int oi = __shfl_down_sync(0xffffffffu, idx, d);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        if (lane == 0) { s_val[0] = v; s_idx[0] = idx; }
+    }
+    __syncthreads();
+    out_v = s_val[0];
+    out_i = s_idx[0];
+    __syncthreads();
+}
+
+// One CTA.  Arrangement-free restatement of the reference's in-place selection sort with swaps: each round picks
+// the live, not yet selected box with the highest (decayed) score, decays every other live box by the overlap
+// weight and drops boxes whose score falls below `threshold`.  With distinct scores the selected sequence is
+// independent of the physical row order the reference maintains (ties: lowest original index first).
+__global__ void __launch_bounds__(kT)
+soft_nms_kernel(const double* __restrict__ dets, int N, double sigma, double Nt, double threshold, int method,
+                double shift, int32_t* __restrict__ keep, double* __restrict__ keep_scores, int32_t* __restrict__ n_keep,
+                double* __restrict__ score, int32_t* __restrict__ state) {
+    __shared__ double s_val[kT / 32];
+    __shared__ int s_idx[kT / 32];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < N; i += kT) { score[i] = dets[(size_t)i * 5 + 4]; state[i] = 0; }   // 0 live, 1 selected, 2 dropped
+    __syncthreads();
+    int nsel = 0;
+    for (int round = 0; round < N; ++round) {
+        double bv = -INFINITY;
+        int bi = INT_MAX;
+        for (int i = tid; i < N; i += kT) {
+            if (state[i] == 0) {
+                double v = score[i];
+                if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+            }
+        }
+        double mv; int mi;
+        block_argmax(bv, bi, s_val, s_idx, mv, mi);
+        if (mi == INT_MAX) break;                       // nothing live
+        if (tid == 0) { keep[nsel] = mi; keep_scores[nsel] = mv; state[mi] = 1; }
+        ++nsel;
+        const double tx1 = dets[(size_t)mi * 5 + 0], ty1 = dets[(size_t)mi * 5 + 1];
+        const double tx2 = dets[(size_t)mi * 5 + 2], ty2 = dets[(size_t)mi * 5 + 3];
+        __syncthreads();
+        for (int i = tid; i < N; i += kT) {
+            if (state[i] != 0) continue;
+            const double x1 = dets[(size_t)i * 5 + 0], y1 = dets[(size_t)i * 5 + 1];
+            const double x2 = dets[(size_t)i * 5 + 2], y2 = dets[(size_t)i * 5 + 3];
+            const double area = __dmul_rn(__dadd_rn(__dsub_rn(x2, x1), shift), __dadd_rn(__dsub_rn(y2, y1), shift));
+            const double iw = __dadd_rn(__dsub_rn(fmin(tx2, x2), fmax(tx1, x1)), shift);       // :73
+            if (iw > 0) {
+                const double ih = __dadd_rn(__dsub_rn(fmin(ty2, y2), fmax(ty1, y1)), shift);   // :75
+                if (ih > 0) {
+                    const double ua = __dsub_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dsub_rn(tx2, tx1), shift),
+                                                                    __dadd_rn(__dsub_rn(ty2, ty1), shift)), area),
+                                                __dmul_rn(iw, ih));                              // :77
+                    const double ov = __ddiv_rn(__dmul_rn(iw, ih), ua);                          // :78
+                    double wgt;
+                    if (method == 1) wgt = ov > Nt ? __dsub_rn(1.0, ov) : 1.0;                   // :80-84
+                    else if (method == 2) wgt = exp(-__ddiv_rn(__dmul_rn(ov, ov), sigma));       // :86
+                    else wgt = ov > Nt ? 0.0 : 1.0;                                              // :88-91
+                    const double sc = __dmul_rn(wgt, score[i]);                                  // :93
+                    score[i] = sc;
+                    if (sc < threshold) state[i] = 2;                                            // :97
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *n_keep = nsel;
+}
+
+// ------------------------------------------------------------------------------------------ AP loss
+// One CTA.  lib/loss/aploss.py:16-81 with delta = 1 (:18).  Workspace: fg index list (int32[n]), a+b / scale
+// per positive (float[2n]), prec per positive (float[n]).
+__global__ void __launch_bounds__(kT)
+aploss_kernel(const float* __restrict__ logits, const float* __restrict__ targets, int n, float* __restrict__ loss,
+              float* __restrict__ grad, int32_t* __restrict__ fg_list, float* __restrict__ fg_ab,
+              float* __restrict__ fg_prec, unsigned long long* __restrict__ fg_keys) {
+    __shared__ int s_nfg;
+    __shared__ float s_red[kT / 32];
+    __shared__ float s_thr;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_nfg = 0;
+    for (int i = tid; i < n; i += kT) grad[i] = 0.f;
+    __syncthreads();
+    // positives (targets == 1), listed in index order is not required: they are sorted by logit below
+    for (int i = tid; i < n; i += kT)
+        if (targets[i] == 1.f) fg_list[atomicAdd(&s_nfg, 1)] = i;
+    __syncthreads();
+    const int nfg = s_nfg;
+    if (nfg == 0) {                                                          // :27-29  (max(targets) <= 0)
+        if (tid == 0) *loss = 0.f;
+        return;
+    }
+    // sort positives by (logit asc, index asc): torch.sort(fg_logits) (:47); small list -> rank by counting
+    for (int a = tid; a < nfg; a += kT) {
+        const int ia = fg_list[a];
+        const float va = logits[ia];
+        int r = 0;
+        for (int c = 0; c < nfg; ++c) {
+            const int ic = fg_list[c];
+            const float vc = logits[ic];
+            r += (vc < va) || (vc == va && ic < ia);
+        }
+        fg_keys[r] = (unsigned long long)(uint32_t)ia;
+    }
+    __syncthreads();
+    float mn = INFINITY;
+    for (int a = tid; a < nfg; a += kT) mn = fminf(mn, logits[(int)fg_keys[a]]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+    if (lane == 0) s_red[warp] = mn;
+    __syncthreads();
+    if (tid == 0) {
+        float m = s_red[0];
+        for (int k = 1; k < kT / 32; ++k) m = fminf(m, s_red[k]);
+        s_thr = __fsub_rn(m, 1.0f);                                          // :33 threshold_logit = min(fg) - delta
+    }
+    __syncthreads();
+    const float thr = s_thr;
+    // per positive (in ascending order): a = sum_fg clamp((fg - x)/2 + .5) + .5 ; b = sum_validbg clamp((bg - x)/2 + .5)
+    for (int a = 0; a < nfg; ++a) {
+        const float x = logits[(int)fg_keys[a]];
+        float sa = 0.f, sb = 0.f;
+        for (int i = tid; i < n; i += kT) {
+            const float t = targets[i], v = logits[i];
+            const float c = fminf(fmaxf(__fadd_rn(__fdiv_rn(__fsub_rn(v, x), 2.0f), 0.5f), 0.f), 1.f);
+            if (t == 1.f) sa += c;
+            else if (t == 0.f && v >= thr) sb += c;                          // :36 valid negatives
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, d);
+            sb += __shfl_xor_sync(0xffffffffu, sb, d);
+        }
+        __syncthreads();
+        if (lane == 0) { s_red[warp] = sa; }
+        __syncthreads();
+        float ta = 0.f;
+        if (tid == 0) { for (int k = 0; k < kT / 32; ++k) ta += s_red[k]; }
+        __syncthreads();
+        if (lane == 0) { s_red[warp] = sb; }
+        __syncthreads();
+        if (tid == 0) {
+            float tb = 0.f;
+            for (int k = 0; k < kT / 32; ++k) tb += s_red[k];
+            fg_ab[2 * a] = __fadd_rn(ta, 0.5f);                              // :57
+            fg_ab[2 * a + 1] = tb;                                           // :59
+        }
+        __syncthreads();
+    }
+    // running max of the interpolated precision in ascending-logit order (:62-66), per-positive scale for bg grads
+    if (tid == 0) {
+        float max_prec = 0.f, sum_prec = 0.f;
+        for (int a = 0; a < nfg; ++a) {
+            const float A = fg_ab[2 * a], B = fg_ab[2 * a + 1];
+            const float cur = __fdiv_rn(A, __fadd_rn(A, B));
+            float scale = 1.f;
+            if (max_prec <= cur) max_prec = cur;
+            else scale = __fdiv_rn(__fsub_rn(1.f, max_prec), __fsub_rn(1.f, cur));
+            fg_prec[a] = max_prec;
+            fg_ab[2 * a] = __fadd_rn(A, B);      // reuse: a+b
+            fg_ab[2 * a + 1] = scale;
+            sum_prec += max_prec;
+        }
+        const float fn = (float)nfg;
+        *loss = __fsub_rn(1.f, __fdiv_rn(sum_prec, fn));                     // :79-81
+    }
+    __syncthreads();
+    const float fn = (float)nfg;
+    for (int a = tid; a < nfg; a += kT)
+        grad[(int)fg_keys[a]] = __fdiv_rn(-__fsub_rn(1.f, fg_prec[a]), fn);   // :71,75
+    for (int i = tid; i < n; i += kT) {
+        const float t = targets[i], v = logits[i];
+        if (t == 0.f && v >= thr) {
+            float g = 0.f;
+            for (int a = 0; a < nfg; ++a) {                                   // same order as `valid_bg_grad += tmp2`
+                const float x = logits[(int)fg_keys[a]];
+                float c = fminf(fmaxf(__fadd_rn(__fdiv_rn(__fsub_rn(v, x), 2.0f), 0.5f), 0.f), 1.f);
+                c = __fdiv_rn(c, fg_ab[2 * a]);                               // :60 tmp2 /= (a+b)
+                const float sc = fg_ab[2 * a + 1];
+                if (sc != 1.f) c = __fmul_rn(c, sc);                          // :66
+                g = __fadd_rn(g, c);
+            }
+            grad[i] = __fdiv_rn(g, fn);                                       // :70,75
+        }
+    }
+}
+
+__global__ void prune_kernel(const float* __restrict__ x, int64_t n, int method, float thr, float temp,
+                             float* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = prune(x[i], method, thr, temp);
+}
+
+// A[ra,ca,:] = B[rb,cb,:]; product form when ca == nullptr (see header)
+__global__ void indices_copy_kernel(float* __restrict__ A, int64_t colsA, const float* __restrict__ B, int64_t colsB,
+                                    int64_t C, const int64_t* __restrict__ ra, const int64_t* __restrict__ ca,
+                                    const int64_t* __restrict__ rb, const int64_t* __restrict__ cb, int64_t npairs) {
+    const int64_t total = (ca ? npairs : npairs * npairs) * C;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        const int64_t k = t / C, c = t - k * C;
+        int64_t r_a, c_a, r_b, c_b;
+        if (ca) {
+            r_a = ra[k]; c_a = ca[k]; r_b = rb[k]; c_b = cb[k];
+        } else {
+            const int64_t i = k / npairs, j = k - i * npairs;
+            r_a = ra[i]; c_a = ra[j]; r_b = i; c_b = j;
+        }
+        A[(r_a * colsA + c_a) * C + c] = B[(r_b * colsB + c_b) * C + c];
+    }
+}
+
+}  // namespace gnms
+
+using namespace gnms;
+
+extern "C" int gnms_prune_f32(const float* x, int64_t n, int pruning_method, float nms_threshold, float temperature,
+                              float* out, void* stream) {
+    if (n < 0 || pruning_method < 0 || pruning_method > 2) return GNMS_E_BADARG;
+    if (n == 0) return 0;
+    if (!x || !out) return GNMS_E_BADARG;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    prune_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, pruning_method, nms_threshold, temperature, out);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gnms_indices_copy_f32(float* A, int64_t colsA, const float* B, int64_t colsB, int64_t C,
+                                     const int64_t* ra, const int64_t* ca, const int64_t* rb, const int64_t* cb,
+                                     int64_t npairs, void* stream) {
+    if (npairs < 0 || C <= 0 || colsA <= 0 || colsB <= 0) return GNMS_E_BADARG;
+    if (npairs == 0) return 0;
+    if (!A || !B || !ra || (ca && (!rb || !cb))) return GNMS_E_BADARG;
+    const int64_t total = (ca ? npairs : npairs * npairs) * C;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    indices_copy_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(A, colsA, B, colsB, C, ra, ca, rb, cb, npairs);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
+
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t gnms_soft_nms_workspace_bytes(int N) {
+    if (N <= 0) return 256;
+    return al256((size_t)N * 8) + al256((size_t)N * 4);
+}
+
+extern "C" int gnms_soft_nms_f64(const double* dets, int N, double sigma, double Nt, double threshold, int method,
+                                 double shift, int32_t* keep, double* keep_scores, int32_t* n_keep, void* workspace,
+                                 void* stream) {
+    if (N < 0 || method < 0 || method > 2 || !n_keep) return GNMS_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (N == 0) return (int)cudaMemsetAsync(n_keep, 0, sizeof(int32_t), s);
+    if (!dets || !keep || !keep_scores || !workspace) return GNMS_E_BADARG;
+    double* score = reinterpret_cast<double*>(workspace);
+    int32_t* state = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + al256((size_t)N * 8));
+    soft_nms_kernel<<<1, kT, 0, s>>>(dets, N, sigma, Nt, threshold, method, shift, keep, keep_scores, n_keep, score, state);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" size_t gnms_aploss_workspace_bytes(int n) {
+    if (n <= 0) return 256;
+    return al256((size_t)n * 4) + al256((size_t)n * 8) + al256((size_t)n * 4) + al256((size_t)n * 8);
+}
+
+extern "C" int gnms_aploss_f32(const float* logits, const float* targets, int n, float* loss, float* grad,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    if (n < 0 || !loss) return GNMS_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) return (int)cudaMemsetAsync(loss, 0, sizeof(float), s);
+    if (!logits || !targets || !grad || !workspace || workspace_bytes < gnms_aploss_workspace_bytes(n)) return GNMS_E_BADARG;
+    char* w = reinterpret_cast<char*>(workspace);
+    int32_t* fg_list = reinterpret_cast<int32_t*>(w);
+    float* fg_ab = reinterpret_cast<float*>(w + al256((size_t)n * 4));
+    float* fg_prec = reinterpret_cast<float*>(w + al256((size_t)n * 4) + al256((size_t)n * 8));
+    unsigned long long* fg_keys = reinterpret_cast<unsigned long long*>(w + al256((size_t)n * 4) + al256((size_t)n * 8) + al256((size_t)n * 4));
+    aploss_kernel<<<1, kT, 0, s>>>(logits, targets, n, loss, grad, fg_list, fg_ab, fg_prec, fg_keys);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}

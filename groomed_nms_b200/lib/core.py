@@ -1,0 +1,110 @@
+"""Mirror of the overlap functions of the reference's lib/core.py:178-532 on the sm_100a tile kernels.
+
+Public names and argument meaning follow the reference: intersect, iou, iou3d_approximate, get_volume, get_hull,
+remove_rotation_in_boxes.  Results are bitwise equal to the reference's torch CPU ops (separately rounded fp32)."""
+import numpy as np
+import torch
+
+from .. import _lib, ops
+from ._util import Origin, to_cuda_f32
+
+
+def _check_type(data_type, x):
+    if data_type is None:
+        data_type = type(x)
+    if data_type not in (np.ndarray, torch.Tensor):
+        raise ValueError('type {} is not implemented'.format(data_type))      # lib/core.py:216
+    return data_type
+
+
+def intersect(box_a, box_b, mode='combinations', data_type=None):
+    """Intersection areas (reference lib/core.py:178-243).  combinations: box_a[M,4], box_b[N,4] -> [N,M]
+    (b-major, like the reference :210-218); list: [M]."""
+    _check_type(data_type, box_a)
+    origin = Origin(box_a)
+    a, b = to_cuda_f32(box_a), to_cuda_f32(box_b)
+    if mode == 'combinations':
+        out = ops.overlap2d(b[:, :4], a[:, :4], _lib.KIND_INTERSECT)
+    elif mode == 'list':
+        out = ops.overlap2d_list(a[:, :4], b[:, :4], _lib.KIND_INTERSECT)
+    else:
+        raise ValueError('unknown mode {}'.format(mode))                       # lib/core.py:243
+    return origin.back(out, keep_np_dtype=True)
+
+
+def iou(box_a, box_b, mode='combinations', data_type=None):
+    """IoU (reference lib/core.py:480-532).  combinations: [M,4] x [N,4] -> [M,N]; list: [M].  No +1 convention;
+    0/0 (coincident zero-area boxes) is NaN as in the reference.  The reference returns the combinations result
+    as a transposed view (:508); this returns the same values contiguous."""
+    _check_type(data_type, box_a)
+    origin = Origin(box_a)
+    a, b = to_cuda_f32(box_a), to_cuda_f32(box_b)
+    if mode == 'combinations':
+        out = ops.Overlap2dFunction.apply(a[:, :4], b[:, :4], False)
+    elif mode == 'list':
+        out = ops.Overlap2dFunction.apply(a[:, :4], b[:, :4], True)
+    else:
+        raise ValueError('unknown mode {}'.format(mode))                       # lib/core.py:532
+    return origin.back(out, keep_np_dtype=True)
+
+
+def get_volume(corners_3d):
+    """Axis-aligned volume of [N,3,8] (or [3,8]) corners (reference lib/core.py:434-451)."""
+    origin = Origin(corners_3d)
+    c = to_cuda_f32(corners_3d)
+    if c.dim() == 2:
+        c = c.unsqueeze(0)
+    rec = ops.box3d_records(c.contiguous(), mutate_input=False)
+    vol = rec[:, 6].contiguous()
+    if origin.numpy:
+        return origin.back(vol, keep_np_dtype=True)[0]                         # numpy branch returns a scalar (:449)
+    return origin.back(vol)
+
+
+def remove_rotation_in_boxes(boxes):
+    """[N,4,2] -> [N,4] axis-aligned hull x1,y1,x2,y2 (reference lib/core.py:463-477)."""
+    x1 = torch.min(boxes[:, :, 0], dim=1)[0]
+    x2 = torch.max(boxes[:, :, 0], dim=1)[0]
+    y1 = torch.min(boxes[:, :, 1], dim=1)[0]
+    y2 = torch.max(boxes[:, :, 1], dim=1)[0]
+    return torch.stack((x1, y1, x2, y2), dim=1)
+
+
+def get_hull(y_min_b1, y_max_b1, y_min_b2, y_max_b2, mode="list"):
+    """Hull extent along one axis (reference lib/core.py:423-432)."""
+    if mode == "combinations":
+        lo = torch.min(y_min_b1.unsqueeze(1), y_min_b2.unsqueeze(0))
+        hi = torch.max(y_max_b1.unsqueeze(1), y_max_b2.unsqueeze(0))
+    else:
+        lo = torch.min(y_min_b1, y_min_b2)
+        hi = torch.max(y_max_b1, y_max_b2)
+    return torch.clamp(hi - lo, min=0)
+
+
+def iou3d_approximate(corners_3d_b1, corners_3d_b2, mode="list", method="normal"):
+    """Axis-aligned approximate 3D IoU (reference lib/core.py:305-421) -> (iou_bev, iou_3d).
+
+    corners are [M,3,8] / [N,3,8] (or [3,8]); combinations -> [M,N], list -> [M].  method "generalized" adds the
+    GIoU hull term (:390-419).  Like the reference this OVERWRITES the Y row of its inputs with Z (:379-380) when
+    they are contiguous fp32 CUDA tensors -- the training loss relies on that quirk (lib/loss/rpn_3d.py:813)."""
+    if mode not in ("list", "combinations"):
+        raise ValueError('unknown mode {}'.format(mode))
+    origin = Origin(corners_3d_b1)
+    c1, c2 = to_cuda_f32(corners_3d_b1), to_cuda_f32(corners_3d_b2)
+    if c1.dim() == 2:
+        c1, c2 = c1.unsqueeze(0), c2.unsqueeze(0)
+    gen = method == "generalized"
+
+    def records(c, orig):
+        inplace = isinstance(orig, torch.Tensor) and orig.is_cuda and orig.dtype == torch.float32 and c.is_contiguous() \
+            and c.data_ptr() == orig.data_ptr()
+        return ops.box3d_records(c if inplace else c.contiguous(), mutate_input=inplace)
+
+    same = isinstance(corners_3d_b1, torch.Tensor) and corners_3d_b1 is corners_3d_b2
+    r1 = records(c1, corners_3d_b1)
+    r2 = r1 if same else records(c2, corners_3d_b2)
+    if mode == "combinations":
+        bev, i3d = ops.overlap3d(r1, r2, True, True, generalized=gen, affine=False)
+    else:
+        bev, i3d = ops.overlap3d_list(r1, r2, generalized=gen, affine=False)
+    return origin.back(bev), origin.back(i3d)

@@ -1,0 +1,14 @@
+"""Mirror of the reference's Cython lib/nms/cpu_nms.pyx:17-68 (suppress when IoU >= thresh, :65)."""
+import numpy as np
+import torch
+
+from ... import _lib, ops
+from .._util import device
+
+
+def cpu_nms(dets, thresh):
+    dets = np.ascontiguousarray(dets, dtype=np.float32)
+    if dets.shape[0] == 0:
+        return []
+    keep, nk = ops.hard_nms(torch.from_numpy(dets).to(device()), thresh, shift=1.0, cmp=_lib.CMP_GE)
+    return keep[:int(nk.item())].cpu().numpy().astype(np.int64).tolist()

@@ -1,0 +1,402 @@
+"""Device-tensor operators over the C-ABI (libgroomed_b200.so).
+
+PyTorch is plumbing here: it owns device memory and streams; every computation below is a call into the
+hand-written sm_100a kernels through ctypes.  All functions take CUDA tensors, enqueue on the current stream of
+the tensor's device and never synchronise unless they must return a python int.  There is no CPU fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import Params, Saved, check
+
+MAX_BOXES = _lib.MAX_BOXES
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError("groomed_nms_b200: %s must be a CUDA tensor (no CPU fallback)" % name)
+
+
+# ------------------------------------------------------------------------------------------------ overlaps
+def overlap2d(box_a, box_b, kind=_lib.KIND_IOU):
+    """[M,4] x [N,4] -> [M,N] IoU (lib/core.py:480) or intersection area (lib/core.py:178, transposed to [M,N])."""
+    _require_cuda(box_a, "box_a")
+    a, b = _f32c(box_a), _f32c(box_b)
+    M, N = a.shape[0], b.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if M and N:
+        with torch.cuda.device(a.device):
+            check(_lib.load().gnms_overlap2d_f32(_p(a), M, _p(b), N, _p(out), N, kind, _stream(a.device)), "gnms_overlap2d_f32")
+    return out
+
+
+def overlap2d_list(box_a, box_b, kind=_lib.KIND_IOU):
+    _require_cuda(box_a, "box_a")
+    a, b = _f32c(box_a), _f32c(box_b)
+    M = a.shape[0]
+    if b.shape[0] != M:
+        raise ValueError("list mode needs the same number of boxes")
+    out = torch.empty((M,), dtype=torch.float32, device=a.device)
+    if M:
+        with torch.cuda.device(a.device):
+            check(_lib.load().gnms_overlap2d_list_f32(_p(a), _p(b), M, _p(out), kind, _stream(a.device)), "gnms_overlap2d_list_f32")
+    return out
+
+
+class Overlap2dFunction(torch.autograd.Function):
+    """iou() with autograd (the reference's iou is a differentiable torch composite; the detection loss
+    back-propagates through the list mode, lib/loss/rpn_3d.py:620)."""
+
+    @staticmethod
+    def forward(ctx, box_a, box_b, list_mode):
+        ctx.list_mode = list_mode
+        ctx.save_for_backward(box_a, box_b)
+        if list_mode:
+            return overlap2d_list(box_a, box_b, _lib.KIND_IOU)
+        return overlap2d(box_a, box_b, _lib.KIND_IOU)
+
+    @staticmethod
+    def backward(ctx, g):
+        box_a, box_b = ctx.saved_tensors
+        ga, gb = overlap2d_backward(box_a, box_b, g, ctx.list_mode)
+        return ga, gb, None
+
+
+def overlap2d_backward(box_a, box_b, g, list_mode):
+    a, b, g = _f32c(box_a), _f32c(box_b), _f32c(g)
+    ga, gb = torch.zeros_like(a), torch.zeros_like(b)
+    M, N = a.shape[0], b.shape[0]
+    if M and N:
+        with torch.cuda.device(a.device):
+            check(_lib.load().gnms_iou2d_backward_f32(_p(a), M, _p(b), N, _p(g), int(list_mode), _p(ga), _p(gb),
+                                                      _stream(a.device)), "gnms_iou2d_backward_f32")
+    return ga, gb
+
+
+def project_points(p2, pts, pad_ones):
+    """lib/math_3d.py:47-72 on device: p2 [4,4], pts [3,n] (pad_ones) or [4,n] -> [4,n]."""
+    _require_cuda(pts, "points")
+    P, X = _f32c(p2), _f32c(pts)
+    n = X.shape[1]
+    out = torch.empty((4, n), dtype=torch.float32, device=X.device)
+    if n:
+        with torch.cuda.device(X.device):
+            check(_lib.load().gnms_project_points_f32(_p(P), _p(X), n, int(pad_ones), _p(out), _stream(X.device)), "gnms_project_points_f32")
+    return out
+
+
+def corners_from_boxes7(boxes7):
+    """[N,7] (x,y,z,w,h,l,ry) -> corners [N,3,8] (lib/math_3d.py:364-435)."""
+    _require_cuda(boxes7, "boxes7")
+    b = _f32c(boxes7)
+    N = b.shape[0]
+    out = torch.empty((N, 3, 8), dtype=torch.float32, device=b.device)
+    if N:
+        with torch.cuda.device(b.device):
+            check(_lib.load().gnms_corners_from_boxes7_f32(_p(b), b.stride(0), N, _p(out), _stream(b.device)), "gnms_corners_from_boxes7_f32")
+    return out
+
+
+def box3d_records(corners, mutate_input=False):
+    """corners [N,3,8] (contiguous fp32) -> records [N,8]; optionally reproduces the reference's Y<-Z write."""
+    _require_cuda(corners, "corners")
+    if corners.dtype != torch.float32 or not corners.is_contiguous():
+        if mutate_input:
+            raise RuntimeError("mutate_input needs a contiguous fp32 corners tensor")
+        corners = _f32c(corners)
+    N = corners.shape[0]
+    rec = torch.empty((N, 8), dtype=torch.float32, device=corners.device)
+    if N:
+        with torch.cuda.device(corners.device):
+            check(_lib.load().gnms_box3d_records_f32(_p(corners), N, _p(rec), int(bool(mutate_input)), _stream(corners.device)), "gnms_box3d_records_f32")
+    return rec
+
+
+def overlap3d(rec_a, rec_b, want_bev=True, want_3d=True, generalized=False, affine=False, mul2d=None):
+    M, N = rec_a.shape[0], rec_b.shape[0]
+    dev = rec_a.device
+    bev = torch.empty((M, N), dtype=torch.float32, device=dev) if want_bev else None
+    o3d = torch.empty((M, N), dtype=torch.float32, device=dev) if want_3d else None
+    if mul2d is not None:
+        mul2d = _f32c(mul2d)
+    if M and N:
+        with torch.cuda.device(dev):
+            check(_lib.load().gnms_overlap3d_f32(_p(rec_a), M, _p(rec_b), N, _p(bev), _p(o3d), N, int(generalized),
+                                                 int(affine), _p(mul2d), _stream(dev)), "gnms_overlap3d_f32")
+    return bev, o3d
+
+
+def overlap3d_list(rec_a, rec_b, generalized=False, affine=False):
+    M = rec_a.shape[0]
+    dev = rec_a.device
+    bev = torch.empty((M,), dtype=torch.float32, device=dev)
+    o3d = torch.empty((M,), dtype=torch.float32, device=dev)
+    if M:
+        with torch.cuda.device(dev):
+            check(_lib.load().gnms_overlap3d_list_f32(_p(rec_a), _p(rec_b), M, _p(bev), _p(o3d), int(generalized),
+                                                      int(affine), _stream(dev)), "gnms_overlap3d_list_f32")
+    return bev, o3d
+
+
+# ------------------------------------------------------------------------------------------------ GrooMeD-NMS
+def make_params(nms_threshold=0.4, pruning_method="linear", temperature=0.01, valid_box_prob_threshold=0.3,
+                return_sorted_prob=False, group_boxes=True, mask_group_boxes=True, group_size=100):
+    if pruning_method not in _lib.PRUNE:
+        raise NotImplementedError("Pruning method not implemented!")      # lib/groomed_nms.py:177
+    mode = _lib.MODE_GROUP_MASK if (group_boxes and mask_group_boxes) else (
+        _lib.MODE_GROUP_NOMASK if group_boxes else _lib.MODE_NOGROUP)
+    p = Params()
+    p.nms_threshold = float(nms_threshold)
+    p.temperature = float(temperature)
+    p.valid_box_prob_threshold = float(valid_box_prob_threshold)
+    p.pruning_method = _lib.PRUNE[pruning_method]
+    p.mode = mode
+    p.group_size = int(min(int(group_size), 2 ** 31 - 2))
+    p.thresholded_output = 0 if group_boxes else 1
+    p.sorted_output = 1 if return_sorted_prob else 0
+    return p
+
+
+_ws_cache = {}
+
+
+def workspace(dev, N, batch):
+    """Per-(device, stream) scratch, grown on demand; kernels are stream ordered so one buffer per stream is safe."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    need = _lib.load().gnms_workspace_bytes(N, batch)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty((int(need),), dtype=torch.uint8, device=dev)
+        _ws_cache[key] = buf
+    return buf
+
+
+class ForwardState(object):
+    """Outputs + saved tensors of one forward call (batch of B images, N boxes each)."""
+    __slots__ = ("params", "B", "N", "prob", "valid_idx", "invalid_idx", "counts", "order", "sorted_scores", "lead",
+                 "pval", "dpval", "pre", "ws", "n_per_image", "iou")
+
+    def saved(self):
+        return Saved(_p(self.order), _p(self.sorted_scores), _p(self.lead), _p(self.pval), _p(self.dpval), _p(self.pre))
+
+
+def _alloc_state(dev, B, N, params, n_per_image, private_ws):
+    st = ForwardState()
+    st.params, st.B, st.N, st.n_per_image = params, B, N, n_per_image
+    st.prob = torch.empty((B, N), dtype=torch.float32, device=dev)
+    st.valid_idx = torch.empty((B, N), dtype=torch.int64, device=dev)
+    st.invalid_idx = torch.empty((B, N), dtype=torch.int64, device=dev)
+    st.counts = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    st.order = torch.empty((B, N), dtype=torch.int32, device=dev)
+    st.lead = torch.empty((B, N), dtype=torch.int32, device=dev)
+    fl = torch.empty((4, B, N), dtype=torch.float32, device=dev)
+    st.sorted_scores, st.pval, st.dpval, st.pre = fl[0], fl[1], fl[2], fl[3]
+    if private_ws:   # the backward of sorted_output / no-mask modes reads state kept in the workspace
+        st.ws = torch.empty((int(_lib.load().gnms_workspace_bytes(N, B)),), dtype=torch.uint8, device=dev)
+    else:
+        st.ws = workspace(dev, N, B)
+    st.iou = None
+    return st
+
+
+def forward_matrix(scores, iou, params, n_per_image=None, private_ws=None):
+    """scores [B,N] fp32 cuda, iou [B,N,N] fp32 cuda (unit column stride) -> ForwardState."""
+    _require_cuda(scores, "scores")
+    scores = _f32c(scores)
+    if iou.dtype != torch.float32:
+        iou = iou.float()
+    if iou.stride(-1) != 1 or (iou.dim() == 3 and iou.stride(0) != iou.shape[1] * iou.stride(1)):
+        iou = iou.contiguous()
+    B, N = scores.shape
+    if N > MAX_BOXES:
+        raise RuntimeError("groomed_nms_b200: at most %d boxes per image (got %d)" % (MAX_BOXES, N))
+    dev = scores.device
+    if private_ws is None:
+        private_ws = bool(params.sorted_output) or params.mode != _lib.MODE_GROUP_MASK
+    st = _alloc_state(dev, B, N, params, n_per_image, private_ws)
+    st.iou = iou
+    if B and N:
+        ld = iou.stride(-2)
+        with torch.cuda.device(dev):
+            check(_lib.load().gnms_forward_f32(_p(scores), _p(iou), ld, N, B, _p(n_per_image), ctypes.byref(params),
+                                               _p(st.prob), _p(st.valid_idx), _p(st.invalid_idx), _p(st.counts),
+                                               st.saved(), _p(st.ws), _stream(dev)), "gnms_forward_f32")
+    else:
+        st.counts.zero_()
+    return st
+
+
+def forward_boxes(scores, boxes, box_kind, params, generalized=False, affine=False, n_per_image=None, private_ws=None):
+    """Matrix-free forward: boxes [B,N,4] (box_kind BOX_2D) or records [B,N,8] (BOX_3D_REC)."""
+    _require_cuda(scores, "scores")
+    scores, boxes = _f32c(scores), _f32c(boxes)
+    B, N = scores.shape
+    if N > MAX_BOXES:
+        raise RuntimeError("groomed_nms_b200: at most %d boxes per image (got %d)" % (MAX_BOXES, N))
+    dev = scores.device
+    if private_ws is None:
+        private_ws = bool(params.sorted_output)
+    st = _alloc_state(dev, B, N, params, n_per_image, private_ws)
+    if B and N:
+        with torch.cuda.device(dev):
+            check(_lib.load().gnms_forward_boxes_f32(_p(scores), _p(boxes), box_kind, int(generalized), int(affine), N, B,
+                                                     _p(n_per_image), ctypes.byref(params), _p(st.prob),
+                                                     _p(st.valid_idx), _p(st.invalid_idx), _p(st.counts), st.saved(),
+                                                     _p(st.ws), _stream(dev)), "gnms_forward_boxes_f32")
+    else:
+        st.counts.zero_()
+    return st
+
+
+def backward(st, grad_prob, need_grad_iou=False):
+    """-> (grad_scores [B,N], grad_iou [B,N,N] or None)."""
+    dev = grad_prob.device
+    g = _f32c(grad_prob)
+    B, N = st.B, st.N
+    gs = torch.empty((B, N), dtype=torch.float32, device=dev)
+    gi = torch.zeros((B, N, N), dtype=torch.float32, device=dev) if need_grad_iou else None
+    if B and N:
+        iou = st.iou
+        with torch.cuda.device(dev):
+            check(_lib.load().gnms_backward_f32(_p(g), _p(st.prob), _p(iou), iou.stride(-2) if iou is not None else 0, N, B,
+                                                _p(st.n_per_image), ctypes.byref(st.params), st.saved(), _p(gs), _p(gi),
+                                                N, _p(st.ws), _stream(dev)), "gnms_backward_f32")
+    return gs, gi
+
+
+class GroomedNMSFunction(torch.autograd.Function):
+    """The autograd.Function that sits behind differentiable_nms: forward and the analytic
+    backward are single C-ABI calls; iou receives a gradient only if it requires one (the training loss detaches
+    it, lib/loss/rpn_3d.py:791)."""
+
+    @staticmethod
+    def forward(ctx, scores, iou, params):
+        st = forward_matrix(scores.detach().unsqueeze(0), iou.detach().unsqueeze(0), params)
+        ctx.st = st
+        ctx.need_gi = iou.requires_grad
+        ctx.mark_non_differentiable(st.valid_idx, st.invalid_idx, st.counts)
+        return st.prob[0], st.valid_idx[0], st.invalid_idx[0], st.counts[0]
+
+    @staticmethod
+    def backward(ctx, g_prob, g_valid, g_invalid, g_counts):
+        gs, gi = backward(ctx.st, g_prob.unsqueeze(0), need_grad_iou=ctx.need_gi)
+        return gs[0], (gi[0] if gi is not None else None), None
+
+
+class GroomedNMSBoxesFunction(torch.autograd.Function):
+    """Matrix-free variant: overlaps are evaluated on the fly from boxes / 3D records (no gradient to the boxes,
+    matching the detached overlap matrix of the training loss)."""
+
+    @staticmethod
+    def forward(ctx, scores, boxes, box_kind, params, generalized, affine):
+        st = forward_boxes(scores.detach().unsqueeze(0), boxes.detach().unsqueeze(0), box_kind, params, generalized, affine)
+        ctx.st = st
+        ctx.mark_non_differentiable(st.valid_idx, st.invalid_idx, st.counts)
+        return st.prob[0], st.valid_idx[0], st.invalid_idx[0], st.counts[0]
+
+    @staticmethod
+    def backward(ctx, g_prob, g_valid, g_invalid, g_counts):
+        gs, _ = backward(ctx.st, g_prob.unsqueeze(0), need_grad_iou=False)
+        return gs[0], None, None, None, None, None
+
+
+def prune(x, nms_threshold, temperature, pruning_method):
+    """Elementwise pruning function (lib/groomed_nms.py:167-189)."""
+    _require_cuda(x, "iou")
+    xc = _f32c(x)
+    out = torch.empty_like(xc)
+    n = xc.numel()
+    if n:
+        with torch.cuda.device(xc.device):
+            check(_lib.load().gnms_prune_f32(_p(xc), n, _lib.PRUNE[pruning_method], float(nms_threshold),
+                                             float(temperature), _p(out), _stream(xc.device)), "gnms_prune_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ groups / classical NMS
+def get_groups_raw(scores, iou, group_threshold, group_size):
+    """-> (group_id[N] int32 by input index, group_rank[N] int32, n_groups int32[1]) on device."""
+    _require_cuda(scores, "scores")
+    scores = _f32c(scores)
+    if iou.dtype != torch.float32:
+        iou = iou.float()
+    if iou.stride(-1) != 1:
+        iou = iou.contiguous()
+    N = scores.shape[0]
+    dev = scores.device
+    gid = torch.empty((N,), dtype=torch.int32, device=dev)
+    grk = torch.empty((N,), dtype=torch.int32, device=dev)
+    ng = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if N:
+        ws = workspace(dev, N, 1)
+        with torch.cuda.device(dev):
+            check(_lib.load().gnms_get_groups_f32(_p(scores), _p(iou), iou.stride(0), N, float(group_threshold),
+                                                  int(min(int(group_size), 2 ** 31 - 2)), _p(gid), _p(grk), _p(ng),
+                                                  _p(ws), _stream(dev)), "gnms_get_groups_f32")
+    return gid, grk, ng
+
+
+def hard_nms(dets, thresh, shift=1.0, cmp=_lib.CMP_GT):
+    """dets [N,5] cuda -> (keep int32[N], n_keep int32[1]) on device; keep[:n_keep] are original indices."""
+    _require_cuda(dets, "dets")
+    d = _f32c(dets)
+    N = d.shape[0]
+    dev = d.device
+    keep = torch.empty((max(N, 1),), dtype=torch.int32, device=dev)
+    nk = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if N:
+        ws = workspace(dev, N, 1)
+        with torch.cuda.device(dev):
+            check(_lib.load().gnms_hard_nms_f32(_p(d), N, float(thresh), float(shift), int(cmp), _p(keep), _p(nk), _p(ws),
+                                                _stream(dev)), "gnms_hard_nms_f32")
+    return keep, nk
+
+
+def soft_nms(dets64, sigma, Nt, threshold, method, shift):
+    """dets [N,5] float64 cuda -> (keep int32[N], scores f64[N], n_keep int32[1])."""
+    _require_cuda(dets64, "dets")
+    d = dets64.double().contiguous()
+    N = d.shape[0]
+    dev = d.device
+    keep = torch.empty((max(N, 1),), dtype=torch.int32, device=dev)
+    ks = torch.empty((max(N, 1),), dtype=torch.float64, device=dev)
+    nk = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if N:
+        ws = torch.empty((int(_lib.load().gnms_soft_nms_workspace_bytes(N)),), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.load().gnms_soft_nms_f64(_p(d), N, float(sigma), float(Nt), float(threshold), int(method),
+                                                float(shift), _p(keep), _p(ks), _p(nk), _p(ws), _stream(dev)), "gnms_soft_nms_f64")
+    return keep, ks, nk
+
+
+def aploss(logits, targets):
+    """logits[n], targets[n] cuda -> (loss[1], grad[n]) (lib/loss/aploss.py:16-81)."""
+    _require_cuda(logits, "logits")
+    x = _f32c(logits.reshape(-1))
+    t = _f32c(targets.reshape(-1))
+    n = x.shape[0]
+    dev = x.device
+    loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+    grad = torch.zeros((n,), dtype=torch.float32, device=dev)
+    if n:
+        nb = int(_lib.load().gnms_aploss_workspace_bytes(n))
+        ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.load().gnms_aploss_f32(_p(x), _p(t), n, _p(loss), _p(grad), _p(ws), nb, _stream(dev)), "gnms_aploss_f32")
+    return loss, grad

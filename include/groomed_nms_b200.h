@@ -1,0 +1,208 @@
+/*
+ * groomed_nms_b200 -- C-ABI of the B200-native GrooMeD-NMS hot path (libgroomed_b200.so).
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes (no torch types), returns an int
+ * (0 = success, >0 = cudaError_t, <0 = GNMS_E_* argument error), never throws, never prints, keeps no global
+ * state and is re-entrant.  Unless stated otherwise all pointers are DEVICE pointers, outputs and workspaces
+ * are caller-allocated, and work is enqueued on `stream` (a cudaStream_t passed as void*) without synchronising.
+ *
+ * Reference interfaces replaced (paths relative to abhi1kumar/groomed_nms @ ad10dbb):
+ *   lib/core.py:178-243   intersect            -> gnms_overlap2d_f32 / gnms_overlap2d_list_f32 (kind = INTERSECT)
+ *   lib/core.py:480-532   iou                  -> gnms_overlap2d_f32 / gnms_overlap2d_list_f32 (kind = IOU)
+ *   lib/math_3d.py:364-435 get_corners_of_cuboid -> gnms_corners_from_boxes7_f32
+ *   lib/core.py:354-388,434-477 get_volume / remove_rotation_in_boxes / per-box min-max -> gnms_box3d_records_f32
+ *   lib/core.py:305-421   iou3d_approximate    -> gnms_overlap3d_f32 / gnms_overlap3d_list_f32
+ *   lib/groomed_nms.py:10-129 differentiable_nms (+ :167-189 pruning_function, :208-270 get_groups,
+ *                         :272-336 indices_copy folded away) -> gnms_forward_f32 / gnms_backward_f32 and the
+ *                         matrix-free gnms_forward_boxes_f32
+ *   lib/nms/gpu_nms.hpp:1-2 `_nms` (the reference's only native ABI), lib/nms/nms_kernel.cu:24-144,
+ *   lib/nms/cpu_nms.pyx:17-68, lib/nms/py_cpu_nms.py:10-38, lib/nms_others.py:119-150 girshick_nms
+ *                                              -> gnms_hard_nms_f32 and the host-pointer `gnms_nms_host`
+ *   lib/nms_others.py:6-116 navneeth_soft_nms  -> gnms_soft_nms_f64
+ *   lib/loss/aploss.py:14-97 backpropAPLoss    -> gnms_aploss_f32
+ */
+#ifndef GROOMED_NMS_B200_H_
+#define GROOMED_NMS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNMS_VERSION 100
+
+/* argument errors (negative); positive return codes are cudaError_t values */
+#define GNMS_E_BADARG   (-1)
+#define GNMS_E_TOOLARGE (-2)   /* N above GNMS_MAX_BOXES */
+#define GNMS_E_ALIGN    (-3)
+#define GNMS_E_UNSUPPORTED (-4)
+
+#define GNMS_MAX_BOXES 8192    /* per image; the greedy chain runs in one CTA's shared memory */
+
+/* pruning_function, lib/groomed_nms.py:167-189 */
+#define GNMS_PRUNE_LINEAR    0
+#define GNMS_PRUNE_SIGMOIDAL 1
+#define GNMS_PRUNE_SOFT_NMS  2
+
+/* inversion mode, lib/groomed_nms.py:95-110 */
+#define GNMS_MODE_GROUP_MASK   0   /* group_boxes=True,  mask_group_boxes=True  (shipped default) */
+#define GNMS_MODE_GROUP_NOMASK 1   /* group_boxes=True,  mask_group_boxes=False: per-group (I+Phi_g)^-1 */
+#define GNMS_MODE_NOGROUP      2   /* group_boxes=False: full (I+Phi)^-1 */
+
+/* 2D overlap kinds */
+#define GNMS_KIND_IOU       0      /* lib/core.py:480 */
+#define GNMS_KIND_INTERSECT 1      /* lib/core.py:178 */
+
+/* box sources of the matrix-free forward */
+#define GNMS_BOX_2D       0        /* float[N,4] x1,y1,x2,y2 ; overlap = iou (lib/core.py:480) */
+#define GNMS_BOX_3D_REC   1        /* float[N,8] records from gnms_box3d_records_f32 ; overlap = iou3d_approximate */
+
+/* comparison used to mark a lower-scored box as suppressed by a kept one */
+#define GNMS_CMP_GT   0            /* iou >  thr   lib/nms/nms_kernel.cu:71 (NaN is not suppressed) */
+#define GNMS_CMP_GE   1            /* iou >= thr   lib/nms/cpu_nms.pyx:65 */
+#define GNMS_CMP_NLE  2            /* !(iou <= thr) lib/nms/py_cpu_nms.py:35, lib/nms_others.py:146 (NaN is suppressed) */
+
+typedef struct gnms_params {
+    float nms_threshold;           /* group / prune threshold                  (lib/groomed_nms.py:10) */
+    float temperature;             /* pruning temperature                       */
+    float valid_box_prob_threshold;
+    int32_t pruning_method;        /* GNMS_PRUNE_*                              */
+    int32_t mode;                  /* GNMS_MODE_*                               */
+    int32_t group_size;            /* groups keep group_size+1 boxes (:254-255) */
+    int32_t thresholded_output;    /* 1: `prob` is the thresholded vector (group_boxes=False, :127) */
+    int32_t sorted_output;         /* 1: return_sorted_prob=True (:116-119): prob is sorted descending */
+} gnms_params;
+
+int gnms_version(void);
+const char* gnms_error_string(int rc);
+
+/* ---------------------------------------------------------------- pairwise overlaps ---------------- */
+/* out[i*ld_out + j] = overlap(a_i, b_j), i<M, j<N ("combinations"); a,b are [.,4] row-major boxes.
+ * kind=IOU gives the LOGICAL [M,N] result of lib/core.py:480 iou (the reference returns it as a transposed
+ * view); kind=INTERSECT gives lib/core.py:178 intersect TRANSPOSED to [M,N] as well (the reference returns [N,M]).
+ * fp32, separately rounded ops in the reference's order (bitwise equal to torch CPU). */
+int gnms_overlap2d_f32(const float* a, int M, const float* b, int N, float* out, int64_t ld_out, int kind,
+                       void* stream);
+/* "list" mode: out[i] = overlap(a_i, b_i). */
+int gnms_overlap2d_list_f32(const float* a, const float* b, int M, float* out, int kind, void* stream);
+
+/* Backward of the IoU above (the reference's iou is a differentiable torch composite, lib/core.py:480-532, and
+ * the detection loss differentiates its list mode, lib/loss/rpn_3d.py:620).  g is [M,N] (combinations, ld = N)
+ * or [M] (list_mode!=0, then N must equal M); grad_a[M,4] / grad_b[N,4] are fully written.  min/max ties split the
+ * gradient evenly and clamp(.,0) passes it on the closed side, as torch does. */
+int gnms_iou2d_backward_f32(const float* a, int M, const float* b, int N, const float* g, int list_mode,
+                            float* grad_a, float* grad_b, void* stream);
+
+/* boxes7[N,7] = (x3d,y3d,z3d,w3d,h3d,l3d,ry3d) row-major with row stride `ld` floats -> corners[N,3,8]
+ * (lib/math_3d.py:364-435, iou_3d_convention=True). */
+int gnms_corners_from_boxes7_f32(const float* boxes7, int64_t ld, int N, float* corners, void* stream);
+
+/* lib/math_3d.py:47-72 project_3d_points_in_4D_format: out[4,n] = p2[4,4] @ [pts;1] (pts is [3,n] when
+ * pad_ones!=0, else [4,n]); rows 0,1 divided by row 2 where |row 2| > 1e-2. */
+int gnms_project_points_f32(const float* p2, const float* pts, int64_t n, int pad_ones, float* out, void* stream);
+
+/* corners[N,3,8] -> rec[N,8] = (ymin,ymax,bx1,bx2,bz1,bz2,vol,area_bev) exactly as iou3d_approximate derives
+ * them (lib/core.py:354-388).  mutate_input!=0 reproduces the reference's in-place Y<-Z write (:379-380). */
+int gnms_box3d_records_f32(float* corners, int N, float* rec, int mutate_input, void* stream);
+
+/* rec_a[M,8], rec_b[N,8] -> out_bev / out_3d [M,N] (either may be NULL).  generalized!=0: GIoU hull term
+ * (lib/core.py:390-419).  affine!=0 additionally maps out_3d to 0.5*(1+x) (lib/loss/rpn_3d.py:781).
+ * mul2d (NULL or [M,N] with ld_out): out_3d *= mul2d  (overlap_in_nms="product", lib/loss/rpn_3d.py:786). */
+int gnms_overlap3d_f32(const float* rec_a, int M, const float* rec_b, int N, float* out_bev, float* out_3d,
+                       int64_t ld_out, int generalized, int affine, const float* mul2d, void* stream);
+int gnms_overlap3d_list_f32(const float* rec_a, const float* rec_b, int M, float* out_bev, float* out_3d,
+                            int generalized, int affine, void* stream);
+
+/* ---------------------------------------------------------------- GrooMeD-NMS ---------------------- */
+/* Bytes of scratch for a batch of `batch` images of up to N boxes each. */
+size_t gnms_workspace_bytes(int N, int batch);
+
+/* State saved by the forward for the backward (all device, caller-allocated, [batch,N] each):
+ *   order  int32  sorted position -> input index            sorted_scores f32
+ *   lead   int32  sorted position of the group leader (self for leaders, -1 if in no group)
+ *   pval   f32    p(iou[m, leader])   dpval f32  p'(iou[m, leader])   pre f32  pre-clamp rescored value */
+typedef struct gnms_saved {
+    int32_t* order;
+    float* sorted_scores;
+    int32_t* lead;
+    float* pval;
+    float* dpval;
+    float* pre;
+} gnms_saved;
+
+/* differentiable_nms forward from an overlap MATRIX (lib/groomed_nms.py:10-129, sorting_method="hard").
+ *   scores[batch,N]; iou[batch,N,ld] row-major, unit column stride (row i = box i as the lower-scored box);
+ *   n_per_image: NULL (all N) or device int32[batch] with the live box count of each image (<= N).
+ * outputs: prob[batch,N] (score-sorted order unless sorted_output), valid_idx/invalid_idx int64[batch,N]
+ * (input index space; valid by rescored prob descending, ties by sorted position; invalid by sorted position),
+ * counts int32[batch,2] = (n_valid, n_invalid). */
+int gnms_forward_f32(const float* scores, const float* iou, int64_t ld, int N, int batch,
+                     const int32_t* n_per_image, const gnms_params* p, float* prob, int64_t* valid_idx,
+                     int64_t* invalid_idx, int32_t* counts, gnms_saved saved, void* workspace, void* stream);
+
+/* Matrix-free forward: overlaps are evaluated on the fly from `boxes` (box_kind GNMS_BOX_*), never written to
+ * HBM.  overlap3d flags as in gnms_overlap3d_f32 (generalized, affine).  Same outputs as gnms_forward_f32. */
+int gnms_forward_boxes_f32(const float* scores, const float* boxes, int box_kind, int generalized, int affine,
+                           int N, int batch, const int32_t* n_per_image, const gnms_params* p, float* prob,
+                           int64_t* valid_idx, int64_t* invalid_idx, int32_t* counts, gnms_saved saved,
+                           void* workspace, void* stream);
+
+/* Analytic backward.  grad_prob[batch,N] is dL/dprob for the prob the forward returned.
+ * grad_scores[batch,N] (input order) is fully written.  grad_iou: NULL, or [batch,N,ld_gi] which must be
+ * zero-filled by the caller for mode GROUP_MASK (only the <=N (member,leader) entries are written); modes
+ * GROUP_NOMASK / NOGROUP write their lower-triangular blocks.  iou/ld are needed for modes NOMASK/NOGROUP only. */
+int gnms_backward_f32(const float* grad_prob, const float* prob, const float* iou, int64_t ld, int N, int batch,
+                      const int32_t* n_per_image, const gnms_params* p, gnms_saved saved, float* grad_scores,
+                      float* grad_iou, int64_t ld_gi, void* workspace, void* stream);
+
+/* get_groups (lib/groomed_nms.py:208-270) from a matrix: group_id[N] int32 = index (in leader order) of the
+ * group of INPUT box i or -1, group_rank[N] int32 = position inside the group (0 = leader), n_groups int32[1]. */
+int gnms_get_groups_f32(const float* scores, const float* iou, int64_t ld, int N, float group_threshold,
+                        int group_size, int32_t* group_id, int32_t* group_rank, int32_t* n_groups,
+                        void* workspace, void* stream);
+
+/* pruning_function (lib/groomed_nms.py:167-189), elementwise: out[i] = p(x[i]). */
+int gnms_prune_f32(const float* x, int64_t n, int pruning_method, float nms_threshold, float temperature,
+                   float* out, void* stream);
+
+/* indices_copy (lib/groomed_nms.py:272-336): A[ra[k], ca[k], :] = B[rb[k], cb[k], :] for k < npairs, with
+ * A [rowsA, colsA, C], B [rowsB, colsB, C] row-major.  If ca == NULL the pairs are the cartesian product of the
+ * index list ra (length npairs) with itself and B is read densely: A[ra[i], ra[j], :] = B[i, j, :]. */
+int gnms_indices_copy_f32(float* A, int64_t colsA, const float* B, int64_t colsB, int64_t C, const int64_t* ra,
+                          const int64_t* ca, const int64_t* rb, const int64_t* cb, int64_t npairs, void* stream);
+
+/* ---------------------------------------------------------------- classical NMS -------------------- */
+/* dets[N,5] = (x1,y1,x2,y2,score) device.  shift = the "+1" pixel convention (1.0 for lib/nms, any for
+ * girshick_nms).  cmp = GNMS_CMP_*.  keep int32[N] = kept ORIGINAL indices in descending score order,
+ * n_keep int32[1].  Replaces lib/nms/nms_kernel.cu:34-144 (device-resident, no malloc, no host reduce). */
+int gnms_hard_nms_f32(const float* dets, int N, float thresh, float shift, int cmp, int32_t* keep,
+                      int32_t* n_keep, void* workspace, void* stream);
+
+/* Drop-in for the reference's only native symbol, `_nms` (lib/nms/gpu_nms.hpp:1-2): HOST pointers, boxes
+ * already sorted by descending score, keep_out indexes into that sorted order, synchronous.  Unlike the
+ * reference it returns an error code instead of printing. */
+int gnms_nms_host(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim,
+                  float nms_overlap_thresh, int device_id);
+
+/* Soft-NMS (lib/nms_others.py:6-116), float64 like the reference's numpy arithmetic on a float64 array.
+ * dets[N,5] device f64 (not modified).  keep int32[N] = the reference's `keep_orig[:N_final]` (original indices in
+ * selection order), keep_scores f64[N] = their decayed scores (the reference leaves them in boxes[:N_final,4]),
+ * n_keep int32[1].  method: 0 hard, 1 linear, 2 gaussian.  scratch: device f64[N] + int32[N] workspace
+ * (gnms_soft_nms_workspace_bytes). */
+int gnms_soft_nms_f64(const double* dets, int N, double sigma, double Nt, double threshold, int method,
+                      double shift, int32_t* keep, double* keep_scores, int32_t* n_keep, void* workspace,
+                      void* stream);
+size_t gnms_soft_nms_workspace_bytes(int N);
+
+/* ---------------------------------------------------------------- AP loss -------------------------- */
+/* lib/loss/aploss.py:16-81: logits[n], targets[n] in {1,0,-1} -> loss[1], grad[n] (= ctx.grad). */
+int gnms_aploss_f32(const float* logits, const float* targets, int n, float* loss, float* grad,
+                    void* workspace, size_t workspace_bytes, void* stream);
+size_t gnms_aploss_workspace_bytes(int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GROOMED_NMS_B200_H_ */

@@ -1,0 +1,340 @@
+"""GPU parity: GrooMeD-NMS forward + analytic backward (through the reference-named API and the C-ABI) against
+the reference's golden vectors and the oracle.  Bar (BASELINE.json north_star): group / keep indices bit-exact,
+rescored scores and gradients within 1e-5 relative fp32."""
+import ast
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, unflatten_groups
+from gpu_util import bits_equal, cuda
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def G():
+    from groomed_nms_b200.lib import groomed_nms
+    return groomed_nms
+
+
+def check_against(o, prob, valid, invalid, cond=1.0):
+    """o: oracle forward dict; prob/valid/invalid: numpy from the CUDA path."""
+    assert np.allclose(prob, o["prob"], rtol=RTOL, atol=1e-6 * cond), np.abs(prob - o["prob"]).max()
+    thr = o["cfg"]["valid_box_prob_threshold"]
+    vals = o["r_thr"][o["r_thr"] >= thr]
+    if len(np.unique(vals)) == len(vals) and cond == 1.0:
+        assert list(valid) == list(o["valid"])
+    else:
+        assert set(valid) == set(o["valid"])
+    assert set(invalid) == set(o["invalid"])
+    assert len(valid) + len(invalid) == len(o["prob"])
+
+
+def test_kats_of_the_reference_tests(G):
+    g = load_golden("kat_forward")
+    for n in ("4", "5"):
+        v, i, p = G.differentiable_nms(cuda(g["s" + n]), cuda(g["iou" + n]), nms_threshold=0.4, temperature=0.1,
+                                       valid_box_prob_threshold=0.3, pruning_method="linear", sorting_method="hard",
+                                       return_sorted_prob=False, group_boxes="True", debug=False)
+        assert np.allclose(p.cpu().numpy(), g["printed" + n], atol=5e-4)
+        assert np.array_equal(p.cpu().numpy(), g["prob" + n])
+        assert v.dtype == torch.int64 and list(v.cpu().numpy()) == list(g["valid" + n])
+        assert set(i.cpu().numpy()) == set(g["invalid" + n])
+
+
+def test_seeded_5box_keep_matches_every_nms(G):
+    from groomed_nms_b200.lib import core
+    from groomed_nms_b200.lib.nms.gpu_nms import gpu_nms
+    from groomed_nms_b200.lib.nms_others import girshick_nms, navneeth_soft_nms
+    g = load_golden("seeded_5box")
+    ab = g["aboxes"]
+    iou = core.iou(cuda(ab[:, :4]), cuda(ab[:, :4]))
+    assert bits_equal(iou.cpu().numpy(), g["iou"])
+    v, i, p = G.differentiable_nms(cuda(ab[:, 4]), iou, nms_threshold=0.4, temperature=0.1, valid_box_prob_threshold=0.3)
+    assert list(v.cpu().numpy()) == [1, 0, 4] == list(g["keep_ours"])
+    assert np.array_equal(p.cpu().numpy(), g["prob_ours"])
+    assert gpu_nms(ab.astype(np.float32), 0.4, device_id=0) == [1, 0, 4]
+    assert girshick_nms(ab, 0.4, shift=1) == list(g["keep_girshick"])
+    assert navneeth_soft_nms(ab.copy(), Nt=0.4, shift=1).tolist() == list(g["keep_soft"])
+    # numpy in -> CPU tensors out, like the reference (lib/groomed_nms.py:34-36)
+    v2, _, p2 = G.differentiable_nms(ab[:, 4], g["iou"], nms_threshold=0.4, temperature=0.1)
+    assert not p2.is_cuda and list(v2.numpy()) == [1, 0, 4]
+
+
+def test_get_groups_reference_case_and_golden(G):
+    g = load_golden("get_groups_10")
+    got = G.get_groups(scores_unsorted=cuda(g["scores"]), iou_unsorted=cuda(g["iou"]), group_threshold=0.4)
+    assert [x.tolist() for x in got] == [[0, 1, 4, 5, 6, 7, 9], [2, 3, 8]]
+    assert all(x.dtype == torch.int64 for x in got)
+    gg = load_golden("groups")
+    inp = load_golden("dnms_inputs")
+    for tag, (sc, io) in dict(g240=(inp["scores240"], inp["iou240"]), g96=(inp["scores96"], inp["iou96"]),
+                              gns=(inp["s_ns"], inp["iou_ns"])).items():
+        for gs in (1, 7, 100):
+            want = unflatten_groups(gg["%s_gs%d_flat" % (tag, gs)], gg["%s_gs%d_len" % (tag, gs)])
+            got = G.get_groups(cuda(io), 0.4, cuda(sc), group_size=gs)
+            assert [x.tolist() for x in got] == [list(x) for x in want]
+
+
+def _cases():
+    g = load_golden("dnms_cases")
+    return sorted({k.split("__")[0] for k in g.files})
+
+
+@pytest.mark.parametrize("tag", _cases())
+def test_golden_forward_backward(G, tag):
+    """Every differentiable_nms case the real reference produced (modes A/B/C x pruning x group sizes)."""
+    from oracle import groomed_oracle as O
+    g = load_golden("dnms_cases")
+    inp = load_golden("dnms_inputs")
+    cfg = dict(ast.literal_eval(str(g[tag + "__cfg"])))
+    if "240" in tag:
+        sc, io, up = inp["scores240"], inp["iou240"], inp["g240"]
+    elif "120ns" in tag:
+        sc, io, up = inp["s_ns"], inp["iou_ns"], inp["g_ns"]
+    else:
+        sc, io, up = inp["scores96"], inp["iou96"], inp["g96"]
+    need_gi = (tag + "__grad_iou") in g.files
+    s = cuda(sc).requires_grad_(True)
+    m = cuda(io).requires_grad_(need_gi)
+    v, i, p = G.differentiable_nms(s, m, **cfg)
+    o = O.differentiable_nms(sc, io, **cfg)
+    cond = 1.0 if o["T"] is None else max(1.0, float(np.abs(o["T"]).max()))
+    want = g[tag + "__prob"]
+    assert np.allclose(p.detach().cpu().numpy(), want, rtol=RTOL, atol=1e-6 * cond)
+    check_against(o, p.detach().cpu().numpy(), v.cpu().numpy(), i.cpu().numpy(), cond)
+    assert set(v.cpu().numpy()) == set(g[tag + "__valid"]) and set(i.cpu().numpy()) == set(g[tag + "__invalid"])
+    p.backward(cuda(up))
+    wgs = g[tag + "__grad_scores"]
+    sc_ = max(1.0, np.abs(wgs).max())
+    assert np.allclose(s.grad.cpu().numpy(), wgs, rtol=RTOL, atol=2e-6 * sc_ * cond), np.abs(s.grad.cpu().numpy() - wgs).max()
+    if need_gi:
+        wgi = g[tag + "__grad_iou"]
+        sc_ = max(1.0, np.abs(wgi).max())
+        assert np.allclose(m.grad.cpu().numpy(), wgi, rtol=RTOL, atol=2e-6 * sc_ * cond)
+
+
+def _rand_case(seed, n, k, nonsym=False):
+    from groomed_nms_b200 import synthetic
+    from oracle import groomed_oracle as O
+    rng = np.random.default_rng(seed)
+    if nonsym:
+        iou = (rng.uniform(0, 1, (n, n)) ** 4).astype(np.float32)
+        np.fill_diagonal(iou, 1.0)
+        sc = synthetic.distinct_scores(rng, n, 0.05, 1.0)
+    else:
+        boxes, sc, _ = synthetic.clustered_boxes_2d(n, k, seed=seed, jitter=0.08)
+        iou = O.iou(boxes, boxes)
+    return sc, iou, rng.standard_normal(n).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,k,nonsym", [(1, 1, False), (2, 1, False), (33, 2, False), (200, 4, False), (500, 9, False),
+                                        (257, 1, True), (1000, 20, False), (64, 64, False)])
+@pytest.mark.parametrize("pm,temp", [("linear", 0.1), ("sigmoidal", 0.1), ("soft_nms", 0.5)])
+@pytest.mark.parametrize("gs", [1, 20, 100, 10 ** 9])
+def test_mode_a_random_vs_oracle(G, n, k, nonsym, pm, temp, gs):
+    from oracle import groomed_oracle as O
+    sc, iou, up = _rand_case(1000 + n, n, k, nonsym)
+    cfg = dict(nms_threshold=0.4, pruning_method=pm, temperature=temp, valid_box_prob_threshold=0.3, group_size=gs)
+    o = O.differentiable_nms(sc, iou, dense=False, **cfg)
+    s = cuda(sc).requires_grad_(True)
+    m = cuda(iou).requires_grad_(n <= 257)
+    v, i, p = G.differentiable_nms(s, m, **cfg)
+    check_against(o, p.detach().cpu().numpy(), v.cpu().numpy(), i.cpu().numpy())
+    p.backward(cuda(up))
+    gs_, gi_ = O.differentiable_nms_backward(o, up, need_grad_iou=(n <= 257))
+    assert np.allclose(s.grad.cpu().numpy(), gs_, rtol=RTOL, atol=2e-6 * max(1.0, np.abs(gs_).max()))
+    if n <= 257:
+        assert np.allclose(m.grad.cpu().numpy(), gi_, rtol=RTOL, atol=2e-6 * max(1.0, np.abs(gi_).max()))
+
+
+def test_saved_state_groups_are_bit_exact():
+    """lead[] (group of every box) and order[] from the C-ABI state vs the oracle, incl. the group_size cap."""
+    from groomed_nms_b200 import ops
+    from oracle import groomed_oracle as O
+    for seed, n, k, gs in [(5, 700, 6, 100), (6, 700, 6, 15), (7, 1500, 3, 100), (8, 300, 300, 5)]:
+        sc, iou, _ = _rand_case(seed, n, k)
+        o = O.differentiable_nms(sc, iou, group_size=gs, dense=False)
+        st = ops.forward_matrix(cuda(sc)[None], cuda(iou)[None], ops.make_params(group_size=gs))
+        assert np.array_equal(st.order[0].cpu().numpy(), o["order"])
+        assert np.array_equal(st.lead[0].cpu().numpy(), o["lead"])
+        assert np.array_equal(st.pre[0].cpu().numpy(), o["pre"])
+
+
+def test_nan_overlap_leaves_the_pool_silently(G):
+    """NaN compares false on both `>` and `<=` (lib/groomed_nms.py:249-250): the box joins no group, r = 0."""
+    from oracle import groomed_oracle as O
+    sc, iou, _ = _rand_case(77, 120, 3)
+    order = np.argsort(-sc)
+    iou = iou.copy()
+    iou[order[5], order[0]] = np.nan
+    iou[order[40], order[1]] = np.nan
+    o = O.differentiable_nms(sc, iou, dense=False)
+    v, i, p = G.differentiable_nms(cuda(sc), cuda(iou))
+    check_against(o, p.cpu().numpy(), v.cpu().numpy(), i.cpu().numpy())
+    assert p[5].item() == 0.0
+
+
+@pytest.mark.parametrize("box_kind", ["2d", "3d"])
+def test_matrix_free_forward_equals_matrix_path(box_kind):
+    """gnms_forward_boxes_f32 (overlaps on the fly, nothing N^2 in HBM) == overlap kernel + gnms_forward_f32."""
+    from groomed_nms_b200 import synthetic, ops, _lib
+    if box_kind == "2d":
+        boxes, sc, _ = synthetic.clustered_boxes_2d(1500, 7, seed=9, jitter=0.06)
+        bx = cuda(boxes)
+        iou = ops.overlap2d(bx, bx)
+        p = ops.make_params(group_size=50)
+        st2 = ops.forward_boxes(cuda(sc)[None], bx[None], _lib.BOX_2D, p)
+    else:
+        b7, sc = synthetic.config_c3(seed=4, n=2000, k=16)
+        rec = ops.box3d_records(ops.corners_from_boxes7(cuda(b7)))
+        _, iou = ops.overlap3d(rec, rec, False, True, generalized=True, affine=True)
+        p = ops.make_params(group_size=50)
+        st2 = ops.forward_boxes(cuda(sc)[None], rec[None], _lib.BOX_3D_REC, p, generalized=True, affine=True)
+    st1 = ops.forward_matrix(cuda(sc)[None], iou[None], p)
+    torch.cuda.synchronize()
+    for f in ("prob", "order", "lead", "pre", "pval", "counts"):
+        assert torch.equal(getattr(st1, f), getattr(st2, f)), f
+    nv = int(st1.counts[0, 0])
+    assert torch.equal(st1.valid_idx[0, :nv], st2.valid_idx[0, :nv])
+    g = torch.randn(1, sc.shape[0], device="cuda")
+    g1, _ = ops.backward(st1, g)
+    g2, _ = ops.backward(st2, g)
+    assert torch.allclose(g1, g2, rtol=1e-6, atol=1e-7)
+
+
+def test_batched_ragged_equals_per_image():
+    """[B,N] batch with n_per_image (padding) == B independent calls."""
+    from groomed_nms_b200 import ops
+    B, N = 5, 640
+    ns = [640, 1, 333, 0, 500]
+    sc = np.zeros((B, N), np.float32); iou = np.zeros((B, N, N), np.float32)
+    singles = []
+    for b, n in enumerate(ns):
+        if n:
+            s, m, _ = _rand_case(300 + b, n, 5)
+            sc[b, :n] = s; iou[b, :n, :n] = m
+        singles.append(n)
+    p = ops.make_params(group_size=30)
+    npi = torch.tensor(ns, dtype=torch.int32, device="cuda")
+    st = ops.forward_matrix(cuda(sc), cuda(iou), p, n_per_image=npi)
+    g = torch.randn(B, N, device="cuda")
+    gs, _ = ops.backward(st, g)
+    for b, n in enumerate(ns):
+        assert st.counts[b].sum().item() == n
+        if n == 0:
+            continue
+        s1 = ops.forward_matrix(cuda(sc[b:b + 1, :n]), cuda(iou[b:b + 1, :n, :n]), p)
+        assert torch.equal(s1.prob[0], st.prob[b, :n])
+        nv = int(s1.counts[0, 0])
+        assert torch.equal(s1.valid_idx[0, :nv], st.valid_idx[b, :nv])
+        g1, _ = ops.backward(s1, g[b:b + 1, :n].contiguous())
+        assert torch.allclose(g1[0], gs[b, :n], rtol=1e-6, atol=1e-7)
+        assert (gs[b, n:] == 0).all() and (st.prob[b, n:] == 0).all()
+
+
+def test_config_c1_one_group(G):
+    from groomed_nms_b200 import synthetic
+    from groomed_nms_b200.lib import core
+    from oracle import groomed_oracle as O
+    boxes, sc = synthetic.config_c1()
+    iou = core.iou(cuda(boxes), cuda(boxes))
+    assert len(O.get_groups(iou.cpu().numpy(), 0.4, sc)) == 1
+    v, i, p = G.differentiable_nms(cuda(sc), iou, nms_threshold=0.4, temperature=0.1, valid_box_prob_threshold=0.3)
+    o = O.differentiable_nms(sc, iou.cpu().numpy(), temperature=0.1)
+    check_against(o, p.cpu().numpy(), v.cpu().numpy(), i.cpu().numpy())
+    assert len(G.get_groups(iou, 0.4, cuda(sc))) == 1
+
+
+def test_config_c2_four_groups_fwd_bwd(G):
+    from groomed_nms_b200 import synthetic
+    from groomed_nms_b200.lib import core
+    from oracle import groomed_oracle as O
+    boxes, sc = synthetic.config_c2()
+    iou = core.iou(cuda(boxes), cuda(boxes))
+    iou_np = iou.cpu().numpy()
+    assert bits_equal(iou_np, O.iou(boxes, boxes))
+    assert len(O.get_groups(iou_np, 0.4, sc)) == 4
+    up = np.random.default_rng(2).standard_normal(1024).astype(np.float32)
+    for gs in (100, 10 ** 9):
+        s = cuda(sc).requires_grad_(True)
+        v, i, p = G.differentiable_nms(s, iou.clone().detach(), group_size=gs)
+        o = O.differentiable_nms(sc, iou_np, group_size=gs, dense=False)
+        check_against(o, p.detach().cpu().numpy(), v.cpu().numpy(), i.cpu().numpy())
+        assert int((o["lead"] >= 0).sum()) == (404 if gs == 100 else 1024)
+        p.backward(cuda(up))
+        want, _ = O.differentiable_nms_backward(o, up, need_grad_iou=False)
+        assert np.allclose(s.grad.cpu().numpy(), want, rtol=RTOL, atol=2e-6 * np.abs(want).max())
+
+
+def test_config_c3_full_size_fwd_bwd():
+    """BASELINE headline config: N=4096 7-DoF boxes, overlap = 0.5*(1+giou3d); matrix path and matrix-free path
+    against the oracle (fed with the CUDA corners: parity is defined from the corners onward)."""
+    from groomed_nms_b200 import synthetic, ops, _lib
+    from oracle import groomed_oracle as O
+    b7, sc = synthetic.config_c3()
+    corners = ops.corners_from_boxes7(cuda(b7))
+    rec = ops.box3d_records(corners)
+    _, ov = ops.overlap3d(rec, rec, False, True, generalized=True, affine=True)
+    cn = corners.cpu().numpy()
+    _, want_ov = O.iou3d_approximate(cn, cn, "combinations", "generalized")
+    want_ov = (np.float32(0.5) * (np.float32(1) + want_ov)).astype(np.float32)
+    assert bits_equal(ov.cpu().numpy(), want_ov)
+    o = O.differentiable_nms(sc, want_ov, dense=False)
+    up = np.random.default_rng(5).standard_normal(4096).astype(np.float32)
+    want_g, _ = O.differentiable_nms_backward(o, up, need_grad_iou=False)
+    p = ops.make_params()
+    for st in (ops.forward_matrix(cuda(sc)[None], ov[None], p),
+               ops.forward_boxes(cuda(sc)[None], rec[None], _lib.BOX_3D_REC, p, generalized=True, affine=True)):
+        nv, ni = st.counts[0].tolist()
+        check_against(o, st.prob[0].cpu().numpy(), st.valid_idx[0, :nv].cpu().numpy(), st.invalid_idx[0, :ni].cpu().numpy())
+        assert np.array_equal(st.lead[0].cpu().numpy(), o["lead"])
+        gs, _ = ops.backward(st, cuda(up)[None])
+        assert np.allclose(gs[0].cpu().numpy(), want_g, rtol=RTOL, atol=2e-6 * np.abs(want_g).max())
+        # size-independent properties: leaders keep their score, members never gain, counts add up
+        lead = st.lead[0].cpu().numpy(); r = st.prob[0].cpu().numpy(); ss = st.sorted_scores[0].cpu().numpy()
+        L = lead == np.arange(4096)
+        assert np.array_equal(r[L], np.clip(ss[L], 0, 1)) and (r <= ss + 1e-7).all() and (r[lead < 0] == 0).all()
+        assert nv + ni == 4096
+
+
+def test_idempotent_and_deterministic_forward():
+    from groomed_nms_b200 import ops
+    sc, iou, _ = _rand_case(11, 2048, 16)
+    p = ops.make_params()
+    a = ops.forward_matrix(cuda(sc)[None], cuda(iou)[None], p, private_ws=True)
+    b = ops.forward_matrix(cuda(sc)[None], cuda(iou)[None], p, private_ws=True)
+    for f in ("prob", "valid_idx", "counts", "lead", "pre"):
+        assert torch.equal(getattr(a, f)[..., :int(a.counts[0, 0])] if f == "valid_idx" else getattr(a, f),
+                           getattr(b, f)[..., :int(a.counts[0, 0])] if f == "valid_idx" else getattr(b, f))
+
+
+def test_errors(G):
+    s, m = torch.rand(4, device="cuda"), torch.eye(4, device="cuda")
+    with pytest.raises(NotImplementedError):
+        G.differentiable_nms(s, m, pruning_method="bogus")
+    with pytest.raises(NotImplementedError):
+        G.pruning_function(m, pruning_method="bogus")
+    with pytest.raises(RuntimeError):
+        G.differentiable_nms(torch.rand(9000, device="cuda"), torch.zeros(1, 1, device="cuda").expand(9000, 9000))
+
+
+def test_pruning_function_and_indices_copy(G):
+    from oracle import groomed_oracle as O
+    x = np.random.default_rng(1).uniform(0, 1, (50, 50)).astype(np.float32)
+    for pm, t in (("linear", 0.1), ("sigmoidal", 0.1), ("soft_nms", 0.5)):
+        got = G.pruning_function(cuda(x), 0.4, t, pm).cpu().numpy()
+        assert np.allclose(got, O.pruning_function(x, 0.4, t, pm), rtol=2e-6, atol=1e-7)
+        assert isinstance(G.pruning_function(x, 0.4, t, pm), np.ndarray)
+    A = torch.zeros(5, 5, device="cuda"); B = torch.rand(3, 3, device="cuda")
+    ind = torch.tensor([1, 2, 4], device="cuda")
+    out = G.indices_copy(A, B, ind)
+    want = torch.zeros(5, 5, device="cuda"); want[ind.unsqueeze(1), ind.unsqueeze(0)] = B
+    assert torch.equal(out, want) and torch.equal(A, want)
+    A2 = torch.zeros(3, 4, device="cuda")
+    out2 = G.indices_copy(A2, B, torch.tensor([[0, 0], [0, 1], [1, 1]], device="cuda"),
+                          torch.tensor([[1, 1], [2, 1], [2, 2]], device="cuda"), inplace=False)
+    assert out2[0, 0] == B[1, 1] and out2[0, 1] == B[2, 1] and out2[1, 1] == B[2, 2] and A2.abs().sum() == 0
