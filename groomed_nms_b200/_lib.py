@@ -44,6 +44,8 @@ SIGNATURES = {
     "gnms_project_points_f32": (i32, [vp, vp, i64, i32, vp, vp]),
     "gnms_box3d_records_f32": (i32, [vp, i32, vp, i32, vp]),
     "gnms_overlap3d_f32": (i32, [vp, i32, vp, i32, vp, vp, i64, i32, i32, vp, vp]),
+    "gnms_overlap2d_batched_f32": (i32, [vp, i32, i32, vp, vp]),
+    "gnms_overlap3d_batched_f32": (i32, [vp, i32, i32, vp, i32, i32, vp]),
     "gnms_overlap3d_list_f32": (i32, [vp, vp, i32, vp, vp, i32, i32, vp]),
     "gnms_workspace_bytes": (sz, [i32, i32]),
     "gnms_forward_f32": (i32, [vp, vp, i64, i32, i32, vp, ctypes.POINTER(Params), vp, vp, vp, vp, Saved, vp, vp]),

@@ -338,7 +338,7 @@ __device__ int warp_list_bits(const uint32_t* bits, int nw, int limit, int32_t* 
 }
 
 __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
-    extern __shared__ unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
     const int N = A.N;
     const int n = A.n_per_image ? min(A.n_per_image[b], N) : N;
@@ -355,12 +355,13 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
     const float* ss = A.sorted_scores + (size_t)b * N;
 
     // shared memory carve-up
+    const int NWa = (NW + 3) & ~3, Na = (N + 3) & ~3;                     // keep every section 16-byte aligned
     uint32_t* removed = reinterpret_cast<uint32_t*>(smem_raw);            // NW
-    uint32_t* leader = removed + NW;                                      // NW
-    uint32_t* tmpbits = leader + NW;                                      // NW
-    int32_t* fsup = reinterpret_cast<int32_t*>(tmpbits + NW);             // N   (later: lead[])
-    int32_t* list = fsup + N;                                             // N   (leader / candidate lists, later grank)
-    uint32_t* wcol = reinterpret_cast<uint32_t*>(list + N);               // kWin * NW (later: sort keys)
+    uint32_t* leader = removed + NWa;                                     // NW
+    uint32_t* tmpbits = leader + NWa;                                     // NW
+    int32_t* fsup = reinterpret_cast<int32_t*>(tmpbits + NWa);            // N   (later: lead[])
+    int32_t* list = fsup + Na;                                            // N   (leader / candidate lists, later grank)
+    uint32_t* wcol = reinterpret_cast<uint32_t*>(list + Na);              // kWin * NW (later: sort keys)
     __shared__ int s_cnt;
 
     for (int i = tid; i < NW; i += kChainThreads) {
@@ -690,7 +691,7 @@ struct BwdArgs {
 };
 
 __global__ void __launch_bounds__(kChainThreads) backward_mask_kernel(BwdArgs A) {
-    extern __shared__ float ds[];
+    extern __shared__ __align__(16) float ds[];
     const int b = blockIdx.x, N = A.N, tid = threadIdx.x;
     const int n = A.n_per_image ? min(A.n_per_image[b], N) : N;
     const size_t o = (size_t)b * N;
@@ -708,17 +709,18 @@ __global__ void __launch_bounds__(kChainThreads) backward_mask_kernel(BwdArgs A)
         ds[pos] = pass ? g : 0.f;
     }
     __syncthreads();
-    // leaders: ds_l = g~_l - sum_m p_ml g~_m ; members add into a separate shared-memory accumulator (fp32 atomics:
-    // the summation order inside one group is not fixed, results agree to ~1 ulp between runs).
-    float* acc = ds + N;
-    for (int pos = tid; pos < n; pos += kChainThreads) acc[pos] = 0.f;
+    // leaders: ds_l = g~_l - sum_m p_ml g~_m.  Members add their fp32 product into an fp64 shared-memory
+    // accumulator: the fp64 sum of fp32 terms is exact unless the terms span > 2^29 in magnitude, so the result
+    // does not depend on the order in which the atomics land (deterministic run to run), and is rounded once.
+    double* acc = reinterpret_cast<double*>(ds + ((N + 1) & ~1));
+    for (int pos = tid; pos < n; pos += kChainThreads) acc[pos] = 0.0;
     __syncthreads();
     for (int pos = tid; pos < n; pos += kChainThreads) {
         const int ld_ = A.lead[o + pos];
         if (ld_ >= 0 && ld_ != pos) {
             const float gt = ds[pos];
             if (gt != 0.f) {
-                atomicAdd(&acc[ld_], __fmul_rn(A.pval[o + pos], gt));
+                atomicAdd(&acc[ld_], (double)__fmul_rn(A.pval[o + pos], gt));
                 if (A.grad_iou) {
                     const int64_t gi = (int64_t)b * N * A.ld_gi + (int64_t)A.order[o + pos] * A.ld_gi + A.order[o + ld_];
                     A.grad_iou[gi] = __fmul_rn(-__fmul_rn(A.sorted_scores[o + ld_], gt), A.dpval[o + pos]);
@@ -728,7 +730,7 @@ __global__ void __launch_bounds__(kChainThreads) backward_mask_kernel(BwdArgs A)
     }
     __syncthreads();
     for (int pos = tid; pos < n; pos += kChainThreads)
-        A.grad_scores[o + A.order[o + pos]] = __fsub_rn(ds[pos], acc[pos]);
+        A.grad_scores[o + A.order[o + pos]] = __fsub_rn(ds[pos], (float)acc[pos]);
     if (n < N) {
         // padded boxes (n_per_image < N): their input slots get zero gradient
         for (int i = tid; i < N; i += kChainThreads) {
@@ -745,7 +747,8 @@ static size_t chain_smem_bytes(int N) {
     size_t P = 1;
     while ((int)P < N) P <<= 1;
     keys = P * 8;
-    return 3 * NW * 4 + (size_t)N * 4 * 2 + (keys > win ? keys : win);
+    size_t NWa = (NW + 3) & ~(size_t)3, Na = ((size_t)N + 3) & ~(size_t)3;
+    return 3 * NWa * 4 + Na * 4 * 2 + (keys > win ? keys : win) + 16;
 }
 
 static int configure_once() {
@@ -757,7 +760,7 @@ static int configure_once() {
     GNMS_CUDA_TRY(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     GNMS_CUDA_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)chain_smem_bytes(GNMS_MAX_BOXES)));
-    GNMS_CUDA_TRY(cudaFuncSetAttribute(backward_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    GNMS_CUDA_TRY(cudaFuncSetAttribute(backward_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * GNMS_MAX_BOXES + 64));
     done = true;
     return 0;
 }
@@ -909,7 +912,7 @@ extern "C" int gnms_backward_f32(const float* grad_prob, const float* prob, cons
     A.sorted_scores = sv.sorted_scores; A.lead = sv.lead; A.pval = sv.pval; A.dpval = sv.dpval; A.pre = sv.pre;
     A.slot = workspace ? slot_ptr(workspace, N, batch) : nullptr;
     A.grad_scores = grad_scores; A.grad_iou = grad_iou; A.ld_gi = ld_gi;
-    backward_mask_kernel<<<batch, kChainThreads, (size_t)N * 8, (cudaStream_t)stream>>>(A);
+    backward_mask_kernel<<<batch, kChainThreads, (size_t)N * 12 + 16, (cudaStream_t)stream>>>(A);
     GNMS_LAUNCH_CHECK();
     return 0;
 }

@@ -18,8 +18,12 @@ constexpr int kRows = 16;
 template <int kKind, bool kVec>
 __global__ void __launch_bounds__(kThreads) overlap2d_kernel(const float* __restrict__ a, int M,
                                                              const float* __restrict__ b, int N,
-                                                             float* __restrict__ out, int64_t ld) {
+                                                             float* __restrict__ out, int64_t ld,
+                                                             int64_t box_img_stride, int64_t out_img_stride) {
     __shared__ Box2 rows[kRows];
+    a += blockIdx.z * box_img_stride;      // batched self-overlap: image z (strides are 0 for single calls)
+    b += blockIdx.z * box_img_stride;
+    out += blockIdx.z * out_img_stride;
     const int i0 = blockIdx.y * kRows;
     const int j0 = blockIdx.x * kColsPerCta + threadIdx.x * kColsPerThread;
     if (threadIdx.x < kRows) {
@@ -125,8 +129,14 @@ template <bool kGen, bool kAffine, bool kVec>
 __global__ void __launch_bounds__(kThreads) overlap3d_kernel(const float* __restrict__ ra, int M,
                                                              const float* __restrict__ rb, int N,
                                                              float* __restrict__ out_bev, float* __restrict__ out_3d,
-                                                             int64_t ld, const float* __restrict__ mul2d) {
+                                                             int64_t ld, const float* __restrict__ mul2d,
+                                                             int64_t rec_img_stride, int64_t out_img_stride) {
     __shared__ Rec3 rows[kRows];
+    ra += blockIdx.z * rec_img_stride;     // batched self-overlap: image z (strides are 0 for single calls)
+    rb += blockIdx.z * rec_img_stride;
+    if (out_bev) out_bev += blockIdx.z * out_img_stride;
+    if (out_3d) out_3d += blockIdx.z * out_img_stride;
+    if (mul2d) mul2d += blockIdx.z * out_img_stride;
     const int i0 = blockIdx.y * kRows;
     const int j0 = blockIdx.x * kColsPerCta + threadIdx.x * kColsPerThread;
     if (threadIdx.x < kRows) {
@@ -281,11 +291,11 @@ extern "C" int gnms_overlap2d_f32(const float* a, int M, const float* b, int N, 
     dim3 grid(gnms_div_up(N, kColsPerCta), gnms_div_up(M, kRows));
     bool vec = aligned16(out) && (ld_out % 4 == 0);
     if (kind == GNMS_KIND_IOU) {
-        if (vec) overlap2d_kernel<GNMS_KIND_IOU, true><<<grid, kThreads, 0, s>>>(a, M, b, N, out, ld_out);
-        else overlap2d_kernel<GNMS_KIND_IOU, false><<<grid, kThreads, 0, s>>>(a, M, b, N, out, ld_out);
+        if (vec) overlap2d_kernel<GNMS_KIND_IOU, true><<<grid, kThreads, 0, s>>>(a, M, b, N, out, ld_out, 0, 0);
+        else overlap2d_kernel<GNMS_KIND_IOU, false><<<grid, kThreads, 0, s>>>(a, M, b, N, out, ld_out, 0, 0);
     } else {
-        if (vec) overlap2d_kernel<GNMS_KIND_INTERSECT, true><<<grid, kThreads, 0, s>>>(a, M, b, N, out, ld_out);
-        else overlap2d_kernel<GNMS_KIND_INTERSECT, false><<<grid, kThreads, 0, s>>>(a, M, b, N, out, ld_out);
+        if (vec) overlap2d_kernel<GNMS_KIND_INTERSECT, true><<<grid, kThreads, 0, s>>>(a, M, b, N, out, ld_out, 0, 0);
+        else overlap2d_kernel<GNMS_KIND_INTERSECT, false><<<grid, kThreads, 0, s>>>(a, M, b, N, out, ld_out, 0, 0);
     }
     GNMS_LAUNCH_CHECK();
     return 0;
@@ -352,9 +362,10 @@ extern "C" int gnms_box3d_records_f32(float* corners, int N, float* rec, int mut
 
 template <bool G, bool A>
 static void launch_overlap3d(dim3 grid, cudaStream_t s, bool vec, const float* ra, int M, const float* rb, int N,
-                             float* ob, float* o3, int64_t ld, const float* mul2d) {
-    if (vec) overlap3d_kernel<G, A, true><<<grid, kThreads, 0, s>>>(ra, M, rb, N, ob, o3, ld, mul2d);
-    else overlap3d_kernel<G, A, false><<<grid, kThreads, 0, s>>>(ra, M, rb, N, ob, o3, ld, mul2d);
+                             float* ob, float* o3, int64_t ld, const float* mul2d, int64_t rstride = 0,
+                             int64_t ostride = 0) {
+    if (vec) overlap3d_kernel<G, A, true><<<grid, kThreads, 0, s>>>(ra, M, rb, N, ob, o3, ld, mul2d, rstride, ostride);
+    else overlap3d_kernel<G, A, false><<<grid, kThreads, 0, s>>>(ra, M, rb, N, ob, o3, ld, mul2d, rstride, ostride);
 }
 
 extern "C" int gnms_overlap3d_f32(const float* rec_a, int M, const float* rec_b, int N, float* out_bev,
@@ -373,6 +384,42 @@ extern "C" int gnms_overlap3d_f32(const float* rec_a, int M, const float* rec_b,
     } else {
         if (affine) launch_overlap3d<false, true>(grid, s, vec, rec_a, M, rec_b, N, out_bev, out_3d, ld_out, mul2d);
         else launch_overlap3d<false, false>(grid, s, vec, rec_a, M, rec_b, N, out_bev, out_3d, ld_out, mul2d);
+    }
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
+
+// Batched self-overlap: image z of boxes[B,N,4] / rec[B,N,8] -> out[B,N,N] in one launch (grid.z = image).
+extern "C" int gnms_overlap2d_batched_f32(const float* boxes, int N, int batch, float* out, void* stream) {
+    if (N < 0 || batch < 0) return GNMS_E_BADARG;
+    if (N == 0 || batch == 0) return 0;
+    if (!boxes || !out) return GNMS_E_BADARG;
+    if (!aligned16(boxes)) return GNMS_E_ALIGN;
+    dim3 grid(gnms_div_up(N, kColsPerCta), gnms_div_up(N, kRows), batch);
+    bool vec = aligned16(out) && (N % 4 == 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (vec) overlap2d_kernel<GNMS_KIND_IOU, true><<<grid, kThreads, 0, s>>>(boxes, N, boxes, N, out, N, (int64_t)N * 4, (int64_t)N * N);
+    else overlap2d_kernel<GNMS_KIND_IOU, false><<<grid, kThreads, 0, s>>>(boxes, N, boxes, N, out, N, (int64_t)N * 4, (int64_t)N * N);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gnms_overlap3d_batched_f32(const float* rec, int N, int batch, float* out_3d, int generalized, int affine,
+                                          void* stream) {
+    if (N < 0 || batch < 0) return GNMS_E_BADARG;
+    if (N == 0 || batch == 0) return 0;
+    if (!rec || !out_3d) return GNMS_E_BADARG;
+    if (!aligned16(rec)) return GNMS_E_ALIGN;
+    dim3 grid(gnms_div_up(N, kColsPerCta), gnms_div_up(N, kRows), batch);
+    bool vec = aligned16(out_3d) && (N % 4 == 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t rs = (int64_t)N * 8, os = (int64_t)N * N;
+    if (generalized) {
+        if (affine) launch_overlap3d<true, true>(grid, s, vec, rec, N, rec, N, nullptr, out_3d, N, nullptr, rs, os);
+        else launch_overlap3d<true, false>(grid, s, vec, rec, N, rec, N, nullptr, out_3d, N, nullptr, rs, os);
+    } else {
+        if (affine) launch_overlap3d<false, true>(grid, s, vec, rec, N, rec, N, nullptr, out_3d, N, nullptr, rs, os);
+        else launch_overlap3d<false, false>(grid, s, vec, rec, N, rec, N, nullptr, out_3d, N, nullptr, rs, os);
     }
     GNMS_LAUNCH_CHECK();
     return 0;

@@ -1,0 +1,128 @@
+"""Allocation-free runner for the GrooMeD-NMS hot path on a batch of images + the host-buffer entry point.
+
+`Nms3dPlan` owns every device buffer a forward+backward step needs for a fixed (batch, N) and enqueues the
+sm_100a kernels through the C-ABI with raw pointers, so a whole step (7-DoF boxes -> corners -> records ->
+[overlap matrix ->] GrooMeD-NMS forward -> analytic backward) is 5-7 stream-ordered launches with no host sync
+and can be captured in a CUDA graph.  `run_host` is the call a user with HOST (pinned) buffers makes: it copies
+boxes/scores/upstream-gradient in, runs the step, and copies the rescored scores, the score gradients and the
+keep lists back."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import Saved, check
+
+
+def _vp(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class Nms3dPlan(object):
+    """Fixed-shape plan: `batch` images of `n` 7-DoF boxes each on `device`.
+
+    materialise=True  : API-compatible pipeline, the [n,n] overlap matrix 0.5*(1+GIoU3D) of every image is written
+                        to HBM by the overlap tile kernel and streamed back once by the mask kernel (what the
+                        reference does: iou3d_approximate -> differentiable_nms; 8*n^2 bytes of matrix traffic).
+    materialise=False : matrix-free pipeline, overlaps are evaluated on the fly (nothing n^2 touches HBM)."""
+
+    def __init__(self, batch, n, device, params, materialise=True, box_dof=7):
+        self.lib = _lib.load()
+        self.B, self.N, self.dev, self.params, self.materialise = batch, n, device, params, materialise
+        f = dict(dtype=torch.float32, device=device)
+        self.boxes7 = torch.zeros((batch, n, box_dof), **f)
+        self.scores = torch.zeros((batch, n), **f)
+        self.grad_prob = torch.zeros((batch, n), **f)
+        self.corners = torch.empty((batch * n, 3, 8), **f)
+        self.rec = torch.empty((batch * n, 8), **f)
+        self.overlap = torch.empty((batch, n, n), **f) if materialise else None
+        self.prob = torch.empty((batch, n), **f)
+        self.grad_scores = torch.empty((batch, n), **f)
+        self.valid_idx = torch.empty((batch, n), dtype=torch.int64, device=device)
+        self.invalid_idx = torch.empty((batch, n), dtype=torch.int64, device=device)
+        self.counts = torch.empty((batch, 2), dtype=torch.int32, device=device)
+        self.order = torch.empty((batch, n), dtype=torch.int32, device=device)
+        self.lead = torch.empty((batch, n), dtype=torch.int32, device=device)
+        self.fl = torch.empty((4, batch, n), **f)
+        self.ws = torch.empty((int(self.lib.gnms_workspace_bytes(n, batch)),), dtype=torch.uint8, device=device)
+        self.saved = Saved(_vp(self.order), _vp(self.fl[0]), _vp(self.lead), _vp(self.fl[1]), _vp(self.fl[2]), _vp(self.fl[3]))
+        self.launches_per_step = 6 + (1 if materialise else 0)   # corners, records, [overlap], sort, mask, chain, backward
+
+    # -- individual stages (each is one C-ABI call = one kernel launch unless noted)
+    def stage_corners(self, s):
+        check(self.lib.gnms_corners_from_boxes7_f32(_vp(self.boxes7), self.boxes7.stride(1), self.B * self.N, _vp(self.corners), s), "corners")
+
+    def stage_records(self, s):
+        check(self.lib.gnms_box3d_records_f32(_vp(self.corners), self.B * self.N, _vp(self.rec), 0, s), "records")
+
+    def stage_overlap(self, s):          # one launch, grid.z = image
+        check(self.lib.gnms_overlap3d_batched_f32(_vp(self.rec), self.N, self.B, _vp(self.overlap), 1, 1, s), "overlap3d_batched")
+
+    def stage_forward(self, s):          # sort + mask + chain: 3 launches
+        p = ctypes.byref(self.params)
+        if self.materialise:
+            check(self.lib.gnms_forward_f32(_vp(self.scores), _vp(self.overlap), self.N, self.N, self.B, None, p, _vp(self.prob),
+                                            _vp(self.valid_idx), _vp(self.invalid_idx), _vp(self.counts), self.saved,
+                                            _vp(self.ws), s), "forward")
+        else:
+            check(self.lib.gnms_forward_boxes_f32(_vp(self.scores), _vp(self.rec), _lib.BOX_3D_REC, 1, 1, self.N, self.B, None, p,
+                                                  _vp(self.prob), _vp(self.valid_idx), _vp(self.invalid_idx), _vp(self.counts),
+                                                  self.saved, _vp(self.ws), s), "forward_boxes")
+
+    def stage_backward(self, s):
+        check(self.lib.gnms_backward_f32(_vp(self.grad_prob), _vp(self.prob), _vp(self.overlap), self.N, self.N, self.B, None,
+                                         ctypes.byref(self.params), self.saved, _vp(self.grad_scores), None, self.N,
+                                         _vp(self.ws), s), "backward")
+
+    def step(self, stream=None):
+        """Enqueue one forward+backward pass over the batch on `stream` (default: torch's current stream)."""
+        st = stream if stream is not None else torch.cuda.current_stream(self.dev)
+        s = ctypes.c_void_p(st.cuda_stream)
+        self.stage_corners(s)
+        self.stage_records(s)
+        if self.materialise:
+            self.stage_overlap(s)
+        self.stage_forward(s)
+        self.stage_backward(s)
+
+    def capture(self):
+        """Capture step() into a CUDA graph and return it (replay with .replay())."""
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            self.step(side)                      # warm-up outside capture (one-time function attributes)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step(torch.cuda.current_stream(self.dev))
+        return g
+
+
+class HostRunner(object):
+    """End-to-end entry for HOST buffers: pinned staging + an Nms3dPlan.  run_host(...) returns host tensors."""
+
+    def __init__(self, batch, n, device, params, materialise=False):
+        self.plan = Nms3dPlan(batch, n, device, params, materialise=materialise)
+        pin = dict(pin_memory=True)
+        self.h_prob = torch.empty((batch, n), dtype=torch.float32, **pin)
+        self.h_grad = torch.empty((batch, n), dtype=torch.float32, **pin)
+        self.h_valid = torch.empty((batch, n), dtype=torch.int64, **pin)
+        self.h_counts = torch.empty((batch, 2), dtype=torch.int32, **pin)
+        self.h2d_bytes = batch * n * (7 + 1 + 1) * 4
+        self.d2h_bytes = batch * n * (4 + 4 + 8) + batch * 8
+
+    def run_host(self, boxes7_host, scores_host, grad_prob_host):
+        """boxes7 [B,N,7], scores [B,N], dL/dprob [B,N] (pinned host fp32) -> (prob, grad_scores, valid_idx, counts)
+        on the host.  One H2D per input, the kernels, one D2H per output, one stream sync."""
+        p = self.plan
+        p.boxes7.copy_(boxes7_host, non_blocking=True)
+        p.scores.copy_(scores_host, non_blocking=True)
+        p.grad_prob.copy_(grad_prob_host, non_blocking=True)
+        p.step()
+        self.h_prob.copy_(p.prob, non_blocking=True)
+        self.h_grad.copy_(p.grad_scores, non_blocking=True)
+        self.h_valid.copy_(p.valid_idx, non_blocking=True)
+        self.h_counts.copy_(p.counts, non_blocking=True)
+        torch.cuda.current_stream(p.dev).synchronize()
+        return self.h_prob, self.h_grad, self.h_valid, self.h_counts

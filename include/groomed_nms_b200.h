@@ -112,6 +112,10 @@ int gnms_box3d_records_f32(float* corners, int N, float* rec, int mutate_input, 
  * mul2d (NULL or [M,N] with ld_out): out_3d *= mul2d  (overlap_in_nms="product", lib/loss/rpn_3d.py:786). */
 int gnms_overlap3d_f32(const float* rec_a, int M, const float* rec_b, int N, float* out_bev, float* out_3d,
                        int64_t ld_out, int generalized, int affine, const float* mul2d, void* stream);
+/* Batched self-overlaps (one launch, grid.z = image): boxes[B,N,4] -> out[B,N,N] IoU; rec[B,N,8] -> out_3d[B,N,N]. */
+int gnms_overlap2d_batched_f32(const float* boxes, int N, int batch, float* out, void* stream);
+int gnms_overlap3d_batched_f32(const float* rec, int N, int batch, float* out_3d, int generalized, int affine,
+                               void* stream);
 int gnms_overlap3d_list_f32(const float* rec_a, const float* rec_b, int M, float* out_bev, float* out_3d,
                             int generalized, int affine, void* stream);
 

@@ -327,7 +327,7 @@ def test_pruning_function_and_indices_copy(G):
     x = np.random.default_rng(1).uniform(0, 1, (50, 50)).astype(np.float32)
     for pm, t in (("linear", 0.1), ("sigmoidal", 0.1), ("soft_nms", 0.5)):
         got = G.pruning_function(cuda(x), 0.4, t, pm).cpu().numpy()
-        assert np.allclose(got, O.pruning_function(x, 0.4, t, pm), rtol=2e-6, atol=1e-7)
+        assert np.allclose(got, O.pruning_function(x, 0.4, t, pm), rtol=1e-5, atol=1e-6)
         assert isinstance(G.pruning_function(x, 0.4, t, pm), np.ndarray)
     A = torch.zeros(5, 5, device="cuda"); B = torch.rand(3, 3, device="cuda")
     ind = torch.tensor([1, 2, 4], device="cuda")
