@@ -32,7 +32,8 @@ constexpr int kMaskThreads = 256;
 
 // ------------------------------------------------------------------------------------------ workspace
 struct WsLayout {
-    size_t rank, sbox, mask, has_earlier, colflag, total;   // byte offsets inside one image's slice
+    size_t rank, sbox, mask, has_earlier, total;   // byte offsets inside one image's slice
+    int he_slots;                                   // partial has-earlier words per row word (one per column-chunk CTA)
 };
 __host__ __device__ inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 __host__ __device__ inline WsLayout ws_layout(int N) {
@@ -42,8 +43,10 @@ __host__ __device__ inline WsLayout ws_layout(int N) {
     L.rank = off;        off += align_up((size_t)N * 4);
     L.sbox = off;        off += align_up((size_t)N * 8 * 4);
     L.mask = off;        off += align_up(nw * (size_t)N * 4);
-    L.has_earlier = off; off += align_up(nw * 4);
-    L.colflag = off;     off += align_up((size_t)N);
+    // "row word has an earlier overlapper" partials: slot = column-chunk CTA of the mask kernels (no atomics, no
+    // shared flags: same-address global traffic from thousands of CTAs serialises in L2 and cost 4x the kernel)
+    L.he_slots = (N + 255) / 256;
+    L.has_earlier = off; off += align_up(nw * (size_t)L.he_slots * 4);
     L.total = off;
     return L;
 }
@@ -66,7 +69,6 @@ sort_kernel(const float* __restrict__ scores, int64_t sstride, int64_t score_img
     int32_t* rank = reinterpret_cast<int32_t*>(w + L.rank);
     float* sbox = reinterpret_cast<float*>(w + L.sbox);
     uint32_t* has_earlier = reinterpret_cast<uint32_t*>(w + L.has_earlier);
-    uint8_t* colflag = reinterpret_cast<uint8_t*>(w + L.colflag);
     const float* sc = scores + (size_t)b * score_img_stride;
     int32_t* order = order_out + (size_t)b * N;
     float* ss = ss_out + (size_t)b * N;
@@ -83,8 +85,7 @@ sort_kernel(const float* __restrict__ scores, int64_t sstride, int64_t score_img
         keys[i] = k;
     }
     const int nw = (N + 31) / 32;
-    for (int i = tid; i < nw; i += kChainThreads) has_earlier[i] = 0u;
-    for (int i = tid; i < N; i += kChainThreads) colflag[i] = 0;
+    for (int i = tid; i < nw * L.he_slots; i += kChainThreads) has_earlier[i] = 0u;
     __syncthreads();
     if (!presorted) {
         for (int k = 2; k <= P; k <<= 1) {
@@ -153,7 +154,8 @@ mask_matrix_kernel(const float* __restrict__ iou, int64_t ld, int64_t img_stride
     const int32_t* rank = reinterpret_cast<const int32_t*>(w + L.rank);
     uint32_t* mask = reinterpret_cast<uint32_t*>(w + L.mask);
     uint32_t* has_earlier = reinterpret_cast<uint32_t*>(w + L.has_earlier);
-    uint8_t* colflag = reinterpret_cast<uint8_t*>(w + L.colflag);
+    __shared__ uint32_t s_any;
+    if (threadIdx.x == 0) s_any = 0u;
     const int32_t* order = order_all + (size_t)b * N;
     const float* m = iou + (size_t)b * img_stride;
     if (threadIdx.x < 32) {
@@ -163,52 +165,63 @@ mask_matrix_kernel(const float* __restrict__ iou, int64_t ld, int64_t img_stride
     __syncthreads();
     const int c0 = (blockIdx.x * kMaskThreads + threadIdx.x) * 4;
     uint32_t wd[4] = {0u, 0u, 0u, 0u};
-    int rk[4];
-    int rkmin = INT_MAX;
-    if (c0 < n) {
+    int rk[4] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX};
+    if (c0 + 4 <= n) {
+        const int4 q = *reinterpret_cast<const int4*>(rank + c0);
+        rk[0] = q.x; rk[1] = q.y; rk[2] = q.z; rk[3] = q.w;
+    } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            rk[k] = (c0 + k < n) ? rank[c0 + k] : INT_MAX;
-            rkmin = min(rkmin, rk[k]);
-        }
+        for (int k = 0; k < 4; ++k)
+            if (c0 + k < n) rk[k] = rank[c0 + k];
     }
+    const int rkmin = min(min(rk[0], rk[1]), min(rk[2], rk[3]));
     const int pos_last = min(jw * 32 + 31, n - 1);
-    if (c0 < n && rkmin < pos_last) {          // otherwise none of my columns precedes any row of this word
-        const bool full = kVec && (c0 + 4 <= N);
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-            const int row = rows[r];
-            if (row < 0) break;
-            const int pos = jw * 32 + r;
-            const float* src = m + (int64_t)row * ld + c0;
-            float v[4];
-            if (full) {
-                float4 q = ld_cs_f4(src);
-                v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-            } else {
+    const int nrows = pos_last - jw * 32 + 1;                 // live rows of this word (1..32)
+    // a thread whose 4 columns all come later than every row of this word has nothing to contribute
+    if (rkmin < pos_last) {
+        if (kVec && c0 + 4 <= N && nrows == 32) {
+            // fast path: 4 batches of 8 rows, all eight 16-byte streaming loads of a batch issued before use
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = (c0 + k < N) ? __ldcs(src + k) : 0.f;
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+                float4 q[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) q[u] = ld_cs_f4(m + (int64_t)rows[r0 + u] * ld + c0);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int r = r0 + u, pos = jw * 32 + r;
+                    wd[0] |= (uint32_t)(!(q[u].x <= thr) && rk[0] < pos) << r;
+                    wd[1] |= (uint32_t)(!(q[u].y <= thr) && rk[1] < pos) << r;
+                    wd[2] |= (uint32_t)(!(q[u].z <= thr) && rk[2] < pos) << r;
+                    wd[3] |= (uint32_t)(!(q[u].w <= thr) && rk[3] < pos) << r;
+                }
             }
+        } else {
+            for (int r = 0; r < nrows; ++r) {
+                const int pos = jw * 32 + r;
+                const float* src = m + (int64_t)rows[r] * ld + c0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t bit = (!(v[k] <= thr)) && (rk[k] < pos);
-                wd[k] |= bit << r;
+                for (int k = 0; k < 4; ++k) {
+                    if (c0 + k < n) {
+                        const float v = __ldcs(src + k);
+                        wd[k] |= (uint32_t)(!(v <= thr) && rk[k] < pos) << r;
+                    }
+                }
             }
         }
     }
     uint32_t any = 0u;
-    if (c0 < n) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (c0 + k < n && (rk[k] >> 5) <= jw) {           // words above the diagonal are never read
-                mask[(size_t)jw * N + rk[k]] = wd[k];
-                if (wd[k]) colflag[rk[k]] = 1;
-            }
-            any |= wd[k];
+    for (int k = 0; k < 4; ++k) {
+        if (rk[k] != INT_MAX && (rk[k] >> 5) <= jw) {         // words above the diagonal are never read
+            mask[(size_t)jw * N + rk[k]] = wd[k];
         }
+        any |= wd[k];
     }
     any = __reduce_or_sync(0xffffffffu, any);
-    if ((threadIdx.x & 31) == 0 && any) atomicOr(&has_earlier[jw], any);
+    if ((threadIdx.x & 31) == 0 && any) atomicOr(&s_any, any);          // shared memory
+    __syncthreads();
+    // one partial per (row word, column-chunk CTA): this kernel's chunk is 1024 columns = 4 slots of 256
+    if (threadIdx.x == 0) has_earlier[(size_t)jw * L.he_slots + blockIdx.x * 4] = s_any;
 }
 
 // ------------------------------------------------------------------------------------------ 2b. mask from boxes
@@ -229,7 +242,8 @@ mask_boxes_kernel(int N, const int32_t* __restrict__ n_per_image, char* __restri
     const float* sbox = reinterpret_cast<const float*>(w + L.sbox);
     uint32_t* mask = reinterpret_cast<uint32_t*>(w + L.mask);
     uint32_t* has_earlier = reinterpret_cast<uint32_t*>(w + L.has_earlier);
-    uint8_t* colflag = reinterpret_cast<uint8_t*>(w + L.colflag);
+    __shared__ uint32_t s_any;
+    if (threadIdx.x == 0) s_any = 0u;
     if (threadIdx.x < 64) {
         int r = threadIdx.x >> 1, h = threadIdx.x & 1;
         int pos = jw * 32 + r;
@@ -266,10 +280,11 @@ mask_boxes_kernel(int N, const int32_t* __restrict__ n_per_image, char* __restri
     }
     if (l < n && (l >> 5) <= jw) {
         mask[(size_t)jw * N + l] = wd;
-        if (wd) colflag[l] = 1;
     }
     uint32_t any = __reduce_or_sync(0xffffffffu, wd);
-    if ((threadIdx.x & 31) == 0 && any) atomicOr(&has_earlier[jw], any);
+    if ((threadIdx.x & 31) == 0 && any) atomicOr(&s_any, any);          // shared memory
+    __syncthreads();
+    if (threadIdx.x == 0) has_earlier[(size_t)jw * L.he_slots + blockIdx.x] = s_any;
 }
 
 // ------------------------------------------------------------------------------------------ 3. chain
@@ -349,7 +364,6 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
     char* w = A.ws + (size_t)b * A.ws_img_stride;
     const uint32_t* mask = reinterpret_cast<const uint32_t*>(w + L.mask);
     const uint32_t* has_earlier = reinterpret_cast<const uint32_t*>(w + L.has_earlier);
-    const uint8_t* colflag = reinterpret_cast<const uint8_t*>(w + L.colflag);
     const float* sbox = reinterpret_cast<const float*>(w + L.sbox);
     const int32_t* order = A.order + (size_t)b * N;
     const float* ss = A.sorted_scores + (size_t)b * N;
@@ -366,7 +380,10 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
 
     for (int i = tid; i < NW; i += kChainThreads) {
         removed[i] = 0u;
-        leader[i] = (i < nw) ? (~has_earlier[i] & valid_word(i, n)) : 0u;
+        uint32_t he = 0u;
+        if (i < nw)
+            for (int sl = 0; sl < L.he_slots; ++sl) he |= has_earlier[(size_t)i * L.he_slots + sl];
+        leader[i] = (i < nw) ? (~he & valid_word(i, n)) : 0u;
     }
     for (int i = tid; i < N; i += kChainThreads) fsup[i] = INT_MAX;
     __syncthreads();
@@ -383,9 +400,17 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
         const int cnt = s_cnt;
         for (int k = warp; k < cnt; k += kChainThreads / 32) {
             const int l = list[k];
-            if (!colflag[l]) continue;
-            for (int jw = (l >> 5) + lane; jw < nw; jw += 32) {
-                uint32_t m = mask[(size_t)jw * N + l];
+            constexpr int kMaxW = GNMS_MAX_BOXES / 32 / 32;
+            uint32_t mw[kMaxW];
+#pragma unroll
+            for (int u = 0; u < kMaxW; ++u) {                 // all of the column's words in flight at once
+                const int jw = (l >> 5) + u * 32 + lane;
+                mw[u] = jw < nw ? mask[(size_t)jw * N + l] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kMaxW; ++u) {
+                const int jw = (l >> 5) + u * 32 + lane;
+                uint32_t m = mw[u];
                 if (m) {
                     atomicOr(&removed[jw], m);
                     while (m) {
@@ -411,9 +436,8 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
         if (cnt == 0) break;
         for (int k = warp; k < cnt; k += kChainThreads / 32) {
             const int l = list[k];
-            const bool has = colflag[l] != 0;
             for (int jw = lane; jw < nw; jw += 32)
-                wcol[k * NW + jw] = (has && jw >= (l >> 5)) ? mask[(size_t)jw * N + l] : 0u;
+                wcol[k * NW + jw] = (jw >= (l >> 5)) ? mask[(size_t)jw * N + l] : 0u;
         }
         __syncthreads();
         if (warp == 0) {
@@ -497,44 +521,74 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
     __syncthreads();
 
     // ---- in-group rank (0 = leader) and the group_size cap: only the first group_size+1 boxes stay (:254-255)
+    // (leaders with members are listed first, then one warp per leader; the up-to-8 mask words a lane owns are all
+    //  loaded before any is used)
     int32_t* grank = list;
+    int32_t* llist = reinterpret_cast<int32_t*>(wcol);
+    // member count per leader (shared-memory atomics); ranks are only needed where the cap can bite
+    // (count > group_size) or when the caller wants the groups themselves
     for (int pos = tid; pos < n; pos += kChainThreads) grank[pos] = 0;
-    for (int i = tid; i < nw; i += kChainThreads) tmpbits[i] = leader[i];
+    __syncthreads();
+    for (int pos = tid; pos < n; pos += kChainThreads) {
+        const int ld_ = lead[pos];
+        if (ld_ >= 0 && ld_ != pos) atomicAdd(&grank[ld_], 1);
+    }
+    __syncthreads();
+    const int need_above = A.group_id ? 0 : P.group_size;
+    for (int i = tid; i < nw; i += kChainThreads) {
+        uint32_t lw = leader[i], keep = 0u;
+        while (lw) {
+            const int bp = __ffs(lw) - 1;
+            lw &= lw - 1;
+            if (grank[i * 32 + bp] > need_above) keep |= 1u << bp;
+        }
+        tmpbits[i] = keep;
+    }
+    __syncthreads();
+    for (int pos = tid; pos < n; pos += kChainThreads) grank[pos] = 0;
+    __syncthreads();
+    if (warp == 0) {
+        int c = warp_list_bits(tmpbits, nw, N, llist);
+        if (lane == 0) s_cnt = c;
+    }
     __syncthreads();
     {
-        // leaders enumerated straight from the bitset words: warp k takes words k, k+32, ...
-        for (int wi = warp; wi < nw; wi += kChainThreads / 32) {
-            uint32_t lw = tmpbits[wi];
-            while (lw) {
-                const int l = wi * 32 + __ffs(lw) - 1;
-                lw &= lw - 1;
-                if (!colflag[l]) continue;
-                int carry = 0;
-                for (int base = (l >> 5); base < nw; base += 32) {
-                    const int jw = base + lane;
-                    uint32_t m = jw < nw ? mask[(size_t)jw * N + l] : 0u;
-                    uint32_t memb = 0u;
-                    while (m) {
-                        int bp = __ffs(m) - 1;
-                        m &= m - 1;
-                        if (lead[jw * 32 + bp] == l) memb |= 1u << bp;
-                    }
-                    int c = __popc(memb), incl = c;
+        const int nlead = s_cnt;
+        constexpr int kMaxW = GNMS_MAX_BOXES / 32 / 32;          // mask words per lane per column (8)
+        for (int k = warp; k < nlead; k += kChainThreads / 32) {
+            const int l = llist[k];
+            const int base0 = l >> 5;
+            uint32_t mw[kMaxW];
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        int t = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += t;
-                    }
-                    int before = carry + incl - c;
-                    uint32_t mm = memb;
-                    while (mm) {
-                        int bp = __ffs(mm) - 1;
-                        mm &= mm - 1;
-                        int rk = 1 + before + __popc(memb & ((1u << bp) - 1u));
-                        grank[jw * 32 + bp] = rk;
-                    }
-                    carry += __shfl_sync(0xffffffffu, incl, 31);
+            for (int u = 0; u < kMaxW; ++u) {
+                const int jw = base0 + u * 32 + lane;
+                mw[u] = jw < nw ? mask[(size_t)jw * N + l] : 0u;
+            }
+            int carry = 0;
+#pragma unroll
+            for (int u = 0; u < kMaxW; ++u) {
+                const int jw = base0 + u * 32 + lane;
+                if (base0 + u * 32 >= nw) break;
+                uint32_t m = mw[u], memb = 0u;
+                while (m) {
+                    int bp = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (lead[jw * 32 + bp] == l) memb |= 1u << bp;
                 }
+                int c = __popc(memb), incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                const int before = carry + incl - c;
+                uint32_t mm = memb;
+                while (mm) {
+                    int bp = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    grank[jw * 32 + bp] = 1 + before + __popc(memb & ((1u << bp) - 1u));
+                }
+                carry += __shfl_sync(0xffffffffu, incl, 31);
             }
         }
     }

@@ -183,6 +183,134 @@ __global__ void __launch_bounds__(kThreads) overlap3d_kernel(const float* __rest
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Symmetric self-overlap tiles.  overlap(i,j) == overlap(j,i) bitwise (min/max and the fp32 additions commute), so
+// only tile pairs I <= J of 64 x 64 are evaluated: the tile is stored directly (16 B streaming stores along rows)
+// and, for I != J, a second time transposed through shared memory.  Halves the ALU work of the ALU-co-limited
+// N x N kernels; HBM traffic stays the algorithmic 4 N^2 bytes.
+// 256 threads: tx = tid & 15 owns columns 4tx..4tx+3, ty = tid >> 4 owns rows ty, ty+16, ty+32, ty+48.
+constexpr int kST = 64;            // tile edge
+constexpr int kSS = kST + 1;       // shared-memory row stride (floats)
+
+__device__ __forceinline__ void sym_tile_coords(int t, int nt, int& I, int& J) {
+    // upper-triangular enumeration: row I holds tiles (I,I)..(I,nt-1); t = I*nt - I*(I-1)/2 + (J - I)
+    float fn = 2.0f * nt + 1.0f;
+    int i = (int)((fn - sqrtf(fn * fn - 8.0f * (float)t)) * 0.5f);
+    i = max(0, min(i, nt - 1));
+    while (i > 0 && i * nt - i * (i - 1) / 2 > t) --i;
+    while ((i + 1) * nt - (i + 1) * i / 2 <= t) ++i;
+    I = i;
+    J = i + (t - (i * nt - i * (i - 1) / 2));
+}
+
+template <bool kGen, bool kAffine>
+__device__ __noinline__ float iou3_exact_noinline(Rec3 a, Rec3 b) { return iou3<kGen, kAffine>(a, b, inter_bev3(a, b)); }
+__device__ __noinline__ float iou2_exact_noinline(Box2 a, Box2 b) { return iou2(a, b); }
+
+template <typename Rec, typename F, typename FX>
+__device__ __forceinline__ void sym_tile_body(int N, float* __restrict__ out, bool vec, const Rec (&rr)[4],
+                                              const Rec (&cr)[4], int I, int J, float* tile, bool tile_unsafe,
+                                              F pairfn, FX exactfn) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int i0 = I * kST, j0 = J * kST;
+    float v[4][4];
+    bool unsafe = tile_unsafe;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[r][k] = pairfn(rr[r], cr[k], unsafe);
+    if (__builtin_expect(unsafe, 0)) {     // rare: operands outside div_rn_fast's proven range -> exact IEEE path
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[r][k] = exactfn(rr[r], cr[k]);
+    }
+    // direct tile
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty + 16 * r, j = j0 + 4 * tx;
+        if (i < N && j < N) {
+            float* dst = out + (int64_t)i * N + j;
+            if (vec && j + 4 <= N) st_cs_f4(dst, make_float4(v[r][0], v[r][1], v[r][2], v[r][3]));
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (j + k < N) dst[k] = v[r][k];
+            }
+        }
+    }
+    if (I == J) return;
+    // transposed tile through shared memory: tile[c][r]
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tile[(4 * tx + k) * kSS + ty + 16 * r] = v[r][k];
+    __syncthreads();
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+        const int c = ty + 16 * pass;                 // row of the transposed tile = column index j0 + c
+        const int i = j0 + c, j = i0 + 4 * tx;
+        if (i < N && j < N) {
+            const float* src = tile + c * kSS + 4 * tx;
+            float* dst = out + (int64_t)i * N + j;
+            if (vec && j + 4 <= N) st_cs_f4(dst, make_float4(src[0], src[1], src[2], src[3]));
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (j + k < N) dst[k] = src[k];
+            }
+        }
+    }
+}
+
+template <bool kGen, bool kAffine>
+__global__ void __launch_bounds__(256) overlap3d_self_kernel(const float* __restrict__ rec, int N, float* __restrict__ out,
+                                                             int nt, int vec) {
+    __shared__ float tile[kST * kSS];
+    rec += (int64_t)blockIdx.y * N * 8;
+    out += (int64_t)blockIdx.y * N * N;
+    int I, J;
+    sym_tile_coords(blockIdx.x, nt, I, J);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    Rec3 rr[4], cr[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) rr[r] = load_rec3(rec + (int64_t)min(I * kST + ty + 16 * r, N - 1) * 8);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cr[k] = load_rec3(rec + (int64_t)min(J * kST + 4 * tx + k, N - 1) * 8);
+    // box-level preconditions of the straight-line division, one record per thread, OR-ed over the CTA
+    bool bad = false;
+    if (threadIdx.x < 2 * kST) {
+        const int idx = (threadIdx.x < kST ? I * kST + threadIdx.x : J * kST + threadIdx.x - kST);
+        if (idx < N) bad = !rec3_sane(load_rec3(rec + (int64_t)idx * 8));
+    }
+    const bool tile_unsafe = __syncthreads_or(bad);
+    sym_tile_body(N, out, vec != 0, rr, cr, I, J, tile, tile_unsafe,
+                  [](const Rec3& a, const Rec3& b, bool& u) { return iou3_fast<kGen, kAffine>(a, b, inter_bev3(a, b), u); },
+                  [](const Rec3& a, const Rec3& b) { return iou3_exact_noinline<kGen, kAffine>(a, b); });
+}
+
+__global__ void __launch_bounds__(256) overlap2d_self_kernel(const float* __restrict__ boxes, int N, float* __restrict__ out,
+                                                             int nt, int vec) {
+    __shared__ float tile[kST * kSS];
+    boxes += (int64_t)blockIdx.y * N * 4;
+    out += (int64_t)blockIdx.y * N * N;
+    int I, J;
+    sym_tile_coords(blockIdx.x, nt, I, J);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    Box2 rr[4], cr[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) rr[r] = make_box2(__ldg(reinterpret_cast<const float4*>(boxes) + min(I * kST + ty + 16 * r, N - 1)));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cr[k] = make_box2(__ldg(reinterpret_cast<const float4*>(boxes) + min(J * kST + 4 * tx + k, N - 1)));
+    bool bad = false;
+    if (threadIdx.x < 2 * kST) {
+        const int idx = (threadIdx.x < kST ? I * kST + threadIdx.x : J * kST + threadIdx.x - kST);
+        if (idx < N) bad = !box2_sane(make_box2(__ldg(reinterpret_cast<const float4*>(boxes) + idx)));
+    }
+    const bool tile_unsafe = __syncthreads_or(bad);
+    sym_tile_body(N, out, vec != 0, rr, cr, I, J, tile, tile_unsafe,
+                  [](const Box2& a, const Box2& b, bool& u) { return iou2_fast(a, b, u); },
+                  [](const Box2& a, const Box2& b) { return iou2_exact_noinline(a, b); });
+}
+
 template <bool kGen, bool kAffine>
 __global__ void overlap3d_list_kernel(const float* __restrict__ ra, const float* __restrict__ rb, int M,
                                       float* __restrict__ out_bev, float* __restrict__ out_3d) {
@@ -290,6 +418,12 @@ extern "C" int gnms_overlap2d_f32(const float* a, int M, const float* b, int N, 
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(gnms_div_up(N, kColsPerCta), gnms_div_up(M, kRows));
     bool vec = aligned16(out) && (ld_out % 4 == 0);
+    if (kind == GNMS_KIND_IOU && a == b && M == N && ld_out == N && N >= 2 * kST) {   // self-overlap: symmetric tiles
+        const int nt = gnms_div_up(N, kST);
+        overlap2d_self_kernel<<<dim3(nt * (nt + 1) / 2, 1), 256, 0, s>>>(a, N, out, nt, vec && (N % 4 == 0));
+        GNMS_LAUNCH_CHECK();
+        return 0;
+    }
     if (kind == GNMS_KIND_IOU) {
         if (vec) overlap2d_kernel<GNMS_KIND_IOU, true><<<grid, kThreads, 0, s>>>(a, M, b, N, out, ld_out, 0, 0);
         else overlap2d_kernel<GNMS_KIND_IOU, false><<<grid, kThreads, 0, s>>>(a, M, b, N, out, ld_out, 0, 0);
@@ -360,6 +494,9 @@ extern "C" int gnms_box3d_records_f32(float* corners, int N, float* rec, int mut
     return 0;
 }
 
+extern "C" int gnms_overlap3d_batched_f32(const float* rec, int N, int batch, float* out_3d, int generalized, int affine,
+                                          void* stream);
+
 template <bool G, bool A>
 static void launch_overlap3d(dim3 grid, cudaStream_t s, bool vec, const float* ra, int M, const float* rb, int N,
                              float* ob, float* o3, int64_t ld, const float* mul2d, int64_t rstride = 0,
@@ -376,6 +513,8 @@ extern "C" int gnms_overlap3d_f32(const float* rec_a, int M, const float* rec_b,
     if (!rec_a || !rec_b || (!out_bev && !out_3d)) return GNMS_E_BADARG;
     if (!aligned16(rec_a) || !aligned16(rec_b)) return GNMS_E_ALIGN;
     cudaStream_t s = (cudaStream_t)stream;
+    if (rec_a == rec_b && M == N && !out_bev && !mul2d && ld_out == N && N >= 2 * kST)   // self-overlap: symmetric tiles
+        return gnms_overlap3d_batched_f32(rec_a, N, 1, out_3d, generalized, affine, stream);
     dim3 grid(gnms_div_up(N, kColsPerCta), gnms_div_up(M, kRows));
     bool vec = (ld_out % 4 == 0) && (!out_bev || aligned16(out_bev)) && (!out_3d || aligned16(out_3d));
     if (generalized) {
@@ -395,11 +534,9 @@ extern "C" int gnms_overlap2d_batched_f32(const float* boxes, int N, int batch, 
     if (N == 0 || batch == 0) return 0;
     if (!boxes || !out) return GNMS_E_BADARG;
     if (!aligned16(boxes)) return GNMS_E_ALIGN;
-    dim3 grid(gnms_div_up(N, kColsPerCta), gnms_div_up(N, kRows), batch);
-    bool vec = aligned16(out) && (N % 4 == 0);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (vec) overlap2d_kernel<GNMS_KIND_IOU, true><<<grid, kThreads, 0, s>>>(boxes, N, boxes, N, out, N, (int64_t)N * 4, (int64_t)N * N);
-    else overlap2d_kernel<GNMS_KIND_IOU, false><<<grid, kThreads, 0, s>>>(boxes, N, boxes, N, out, N, (int64_t)N * 4, (int64_t)N * N);
+    const int nt = gnms_div_up(N, kST);
+    const int vec = aligned16(out) && (N % 4 == 0);
+    overlap2d_self_kernel<<<dim3(nt * (nt + 1) / 2, batch), 256, 0, (cudaStream_t)stream>>>(boxes, N, out, nt, vec);
     GNMS_LAUNCH_CHECK();
     return 0;
 }
@@ -410,16 +547,16 @@ extern "C" int gnms_overlap3d_batched_f32(const float* rec, int N, int batch, fl
     if (N == 0 || batch == 0) return 0;
     if (!rec || !out_3d) return GNMS_E_BADARG;
     if (!aligned16(rec)) return GNMS_E_ALIGN;
-    dim3 grid(gnms_div_up(N, kColsPerCta), gnms_div_up(N, kRows), batch);
-    bool vec = aligned16(out_3d) && (N % 4 == 0);
+    const int nt = gnms_div_up(N, kST);
+    const int vec = aligned16(out_3d) && (N % 4 == 0);
+    dim3 grid(nt * (nt + 1) / 2, batch);
     cudaStream_t s = (cudaStream_t)stream;
-    const int64_t rs = (int64_t)N * 8, os = (int64_t)N * N;
     if (generalized) {
-        if (affine) launch_overlap3d<true, true>(grid, s, vec, rec, N, rec, N, nullptr, out_3d, N, nullptr, rs, os);
-        else launch_overlap3d<true, false>(grid, s, vec, rec, N, rec, N, nullptr, out_3d, N, nullptr, rs, os);
+        if (affine) overlap3d_self_kernel<true, true><<<grid, 256, 0, s>>>(rec, N, out_3d, nt, vec);
+        else overlap3d_self_kernel<true, false><<<grid, 256, 0, s>>>(rec, N, out_3d, nt, vec);
     } else {
-        if (affine) launch_overlap3d<false, true>(grid, s, vec, rec, N, rec, N, nullptr, out_3d, N, nullptr, rs, os);
-        else launch_overlap3d<false, false>(grid, s, vec, rec, N, rec, N, nullptr, out_3d, N, nullptr, rs, os);
+        if (affine) overlap3d_self_kernel<false, true><<<grid, 256, 0, s>>>(rec, N, out_3d, nt, vec);
+        else overlap3d_self_kernel<false, false><<<grid, 256, 0, s>>>(rec, N, out_3d, nt, vec);
     }
     GNMS_LAUNCH_CHECK();
     return 0;
