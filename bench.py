@@ -258,10 +258,15 @@ def run_ours(args, rank, world):
         it = max(10, args.steps)
         stages["corners"] = time_stage(torch, pl.stage_corners, st, it)
         stages["records"] = time_stage(torch, pl.stage_records, st, it)
-        stages["overlap3d_matrix"] = time_stage(torch, pl.stage_overlap, st, it)
-        stages["forward_from_matrix(sort+mask+chain)"] = time_stage(torch, pl.stage_forward, st, it)
+        stages["forward_boxes+matrix_out(rank+tile+has_earlier+chain)"] = time_stage(torch, pl.stage_forward, st, it)
         stages["backward"] = time_stage(torch, pl.stage_backward, st, it)
-        stages["forward_from_boxes(sort+mask+chain)"] = time_stage(torch, plans["fused"].stage_forward, st, it)
+        stages["forward_boxes_no_matrix(rank+tile+has_earlier+chain)"] = time_stage(torch, plans["fused"].stage_forward, st, it)
+        tk = Nms3dPlan(B, N, dev, params, materialise=True, two_kernel=True)
+        tk.boxes7.copy_(pl.boxes7); tk.scores.copy_(pl.scores); tk.grad_prob.copy_(pl.grad_prob)
+        tk.stage_corners(__import__("ctypes").c_void_p(st.cuda_stream)); tk.stage_records(__import__("ctypes").c_void_p(st.cuda_stream))
+        stages["two_kernel:overlap3d_matrix"] = time_stage(torch, tk.stage_overlap, st, it)
+        stages["two_kernel:forward_from_matrix(rank+mask+chain)"] = time_stage(torch, tk.stage_forward, st, it)
+        del tk
 
     if world > 1:
         dist.barrier()
@@ -273,7 +278,7 @@ def run_ours(args, rank, world):
         step_bytes = algorithmic_bytes(N, BOX_DOF) * B
         # dominant kernel of the materialised path: the N x N overlap tile kernel (writes 4 N^2 per image) or the
         # matrix -> bitmask stream (reads 4 N^2 per image); algorithmic bytes per launch stated in DESIGN.md
-        k_ms = stages["overlap3d_matrix"]
+        k_ms = stages["forward_boxes+matrix_out(rank+tile+has_earlier+chain)"]
         k_bytes = B * (4 * N * N + 2 * 32 * N)
         ach = k_bytes / (k_ms * 1e-3) / 1e9
         line = {

@@ -49,7 +49,7 @@ SIGNATURES = {
     "gnms_overlap3d_list_f32": (i32, [vp, vp, i32, vp, vp, i32, i32, vp]),
     "gnms_workspace_bytes": (sz, [i32, i32]),
     "gnms_forward_f32": (i32, [vp, vp, i64, i32, i32, vp, ctypes.POINTER(Params), vp, vp, vp, vp, Saved, vp, vp]),
-    "gnms_forward_boxes_f32": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, ctypes.POINTER(Params), vp, vp, vp, vp,
+    "gnms_forward_boxes_f32": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, ctypes.POINTER(Params), vp, vp, vp, vp, vp,
                                      Saved, vp, vp]),
     "gnms_backward_f32": (i32, [vp, vp, vp, i64, i32, i32, vp, ctypes.POINTER(Params), Saved, vp, vp, i64, vp, vp]),
     "gnms_get_groups_f32": (i32, [vp, vp, i64, i32, f32, i32, vp, vp, vp, vp, vp]),

@@ -137,6 +137,105 @@ sort_kernel(const float* __restrict__ scores, int64_t sstride, int64_t score_img
     }
 }
 
+// ------------------------------------------------------------------------------------------ 1b. rank by counting
+// Multi-CTA replacement of the one-CTA bitonic sort: rank[i] = #{j : score_j > score_i or (== and j < i)}.
+// grid (ceil(N/64), batch), 256 threads: 4 threads share one element and each scans a quarter of the keys from
+// shared memory with 16-byte broadcast loads.  N^2 compares, but spread over the whole chip (~1 us per image at
+// N=4096) instead of ~45 us of barrier-bound bitonic stages on one SM.  Also zeroes the has-earlier partials and,
+// if asked, the suppression bitmask (the tile kernel below sets its bits with atomics).
+constexpr int kRankElems = 64;
+__global__ void __launch_bounds__(256)
+rank_kernel(const float* __restrict__ scores, int64_t sstride, int64_t score_img_stride, int N,
+            const int32_t* __restrict__ n_per_image, int32_t* __restrict__ order_out, float* __restrict__ ss_out,
+            char* __restrict__ ws, size_t ws_img_stride, const float* __restrict__ boxes, int box_src,
+            int64_t box_img_stride, float shift, int presorted, int zero_mask) {
+    extern __shared__ __align__(16) uint32_t skeys[];
+    const int b = blockIdx.y;
+    const int n = n_per_image ? min(n_per_image[b], N) : N;
+    const WsLayout L = ws_layout(N);
+    char* w = ws + (size_t)b * ws_img_stride;
+    int32_t* rank = reinterpret_cast<int32_t*>(w + L.rank);
+    float* sbox = reinterpret_cast<float*>(w + L.sbox);
+    uint32_t* has_earlier = reinterpret_cast<uint32_t*>(w + L.has_earlier);
+    uint32_t* mask = reinterpret_cast<uint32_t*>(w + L.mask);
+    const float* sc = scores + (size_t)b * score_img_stride;
+    int32_t* order = order_out + (size_t)b * N;
+    float* ss = ss_out + (size_t)b * N;
+    const int tid = threadIdx.x;
+    const int npad = (N + 15) & ~15;
+    for (int j = tid; j < npad; j += 256) skeys[j] = (j < n && !presorted) ? desc_key(sc[(int64_t)j * sstride]) : 0xffffffffu;
+    // chores, split over the CTAs of this image
+    const int nw = (N + 31) / 32;
+    const size_t ncta = gridDim.x, me = blockIdx.x;
+    for (size_t i = me * 256 + tid; i < (size_t)nw * L.he_slots; i += ncta * 256) has_earlier[i] = 0u;
+    if (zero_mask) {
+        uint4* m4 = reinterpret_cast<uint4*>(mask);
+        const size_t tot4 = ((size_t)nw * N + 3) / 4;                  // the mask slice is 256-byte aligned and padded
+        for (size_t i = me * 256 + tid; i < tot4; i += ncta * 256) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (blockIdx.x == 0) {
+        for (int pos = n + tid; pos < N; pos += 256) { order[pos] = -1; ss[pos] = 0.f; rank[pos] = INT_MAX; }
+    }
+    __syncthreads();
+    const int e = tid >> 2, q = tid & 3;
+    const int i = blockIdx.x * kRankElems + e;
+    if (i >= n) return;                                               // whole quads leave together
+    int r;
+    if (presorted) {
+        r = i;
+    } else {
+        // count keys that sort before (key_i, i): key_j < key_i, or key_j == key_i with j < i.  The four threads of
+        // an element take interleaved 16-byte groups (conflict-free, broadcast across the 8 elements of a warp);
+        // groups entirely below i use `<= key_i` (as `< key_i + 1`), groups above use `<`, i's own group is split.
+        const uint32_t ki = skeys[i];
+        const uint32_t kle = ki == 0xffffffffu ? ki : ki + 1u;
+        const int i4 = i >> 2, n4 = npad >> 2;
+        const uint4* k4 = reinterpret_cast<const uint4*>(skeys);
+        int cnt = 0;
+        int j4 = q;
+#pragma unroll 4
+        for (; j4 < i4; j4 += 4) {
+            const uint4 k = k4[j4];
+            cnt += (k.x < kle) + (k.y < kle) + (k.z < kle) + (k.w < kle);
+        }
+        if (j4 == i4) {
+            const uint4 k = k4[j4];
+            const int sub = i & 3;
+            cnt += (k.x < (sub > 0 ? kle : ki)) + (k.y < (sub > 1 ? kle : ki)) + (k.z < (sub > 2 ? kle : ki)) + (k.w < ki);
+            j4 += 4;
+        }
+#pragma unroll 4
+        for (; j4 < n4; j4 += 4) {
+            const uint4 k = k4[j4];
+            cnt += (k.x < ki) + (k.y < ki) + (k.z < ki) + (k.w < ki);
+        }
+        const unsigned quad_mask = 0xfu << ((tid & 31) & ~3);        // the 4 lanes of this element (they exit together)
+        cnt += __shfl_xor_sync(quad_mask, cnt, 1);
+        cnt += __shfl_xor_sync(quad_mask, cnt, 2);
+        r = cnt;
+    }
+    if (q != 0) return;
+    order[r] = i;
+    rank[i] = r;
+    ss[r] = sc[(int64_t)i * sstride];
+    const float* bx = boxes ? boxes + (size_t)b * box_img_stride : nullptr;
+    float4* o = reinterpret_cast<float4*>(sbox + (size_t)r * 8);
+    if (box_src == kSrcBox2d) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(bx) + i);
+        o[0] = v;
+        o[1] = make_float4(make_box2(v).area, 0.f, 0.f, 0.f);
+    } else if (box_src == kSrcBox3d) {
+        const float4* src = reinterpret_cast<const float4*>(bx + (size_t)i * 8);
+        o[0] = __ldg(src);
+        o[1] = __ldg(src + 1);
+    } else if (box_src == kSrcBoxShift) {
+        const float* d = bx + (size_t)i * 5;
+        const BoxS qb = make_boxs(d[0], d[1], d[2], d[3], shift);
+        o[0] = make_float4(qb.x1, qb.y1, qb.x2, qb.y2);
+        o[1] = make_float4(qb.area, 0.f, 0.f, 0.f);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ 2a. mask from a matrix
 // grid (ceil(N/1024), NW, batch), 256 threads; thread = 4 consecutive INPUT columns x the 32 rows of row word jw.
 template <bool kVec>
@@ -285,6 +384,221 @@ mask_boxes_kernel(int N, const int32_t* __restrict__ n_per_image, char* __restri
     if ((threadIdx.x & 31) == 0 && any) atomicOr(&s_any, any);          // shared memory
     __syncthreads();
     if (threadIdx.x == 0) has_earlier[(size_t)jw * L.he_slots + blockIdx.x] = s_any;
+}
+
+// ------------------------------------------------------------------------------------------ 2c. fused overlap + mask tiles
+// The north-star kernel: every unordered pair of boxes of an image is evaluated ONCE (symmetric 64 x 64 tiles in
+// INPUT index space, values register-resident) and feeds two consumers:
+//   * the API-visible overlap matrix (optional): the tile is streamed to HBM directly and transposed (16-byte
+//     stores, algorithmic 4 N^2 bytes, never read back), and
+//   * the grouping stage: for a pair with !(v <= thr) the later-ranked box gets its bit set in the earlier box's
+//     mask column (sorted space) with a fire-and-forget atomic OR -- ~3 % of the pairs on clustered boxes.
+// Persistent CTAs walk the tile list; the next tile's 128 box records + ranks are prefetched with cp.async into the
+// other half of a double buffer while the current tile is computed.  ALU bound (~55 issue slots per pair).
+struct TileArgs {
+    int N, batch, nt, tiles_per_image, vec;
+    const int32_t* n_per_image;
+    const float* boxes;          // [batch, N, 8] 3D records or [batch, N, 4] 2D boxes (input order)
+    char* ws;
+    size_t ws_img_stride;
+    float* out;                  // [batch, N, N] or nullptr
+    float thr;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+constexpr int kTT = 64;              // tile edge
+constexpr int kTS = kTT + 1;         // transposed-tile row stride
+
+__device__ __forceinline__ void tile_decode(int t, int nt, int& I, int& J) {
+    float fn = 2.0f * nt + 1.0f;
+    int i = (int)((fn - sqrtf(fn * fn - 8.0f * (float)t)) * 0.5f);
+    i = max(0, min(i, nt - 1));
+    while (i > 0 && i * nt - i * (i - 1) / 2 > t) --i;
+    while ((i + 1) * nt - (i + 1) * i / 2 <= t) ++i;
+    I = i;
+    J = i + (t - (i * nt - i * (i - 1) / 2));
+}
+
+template <int kSrc> struct RecOf;
+template <> struct RecOf<kSrcBox3d> {
+    typedef Rec3 type;
+    static __device__ __forceinline__ Rec3 load(const float* p) { return load_rec3(p); }
+    template <bool G, bool Aff> static __device__ __forceinline__ float fast(const Rec3& a, const Rec3& b, bool& u) {
+        return iou3_fast<G, Aff>(a, b, inter_bev3(a, b), u);
+    }
+    template <bool G, bool Aff> static __device__ __forceinline__ float exact(const Rec3& a, const Rec3& b) {
+        return iou3_exact_slow<G, Aff>(a, b);
+    }
+};
+template <> struct RecOf<kSrcBox2d> {
+    typedef Box2 type;
+    static __device__ __forceinline__ Box2 load(const float* p) { return make_box2(*reinterpret_cast<const float4*>(p)); }
+    template <bool G, bool Aff> static __device__ __forceinline__ float fast(const Box2& a, const Box2& b, bool& u) {
+        return iou2_fast(a, b, u);
+    }
+    template <bool G, bool Aff> static __device__ __forceinline__ float exact(const Box2& a, const Box2& b) {
+        return iou2_exact_slow(a, b);
+    }
+};
+
+template <int kSrc, bool kGen, bool kAffine, bool kHasOut>
+__global__ void __launch_bounds__(256, 3) tile_kernel(TileArgs A) {
+    constexpr int kRecF = (kSrc == kSrcBox3d) ? 8 : 4;             // floats per staged record
+    __shared__ __align__(16) float s_rec[2][2][kTT * kRecF];       // [buffer][row/col][record]
+    __shared__ int s_rank[2][2][kTT];
+    __shared__ int s_ij[2][4];                                     // decoded (image, I, J) of the staged tile
+    __shared__ float s_tile[kHasOut ? kTT * kTS : 1];
+    const int N = A.N, tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const WsLayout L = ws_layout(N);
+    const int total = A.tiles_per_image * A.batch;
+
+    auto prefetch = [&](int t, int buf) {
+        const int b = t / A.tiles_per_image;
+        int I, J;
+        tile_decode(t - b * A.tiles_per_image, A.nt, I, J);
+        const float* bx = A.boxes + (size_t)b * N * kRecF;
+        const int32_t* rank = reinterpret_cast<const int32_t*>(A.ws + (size_t)b * A.ws_img_stride + L.rank);
+        if (tid < 2 * kTT) {                                       // thread = one record (rows first, then columns)
+            const int side = tid >> 6, k = tid & 63;
+            const int idx = min((side ? J : I) * kTT + k, N - 1);
+            const float* src = bx + (size_t)idx * kRecF;
+            float* dst = &s_rec[buf][side][k * kRecF];
+            cp_async16(dst, src);
+            if (kRecF == 8) cp_async16(dst + 4, src + 4);
+            cp_async4(&s_rank[buf][side][k], rank + idx);
+            if (tid == 0) { s_ij[buf][0] = b; s_ij[buf][1] = I; s_ij[buf][2] = J; }
+        }
+    };
+
+    int t = blockIdx.x, buf = 0;
+    if (t < total) prefetch(t, 0);
+    for (; t < total; t += gridDim.x, buf ^= 1) {
+        cp_async_wait_all();
+        // box-level preconditions of the straight-line division: every thread checks the record it copied
+        bool bad = false;
+        if (tid < 2 * kTT) {
+            const float* p = &s_rec[buf][tid >> 6][(tid & 63) * kRecF];
+            if (kSrc == kSrcBox3d) {
+                const Rec3 r = {p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7]};
+                bad = !rec3_sane(r);
+            } else {
+                bad = !box2_sane(make_box2(make_float4(p[0], p[1], p[2], p[3])));
+            }
+        }
+        const bool tile_unsafe = __syncthreads_or(bad);              // also publishes the staged records
+        const int b = s_ij[buf][0], I = s_ij[buf][1], J = s_ij[buf][2];
+        uint32_t* mask = reinterpret_cast<uint32_t*>(A.ws + (size_t)b * A.ws_img_stride + L.mask);
+        float* out = kHasOut ? A.out + (size_t)b * N * N : nullptr;
+        if (t + (int)gridDim.x < total) prefetch(t + gridDim.x, buf ^ 1);
+
+        const int i0 = I * kTT, j0 = J * kTT;
+        const bool vec = A.vec != 0;
+        const bool transposed = kHasOut && (I != J);
+        int crk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) crk[k] = s_rank[buf][1][4 * tx + k];
+        typename RecOf<kSrc>::type cr[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cr[k] = RecOf<kSrc>::load(&s_rec[buf][1][(4 * tx + k) * kRecF]);
+        // one row of the thread's 4 x 4 sub-tile at a time keeps the live registers low (3 CTAs per SM)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const typename RecOf<kSrc>::type rr = RecOf<kSrc>::load(&s_rec[buf][0][(ty + 16 * r) * kRecF]);
+            float v[4];
+            bool unsafe = tile_unsafe;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = RecOf<kSrc>::template fast<kGen, kAffine>(rr, cr[k], unsafe);
+            if (__builtin_expect(unsafe, 0)) {      // rare: outside div_rn_fast's proven range -> exact IEEE path
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = RecOf<kSrc>::template exact<kGen, kAffine>(rr, cr[k]);
+            }
+            // ---- consumer 1: suppression bits (sorted space).  Off-diagonal tiles see every unordered pair once;
+            //      the diagonal tile sees (i,j) and (j,i): only the orientation "row is the later box" emits.
+            uint32_t hits = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hits |= (uint32_t)(!(v[k] <= A.thr)) << k;
+            if (hits) {
+                const int ri = s_rank[buf][0][ty + 16 * r];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if ((hits >> k) & 1u) {
+                        const int rj = crk[k];
+                        const int later = max(ri, rj), earlier = min(ri, rj);
+                        // padded boxes (index >= n) carry rank INT_MAX; ri == rj only for a box with itself
+                        if (later != INT_MAX && ri != rj && (I != J || ri > rj))
+                            atomicOr(mask + ((unsigned)(later >> 5) * (unsigned)N + (unsigned)earlier), 1u << (later & 31));
+                    }
+                }
+            }
+            // ---- consumer 2: the overlap matrix (optional): direct row now, transposed tile via shared memory
+            if (kHasOut) {
+                const int i = i0 + ty + 16 * r, j = j0 + 4 * tx;
+                if (i < N && j < N) {
+                    float* dst = out + (int64_t)i * N + j;
+                    if (vec && j + 4 <= N) st_cs_f4(dst, make_float4(v[0], v[1], v[2], v[3]));
+                    else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) if (j + k < N) dst[k] = v[k];
+                    }
+                }
+                if (transposed) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) s_tile[(4 * tx + k) * kTS + ty + 16 * r] = v[k];
+                }
+            }
+        }
+        if (transposed) {
+            __syncthreads();
+#pragma unroll
+            for (int pass = 0; pass < 4; ++pass) {
+                const int c = ty + 16 * pass;
+                const int i = j0 + c, j = i0 + 4 * tx;
+                if (i < N && j < N) {
+                    const float* src = s_tile + c * kTS + 4 * tx;
+                    float* dst = out + (int64_t)i * N + j;
+                    if (vec && j + 4 <= N) st_cs_f4(dst, make_float4(src[0], src[1], src[2], src[3]));
+                    else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) if (j + k < N) dst[k] = src[k];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// has-earlier words from the finished mask: word jw = OR over columns l of mask[jw][l]   (grid (NW, batch))
+__global__ void __launch_bounds__(256) has_earlier_kernel(int N, const int32_t* __restrict__ n_per_image, char* __restrict__ ws,
+                                                          size_t ws_img_stride) {
+    __shared__ uint32_t s_red[8];
+    const int b = blockIdx.y, jw = blockIdx.x;
+    const int n = n_per_image ? min(n_per_image[b], N) : N;
+    const WsLayout L = ws_layout(N);
+    char* w = ws + (size_t)b * ws_img_stride;
+    const uint32_t* mask = reinterpret_cast<const uint32_t*>(w + L.mask);
+    uint32_t* has_earlier = reinterpret_cast<uint32_t*>(w + L.has_earlier);
+    if (jw * 32 >= n) return;
+    const int lend = min(n, jw * 32 + 32);                          // columns at or after the word's last row are empty
+    uint32_t acc = 0u;
+    for (int l = threadIdx.x; l < lend; l += 256) acc |= mask[(size_t)jw * N + l];
+    acc = __reduce_or_sync(0xffffffffu, acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t a = 0u;
+        for (int k = 0; k < 8; ++k) a |= s_red[k];
+        has_earlier[(size_t)jw * L.he_slots] = a;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ 3. chain
@@ -819,6 +1133,8 @@ static int configure_once() {
     return 0;
 }
 
+static size_t rank_smem_bytes(int N) { return (size_t)((N + 15) & ~15) * 4; }
+
 static size_t sort_smem_bytes(int N) {
     size_t P = 1;
     while ((int)P < N) P <<= 1;
@@ -874,7 +1190,8 @@ extern "C" size_t gnms_workspace_bytes(int N, int batch) {
 }
 
 static int run_forward(const float* scores, int src, const float* iou, int64_t ld, const float* boxes,
-                       int generalized, int affine, int N, int batch, const int32_t* npi, const gnms_params* p,
+                       float* overlap_out, int generalized, int affine, int N, int batch, const int32_t* npi,
+                       const gnms_params* p,
                        float* prob, int64_t* valid_idx, int64_t* invalid_idx, int32_t* counts, gnms_saved sv,
                        int32_t* slot, void* workspace, cudaStream_t s) {
     int rc = check_common(N, batch, p);
@@ -891,9 +1208,9 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     char* ws = reinterpret_cast<char*>(workspace);
     const int NW = (N + 31) / 32;
     int box_stride = src == kSrcBox2d ? 4 : 8;
-    sort_kernel<<<batch, kChainThreads, sort_smem_bytes(N), s>>>(
+    rank_kernel<<<dim3(gnms_div_up(N, kRankElems), batch), 256, rank_smem_bytes(N), s>>>(
         scores, 1, N, N, npi, sv.order, sv.sorted_scores, ws, L.total, src == kSrcMatrix ? nullptr : boxes, src,
-        (int64_t)N * box_stride, 0.f, 0);
+        (int64_t)N * box_stride, 0.f, 0, src == kSrcMatrix ? 0 : 1);
     GNMS_LAUNCH_CHECK();
     if (src == kSrcMatrix) {
         if (!iou || ld < N) return GNMS_E_BADARG;
@@ -903,9 +1220,33 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
         else mask_matrix_kernel<false><<<grid, kMaskThreads, 0, s>>>(iou, ld, (int64_t)N * ld, N, npi, sv.order, ws, L.total, p->nms_threshold);
     } else {
         if (!boxes) return GNMS_E_BADARG;
-        dim3 grid(gnms_div_up(N, kMaskThreads), NW, batch);
-        if (src == kSrcBox3d) launch_mask_boxes<kSrcBox3d, GNMS_CMP_NLE>(grid, s, generalized, affine, N, npi, ws, L.total, p->nms_threshold, 0.f);
-        else launch_mask_boxes<kSrcBox2d, GNMS_CMP_NLE>(grid, s, 0, 0, N, npi, ws, L.total, p->nms_threshold, 0.f);
+        TileArgs T = {};
+        T.N = N; T.batch = batch; T.nt = gnms_div_up(N, kTT); T.tiles_per_image = T.nt * (T.nt + 1) / 2;
+        T.vec = overlap_out && ((reinterpret_cast<uintptr_t>(overlap_out) & 15u) == 0) && (N % 4 == 0);
+        T.n_per_image = npi; T.boxes = boxes; T.ws = ws; T.ws_img_stride = L.total; T.out = overlap_out;
+        T.thr = p->nms_threshold;
+        const int total = T.tiles_per_image * batch;
+        const int grid = total < 148 * 3 ? total : 148 * 3;            // persistent: 3 CTAs per SM
+        const bool ho = overlap_out != nullptr;
+#define GNMS_TILE(SRC, G, AF)                                                              \
+    do {                                                                                   \
+        if (ho) tile_kernel<SRC, G, AF, true><<<grid, 256, 0, s>>>(T);                     \
+        else tile_kernel<SRC, G, AF, false><<<grid, 256, 0, s>>>(T);                       \
+    } while (0)
+        if (src == kSrcBox3d) {
+            if (generalized) {
+                if (affine) GNMS_TILE(kSrcBox3d, true, true);
+                else GNMS_TILE(kSrcBox3d, true, false);
+            } else {
+                if (affine) GNMS_TILE(kSrcBox3d, false, true);
+                else GNMS_TILE(kSrcBox3d, false, false);
+            }
+        } else {
+            GNMS_TILE(kSrcBox2d, false, false);
+        }
+#undef GNMS_TILE
+        GNMS_LAUNCH_CHECK();
+        has_earlier_kernel<<<dim3(NW, batch), 256, 0, s>>>(N, npi, ws, L.total);
     }
     GNMS_LAUNCH_CHECK();
     ChainArgs A = {};
@@ -931,18 +1272,18 @@ extern "C" int gnms_forward_f32(const float* scores, const float* iou, int64_t l
                                 const int32_t* n_per_image, const gnms_params* p, float* prob, int64_t* valid_idx,
                                 int64_t* invalid_idx, int32_t* counts, gnms_saved saved, void* workspace,
                                 void* stream) {
-    return run_forward(scores, kSrcMatrix, iou, ld, nullptr, 0, 0, N, batch, n_per_image, p, prob, valid_idx,
+    return run_forward(scores, kSrcMatrix, iou, ld, nullptr, nullptr, 0, 0, N, batch, n_per_image, p, prob, valid_idx,
                        invalid_idx, counts, saved, workspace ? slot_ptr(workspace, N, batch) : nullptr, workspace,
                        (cudaStream_t)stream);
 }
 
 extern "C" int gnms_forward_boxes_f32(const float* scores, const float* boxes, int box_kind, int generalized,
                                       int affine, int N, int batch, const int32_t* n_per_image, const gnms_params* p,
-                                      float* prob, int64_t* valid_idx, int64_t* invalid_idx, int32_t* counts,
-                                      gnms_saved saved, void* workspace, void* stream) {
+                                      float* overlap_out, float* prob, int64_t* valid_idx, int64_t* invalid_idx,
+                                      int32_t* counts, gnms_saved saved, void* workspace, void* stream) {
     if (box_kind != GNMS_BOX_2D && box_kind != GNMS_BOX_3D_REC) return GNMS_E_BADARG;
     if (boxes && (reinterpret_cast<uintptr_t>(boxes) & 15u)) return GNMS_E_ALIGN;
-    return run_forward(scores, box_kind == GNMS_BOX_2D ? kSrcBox2d : kSrcBox3d, nullptr, 0, boxes, generalized, affine,
+    return run_forward(scores, box_kind == GNMS_BOX_2D ? kSrcBox2d : kSrcBox3d, nullptr, 0, boxes, overlap_out, generalized, affine,
                        N, batch, n_per_image, p, prob, valid_idx, invalid_idx, counts, saved,
                        workspace ? slot_ptr(workspace, N, batch) : nullptr, workspace, (cudaStream_t)stream);
 }
@@ -990,8 +1331,8 @@ extern "C" int gnms_get_groups_f32(const float* scores, const float* iou, int64_
     float* pv = reinterpret_cast<float*>(extra + 2 * align_up((size_t)N * 4));
     float* dpv = reinterpret_cast<float*>(extra + 3 * align_up((size_t)N * 4));
     const int NW = (N + 31) / 32;
-    sort_kernel<<<1, kChainThreads, sort_smem_bytes(N), s>>>(scores, 1, N, N, nullptr, order, ss, ws, L.total, nullptr,
-                                                            kSrcMatrix, 0, 0.f, 0);
+    rank_kernel<<<dim3(gnms_div_up(N, kRankElems), 1), 256, rank_smem_bytes(N), s>>>(scores, 1, N, N, nullptr, order, ss, ws, L.total,
+                                                                                    nullptr, kSrcMatrix, 0, 0.f, 0, 0);
     GNMS_LAUNCH_CHECK();
     dim3 grid(gnms_div_up(N, kMaskThreads * 4), NW, 1);
     bool vec = ((reinterpret_cast<uintptr_t>(iou) & 15u) == 0) && (ld % 4 == 0);
@@ -1024,8 +1365,8 @@ static int hard_nms_impl(const float* dets, int N, float thresh, float shift, in
     int32_t* order = reinterpret_cast<int32_t*>(extra);
     float* ss = reinterpret_cast<float*>(extra + align_up((size_t)N * 4));
     const int NW = (N + 31) / 32;
-    sort_kernel<<<1, kChainThreads, sort_smem_bytes(N), s>>>(dets + 4, 5, 0, N, nullptr, order, ss, ws, L.total, dets,
-                                                            kSrcBoxShift, 0, shift, presorted);
+    rank_kernel<<<dim3(gnms_div_up(N, kRankElems), 1), 256, rank_smem_bytes(N), s>>>(dets + 4, 5, 0, N, nullptr, order, ss, ws, L.total,
+                                                                                    dets, kSrcBoxShift, 0, shift, presorted, 0);
     GNMS_LAUNCH_CHECK();
     dim3 grid(gnms_div_up(N, kMaskThreads), NW, 1);
     if (cmp == GNMS_CMP_GT) launch_mask_boxes<kSrcBoxShift, GNMS_CMP_GT>(grid, s, 0, 0, N, nullptr, ws, L.total, thresh, shift);

@@ -21,14 +21,17 @@ def _vp(t):
 class Nms3dPlan(object):
     """Fixed-shape plan: `batch` images of `n` 7-DoF boxes each on `device`.
 
-    materialise=True  : API-compatible pipeline, the [n,n] overlap matrix 0.5*(1+GIoU3D) of every image is written
-                        to HBM by the overlap tile kernel and streamed back once by the mask kernel (what the
-                        reference does: iou3d_approximate -> differentiable_nms; 8*n^2 bytes of matrix traffic).
-    materialise=False : matrix-free pipeline, overlaps are evaluated on the fly (nothing n^2 touches HBM)."""
+    materialise=True  : the [n,n] overlap matrix 0.5*(1+GIoU3D) of every image is an OUTPUT (the API-visible product
+                        of iou3d_approximate): the fused tile kernel streams it to HBM while the same register-
+                        resident values feed the grouping stage, so it is written once and never read back.
+    materialise=False : same kernels, matrix not requested (nothing n^2 touches HBM).
+    two_kernel=True   : the reference's call sequence instead: overlap kernel writes the matrix, then
+                        gnms_forward_f32 streams it back (8*n^2 bytes of matrix traffic); kept for comparison."""
 
-    def __init__(self, batch, n, device, params, materialise=True, box_dof=7):
+    def __init__(self, batch, n, device, params, materialise=True, box_dof=7, two_kernel=False):
         self.lib = _lib.load()
         self.B, self.N, self.dev, self.params, self.materialise = batch, n, device, params, materialise
+        self.two_kernel = two_kernel and materialise
         f = dict(dtype=torch.float32, device=device)
         self.boxes7 = torch.zeros((batch, n, box_dof), **f)
         self.scores = torch.zeros((batch, n), **f)
@@ -46,7 +49,8 @@ class Nms3dPlan(object):
         self.fl = torch.empty((4, batch, n), **f)
         self.ws = torch.empty((int(self.lib.gnms_workspace_bytes(n, batch)),), dtype=torch.uint8, device=device)
         self.saved = Saved(_vp(self.order), _vp(self.fl[0]), _vp(self.lead), _vp(self.fl[1]), _vp(self.fl[2]), _vp(self.fl[3]))
-        self.launches_per_step = 6 + (1 if materialise else 0)   # corners, records, [overlap], sort, mask, chain, backward
+        # corners, records, rank, tile, has_earlier, chain, backward  (two_kernel: + overlap, mask instead of tile/has_earlier)
+        self.launches_per_step = 7
 
     # -- individual stages (each is one C-ABI call = one kernel launch unless noted)
     def stage_corners(self, s):
@@ -60,14 +64,14 @@ class Nms3dPlan(object):
 
     def stage_forward(self, s):          # sort + mask + chain: 3 launches
         p = ctypes.byref(self.params)
-        if self.materialise:
+        if self.two_kernel:
             check(self.lib.gnms_forward_f32(_vp(self.scores), _vp(self.overlap), self.N, self.N, self.B, None, p, _vp(self.prob),
                                             _vp(self.valid_idx), _vp(self.invalid_idx), _vp(self.counts), self.saved,
                                             _vp(self.ws), s), "forward")
         else:
             check(self.lib.gnms_forward_boxes_f32(_vp(self.scores), _vp(self.rec), _lib.BOX_3D_REC, 1, 1, self.N, self.B, None, p,
-                                                  _vp(self.prob), _vp(self.valid_idx), _vp(self.invalid_idx), _vp(self.counts),
-                                                  self.saved, _vp(self.ws), s), "forward_boxes")
+                                                  _vp(self.overlap), _vp(self.prob), _vp(self.valid_idx), _vp(self.invalid_idx),
+                                                  _vp(self.counts), self.saved, _vp(self.ws), s), "forward_boxes")
 
     def stage_backward(self, s):
         check(self.lib.gnms_backward_f32(_vp(self.grad_prob), _vp(self.prob), _vp(self.overlap), self.N, self.N, self.B, None,
@@ -80,7 +84,7 @@ class Nms3dPlan(object):
         s = ctypes.c_void_p(st.cuda_stream)
         self.stage_corners(s)
         self.stage_records(s)
-        if self.materialise:
+        if self.two_kernel:
             self.stage_overlap(s)
         self.stage_forward(s)
         self.stage_backward(s)

@@ -242,8 +242,10 @@ def forward_matrix(scores, iou, params, n_per_image=None, private_ws=None):
     return st
 
 
-def forward_boxes(scores, boxes, box_kind, params, generalized=False, affine=False, n_per_image=None, private_ws=None):
-    """Matrix-free forward: boxes [B,N,4] (box_kind BOX_2D) or records [B,N,8] (BOX_3D_REC)."""
+def forward_boxes(scores, boxes, box_kind, params, generalized=False, affine=False, n_per_image=None, private_ws=None,
+                  overlap_out=None):
+    """Fused forward from boxes [B,N,4] (box_kind BOX_2D) or records [B,N,8] (BOX_3D_REC); overlap_out: optional
+    [B,N,N] fp32 tensor that receives the overlap matrix (written once by the tile kernel)."""
     _require_cuda(scores, "scores")
     scores, boxes = _f32c(scores), _f32c(boxes)
     B, N = scores.shape
@@ -256,7 +258,7 @@ def forward_boxes(scores, boxes, box_kind, params, generalized=False, affine=Fal
     if B and N:
         with torch.cuda.device(dev):
             check(_lib.load().gnms_forward_boxes_f32(_p(scores), _p(boxes), box_kind, int(generalized), int(affine), N, B,
-                                                     _p(n_per_image), ctypes.byref(params), _p(st.prob),
+                                                     _p(n_per_image), ctypes.byref(params), _p(overlap_out), _p(st.prob),
                                                      _p(st.valid_idx), _p(st.invalid_idx), _p(st.counts), st.saved(),
                                                      _p(st.ws), _stream(dev)), "gnms_forward_boxes_f32")
     else:

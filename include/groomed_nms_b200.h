@@ -146,11 +146,15 @@ int gnms_forward_f32(const float* scores, const float* iou, int64_t ld, int N, i
                      const int32_t* n_per_image, const gnms_params* p, float* prob, int64_t* valid_idx,
                      int64_t* invalid_idx, int32_t* counts, gnms_saved saved, void* workspace, void* stream);
 
-/* Matrix-free forward: overlaps are evaluated on the fly from `boxes` (box_kind GNMS_BOX_*), never written to
- * HBM.  overlap3d flags as in gnms_overlap3d_f32 (generalized, affine).  Same outputs as gnms_forward_f32. */
+/* Forward from BOXES (the fused north-star path): every pair of boxes is evaluated once, register-resident, by
+ * the symmetric tile kernel, which feeds the grouping stage directly (suppression bits) and -- if overlap_out is
+ * not NULL -- also streams the API-visible overlap matrix [batch,N,N] to HBM (written once, never read back;
+ * bitwise equal to gnms_overlap2d_f32 / gnms_overlap3d_f32).  boxes: box_kind GNMS_BOX_2D float[batch,N,4] or
+ * GNMS_BOX_3D_REC float[batch,N,8] records; overlap3d flags as in gnms_overlap3d_f32 (generalized, affine).
+ * Same outputs as gnms_forward_f32. */
 int gnms_forward_boxes_f32(const float* scores, const float* boxes, int box_kind, int generalized, int affine,
-                           int N, int batch, const int32_t* n_per_image, const gnms_params* p, float* prob,
-                           int64_t* valid_idx, int64_t* invalid_idx, int32_t* counts, gnms_saved saved,
+                           int N, int batch, const int32_t* n_per_image, const gnms_params* p, float* overlap_out,
+                           float* prob, int64_t* valid_idx, int64_t* invalid_idx, int32_t* counts, gnms_saved saved,
                            void* workspace, void* stream);
 
 /* Analytic backward.  grad_prob[batch,N] is dL/dprob for the prob the forward returned.

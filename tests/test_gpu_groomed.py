@@ -187,15 +187,19 @@ def test_matrix_free_forward_equals_matrix_path(box_kind):
         bx = cuda(boxes)
         iou = ops.overlap2d(bx, bx)
         p = ops.make_params(group_size=50)
-        st2 = ops.forward_boxes(cuda(sc)[None], bx[None], _lib.BOX_2D, p)
+        ov_out = torch.empty(1, 1500, 1500, device="cuda")
+        st2 = ops.forward_boxes(cuda(sc)[None], bx[None], _lib.BOX_2D, p, overlap_out=ov_out)
     else:
         b7, sc = synthetic.config_c3(seed=4, n=2000, k=16)
         rec = ops.box3d_records(ops.corners_from_boxes7(cuda(b7)))
         _, iou = ops.overlap3d(rec, rec, False, True, generalized=True, affine=True)
         p = ops.make_params(group_size=50)
-        st2 = ops.forward_boxes(cuda(sc)[None], rec[None], _lib.BOX_3D_REC, p, generalized=True, affine=True)
+        ov_out = torch.empty(1, 2000, 2000, device="cuda")
+        st2 = ops.forward_boxes(cuda(sc)[None], rec[None], _lib.BOX_3D_REC, p, generalized=True, affine=True,
+                                overlap_out=ov_out)
     st1 = ops.forward_matrix(cuda(sc)[None], iou[None], p)
     torch.cuda.synchronize()
+    assert torch.equal(ov_out[0], iou)          # the tile kernel's matrix output is bitwise the overlap kernel's
     for f in ("prob", "order", "lead", "pre", "pval", "counts"):
         assert torch.equal(getattr(st1, f), getattr(st2, f)), f
     nv = int(st1.counts[0, 0])
