@@ -32,7 +32,7 @@ constexpr int kMaskThreads = 256;
 
 // ------------------------------------------------------------------------------------------ workspace
 struct WsLayout {
-    size_t rank, sbox, mask, has_earlier, total;   // byte offsets inside one image's slice
+    size_t rank, sbox, mask, has_earlier, gbeg, members, ngroups, total;   // byte offsets inside one image's slice
     int he_slots;                                   // partial has-earlier words per row word (one per column-chunk CTA)
 };
 __host__ __device__ inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -47,6 +47,10 @@ __host__ __device__ inline WsLayout ws_layout(int N) {
     // shared flags: same-address global traffic from thousands of CTAs serialises in L2 and cost 4x the kernel)
     L.he_slots = (N + 255) / 256;
     L.has_earlier = off; off += align_up(nw * (size_t)L.he_slots * 4);
+    // group structure for the per-group solves of mode GROUP_NOMASK: gbeg[g]..gbeg[g+1] indexes members[]
+    L.gbeg = off;        off += align_up(((size_t)N + 1) * 4);
+    L.members = off;     off += align_up((size_t)N * 4);
+    L.ngroups = off;     off += 256;
     L.total = off;
     return L;
 }
@@ -632,6 +636,9 @@ struct ChainArgs {
     int32_t* keep;                 // hard NMS: kept input indices in score order
     int32_t* n_keep;
     int leaders_only;              // hard NMS: stop after leader election
+    int stage;                     // 0: grouping + closed-form rescore + lists (mode GROUP_MASK)
+                                   // 1: grouping only, exports the group structure (mode GROUP_NOMASK, before the solve)
+                                   // 2: lists only, from pre[] / lead[] already in global memory (after the solve)
 };
 
 __device__ __forceinline__ uint32_t valid_word(int w, int n) {
@@ -692,6 +699,18 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
     uint32_t* wcol = reinterpret_cast<uint32_t*>(list + Na);              // kWin * NW (later: sort keys)
     __shared__ int s_cnt;
 
+    int32_t* lead = fsup;
+    float* pval = A.pval + (size_t)b * N;
+    float* dpval = A.dpval + (size_t)b * N;
+    const gnms_params P = A.p;
+    if (A.stage == 2) {
+        for (int pos = tid; pos < n; pos += kChainThreads) {
+            fsup[pos] = A.lead[(size_t)b * N + pos];
+            pval[pos] = 0.f;
+            dpval[pos] = 0.f;
+        }
+        __syncthreads();
+    } else {
     for (int i = tid; i < NW; i += kChainThreads) {
         removed[i] = 0u;
         uint32_t he = 0u;
@@ -792,10 +811,6 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
 
     // ---- group of every box: leaders lead themselves, others follow their first suppressor; a NaN overlap with
     //      the leader means the box left the pool without joining the group (lib/groomed_nms.py:249-250)
-    int32_t* lead = fsup;
-    float* pval = A.pval + (size_t)b * N;
-    float* dpval = A.dpval + (size_t)b * N;
-    const gnms_params P = A.p;
     for (int pos = tid; pos < n; pos += kChainThreads) {
         const bool isl = (leader[pos >> 5] >> (pos & 31)) & 1u;
         int f = fsup[pos];
@@ -848,7 +863,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
         if (ld_ >= 0 && ld_ != pos) atomicAdd(&grank[ld_], 1);
     }
     __syncthreads();
-    const int need_above = A.group_id ? 0 : P.group_size;
+    const int need_above = (A.group_id || A.stage == 1) ? 0 : P.group_size;
     for (int i = tid; i < nw; i += kChainThreads) {
         uint32_t lw = leader[i], keep = 0u;
         while (lw) {
@@ -943,6 +958,76 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
         __syncthreads();
     }
 
+    // ---- mode GROUP_NOMASK: export the group structure for the per-group triangular solves and stop
+    if (A.stage == 1) {
+        __shared__ int s_wsum[32];
+        int32_t* gsz = reinterpret_cast<int32_t*>(wcol);              // [Na] group size at the leader's position
+        int32_t* gpre = gsz + Na;                                     // [Na] exclusive prefix
+        int32_t* gbeg = reinterpret_cast<int32_t*>(w + L.gbeg);
+        int32_t* members = reinterpret_cast<int32_t*>(w + L.members);
+        int32_t* ngroups = reinterpret_cast<int32_t*>(w + L.ngroups);
+        int32_t* lead_out = A.lead + (size_t)b * N;
+        for (int pos = tid; pos < Na; pos += kChainThreads) gsz[pos] = 0;
+        __syncthreads();
+        for (int pos = tid; pos < n; pos += kChainThreads) {
+            const int ld_ = lead[pos];
+            if (ld_ >= 0) atomicAdd(&gsz[ld_], 1);                   // leaders count themselves (lead[l] == l)
+        }
+        __syncthreads();
+        // block-wide exclusive scan: thread t owns the chunk [t*C, (t+1)*C)
+        const int C = (n + kChainThreads - 1) / kChainThreads;
+        int local = 0;
+        for (int q = 0; q < C; ++q) { const int pos = tid * C + q; if (pos < n) local += gsz[pos]; }
+        int incl = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int v = s_wsum[lane], iv = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, iv, d);
+                if (lane >= d) iv += t;
+            }
+            s_wsum[lane] = iv - v;
+            if (lane == 31) s_cnt = iv;                               // boxes that are in some group
+        }
+        __syncthreads();
+        int run = s_wsum[warp] + incl - local;
+        for (int q = 0; q < C; ++q) { const int pos = tid * C + q; if (pos < n) { gpre[pos] = run; run += gsz[pos]; } }
+        // dense group index of a leader = number of leaders before it
+        if (warp == 0) {
+            int runl = 0;
+            for (int base = 0; base < nw; base += 32) {
+                int wi = base + lane;
+                int c = wi < nw ? __popc(leader[wi]) : 0, inc2 = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, inc2, d);
+                    if (lane >= d) inc2 += t;
+                }
+                if (wi < nw) tmpbits[wi] = runl + inc2 - c;
+                runl += __shfl_sync(0xffffffffu, inc2, 31);
+            }
+            if (lane == 0) { ngroups[0] = runl; gbeg[runl] = s_cnt; }
+        }
+        __syncthreads();
+        for (int pos = tid; pos < N; pos += kChainThreads) {
+            const int ld_ = pos < n ? lead[pos] : -1;
+            lead_out[pos] = ld_;
+            if (ld_ >= 0) {
+                members[gpre[ld_] + (ld_ == pos ? 0 : grank[pos])] = pos;
+                if (ld_ == pos) gbeg[tmpbits[pos >> 5] + __popc(leader[pos >> 5] & ((1u << (pos & 31)) - 1u))] = gpre[pos];
+            }
+        }
+        return;
+    }
+    }   // A.stage != 2
+
     // ---- rescore (mode GROUP_MASK closed form: row of I - Phi has two non-zeros), clamp, threshold
     float* pre_out = A.pre + (size_t)b * N;
     int32_t* lead_out = A.lead + (size_t)b * N;
@@ -957,7 +1042,8 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
         if (pos < n) {
             const int ld_ = lead[pos];
             float prev = 0.f;
-            if (ld_ == pos) prev = ss[pos];
+            if (A.stage == 2) prev = ld_ >= 0 ? pre_out[pos] : 0.f;          // from the triangular solve
+            else if (ld_ == pos) prev = ss[pos];
             else if (ld_ >= 0) prev = __fsub_rn(ss[pos], __fmul_rn(pval[pos], ss[ld_]));
             r = fminf(fmaxf(prev, 0.f), 1.f);
             rt = (r < vthr) ? 0.f : r;
@@ -1039,6 +1125,10 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
         if (P.sorted_output) prob[i] = rthr[pos];
     }
 }
+
+}  // namespace gnms
+#include "solve.cuh"
+namespace gnms {
 
 // ------------------------------------------------------------------------------------------ 4. backward (mode GROUP_MASK)
 struct BwdArgs {
@@ -1197,7 +1287,6 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     int rc = check_common(N, batch, p);
     if (rc) return rc;
     if (N == 0 || batch == 0) return 0;
-    if (p->mode != GNMS_MODE_GROUP_MASK) return GNMS_E_UNSUPPORTED;
     if (!scores || !prob || !valid_idx || !invalid_idx || !counts || !workspace || !sv.order || !sv.sorted_scores ||
         !sv.lead || !sv.pval || !sv.dpval || !sv.pre)
         return GNMS_E_BADARG;
@@ -1208,23 +1297,28 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     char* ws = reinterpret_cast<char*>(workspace);
     const int NW = (N + 31) / 32;
     int box_stride = src == kSrcBox2d ? 4 : 8;
+    const int mode = p->mode;
+    const bool need_groups = mode != GNMS_MODE_NOGROUP;
+    const bool tiles = need_groups && src != kSrcMatrix;              // fused overlap + mask tile kernel
     rank_kernel<<<dim3(gnms_div_up(N, kRankElems), batch), 256, rank_smem_bytes(N), s>>>(
         scores, 1, N, N, npi, sv.order, sv.sorted_scores, ws, L.total, src == kSrcMatrix ? nullptr : boxes, src,
-        (int64_t)N * box_stride, 0.f, 0, src == kSrcMatrix ? 0 : 1);
+        (int64_t)N * box_stride, 0.f, 0, tiles ? 1 : 0);
     GNMS_LAUNCH_CHECK();
-    if (src == kSrcMatrix) {
-        if (!iou || ld < N) return GNMS_E_BADARG;
+    if (src == kSrcMatrix && (!iou || ld < N)) return GNMS_E_BADARG;
+    if (src != kSrcMatrix && !boxes) return GNMS_E_BADARG;
+    if (need_groups && src == kSrcMatrix) {
         dim3 grid(gnms_div_up(N, kMaskThreads * 4), NW, batch);
         bool vec = ((reinterpret_cast<uintptr_t>(iou) & 15u) == 0) && (ld % 4 == 0) && (((int64_t)N * ld) % 4 == 0);
         if (vec) mask_matrix_kernel<true><<<grid, kMaskThreads, 0, s>>>(iou, ld, (int64_t)N * ld, N, npi, sv.order, ws, L.total, p->nms_threshold);
         else mask_matrix_kernel<false><<<grid, kMaskThreads, 0, s>>>(iou, ld, (int64_t)N * ld, N, npi, sv.order, ws, L.total, p->nms_threshold);
-    } else {
-        if (!boxes) return GNMS_E_BADARG;
+        GNMS_LAUNCH_CHECK();
+    } else if (src != kSrcMatrix && (need_groups || overlap_out)) {
+        // (mode NOGROUP needs no mask; the tile kernel still runs if the caller wants the overlap matrix)
         TileArgs T = {};
         T.N = N; T.batch = batch; T.nt = gnms_div_up(N, kTT); T.tiles_per_image = T.nt * (T.nt + 1) / 2;
         T.vec = overlap_out && ((reinterpret_cast<uintptr_t>(overlap_out) & 15u) == 0) && (N % 4 == 0);
         T.n_per_image = npi; T.boxes = boxes; T.ws = ws; T.ws_img_stride = L.total; T.out = overlap_out;
-        T.thr = p->nms_threshold;
+        T.thr = need_groups ? p->nms_threshold : INFINITY;             // no bits wanted: nothing is > +inf ... NaN aside
         const int total = T.tiles_per_image * batch;
         const int grid = total < 148 * 3 ? total : 148 * 3;            // persistent: 3 CTAs per SM
         const bool ho = overlap_out != nullptr;
@@ -1246,9 +1340,11 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
         }
 #undef GNMS_TILE
         GNMS_LAUNCH_CHECK();
-        has_earlier_kernel<<<dim3(NW, batch), 256, 0, s>>>(N, npi, ws, L.total);
+        if (need_groups) {
+            has_earlier_kernel<<<dim3(NW, batch), 256, 0, s>>>(N, npi, ws, L.total);
+            GNMS_LAUNCH_CHECK();
+        }
     }
-    GNMS_LAUNCH_CHECK();
     ChainArgs A = {};
     A.N = N; A.batch = batch; A.n_per_image = npi; A.ws = ws; A.ws_img_stride = L.total;
     A.src = src; A.iou = iou; A.ld = ld; A.iou_img_stride = (int64_t)N * ld;
@@ -1256,6 +1352,26 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     A.order = sv.order; A.sorted_scores = sv.sorted_scores; A.prob = prob; A.valid_idx = valid_idx;
     A.invalid_idx = invalid_idx; A.counts = counts; A.lead = sv.lead; A.pval = sv.pval; A.dpval = sv.dpval;
     A.pre = sv.pre; A.slot = slot;
+    if (mode == GNMS_MODE_GROUP_MASK) {
+        A.stage = 0;
+        chain_kernel<<<batch, kChainThreads, chain_smem_bytes(N), s>>>(A);
+        GNMS_LAUNCH_CHECK();
+        return 0;
+    }
+    // inverse modes: [grouping ->] triangular solve -> lists
+    if (mode == GNMS_MODE_GROUP_NOMASK) {
+        A.stage = 1;
+        chain_kernel<<<batch, kChainThreads, chain_smem_bytes(N), s>>>(A);
+        GNMS_LAUNCH_CHECK();
+    }
+    SolveArgs S = {};
+    S.N = N; S.batch = batch; S.mode = mode; S.n_per_image = npi; S.ws = ws; S.ws_img_stride = L.total;
+    S.ov.src = src; S.ov.iou = iou; S.ov.ld = ld; S.ov.generalized = generalized; S.ov.affine = affine;
+    S.iou_img_stride = (int64_t)N * ld; S.p = *p; S.sorted_scores = sv.sorted_scores; S.order = sv.order;
+    S.lead = sv.lead; S.pre = sv.pre;
+    solve_fwd_kernel<<<dim3(mode == GNMS_MODE_NOGROUP ? 1 : N, batch), kSolveThreads, ((size_t)N + 40) * 4, s>>>(S);
+    GNMS_LAUNCH_CHECK();
+    A.stage = 2;
     chain_kernel<<<batch, kChainThreads, chain_smem_bytes(N), s>>>(A);
     GNMS_LAUNCH_CHECK();
     return 0;
@@ -1291,17 +1407,32 @@ extern "C" int gnms_forward_boxes_f32(const float* scores, const float* boxes, i
 extern "C" int gnms_backward_f32(const float* grad_prob, const float* prob, const float* iou, int64_t ld, int N,
                                  int batch, const int32_t* n_per_image, const gnms_params* p, gnms_saved sv,
                                  float* grad_scores, float* grad_iou, int64_t ld_gi, void* workspace, void* stream) {
-    (void)prob; (void)iou; (void)ld;
+    (void)prob;
     int rc = check_common(N, batch, p);
     if (rc) return rc;
     if (N == 0 || batch == 0) return 0;
-    if (p->mode != GNMS_MODE_GROUP_MASK) return GNMS_E_UNSUPPORTED;
     if (!grad_prob || !grad_scores || !sv.order || !sv.sorted_scores || !sv.lead || !sv.pval || !sv.dpval || !sv.pre)
         return GNMS_E_BADARG;
     if (grad_iou && ld_gi < N) return GNMS_E_BADARG;
     if (p->sorted_output && !workspace) return GNMS_E_BADARG;
     rc = configure_once();
     if (rc) return rc;
+    if (p->mode != GNMS_MODE_GROUP_MASK) {
+        if (!workspace) return GNMS_E_BADARG;                          // holds the group structure / box records
+        const WsLayout L = ws_layout(N);
+        GNMS_CUDA_TRY(cudaMemsetAsync(grad_scores, 0, (size_t)batch * N * sizeof(float), (cudaStream_t)stream));
+        SolveArgs S = {};
+        S.N = N; S.batch = batch; S.mode = p->mode; S.n_per_image = n_per_image;
+        S.ws = reinterpret_cast<char*>(workspace); S.ws_img_stride = L.total;
+        S.ov.src = kSrcMatrix; S.ov.iou = iou; S.ov.ld = ld; S.iou_img_stride = (int64_t)N * ld; S.p = *p;
+        S.sorted_scores = sv.sorted_scores; S.order = sv.order; S.lead = sv.lead; S.pre = sv.pre;
+        S.grad_prob = grad_prob; S.slot = slot_ptr(workspace, N, batch); S.grad_scores = grad_scores;
+        S.grad_iou = grad_iou; S.ld_gi = ld_gi;
+        solve_bwd_kernel<<<dim3(p->mode == GNMS_MODE_NOGROUP ? 1 : N, batch), kSolveThreads, ((size_t)N + 40) * 4,
+                           (cudaStream_t)stream>>>(S);
+        GNMS_LAUNCH_CHECK();
+        return 0;
+    }
     BwdArgs A = {};
     A.N = N; A.batch = batch; A.n_per_image = n_per_image; A.p = *p; A.grad_prob = grad_prob; A.order = sv.order;
     A.sorted_scores = sv.sorted_scores; A.lead = sv.lead; A.pval = sv.pval; A.dpval = sv.dpval; A.pre = sv.pre;

@@ -253,7 +253,7 @@ def forward_boxes(scores, boxes, box_kind, params, generalized=False, affine=Fal
         raise RuntimeError("groomed_nms_b200: at most %d boxes per image (got %d)" % (MAX_BOXES, N))
     dev = scores.device
     if private_ws is None:
-        private_ws = bool(params.sorted_output)
+        private_ws = bool(params.sorted_output) or params.mode != _lib.MODE_GROUP_MASK
     st = _alloc_state(dev, B, N, params, n_per_image, private_ws)
     if B and N:
         with torch.cuda.device(dev):
