@@ -1,0 +1,62 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy restatement of the GrooMeD branch of the detection loss
+(reference lib/loss/rpn_3d.py:731-825 and :1117-1137, "rank" mode).
+
+PARITY UNPINNED against the reference's own run: RPN_3D_loss.forward hard-codes CUDA (54 .cuda() sites) and cannot be
+executed in the CPU build container, and /root/reference does not exist on the GPU box.  Every step below is a
+composition of functions that ARE pinned by golden vectors (oracle.groomed_oracle: corners, iou, iou3d_approximate,
+differentiable_nms, aploss), in the order of the reference lines cited."""
+import numpy as np
+
+from . import groomed_oracle as O
+
+F32 = np.float32
+
+
+def branch_image(scores, fg_inds, boxes7, coords_2d, gts_2d, gts_3d, overlap_in_nms="2d", nms_thres=0.4, temperature=0.1,
+                 valid_thr=0.3, group_size=100, beta=0.3, max_boxes=500, corners_b1=None):
+    """-> dict(fg_index_for_nms, scores_after_nms (in that order), best (anchor ids), fwd (oracle nms state)).
+    corners_b1: optionally the CUDA path's corners (parity is defined from the corners onward)."""
+    fg_scores = scores[fg_inds]
+    order = O.stable_sort_desc(fg_scores)                                              # :731
+    n = min(max_boxes, order.shape[0])
+    fg_idx = fg_inds[order[:n]]                                                        # :737
+    b7 = boxes7[fg_idx].astype(F32)
+    if corners_b1 is None:
+        corners_b1 = O.get_corners_of_cuboid(*[b7[:, i] for i in range(7)])            # :746-752
+    corners_b1 = corners_b1.astype(F32).copy()
+    box2d = coords_2d[fg_idx].astype(F32)
+    iou2d = O.iou(box2d, box2d)                                                        # :772
+    if overlap_in_nms == "2d":
+        ov = iou2d
+    else:
+        _, g3 = O.iou3d_approximate(corners_b1, corners_b1, "combinations", "generalized")   # :780
+        corners_b1 = O.mutated_corners(corners_b1)                                     # the reference's in-place Y<-Z
+        ov3 = (F32(0.5) * (F32(1) + g3)).astype(F32)                                   # :781
+        ov = ov3 if overlap_in_nms == "3d" else (iou2d * ov3).astype(F32)              # :783,786
+    fwd = O.differentiable_nms(scores[fg_idx], ov, nms_threshold=nms_thres, temperature=temperature,
+                               valid_box_prob_threshold=valid_thr, group_size=group_size, dense=False)   # :791
+    gt7 = np.stack([gts_3d[:, 7], gts_3d[:, 8], gts_3d[:, 9], gts_3d[:, 3], gts_3d[:, 4], gts_3d[:, 5], gts_3d[:, 10]], 1).astype(F32)
+    corners_b2 = O.get_corners_of_cuboid(*[gt7[:, i] for i in range(7)])               # :804-811
+    _, g3gt = O.iou3d_approximate(corners_b1, corners_b2, "combinations", "generalized")   # :813
+    iou2gt = O.iou(box2d, gts_2d[:, :4].astype(F32))                                   # :814
+    score_gt = (iou2gt * (F32(0.5) * (F32(1) + g3gt)).astype(F32)).astype(F32)         # :817 (commuted product, see test)
+    mx = score_gt.argmax(axis=0)                                                       # :818
+    keep = score_gt[mx, np.arange(score_gt.shape[1])] > F32(beta)                      # :820
+    return dict(fg_index_for_nms=fg_idx, scores_after_nms=fwd["prob"], best=fg_idx[mx[keep]], fwd=fwd, score_gt=score_gt)
+
+
+def after_nms_rank_loss(scores_after, targets_after, weights, lam=1.0):
+    """:1117-1137 rank mode, per image mean -> (loss, grad wrt scores_after [B,A])."""
+    B = scores_after.shape[0]
+    grad = np.zeros_like(scores_after, dtype=F32)
+    tot, cnt = F32(0), 0
+    for b in range(B):
+        act = weights[b] > 0
+        if act.sum() > 0:
+            cnt += 1
+            l, g = O.aploss(scores_after[b, act], targets_after[b, act])
+            tot += l
+            grad[b, act] = g
+    if cnt:
+        tot, grad = tot / cnt, grad / cnt
+    return F32(lam) * tot, (F32(lam) * grad).astype(F32)

@@ -342,3 +342,60 @@ def test_pruning_function_and_indices_copy(G):
     out2 = G.indices_copy(A2, B, torch.tensor([[0, 0], [0, 1], [1, 1]], device="cuda"),
                           torch.tensor([[1, 1], [2, 1], [2, 2]], device="cuda"), inplace=False)
     assert out2[0, 0] == B[1, 1] and out2[0, 1] == B[2, 1] and out2[1, 1] == B[2, 2] and A2.abs().sum() == 0
+
+
+@pytest.mark.parametrize("mode", ["B", "C"])
+@pytest.mark.parametrize("n,k,gs", [(150, 3, 20), (400, 6, 100), (64, 64, 5), (333, 1, 10 ** 9)])
+def test_inverse_modes_random_vs_oracle(G, mode, n, k, gs):
+    """group_boxes/mask_group_boxes variants that need (I+Phi)^-1: forward substitution vs the oracle's fp64 inverse."""
+    from oracle import groomed_oracle as O
+    sc, iou, up = _rand_case(4000 + n, n, k)
+    cfg = dict(nms_threshold=0.4, pruning_method="linear", temperature=0.1, valid_box_prob_threshold=0.3, group_size=gs,
+               group_boxes=(mode == "B"), mask_group_boxes=False)
+    o = O.differentiable_nms(sc, iou, **cfg)
+    cond = max(1.0, float(np.abs(o["T"]).max()))
+    s = cuda(sc).requires_grad_(True)
+    m = cuda(iou).requires_grad_(True)
+    v, i, p = G.differentiable_nms(s, m, **cfg)
+    check_against(o, p.detach().cpu().numpy(), v.cpu().numpy(), i.cpu().numpy(), cond if cond > 1.5 else 1.0 + 1e-9)
+    p.backward(cuda(up))
+    gs_, gi_ = O.differentiable_nms_backward(o, up, need_grad_iou=True)
+    assert np.allclose(s.grad.cpu().numpy(), gs_, rtol=RTOL, atol=2e-6 * cond * max(1.0, np.abs(gs_).max()))
+    assert np.allclose(m.grad.cpu().numpy(), gi_, rtol=RTOL, atol=2e-6 * cond * max(1.0, np.abs(gi_).max()))
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_inverse_modes_from_boxes_equal_matrix_path(mode):
+    from groomed_nms_b200 import synthetic, ops, _lib
+    boxes, sc, _ = synthetic.clustered_boxes_2d(700, 5, seed=19, jitter=0.06)
+    bx = cuda(boxes)
+    iou = ops.overlap2d(bx, bx)
+    p = ops.make_params(group_size=30, group_boxes=(mode == 1), mask_group_boxes=False)
+    st1 = ops.forward_matrix(cuda(sc)[None], iou[None], p)
+    st2 = ops.forward_boxes(cuda(sc)[None], bx[None], _lib.BOX_2D, p)
+    for f in ("prob", "lead", "pre", "counts"):
+        assert torch.equal(getattr(st1, f), getattr(st2, f)), f
+    g = torch.randn(1, 700, device="cuda")
+    g1, _ = ops.backward(st1, g)
+    g2, _ = ops.backward(st2, g)
+    assert torch.equal(g1, g2)
+
+
+def test_soft_sort_path_runs_and_matches_torch_composite(G):
+    """sorting_method="soft" (lib/groomed_nms.py:131-165): the soft permutation is applied to the ROWS of the overlap
+    matrix only (:164), then the usual prune / group / rescore runs on (soft scores, row-permuted matrix).  The
+    composite is checked against the oracle fed with exactly those soft-sorted inputs."""
+    from oracle import groomed_oracle as O
+    sc, iou, up = _rand_case(91, 60, 3)
+    s = cuda(sc).requires_grad_(True)
+    v, i, p = G.differentiable_nms(s, cuda(iou), temperature=0.1, sorting_method="soft", sorting_temperature=1e-4)
+    ss, perm, ms = G.soft_sort(cuda(sc), full_matrix=cuda(iou), temperature=1e-4)
+    # (the reference divides by the row sums broadcast along the LAST axis, :155, so rows are not renormalised:
+    #  soft scores are only approximately the sorted scores -- reproduced as written)
+    assert torch.allclose(ss, torch.sort(cuda(sc), descending=True)[0], rtol=2e-2) and perm.shape == (60, 60)
+    o = O.differentiable_nms(ss.cpu().numpy(), ms.cpu().numpy(), temperature=0.1)
+    assert np.allclose(p.detach().cpu().numpy(), o["prob"], rtol=1e-5, atol=1e-6)
+    hard_order = np.argsort(-sc, kind="stable")
+    assert list(v.cpu().numpy()) == list(hard_order[o["valid"]])     # indices map back through the HARD sort (:118)
+    p.sum().backward()
+    assert torch.isfinite(s.grad).all() and s.grad.abs().sum() > 0

@@ -1,0 +1,84 @@
+"""GPU parity: the GrooMeD branch of the detection loss (rows a11/a12) vs the composed oracle."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import cuda
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(seed, n_anchor=3000, n_fg=800, n_gt=5):
+    """Synthetic image: anchors predicting KITTI-like cars around n_gt ground truths (+ background clutter)."""
+    rng = np.random.default_rng(seed)
+    gt7 = np.stack([rng.uniform(-20, 20, n_gt), 1.65 + 0.1 * rng.standard_normal(n_gt), rng.uniform(8, 60, n_gt),
+                    1.63 + 0.1 * rng.standard_normal(n_gt), 1.53 + 0.1 * rng.standard_normal(n_gt),
+                    3.9 + 0.4 * rng.standard_normal(n_gt), rng.uniform(-np.pi, np.pi, n_gt)], 1)
+    f, cx, cy = 721.5, 609.6, 172.9
+
+    def box2d_of(b7):
+        u = f * b7[:, 0] / b7[:, 2] + cx
+        v = f * b7[:, 1] / b7[:, 2] + cy
+        w = f * b7[:, 5] / b7[:, 2]
+        h = f * b7[:, 4] / b7[:, 2]
+        return np.stack([u - w / 2, v - h, u + w / 2, v], 1)
+    who = rng.integers(0, n_gt, n_anchor)
+    b7 = gt7[who] + np.concatenate([0.3 * rng.standard_normal((n_anchor, 3)), 0.05 * rng.standard_normal((n_anchor, 3)),
+                                    0.05 * rng.standard_normal((n_anchor, 1))], 1)
+    far = rng.uniform(0, 1, n_anchor) < 0.3
+    b7[far, 0] += rng.uniform(-15, 15, far.sum()); b7[far, 2] += rng.uniform(-5, 20, far.sum())
+    b7[:, 2] = np.maximum(b7[:, 2], 3.0)
+    c2 = box2d_of(b7) + rng.standard_normal((n_anchor, 4))
+    gts_2d = box2d_of(gt7)
+    gts_3d = np.zeros((n_gt, 16)); gts_3d[:, 7:10] = gt7[:, 0:3]; gts_3d[:, 3:6] = gt7[:, 3:6]; gts_3d[:, 10] = gt7[:, 6]
+    scores = rng.uniform(0.05, 0.99, n_anchor).astype(np.float32)
+    scores = (scores + np.arange(n_anchor) * 1e-7).astype(np.float32)
+    fg = np.sort(rng.choice(n_anchor, n_fg, replace=False))
+    return scores, fg, b7.astype(np.float32), c2.astype(np.float32), gts_2d.astype(np.float32), gts_3d.astype(np.float32)
+
+
+@pytest.mark.parametrize("overlap", ["2d", "3d", "product"])
+def test_branch_image_matches_oracle(overlap):
+    from groomed_nms_b200 import ops
+    from groomed_nms_b200.lib.loss.rpn_3d import GroomedNMSLossBranch
+    from oracle import loss_branch_oracle as LO
+    scores, fg, b7, c2, g2, g3 = _scene(7)
+    conf = dict(use_nms_in_loss=True, diff_nms_temperature=0.1, overlap_in_nms=overlap, nms_thres=0.4, best_target_box_beta=0.3)
+    br = GroomedNMSLossBranch(conf)
+    s = cuda(scores).requires_grad_(True)
+    fg_idx, prob, best = br.image(s, cuda(fg, torch.int64), cuda(b7), cuda(c2), torch.eye(4), 1.0, cuda(g2), cuda(g3))
+    # parity is defined from the corners onward (cos/sin + rotation are backend-defined in the reference)
+    corners = ops.corners_from_boxes7(cuda(b7)[fg_idx]).cpu().numpy()
+    o = LO.branch_image(scores, fg, b7, c2, g2, g3, overlap_in_nms=overlap, corners_b1=corners)
+    assert fg_idx.cpu().tolist() == o["fg_index_for_nms"].tolist() and len(fg_idx) == 500
+    assert np.allclose(prob.detach().cpu().numpy(), o["scores_after_nms"], rtol=1e-5, atol=1e-6)
+    assert sorted(best.cpu().tolist()) == sorted(o["best"].tolist())
+    up = np.random.default_rng(1).standard_normal(500).astype(np.float32)
+    prob.backward(cuda(up))
+    from oracle import groomed_oracle as O
+    want, _ = O.differentiable_nms_backward(o["fwd"], up, need_grad_iou=False)
+    got = s.grad.cpu().numpy()
+    assert np.allclose(got[o["fg_index_for_nms"]], want, rtol=1e-5, atol=2e-6 * np.abs(want).max())
+    rest = np.ones(len(scores), bool); rest[o["fg_index_for_nms"]] = False
+    assert not got[rest].any()
+
+
+def test_after_nms_rank_loss_matches_oracle():
+    from groomed_nms_b200.lib.loss.rpn_3d import GroomedNMSLossBranch
+    from oracle import loss_branch_oracle as LO
+    rng = np.random.default_rng(3)
+    B, A = 3, 600
+    sa = rng.uniform(0, 1, (B, A)).astype(np.float32)
+    ta = (rng.uniform(0, 1, (B, A)) < 0.02).astype(np.float32)
+    w = (rng.uniform(0, 1, (B, A)) < 0.4).astype(np.float32)
+    w[2] = 0                                                   # an image without foreground is skipped (:1123)
+    br = GroomedNMSLossBranch(dict(after_nms_lambda=0.05))
+    x = cuda(sa).requires_grad_(True)
+    loss = br.after_nms_loss(x, cuda(ta), w)
+    loss.backward()
+    want_l, want_g = LO.after_nms_rank_loss(sa, ta, w, lam=0.05)
+    assert np.allclose(loss.item(), want_l, rtol=1e-5)
+    assert np.allclose(x.grad.cpu().numpy(), want_g, rtol=1e-4, atol=1e-8)
+    for mode in ("classify", "regress"):
+        br.after_nms_loss_mode = mode
+        assert torch.isfinite(br.after_nms_loss(cuda(sa).clamp(0.01, 0.99), cuda(ta), w))
