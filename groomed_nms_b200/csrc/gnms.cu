@@ -461,6 +461,8 @@ __global__ void __launch_bounds__(256, 3) tile_kernel(TileArgs A) {
     __shared__ int s_rank[2][2][kTT];
     __shared__ int s_ij[2][4];                                     // decoded (image, I, J) of the staged tile
     __shared__ float s_tile[kHasOut ? kTT * kTS : 1];
+    __shared__ uint16_t s_hit[256 * 4];                            // queued (row, column quad, hit mask) of this tile
+    __shared__ int s_nhit[2];                                      // per staging buffer (reset one tile ahead)
     const int N = A.N, tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const WsLayout L = ws_layout(N);
@@ -485,6 +487,7 @@ __global__ void __launch_bounds__(256, 3) tile_kernel(TileArgs A) {
     };
 
     int t = blockIdx.x, buf = 0;
+    if (tid < 2) s_nhit[tid] = 0;
     if (t < total) prefetch(t, 0);
     for (; t < total; t += gridDim.x, buf ^= 1) {
         cp_async_wait_all();
@@ -506,14 +509,15 @@ __global__ void __launch_bounds__(256, 3) tile_kernel(TileArgs A) {
         if (t + (int)gridDim.x < total) prefetch(t + gridDim.x, buf ^ 1);
 
         const int i0 = I * kTT, j0 = J * kTT;
-        const bool vec = A.vec != 0;
         const bool transposed = kHasOut && (I != J);
-        int crk[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) crk[k] = s_rank[buf][1][4 * tx + k];
+        // whole tile inside the matrix and 16-byte stores legal -> no per-row bounds tests
+        const bool full_tile = kHasOut && A.vec && (i0 + kTT <= N) && (j0 + kTT <= N);
         typename RecOf<kSrc>::type cr[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) cr[k] = RecOf<kSrc>::load(&s_rec[buf][1][(4 * tx + k) * kRecF]);
+        float* drow = kHasOut ? out + (int64_t)(i0 + ty) * N + (j0 + 4 * tx) : nullptr;
+        float* trow = s_tile + (4 * tx) * kTS + ty;
+        const float thr = A.thr;
         // one row of the thread's 4 x 4 sub-tile at a time keeps the live registers low (3 CTAs per SM)
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -526,17 +530,43 @@ __global__ void __launch_bounds__(256, 3) tile_kernel(TileArgs A) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) v[k] = RecOf<kSrc>::template exact<kGen, kAffine>(rr, cr[k]);
             }
-            // ---- consumer 1: suppression bits (sorted space).  Off-diagonal tiles see every unordered pair once;
-            //      the diagonal tile sees (i,j) and (j,i): only the orientation "row is the later box" emits.
-            uint32_t hits = 0u;
+            // ---- consumer 1: threshold tests; rows with a hit are queued (row, column quad, 4-bit mask) and turned
+            //      into mask bits after the tile by all threads together (hits are ~3 % of the pairs: doing the bit
+            //      arithmetic inline would cost every warp ~12 issue slots per pair for the sake of a few lanes)
+            const uint32_t hits = (uint32_t)(!(v[0] <= thr)) | ((uint32_t)(!(v[1] <= thr)) << 1) |
+                                  ((uint32_t)(!(v[2] <= thr)) << 2) | ((uint32_t)(!(v[3] <= thr)) << 3);
+            if (hits) s_hit[atomicAdd(&s_nhit[buf], 1)] = (uint16_t)(((ty + 16 * r) << 8) | (tx << 4) | hits);
+            // ---- consumer 2: the overlap matrix (optional): direct row now, transposed tile via shared memory
+            if (kHasOut) {
+                if (full_tile) {
+                    st_cs_f4(drow + (int64_t)(16 * r) * N, make_float4(v[0], v[1], v[2], v[3]));
+                } else {
+                    const int i = i0 + ty + 16 * r, j = j0 + 4 * tx;
+                    if (i < N) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) hits |= (uint32_t)(!(v[k] <= A.thr)) << k;
-            if (hits) {
-                const int ri = s_rank[buf][0][ty + 16 * r];
+                        for (int k = 0; k < 4; ++k) if (j + k < N) drow[(int64_t)(16 * r) * N + k] = v[k];
+                    }
+                }
+                if (transposed) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) trow[k * kTS + 16 * r] = v[k];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- queued hits -> suppression bits (sorted space).  Off-diagonal tiles see every unordered pair once; the
+        //      diagonal tile sees (i,j) and (j,i): only the orientation "row is the later box" emits.
+        {
+            const int nh = s_nhit[buf];
+            if (tid == 0) s_nhit[buf ^ 1] = 0;                       // next tile appends only after its top barrier
+            for (int h = tid; h < nh; h += 256) {
+                const uint32_t e = s_hit[h];
+                const int ri = s_rank[buf][0][e >> 8];
+                const int cbase = ((e >> 4) & 15) * 4;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if ((hits >> k) & 1u) {
-                        const int rj = crk[k];
+                    if ((e >> k) & 1u) {
+                        const int rj = s_rank[buf][1][cbase + k];
                         const int later = max(ri, rj), earlier = min(ri, rj);
                         // padded boxes (index >= n) carry rank INT_MAX; ri == rj only for a box with itself
                         if (later != INT_MAX && ri != rj && (I != J || ri > rj))
@@ -544,36 +574,20 @@ __global__ void __launch_bounds__(256, 3) tile_kernel(TileArgs A) {
                     }
                 }
             }
-            // ---- consumer 2: the overlap matrix (optional): direct row now, transposed tile via shared memory
-            if (kHasOut) {
-                const int i = i0 + ty + 16 * r, j = j0 + 4 * tx;
-                if (i < N && j < N) {
-                    float* dst = out + (int64_t)i * N + j;
-                    if (vec && j + 4 <= N) st_cs_f4(dst, make_float4(v[0], v[1], v[2], v[3]));
-                    else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) if (j + k < N) dst[k] = v[k];
-                    }
-                }
-                if (transposed) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) s_tile[(4 * tx + k) * kTS + ty + 16 * r] = v[k];
-                }
-            }
         }
         if (transposed) {
-            __syncthreads();
+            float* dcol = out + (int64_t)(j0 + ty) * N + (i0 + 4 * tx);
+            const float* src = s_tile + ty * kTS + 4 * tx;
 #pragma unroll
             for (int pass = 0; pass < 4; ++pass) {
-                const int c = ty + 16 * pass;
-                const int i = j0 + c, j = i0 + 4 * tx;
-                if (i < N && j < N) {
-                    const float* src = s_tile + c * kTS + 4 * tx;
-                    float* dst = out + (int64_t)i * N + j;
-                    if (vec && j + 4 <= N) st_cs_f4(dst, make_float4(src[0], src[1], src[2], src[3]));
-                    else {
+                const float* sp = src + (16 * pass) * kTS;
+                if (full_tile) {
+                    st_cs_f4(dcol + (int64_t)(16 * pass) * N, make_float4(sp[0], sp[1], sp[2], sp[3]));
+                } else {
+                    const int i = j0 + ty + 16 * pass, j = i0 + 4 * tx;
+                    if (i < N) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) if (j + k < N) dst[k] = src[k];
+                        for (int k = 0; k < 4; ++k) if (j + k < N) dcol[(int64_t)(16 * pass) * N + k] = sp[k];
                     }
                 }
             }

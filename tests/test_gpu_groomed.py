@@ -387,6 +387,10 @@ def test_soft_sort_path_runs_and_matches_torch_composite(G):
     composite is checked against the oracle fed with exactly those soft-sorted inputs."""
     from oracle import groomed_oracle as O
     sc, iou, up = _rand_case(91, 60, 3)
+    # (inputs already in score order: with unsorted inputs the row-only permutation leaves a diagonal that is not a
+    #  self-overlap and the reference's own grouping loop never terminates, lib/groomed_nms.py:247-262)
+    pre_order = np.argsort(-sc, kind="stable")
+    sc, iou = sc[pre_order].copy(), iou[pre_order][:, pre_order].copy()
     s = cuda(sc).requires_grad_(True)
     v, i, p = G.differentiable_nms(s, cuda(iou), temperature=0.1, sorting_method="soft", sorting_temperature=1e-4)
     ss, perm, ms = G.soft_sort(cuda(sc), full_matrix=cuda(iou), temperature=1e-4)
