@@ -32,7 +32,7 @@ constexpr int kMaskThreads = 256;
 
 // ------------------------------------------------------------------------------------------ workspace
 struct WsLayout {
-    size_t rank, sbox, mask, has_earlier, gbeg, members, ngroups, total;   // byte offsets inside one image's slice
+    size_t rank, sbox, mask, has_earlier, gbeg, members, ngroups, prec, prank, total;   // byte offsets inside one image's slice
     int he_slots;                                   // partial has-earlier words per row word (one per column-chunk CTA)
 };
 __host__ __device__ inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -51,6 +51,9 @@ __host__ __device__ inline WsLayout ws_layout(int N) {
     L.gbeg = off;        off += align_up(((size_t)N + 1) * 4);
     L.members = off;     off += align_up((size_t)N * 4);
     L.ngroups = off;     off += 256;
+    // spatially ordered copies of the box records / ranks for the culled tile pass (fused, matrix-free path)
+    L.prec = off;        off += align_up((size_t)N * 8 * 4);
+    L.prank = off;       off += align_up((size_t)N * 4);
     L.total = off;
     return L;
 }
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(256)
 rank_kernel(const float* __restrict__ scores, int64_t sstride, int64_t score_img_stride, int N,
             const int32_t* __restrict__ n_per_image, int32_t* __restrict__ order_out, float* __restrict__ ss_out,
             char* __restrict__ ws, size_t ws_img_stride, const float* __restrict__ boxes, int box_src,
-            int64_t box_img_stride, float shift, int presorted, int zero_mask) {
+            int64_t box_img_stride, float shift, int presorted, int zero_mask, int32_t* tile_count) {
     extern __shared__ __align__(16) uint32_t skeys[];
     const int b = blockIdx.y;
     const int n = n_per_image ? min(n_per_image[b], N) : N;
@@ -179,6 +182,7 @@ rank_kernel(const float* __restrict__ scores, int64_t sstride, int64_t score_img
     }
     if (blockIdx.x == 0) {
         for (int pos = n + tid; pos < N; pos += 256) { order[pos] = -1; ss[pos] = 0.f; rank[pos] = INT_MAX; }
+        if (tile_count && b == 0 && tid == 0) *tile_count = 0;
     }
     __syncthreads();
     const int e = tid >> 2, q = tid & 3;
@@ -195,24 +199,34 @@ rank_kernel(const float* __restrict__ scores, int64_t sstride, int64_t score_img
         const uint32_t kle = ki == 0xffffffffu ? ki : ki + 1u;
         const int i4 = i >> 2, n4 = npad >> 2;
         const uint4* k4 = reinterpret_cast<const uint4*>(skeys);
-        int cnt = 0;
+        // a < b as the borrow of a - b, folded into the accumulator by subtract-with-borrow: two integer adds per key
+        // (compare + select + add costs three); four independent accumulators.  Accumulators count DOWN.
+        auto acc_lt = [](uint32_t& c, uint32_t a, uint32_t b) {
+            uint32_t t;
+            asm("{\n\t"
+                "sub.cc.u32 %1, %2, %3;\n\t"
+                "subc.u32 %0, %0, 0;\n\t"
+                "}" : "+r"(c), "=r"(t) : "r"(a), "r"(b));
+        };
+        uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
         int j4 = q;
 #pragma unroll 4
         for (; j4 < i4; j4 += 4) {
             const uint4 k = k4[j4];
-            cnt += (k.x < kle) + (k.y < kle) + (k.z < kle) + (k.w < kle);
+            acc_lt(c0, k.x, kle); acc_lt(c1, k.y, kle); acc_lt(c2, k.z, kle); acc_lt(c3, k.w, kle);
         }
         if (j4 == i4) {
             const uint4 k = k4[j4];
             const int sub = i & 3;
-            cnt += (k.x < (sub > 0 ? kle : ki)) + (k.y < (sub > 1 ? kle : ki)) + (k.z < (sub > 2 ? kle : ki)) + (k.w < ki);
+            acc_lt(c0, k.x, sub > 0 ? kle : ki); acc_lt(c1, k.y, sub > 1 ? kle : ki); acc_lt(c2, k.z, sub > 2 ? kle : ki); acc_lt(c3, k.w, ki);
             j4 += 4;
         }
 #pragma unroll 4
         for (; j4 < n4; j4 += 4) {
             const uint4 k = k4[j4];
-            cnt += (k.x < ki) + (k.y < ki) + (k.z < ki) + (k.w < ki);
+            acc_lt(c0, k.x, ki); acc_lt(c1, k.y, ki); acc_lt(c2, k.z, ki); acc_lt(c3, k.w, ki);
         }
+        int cnt = -(int)(c0 + c1 + c2 + c3);
         const unsigned quad_mask = 0xfu << ((tid & 31) & ~3);        // the 4 lanes of this element (they exit together)
         cnt += __shfl_xor_sync(quad_mask, cnt, 1);
         cnt += __shfl_xor_sync(quad_mask, cnt, 2);
@@ -407,6 +421,7 @@ struct TileArgs {
     size_t ws_img_stride;
     float* out;                  // [batch, N, N] or nullptr
     float thr;
+    const int32_t* tile_list;    // culled pass: [0] = count, [64..] = entries; records/ranks are read from prec/prank
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -454,8 +469,9 @@ template <> struct RecOf<kSrcBox2d> {
     }
 };
 
-template <int kSrc, bool kGen, bool kAffine, bool kHasOut>
+template <int kSrc, bool kGen, bool kAffine, bool kHasOut, bool kList>
 __global__ void __launch_bounds__(256, 3) tile_kernel(TileArgs A) {
+    static_assert(!(kHasOut && kList), "the culled pass does not produce the matrix");
     constexpr int kRecF = (kSrc == kSrcBox3d) ? 8 : 4;             // floats per staged record
     __shared__ __align__(16) float s_rec[2][2][kTT * kRecF];       // [buffer][row/col][record]
     __shared__ int s_rank[2][2][kTT];
@@ -466,14 +482,21 @@ __global__ void __launch_bounds__(256, 3) tile_kernel(TileArgs A) {
     const int N = A.N, tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const WsLayout L = ws_layout(N);
-    const int total = A.tiles_per_image * A.batch;
+    const int total = kList ? A.tile_list[0] : A.tiles_per_image * A.batch;
 
     auto prefetch = [&](int t, int buf) {
-        const int b = t / A.tiles_per_image;
-        int I, J;
-        tile_decode(t - b * A.tiles_per_image, A.nt, I, J);
-        const float* bx = A.boxes + (size_t)b * N * kRecF;
-        const int32_t* rank = reinterpret_cast<const int32_t*>(A.ws + (size_t)b * A.ws_img_stride + L.rank);
+        int b, I, J;
+        if (kList) {
+            const int e = A.tile_list[64 + t];
+            b = e >> 16; I = (e >> 8) & 255; J = e & 255;
+        } else {
+            b = t / A.tiles_per_image;
+            tile_decode(t - b * A.tiles_per_image, A.nt, I, J);
+        }
+        // culled pass: spatially ordered copies (3D: 8-float records, 2D: 4-float boxes) and their ranks
+        const float* bx = kList ? reinterpret_cast<const float*>(A.ws + (size_t)b * A.ws_img_stride + L.prec)
+                                : A.boxes + (size_t)b * N * kRecF;
+        const int32_t* rank = reinterpret_cast<const int32_t*>(A.ws + (size_t)b * A.ws_img_stride + (kList ? L.prank : L.rank));
         if (tid < 2 * kTT) {                                       // thread = one record (rows first, then columns)
             const int side = tid >> 6, k = tid & 63;
             const int idx = min((side ? J : I) * kTT + k, N - 1);
@@ -592,6 +615,212 @@ __global__ void __launch_bounds__(256, 3) tile_kernel(TileArgs A) {
                 }
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ 2d. spatial order + tile culling
+// Matrix-free path only.  Suppression needs a pair's overlap only when it can exceed the threshold, and boxes that
+// are far apart cannot: if two boxes are disjoint along an axis their intersection is EXACTLY 0 in fp32, so
+//   2D IoU / 3D IoU:            v = 0           -> never a hit for thr >= 0
+//   GIoU (v = io - h):          v = -h <= 0     -> never a hit for thr >= 0
+//   0.5 * (1 + GIoU):           v = 0.5 (1 - h), h = (hull - V) / hull >= gap / (w_a + w_b + gap) along the disjoint
+//                               axis, so v <= thr as soon as gap >= c (w_a + w_b), c = (1 - 2 thr + eps) / (2 thr - eps)
+// (eps = 1e-4 swallows the fp32 rounding of hull, V and the division, which is < 1e-6 relative).  One CTA per image
+// buckets the boxes by a 12-bit Morton code of their centre (counting sort in shared memory), writes spatially
+// ordered copies of the records and ranks, reduces each run of 64 boxes to an AABB + max extents, and lists the
+// tile pairs whose groups are NOT provably out of reach.  Groups holding a degenerate / non-finite box are never
+// culled (0/0 = NaN counts as a hit, lib/groomed_nms.py:249-250).  On clustered boxes ~90 % of the tiles disappear.
+struct SpatialArgs {
+    int N, batch, nt, src;
+    const int32_t* n_per_image;
+    const float* boxes;          // [batch, N, 8] records or [batch, N, 4] boxes (input order)
+    char* ws;
+    size_t ws_img_stride;
+    int32_t* tile_list;          // [0] = count (zeroed by the rank kernel), [64..] = entries
+    float cull_c;                // gap factor c (0: any positive gap)
+};
+
+__global__ void __launch_bounds__(1024) spatial_kernel(SpatialArgs A) {
+    __shared__ int s_hist[4096];
+    __shared__ float s_red[4][32];
+    __shared__ float s_gt[128][10];      // per group: xlo,xhi,ylo,yhi,zlo,zhi, wx,wy,wz (max extents), bad
+    __shared__ int s_wsum[32];
+    const int b = blockIdx.x, N = A.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = A.n_per_image ? min(A.n_per_image[b], N) : N;
+    const WsLayout L = ws_layout(N);
+    char* w = A.ws + (size_t)b * A.ws_img_stride;
+    const int32_t* rank = reinterpret_cast<const int32_t*>(w + L.rank);
+    float* prec = reinterpret_cast<float*>(w + L.prec);
+    int32_t* prank = reinterpret_cast<int32_t*>(w + L.prank);
+    const bool is3d = A.src == kSrcBox3d;
+    const int recf = is3d ? 8 : 4;
+    const float* bx = A.boxes + (size_t)b * N * recf;
+    constexpr int kPer = GNMS_MAX_BOXES / 1024;
+    // centre of box i along the two bucketing axes (3D: BEV x,z ; 2D: x,y)
+    auto centre = [&](int i, float& u, float& v) {
+        if (is3d) {
+            const float4 a = *reinterpret_cast<const float4*>(bx + (size_t)i * 8);
+            const float2 c = *reinterpret_cast<const float2*>(bx + (size_t)i * 8 + 4);
+            u = 0.5f * (a.z + a.w); v = 0.5f * (c.x + c.y);
+        } else {
+            const float4 a = *reinterpret_cast<const float4*>(bx + (size_t)i * 4);
+            u = 0.5f * (a.x + a.z); v = 0.5f * (a.y + a.w);
+        }
+    };
+    float cu[kPer], cv[kPer];
+    float ulo = INFINITY, uhi = -INFINITY, vlo = INFINITY, vhi = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        const int i = tid + q * 1024;
+        cu[q] = 0.f; cv[q] = 0.f;
+        if (i < n) {
+            centre(i, cu[q], cv[q]);
+            if (isfinite(cu[q]) && isfinite(cv[q])) {
+                ulo = fminf(ulo, cu[q]); uhi = fmaxf(uhi, cu[q]); vlo = fminf(vlo, cv[q]); vhi = fmaxf(vhi, cv[q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        ulo = fminf(ulo, __shfl_xor_sync(0xffffffffu, ulo, d)); uhi = fmaxf(uhi, __shfl_xor_sync(0xffffffffu, uhi, d));
+        vlo = fminf(vlo, __shfl_xor_sync(0xffffffffu, vlo, d)); vhi = fmaxf(vhi, __shfl_xor_sync(0xffffffffu, vhi, d));
+    }
+    if (lane == 0) { s_red[0][warp] = ulo; s_red[1][warp] = uhi; s_red[2][warp] = vlo; s_red[3][warp] = vhi; }
+    for (int i = tid; i < 4096; i += 1024) s_hist[i] = 0;
+    __syncthreads();
+    ulo = s_red[0][lane]; uhi = s_red[1][lane]; vlo = s_red[2][lane]; vhi = s_red[3][lane];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        ulo = fminf(ulo, __shfl_xor_sync(0xffffffffu, ulo, d)); uhi = fmaxf(uhi, __shfl_xor_sync(0xffffffffu, uhi, d));
+        vlo = fminf(vlo, __shfl_xor_sync(0xffffffffu, vlo, d)); vhi = fmaxf(vhi, __shfl_xor_sync(0xffffffffu, vhi, d));
+    }
+    const float su = (uhi > ulo) ? 64.0f / (uhi - ulo) : 0.f, sv = (vhi > vlo) ? 64.0f / (vhi - vlo) : 0.f;
+    int bucket[kPer], off[kPer];
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        const int i = tid + q * 1024;
+        bucket[q] = 4095; off[q] = 0;
+        if (i < N) {
+            if (i < n && isfinite(cu[q]) && isfinite(cv[q])) {
+                const uint32_t qu = (uint32_t)min(63, max(0, (int)((cu[q] - ulo) * su)));
+                const uint32_t qv = (uint32_t)min(63, max(0, (int)((cv[q] - vlo) * sv)));
+                uint32_t m = 0;                                        // 12-bit Morton code
+#pragma unroll
+                for (int bit = 0; bit < 6; ++bit) m |= ((qu >> bit) & 1u) << (2 * bit) | ((qv >> bit) & 1u) << (2 * bit + 1);
+                bucket[q] = (int)m;
+            }
+            off[q] = atomicAdd(&s_hist[bucket[q]], 1);
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the 4096 bucket counts (4 per thread)
+    {
+        int loc[4], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { loc[q] = s_hist[tid * 4 + q]; sum += loc[q]; }
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int v = s_wsum[lane], iv = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, iv, d);
+                if (lane >= d) iv += t;
+            }
+            s_wsum[lane] = iv - v;
+        }
+        __syncthreads();
+        int run = s_wsum[warp] + incl - sum;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { s_hist[tid * 4 + q] = run; run += loc[q]; }
+    }
+    __syncthreads();
+    // scatter the records / ranks into spatial order
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        const int i = tid + q * 1024;
+        if (i < N) {
+            const int pos = s_hist[bucket[q]] + off[q];
+            if (is3d) {
+                const float4* src = reinterpret_cast<const float4*>(bx + (size_t)i * 8);
+                float4* dst = reinterpret_cast<float4*>(prec + (size_t)pos * 8);
+                dst[0] = src[0]; dst[1] = src[1];
+            } else {
+                reinterpret_cast<float4*>(prec)[pos] = reinterpret_cast<const float4*>(bx)[i];
+            }
+            prank[pos] = i < n ? rank[i] : INT_MAX;
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    // AABB + max extents of every run of 64 boxes (padded boxes, rank INT_MAX, do not count)
+    const int nt = A.nt;
+    for (int g = warp; g < nt; g += 32) {
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, ext[3] = {0.f, 0.f, 0.f};
+        bool bad = false;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int pos = g * 64 + lane + 32 * h;
+            if (pos < N && prank[pos] != INT_MAX) {
+                float a[3][2];
+                if (is3d) {
+                    const Rec3 r = load_rec3(prec + (size_t)pos * 8);
+                    a[0][0] = r.bx1; a[0][1] = r.bx2; a[1][0] = r.ymin; a[1][1] = r.ymax; a[2][0] = r.bz1; a[2][1] = r.bz2;
+                    // the gap bound assumes vol = (BEV x extent)(y extent)(BEV z extent), true for y-rotated cuboids
+                    // (lib/math_3d.py:364-435); records built from other corner sets are simply never culled
+                    bad = bad || !rec3_sane(r) ||
+                          r.vol != __fmul_rn(__fmul_rn(__fsub_rn(r.bx2, r.bx1), __fsub_rn(r.ymax, r.ymin)), __fsub_rn(r.bz2, r.bz1));
+                } else {
+                    const float4 q4 = reinterpret_cast<const float4*>(prec)[pos];
+                    a[0][0] = q4.x; a[0][1] = q4.z; a[1][0] = q4.y; a[1][1] = q4.w; a[2][0] = 0.f; a[2][1] = 0.f;
+                    bad = bad || !box2_sane(make_box2(q4)) || !(fabsf(q4.x) <= 1e18f && fabsf(q4.y) <= 1e18f && fabsf(q4.z) <= 1e18f && fabsf(q4.w) <= 1e18f);
+                }
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+                    lo[ax] = fminf(lo[ax], a[ax][0]); hi[ax] = fmaxf(hi[ax], a[ax][1]);
+                    ext[ax] = fmaxf(ext[ax], a[ax][1] - a[ax][0]);
+                    bad = bad || !(a[ax][1] >= a[ax][0]);
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                lo[ax] = fminf(lo[ax], __shfl_xor_sync(0xffffffffu, lo[ax], d));
+                hi[ax] = fmaxf(hi[ax], __shfl_xor_sync(0xffffffffu, hi[ax], d));
+                ext[ax] = fmaxf(ext[ax], __shfl_xor_sync(0xffffffffu, ext[ax], d));
+            }
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            s_gt[g][0] = lo[0]; s_gt[g][1] = hi[0]; s_gt[g][2] = lo[1]; s_gt[g][3] = hi[1]; s_gt[g][4] = lo[2]; s_gt[g][5] = hi[2];
+            s_gt[g][6] = ext[0]; s_gt[g][7] = ext[1]; s_gt[g][8] = ext[2]; s_gt[g][9] = bad ? 1.f : 0.f;
+        }
+    }
+    __syncthreads();
+    // tile pairs that survive
+    const int tpi = nt * (nt + 1) / 2;
+    const int naxes = is3d ? 3 : 2;
+    const float c = A.cull_c;
+    for (int t = tid; t < tpi; t += 1024) {
+        int I, J;
+        tile_decode(t, nt, I, J);
+        bool cull = false;
+        if (I != J && s_gt[I][9] == 0.f && s_gt[J][9] == 0.f) {
+            for (int ax = 0; ax < naxes; ++ax) {
+                const float gap = fmaxf(s_gt[J][2 * ax] - s_gt[I][2 * ax + 1], s_gt[I][2 * ax] - s_gt[J][2 * ax + 1]);
+                // empty groups have lo = +inf, hi = -inf: gap = +inf -> culled
+                if (gap > 0.f && gap > c * (s_gt[I][6 + ax] + s_gt[J][6 + ax])) cull = true;
+            }
+        }
+        if (!cull) A.tile_list[64 + atomicAdd(&A.tile_list[0], 1)] = (b << 16) | (I << 8) | J;
     }
 }
 
@@ -1237,6 +1466,16 @@ static int configure_once() {
     return 0;
 }
 
+// Tile work list of the culled pass: one int per surviving tile (image << 16 | I << 8 | J), count in front.
+static size_t tile_list_bytes(int N, int batch) {
+    const size_t nt = (size_t)((N + kTT - 1) / kTT);
+    return align_up(256 + (size_t)batch * (nt * (nt + 1) / 2) * 4);
+}
+static int32_t* tile_list_ptr(void* workspace, int N, int batch) {
+    return reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + ws_layout(N).total * (size_t)batch +
+                                      align_up((size_t)batch * N * 4) + 4 * align_up((size_t)N * 4));
+}
+
 static size_t rank_smem_bytes(int N) { return (size_t)((N + 15) & ~15) * 4; }
 
 static size_t sort_smem_bytes(int N) {
@@ -1290,7 +1529,8 @@ extern "C" const char* gnms_error_string(int rc) {
 // Layout: [batch image slices][slot int32[batch*N]][4 scratch arrays of N words (get_groups / hard NMS)]
 extern "C" size_t gnms_workspace_bytes(int N, int batch) {
     if (N <= 0 || batch <= 0) return 256;
-    return ws_layout(N).total * (size_t)batch + align_up((size_t)batch * N * 4) + 4 * align_up((size_t)N * 4);
+    return ws_layout(N).total * (size_t)batch + align_up((size_t)batch * N * 4) + 4 * align_up((size_t)N * 4) +
+           tile_list_bytes(N, batch);
 }
 
 static int run_forward(const float* scores, int src, const float* iou, int64_t ld, const float* boxes,
@@ -1316,7 +1556,7 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     const bool tiles = need_groups && src != kSrcMatrix;              // fused overlap + mask tile kernel
     rank_kernel<<<dim3(gnms_div_up(N, kRankElems), batch), 256, rank_smem_bytes(N), s>>>(
         scores, 1, N, N, npi, sv.order, sv.sorted_scores, ws, L.total, src == kSrcMatrix ? nullptr : boxes, src,
-        (int64_t)N * box_stride, 0.f, 0, tiles ? 1 : 0);
+        (int64_t)N * box_stride, 0.f, 0, tiles ? 1 : 0, tile_list_ptr(workspace, N, batch));
     GNMS_LAUNCH_CHECK();
     if (src == kSrcMatrix && (!iou || ld < N)) return GNMS_E_BADARG;
     if (src != kSrcMatrix && !boxes) return GNMS_E_BADARG;
@@ -1336,10 +1576,29 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
         const int total = T.tiles_per_image * batch;
         const int grid = total < 148 * 3 ? total : 148 * 3;            // persistent: 3 CTAs per SM
         const bool ho = overlap_out != nullptr;
+        // matrix-free pass: spatial order + culling of tile pairs that provably hold no pair above the threshold
+        float cull_c = -1.f;                                           // < 0: culling not applicable
+        const float thr = p->nms_threshold;
+        if (!ho && need_groups && N <= 128 * kTT && batch < 32768 && thr >= 0.f) {
+            if (src == kSrcBox2d) cull_c = 0.f;                        // disjoint -> IoU = 0 <= thr
+            else if (!affine) cull_c = 0.f;                            // IoU3D = 0 or GIoU <= 0 <= thr
+            else if (thr >= 0.5f) cull_c = 0.f;                        // 0.5 (1 + v) <= 0.5 <= thr
+            else if (generalized && thr > 0.05f) cull_c = (1.f - 2.f * thr + 1e-4f) / (2.f * thr - 1e-4f);
+        }
+        const bool culled = cull_c >= 0.f;
+        if (culled) {
+            SpatialArgs SA = {};
+            SA.N = N; SA.batch = batch; SA.nt = T.nt; SA.src = src; SA.n_per_image = npi; SA.boxes = boxes; SA.ws = ws;
+            SA.ws_img_stride = L.total; SA.tile_list = tile_list_ptr(workspace, N, batch); SA.cull_c = cull_c;
+            spatial_kernel<<<batch, 1024, 0, s>>>(SA);
+            GNMS_LAUNCH_CHECK();
+            T.tile_list = SA.tile_list;
+        }
 #define GNMS_TILE(SRC, G, AF)                                                              \
     do {                                                                                   \
-        if (ho) tile_kernel<SRC, G, AF, true><<<grid, 256, 0, s>>>(T);                     \
-        else tile_kernel<SRC, G, AF, false><<<grid, 256, 0, s>>>(T);                       \
+        if (ho) tile_kernel<SRC, G, AF, true, false><<<grid, 256, 0, s>>>(T);              \
+        else if (culled) tile_kernel<SRC, G, AF, false, true><<<grid, 256, 0, s>>>(T);     \
+        else tile_kernel<SRC, G, AF, false, false><<<grid, 256, 0, s>>>(T);                \
     } while (0)
         if (src == kSrcBox3d) {
             if (generalized) {
@@ -1477,7 +1736,7 @@ extern "C" int gnms_get_groups_f32(const float* scores, const float* iou, int64_
     float* dpv = reinterpret_cast<float*>(extra + 3 * align_up((size_t)N * 4));
     const int NW = (N + 31) / 32;
     rank_kernel<<<dim3(gnms_div_up(N, kRankElems), 1), 256, rank_smem_bytes(N), s>>>(scores, 1, N, N, nullptr, order, ss, ws, L.total,
-                                                                                    nullptr, kSrcMatrix, 0, 0.f, 0, 0);
+                                                                                    nullptr, kSrcMatrix, 0, 0.f, 0, 0, nullptr);
     GNMS_LAUNCH_CHECK();
     dim3 grid(gnms_div_up(N, kMaskThreads * 4), NW, 1);
     bool vec = ((reinterpret_cast<uintptr_t>(iou) & 15u) == 0) && (ld % 4 == 0);
@@ -1511,7 +1770,7 @@ static int hard_nms_impl(const float* dets, int N, float thresh, float shift, in
     float* ss = reinterpret_cast<float*>(extra + align_up((size_t)N * 4));
     const int NW = (N + 31) / 32;
     rank_kernel<<<dim3(gnms_div_up(N, kRankElems), 1), 256, rank_smem_bytes(N), s>>>(dets + 4, 5, 0, N, nullptr, order, ss, ws, L.total,
-                                                                                    dets, kSrcBoxShift, 0, shift, presorted, 0);
+                                                                                    dets, kSrcBoxShift, 0, shift, presorted, 0, nullptr);
     GNMS_LAUNCH_CHECK();
     dim3 grid(gnms_div_up(N, kMaskThreads), NW, 1);
     if (cmp == GNMS_CMP_GT) launch_mask_boxes<kSrcBoxShift, GNMS_CMP_GT>(grid, s, 0, 0, N, nullptr, ws, L.total, thresh, shift);

@@ -403,3 +403,38 @@ def test_soft_sort_path_runs_and_matches_torch_composite(G):
     assert list(v.cpu().numpy()) == list(hard_order[o["valid"]])     # indices map back through the HARD sort (:118)
     p.sum().backward()
     assert torch.isfinite(s.grad).all() and s.grad.abs().sum() > 0
+
+
+@pytest.mark.parametrize("kind,n,seed", [("2d", 3000, 1), ("2d", 777, 2), ("3d", 2500, 3), ("3d", 4096, 4), ("3d", 100, 5)])
+def test_culled_fused_pass_equals_matrix_path_on_unclustered_boxes(kind, n, seed):
+    """The matrix-free pass skips tile pairs that provably hold no overlap above the threshold (spatial culling).
+    Uniformly scattered boxes with many near-threshold neighbours, duplicates and zero-size boxes: the group
+    structure and probabilities must still equal the materialise-everything path bit for bit."""
+    from groomed_nms_b200 import ops, _lib
+    rng = np.random.default_rng(seed)
+    sc = (rng.uniform(0.05, 1.0, n) + np.arange(n) * 1e-7).astype(np.float32)
+    if kind == "2d":
+        c = rng.uniform(0, 600, (n, 2)); wh = rng.uniform(10, 60, (n, 2))
+        boxes = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+        boxes[5] = boxes[9]                                   # exact duplicates
+        boxes[7, 2:] = boxes[7, :2]                           # zero-area boxes, two of them coincident (0/0 = NaN)
+        boxes[11] = boxes[7]
+        bx = cuda(boxes)
+        iou = ops.overlap2d(bx, bx)
+        p = ops.make_params(group_size=20)
+        st2 = ops.forward_boxes(cuda(sc)[None], bx[None], _lib.BOX_2D, p)
+    else:
+        b7 = np.stack([rng.uniform(-25, 25, n), 1.6 + 0.2 * rng.standard_normal(n), rng.uniform(5, 60, n),
+                       1.6 + 0.2 * rng.standard_normal(n), 1.5 + 0.1 * rng.standard_normal(n),
+                       4 + 0.5 * rng.standard_normal(n), rng.uniform(-np.pi, np.pi, n)], 1).astype(np.float32)
+        b7[3] = b7[8]
+        rec = ops.box3d_records(ops.corners_from_boxes7(cuda(b7)))
+        _, iou = ops.overlap3d(rec, rec, False, True, generalized=True, affine=True)
+        p = ops.make_params(group_size=20)
+        st2 = ops.forward_boxes(cuda(sc)[None], rec[None], _lib.BOX_3D_REC, p, generalized=True, affine=True)
+    st1 = ops.forward_matrix(cuda(sc)[None], iou[None], p)
+    torch.cuda.synchronize()
+    for f in ("order", "lead", "prob", "pre", "counts"):
+        assert torch.equal(getattr(st1, f), getattr(st2, f)), f
+    nv = int(st1.counts[0, 0])
+    assert torch.equal(st1.valid_idx[0, :nv], st2.valid_idx[0, :nv])
