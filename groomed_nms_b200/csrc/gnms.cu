@@ -849,6 +849,16 @@ __global__ void __launch_bounds__(256) has_earlier_kernel(int N, const int32_t* 
 }
 
 // ------------------------------------------------------------------------------------------ 3. chain
+// shared-memory carve-up of chain_kernel (host and device agree through these two functions)
+__host__ __device__ inline size_t chain_wcol_end(int N) {
+    size_t NW = (size_t)((N + 31) / 32);
+    size_t NWa = (NW + 3) & ~(size_t)3, Na = ((size_t)N + 3) & ~(size_t)3;
+    size_t P = 1;
+    while ((int)P < N) P <<= 1;
+    size_t keys = P * 8, win = (size_t)kWin * NW * 4;
+    return 3 * NWa * 4 + Na * 4 * 2 + (keys > win ? keys : win);
+}
+
 struct ChainArgs {
     int N, batch;
     const int32_t* n_per_image;
@@ -916,7 +926,14 @@ __device__ int warp_list_bits(const uint32_t* bits, int nw, int limit, int32_t* 
     return min(total, limit);
 }
 
+// Optional phase clock (debug): thread 0 of image 0 stamps SM clock values at phase boundaries when enabled through
+// gnms_debug_chain_clock(1); read back with gnms_debug_chain_clock_read.  Costs one predicated branch per phase.
+__device__ long long g_chain_clk[64];
+__device__ int g_chain_clk_on = 0;
+#define GNMS_PHASE(k) do { if (g_chain_clk_on && threadIdx.x == 0 && blockIdx.x == 0) g_chain_clk[k] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
+    GNMS_PHASE(0);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
     const int N = A.N;
@@ -940,7 +957,9 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
     int32_t* fsup = reinterpret_cast<int32_t*>(tmpbits + NWa);            // N   (later: lead[])
     int32_t* list = fsup + Na;                                            // N   (leader / candidate lists, later grank)
     uint32_t* wcol = reinterpret_cast<uint32_t*>(list + Na);              // kWin * NW (later: sort keys)
+    float* ss_s = reinterpret_cast<float*>(smem_raw + chain_wcol_end(N)); // N   sorted scores staged once
     __shared__ int s_cnt;
+    for (int pos = tid; pos < n; pos += kChainThreads) ss_s[pos] = ss[pos];   // consumed after several barriers
 
     int32_t* lead = fsup;
     float* pval = A.pval + (size_t)b * N;
@@ -952,7 +971,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             pval[pos] = 0.f;
             dpval[pos] = 0.f;
         }
-        __syncthreads();
+        __syncthreads(); GNMS_PHASE(1);
     } else {
     for (int i = tid; i < NW; i += kChainThreads) {
         removed[i] = 0u;
@@ -962,16 +981,16 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
         leader[i] = (i < nw) ? (~he & valid_word(i, n)) : 0u;
     }
     for (int i = tid; i < N; i += kChainThreads) fsup[i] = INT_MAX;
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(2);
 
     // ---- certain leaders L0 (no earlier overlapper at all): apply their columns in parallel
     for (int i = tid; i < nw; i += kChainThreads) tmpbits[i] = leader[i];
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(3);
     if (warp == 0) {
         int c = warp_list_bits(tmpbits, nw, N, list);
         if (lane == 0) s_cnt = c;
     }
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(4);
     {
         const int cnt = s_cnt;
         for (int k = warp; k < cnt; k += kChainThreads / 32) {
@@ -1000,14 +1019,14 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
     }
     // ---- unresolved boxes: windows of kWin candidates, resolved exactly in score order by warp 0
     while (true) {
-        __syncthreads();
+        __syncthreads(); GNMS_PHASE(5);
         for (int i = tid; i < nw; i += kChainThreads) tmpbits[i] = ~(leader[i] | removed[i]) & valid_word(i, n);
-        __syncthreads();
+        __syncthreads(); GNMS_PHASE(6);
         if (warp == 0) {
             int c = warp_list_bits(tmpbits, nw, kWin, list);
             if (lane == 0) s_cnt = c;
         }
-        __syncthreads();
+        __syncthreads(); GNMS_PHASE(7);
         const int cnt = s_cnt;
         if (cnt == 0) break;
         for (int k = warp; k < cnt; k += kChainThreads / 32) {
@@ -1015,7 +1034,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             for (int jw = lane; jw < nw; jw += 32)
                 wcol[k * NW + jw] = (jw >= (l >> 5)) ? mask[(size_t)jw * N + l] : 0u;
         }
-        __syncthreads();
+        __syncthreads(); GNMS_PHASE(8);
         if (warp == 0) {
             for (int k = 0; k < cnt; ++k) {
                 const int l = list[k];
@@ -1039,7 +1058,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             }
         }
     }
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(9);
 
     // ---- hard NMS: the leaders are the keep set
     if (A.leaders_only) {
@@ -1047,13 +1066,19 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             int c = warp_list_bits(leader, nw, N, list);
             if (lane == 0) { s_cnt = c; A.n_keep[b] = c; }
         }
-        __syncthreads();
+        __syncthreads(); GNMS_PHASE(10);
         for (int k = tid; k < s_cnt; k += kChainThreads) A.keep[(size_t)b * N + k] = order[list[k]];
         return;
     }
 
     // ---- group of every box: leaders lead themselves, others follow their first suppressor; a NaN overlap with
     //      the leader means the box left the pool without joining the group (lib/groomed_nms.py:249-250)
+    const float* __restrict__ sbox_r = sbox;
+    const float* __restrict__ iou_r = A.iou ? A.iou + (size_t)b * A.iou_img_stride : nullptr;
+    const int32_t* __restrict__ order_r = order;
+    float* __restrict__ pval_r = pval;
+    float* __restrict__ dpval_r = dpval;
+#pragma unroll 4
     for (int pos = tid; pos < n; pos += kChainThreads) {
         const bool isl = (leader[pos >> 5] >> (pos & 31)) & 1u;
         int f = fsup[pos];
@@ -1062,10 +1087,10 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
         if (!isl && ld_ >= 0) {
             float v;
             if (A.src == kSrcMatrix) {
-                v = A.iou[(size_t)b * A.iou_img_stride + (int64_t)order[pos] * A.ld + order[ld_]];
+                v = iou_r[(int64_t)order_r[pos] * A.ld + order_r[ld_]];
             } else {
-                const float4* pa = reinterpret_cast<const float4*>(sbox + (size_t)pos * 8);
-                const float4* pb = reinterpret_cast<const float4*>(sbox + (size_t)ld_ * 8);
+                const float4* pa = reinterpret_cast<const float4*>(sbox_r + (size_t)pos * 8);
+                const float4* pb = reinterpret_cast<const float4*>(sbox_r + (size_t)ld_ * 8);
                 float4 a0 = pa[0], a1 = pa[1], c0 = pb[0], c1 = pb[1];
                 if (A.src == kSrcBox3d) {
                     Rec3 ra = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
@@ -1087,10 +1112,10 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             }
         }
         lead[pos] = ld_;
-        pval[pos] = pv;
-        dpval[pos] = dpv;
+        pval_r[pos] = pv;
+        dpval_r[pos] = dpv;
     }
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(11);
 
     // ---- in-group rank (0 = leader) and the group_size cap: only the first group_size+1 boxes stay (:254-255)
     // (leaders with members are listed first, then one warp per leader; the up-to-8 mask words a lane owns are all
@@ -1100,12 +1125,12 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
     // member count per leader (shared-memory atomics); ranks are only needed where the cap can bite
     // (count > group_size) or when the caller wants the groups themselves
     for (int pos = tid; pos < n; pos += kChainThreads) grank[pos] = 0;
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(12);
     for (int pos = tid; pos < n; pos += kChainThreads) {
         const int ld_ = lead[pos];
         if (ld_ >= 0 && ld_ != pos) atomicAdd(&grank[ld_], 1);
     }
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(13);
     const int need_above = (A.group_id || A.stage == 1) ? 0 : P.group_size;
     for (int i = tid; i < nw; i += kChainThreads) {
         uint32_t lw = leader[i], keep = 0u;
@@ -1116,14 +1141,14 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
         }
         tmpbits[i] = keep;
     }
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(14);
     for (int pos = tid; pos < n; pos += kChainThreads) grank[pos] = 0;
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(15);
     if (warp == 0) {
         int c = warp_list_bits(tmpbits, nw, N, llist);
         if (lane == 0) s_cnt = c;
     }
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(16);
     {
         const int nlead = s_cnt;
         constexpr int kMaxW = GNMS_MAX_BOXES / 32 / 32;          // mask words per lane per column (8)
@@ -1164,12 +1189,12 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             }
         }
     }
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(17);
     const int gs = P.group_size;
     for (int pos = tid; pos < n; pos += kChainThreads) {
         if (lead[pos] >= 0 && lead[pos] != pos && grank[pos] > gs) lead[pos] = -1;
     }
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(18);
 
     // ---- get_groups outputs
     if (A.group_id) {
@@ -1189,7 +1214,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             }
             if (lane == 0) A.n_groups[b] = run;
         }
-        __syncthreads();
+        __syncthreads(); GNMS_PHASE(19);
         for (int pos = tid; pos < n; pos += kChainThreads) {
             int ld_ = lead[pos];
             int gid = -1;
@@ -1198,7 +1223,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             A.group_rank[(size_t)b * N + order[pos]] = ld_ >= 0 ? grank[pos] : -1;
         }
         if (!A.prob) return;
-        __syncthreads();
+        __syncthreads(); GNMS_PHASE(20);
     }
 
     // ---- mode GROUP_NOMASK: export the group structure for the per-group triangular solves and stop
@@ -1211,12 +1236,12 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
         int32_t* ngroups = reinterpret_cast<int32_t*>(w + L.ngroups);
         int32_t* lead_out = A.lead + (size_t)b * N;
         for (int pos = tid; pos < Na; pos += kChainThreads) gsz[pos] = 0;
-        __syncthreads();
+        __syncthreads(); GNMS_PHASE(21);
         for (int pos = tid; pos < n; pos += kChainThreads) {
             const int ld_ = lead[pos];
             if (ld_ >= 0) atomicAdd(&gsz[ld_], 1);                   // leaders count themselves (lead[l] == l)
         }
-        __syncthreads();
+        __syncthreads(); GNMS_PHASE(22);
         // block-wide exclusive scan: thread t owns the chunk [t*C, (t+1)*C)
         const int C = (n + kChainThreads - 1) / kChainThreads;
         int local = 0;
@@ -1228,7 +1253,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             if (lane >= d) incl += t;
         }
         if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
+        __syncthreads(); GNMS_PHASE(23);
         if (warp == 0) {
             int v = s_wsum[lane], iv = v;
 #pragma unroll
@@ -1239,7 +1264,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             s_wsum[lane] = iv - v;
             if (lane == 31) s_cnt = iv;                               // boxes that are in some group
         }
-        __syncthreads();
+        __syncthreads(); GNMS_PHASE(24);
         int run = s_wsum[warp] + incl - local;
         for (int q = 0; q < C; ++q) { const int pos = tid * C + q; if (pos < n) { gpre[pos] = run; run += gsz[pos]; } }
         // dense group index of a leader = number of leaders before it
@@ -1258,7 +1283,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             }
             if (lane == 0) { ngroups[0] = runl; gbeg[runl] = s_cnt; }
         }
-        __syncthreads();
+        __syncthreads(); GNMS_PHASE(25);
         for (int pos = tid; pos < N; pos += kChainThreads) {
             const int ld_ = pos < n ? lead[pos] : -1;
             lead_out[pos] = ld_;
@@ -1286,8 +1311,8 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             const int ld_ = lead[pos];
             float prev = 0.f;
             if (A.stage == 2) prev = ld_ >= 0 ? pre_out[pos] : 0.f;          // from the triangular solve
-            else if (ld_ == pos) prev = ss[pos];
-            else if (ld_ >= 0) prev = __fsub_rn(ss[pos], __fmul_rn(pval[pos], ss[ld_]));
+            else if (ld_ == pos) prev = ss_s[pos];
+            else if (ld_ >= 0) prev = __fsub_rn(ss_s[pos], __fmul_rn(pval[pos], ss_s[ld_]));
             r = fminf(fmaxf(prev, 0.f), 1.f);
             rt = (r < vthr) ? 0.f : r;
             is_valid = rt >= vthr;
@@ -1308,7 +1333,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
         dpval[pos] = 0.f;
         if (A.slot) A.slot[(size_t)b * N + pos] = pos;
     }
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(26);
     // word prefix of valid counts -> tmp in `removed` (no longer needed)
     uint32_t* vpref = removed;
     if (warp == 0) {
@@ -1326,13 +1351,13 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
         }
         if (lane == 0) s_cnt = run;
     }
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(27);
     const int V = s_cnt;
     if (tid == 0) { A.counts[b * 2 + 0] = V; A.counts[b * 2 + 1] = n - V; }
     int PV = 1;
     while (PV < V) PV <<= 1;
     for (int i = tid; i < PV; i += kChainThreads) keys[i] = ~0ull;
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(28);
     const float* rthr = reinterpret_cast<const float*>(list);
     int64_t* invalid_idx = A.invalid_idx + (size_t)b * N;
     int64_t* valid_idx = A.valid_idx + (size_t)b * N;
@@ -1348,7 +1373,20 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             if (P.sorted_output) prob[V + irank] = 0.f;
         }
     }
-    __syncthreads();
+    __syncthreads(); GNMS_PHASE(29);
+    if (V <= kChainThreads) {
+        // short valid list (the usual case): rank by counting, one key per thread, no barriers
+        if (tid < V) {
+            const unsigned long long mine = keys[tid];
+            int r = 0;
+            for (int j = 0; j < V; ++j) r += (keys[j] < mine);
+            const int pos = (int)(uint32_t)(mine & 0xffffffffull);
+            valid_idx[r] = order[pos];
+            if (A.slot) A.slot[(size_t)b * N + pos] = r;
+            if (P.sorted_output) prob[r] = rthr[pos];
+        }
+        return;
+    }
     for (int k = 2; k <= PV; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = tid; t < (PV >> 1); t += kChainThreads) {
@@ -1358,7 +1396,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
                 bool up = ((i & k) == 0);
                 if ((a > c) == up) { keys[i] = c; keys[l] = a; }
             }
-            __syncthreads();
+            __syncthreads(); GNMS_PHASE(30);
         }
     }
     for (int i = tid; i < V; i += kChainThreads) {
@@ -1441,16 +1479,7 @@ __global__ void __launch_bounds__(kChainThreads) backward_mask_kernel(BwdArgs A)
     }
 }
 
-static size_t chain_smem_bytes(int N) {
-    size_t NW = (size_t)((N + 31) / 32);
-    size_t keys = (size_t)N * 8;            // sort keys alias the window columns
-    size_t win = (size_t)kWin * NW * 4;
-    size_t P = 1;
-    while ((int)P < N) P <<= 1;
-    keys = P * 8;
-    size_t NWa = (NW + 3) & ~(size_t)3, Na = ((size_t)N + 3) & ~(size_t)3;
-    return 3 * NWa * 4 + Na * 4 * 2 + (keys > win ? keys : win) + 16;
-}
+static size_t chain_smem_bytes(int N) { return chain_wcol_end(N) + (((size_t)N + 3) & ~(size_t)3) * 4 + 16; }
 
 static int configure_once() {
     static bool done_dev[64] = {false};
@@ -1513,6 +1542,14 @@ static int check_common(int N, int batch, const gnms_params* p) {
 using namespace gnms;
 
 extern "C" int gnms_version(void) { return GNMS_VERSION; }
+
+// debug only (not part of the public header): phase clock of chain_kernel, see GNMS_PHASE
+extern "C" int gnms_debug_chain_clock(int on) {
+    return (int)cudaMemcpyToSymbol(g_chain_clk_on, &on, sizeof(int));
+}
+extern "C" int gnms_debug_chain_clock_read(long long* out64) {
+    return (int)cudaMemcpyFromSymbol(out64, g_chain_clk, sizeof(long long) * 64);
+}
 
 extern "C" const char* gnms_error_string(int rc) {
     if (rc == 0) return "success";
