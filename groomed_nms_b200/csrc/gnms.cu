@@ -7,7 +7,7 @@
 //   1. sort_kernel        one CTA: bitonic argsort of the scores (descending, stable by index) in shared memory;
 //                         writes order / rank / sorted scores (+ box records gathered into sorted order).
 //   2. mask_*_kernel      whole grid: the "suppression bitmask" in SORTED space,
-//                             mask[jw][l] bit r  <=>  box at sorted position j = 32*jw + r leaves the pool when
+//                             mask[l][jw] bit r  <=>  box at sorted position j = 32*jw + r leaves the pool when
 //                                                     the box at sorted position l < j is picked as a leader,
 //                                                     i.e. !(overlap[j,l] <= thr)   (lib/groomed_nms.py:249-250)
 //                         either by streaming the N x N overlap matrix once (coalesced 16 B loads, HBM bound:
@@ -266,6 +266,7 @@ mask_matrix_kernel(const float* __restrict__ iou, int64_t ld, int64_t img_stride
     const int n = n_per_image ? min(n_per_image[b], N) : N;
     const int jw = blockIdx.y;
     if (jw * 32 >= n) return;
+    const int NWm = (N + 31) / 32;
     const WsLayout L = ws_layout(N);
     char* w = ws + (size_t)b * ws_img_stride;
     const int32_t* rank = reinterpret_cast<const int32_t*>(w + L.rank);
@@ -330,7 +331,7 @@ mask_matrix_kernel(const float* __restrict__ iou, int64_t ld, int64_t img_stride
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (rk[k] != INT_MAX && (rk[k] >> 5) <= jw) {         // words above the diagonal are never read
-            mask[(size_t)jw * N + rk[k]] = wd[k];
+            mask[(size_t)rk[k] * NWm + jw] = wd[k];      // column-major: a leader's column is contiguous
         }
         any |= wd[k];
     }
@@ -396,7 +397,7 @@ mask_boxes_kernel(int N, const int32_t* __restrict__ n_per_image, char* __restri
         }
     }
     if (l < n && (l >> 5) <= jw) {
-        mask[(size_t)jw * N + l] = wd;
+        mask[(size_t)l * ((N + 31) / 32) + jw] = wd;
     }
     uint32_t any = __reduce_or_sync(0xffffffffu, wd);
     if ((threadIdx.x & 31) == 0 && any) atomicOr(&s_any, any);          // shared memory
@@ -480,6 +481,7 @@ __global__ void __launch_bounds__(256, 3) tile_kernel(TileArgs A) {
     __shared__ uint16_t s_hit[256 * 4];                            // queued (row, column quad, hit mask) of this tile
     __shared__ int s_nhit[2];                                      // per staging buffer (reset one tile ahead)
     const int N = A.N, tid = threadIdx.x;
+    const int NWt = (N + 31) / 32;
     const int tx = tid & 15, ty = tid >> 4;
     const WsLayout L = ws_layout(N);
     const int total = kList ? A.tile_list[0] : A.tiles_per_image * A.batch;
@@ -593,7 +595,7 @@ __global__ void __launch_bounds__(256, 3) tile_kernel(TileArgs A) {
                         const int later = max(ri, rj), earlier = min(ri, rj);
                         // padded boxes (index >= n) carry rank INT_MAX; ri == rj only for a box with itself
                         if (later != INT_MAX && ri != rj && (I != J || ri > rj))
-                            atomicOr(mask + ((unsigned)(later >> 5) * (unsigned)N + (unsigned)earlier), 1u << (later & 31));
+                            atomicOr(mask + ((unsigned)earlier * (unsigned)NWt + (unsigned)(later >> 5)), 1u << (later & 31));
                     }
                 }
             }
@@ -824,28 +826,32 @@ __global__ void __launch_bounds__(1024) spatial_kernel(SpatialArgs A) {
     }
 }
 
-// has-earlier words from the finished mask: word jw = OR over columns l of mask[jw][l]   (grid (NW, batch))
-__global__ void __launch_bounds__(256) has_earlier_kernel(int N, const int32_t* __restrict__ n_per_image, char* __restrict__ ws,
-                                                          size_t ws_img_stride) {
-    __shared__ uint32_t s_red[8];
-    const int b = blockIdx.y, jw = blockIdx.x;
+// has-earlier partials from the finished mask (column-major): CTA = 256 columns; work item = (row word, 32-column
+// part): 32 independent coalesced loads per thread, parts combined in shared memory   (grid (ceil(N/256), batch) x 1024)
+__global__ void __launch_bounds__(1024) has_earlier_kernel(int N, const int32_t* __restrict__ n_per_image, char* __restrict__ ws,
+                                                           size_t ws_img_stride) {
+    __shared__ uint32_t s_acc[GNMS_MAX_BOXES / 32];
+    const int b = blockIdx.y, NW = (N + 31) / 32;
     const int n = n_per_image ? min(n_per_image[b], N) : N;
     const WsLayout L = ws_layout(N);
     char* w = ws + (size_t)b * ws_img_stride;
     const uint32_t* mask = reinterpret_cast<const uint32_t*>(w + L.mask);
     uint32_t* has_earlier = reinterpret_cast<uint32_t*>(w + L.has_earlier);
-    if (jw * 32 >= n) return;
-    const int lend = min(n, jw * 32 + 32);                          // columns at or after the word's last row are empty
-    uint32_t acc = 0u;
-    for (int l = threadIdx.x; l < lend; l += 256) acc |= mask[(size_t)jw * N + l];
-    acc = __reduce_or_sync(0xffffffffu, acc);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    const int l0 = blockIdx.x * 256;
+    for (int jw = threadIdx.x; jw < NW; jw += 1024) s_acc[jw] = 0u;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t a = 0u;
-        for (int k = 0; k < 8; ++k) a |= s_red[k];
-        has_earlier[(size_t)jw * L.he_slots] = a;
+    for (int item = threadIdx.x; item < NW * 8; item += 1024) {
+        const int jw = item % NW, part = item / NW;
+        const int la = l0 + part * 32;
+        uint32_t acc = 0u;
+        if (jw * 32 < n && la < n && (la >> 5) <= jw) {        // a column only has bits in row words at or after its own
+#pragma unroll
+            for (int q = 0; q < 32; ++q) acc |= (la + q < n) ? mask[(size_t)(la + q) * NW + jw] : 0u;
+        }
+        if (acc) atomicOr(&s_acc[jw], acc);
     }
+    __syncthreads();
+    for (int jw = threadIdx.x; jw < NW; jw += 1024) has_earlier[(size_t)jw * L.he_slots + blockIdx.x] = s_acc[jw];
 }
 
 // ------------------------------------------------------------------------------------------ 3. chain
@@ -992,29 +998,35 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
     }
     __syncthreads(); GNMS_PHASE(4);
     {
+        // one warp per certain leader: its mask column (all words in flight at once) -> first suppressor of every
+        // box it overlaps (atomicMin, distinct addresses).  The `removed` bitset is derived from fsup afterwards:
+        // OR-ing it here made 30 warps fight over the same 128 shared-memory words.
         const int cnt = s_cnt;
         for (int k = warp; k < cnt; k += kChainThreads / 32) {
             const int l = list[k];
             constexpr int kMaxW = GNMS_MAX_BOXES / 32 / 32;
             uint32_t mw[kMaxW];
 #pragma unroll
-            for (int u = 0; u < kMaxW; ++u) {                 // all of the column's words in flight at once
+            for (int u = 0; u < kMaxW; ++u) {
                 const int jw = (l >> 5) + u * 32 + lane;
-                mw[u] = jw < nw ? mask[(size_t)jw * N + l] : 0u;
+                mw[u] = jw < nw ? mask[(size_t)l * NW + jw] : 0u;
             }
 #pragma unroll
             for (int u = 0; u < kMaxW; ++u) {
                 const int jw = (l >> 5) + u * 32 + lane;
                 uint32_t m = mw[u];
-                if (m) {
-                    atomicOr(&removed[jw], m);
-                    while (m) {
-                        int bp = __ffs(m) - 1;
-                        m &= m - 1;
-                        atomicMin(&fsup[jw * 32 + bp], l);
-                    }
+                while (m) {
+                    int bp = __ffs(m) - 1;
+                    m &= m - 1;
+                    atomicMin(&fsup[jw * 32 + bp], l);
                 }
             }
+        }
+        __syncthreads();
+        for (int base = 0; base < nw * 32; base += kChainThreads) {
+            const int pos = base + tid;
+            const uint32_t bal = __ballot_sync(0xffffffffu, pos < n && fsup[pos] != INT_MAX);
+            if (lane == 0 && (pos >> 5) < nw) removed[pos >> 5] = bal;
         }
     }
     // ---- unresolved boxes: windows of kWin candidates, resolved exactly in score order by warp 0
@@ -1032,7 +1044,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
         for (int k = warp; k < cnt; k += kChainThreads / 32) {
             const int l = list[k];
             for (int jw = lane; jw < nw; jw += 32)
-                wcol[k * NW + jw] = (jw >= (l >> 5)) ? mask[(size_t)jw * N + l] : 0u;
+                wcol[k * NW + jw] = (jw >= (l >> 5)) ? mask[(size_t)l * NW + jw] : 0u;
         }
         __syncthreads(); GNMS_PHASE(8);
         if (warp == 0) {
@@ -1096,12 +1108,18 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
                     Rec3 ra = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                     Rec3 rb = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
                     float ib = inter_bev3(ra, rb);
-                    v = A.generalized ? (A.affine ? iou3<true, true>(ra, rb, ib) : iou3<true, false>(ra, rb, ib))
-                                      : (A.affine ? iou3<false, true>(ra, rb, ib) : iou3<false, false>(ra, rb, ib));
+                    bool unsafe = !rec3_sane(ra) || !rec3_sane(rb);              // straight-line division first
+                    v = A.generalized ? (A.affine ? iou3_fast<true, true>(ra, rb, ib, unsafe) : iou3_fast<true, false>(ra, rb, ib, unsafe))
+                                      : (A.affine ? iou3_fast<false, true>(ra, rb, ib, unsafe) : iou3_fast<false, false>(ra, rb, ib, unsafe));
+                    if (__builtin_expect(unsafe, 0))
+                        v = A.generalized ? (A.affine ? iou3_exact_slow<true, true>(ra, rb) : iou3_exact_slow<true, false>(ra, rb))
+                                          : (A.affine ? iou3_exact_slow<false, true>(ra, rb) : iou3_exact_slow<false, false>(ra, rb));
                 } else {
                     Box2 ra = {a0.x, a0.y, a0.z, a0.w, a1.x};
                     Box2 rb = {c0.x, c0.y, c0.z, c0.w, c1.x};
-                    v = iou2(ra, rb);
+                    bool unsafe = !box2_sane(ra) || !box2_sane(rb);
+                    v = iou2_fast(ra, rb, unsafe);
+                    if (__builtin_expect(unsafe, 0)) v = iou2_exact_slow(ra, rb);
                 }
             }
             if (v != v) {
@@ -1150,6 +1168,8 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
     }
     __syncthreads(); GNMS_PHASE(16);
     {
+        // one warp per listed leader: its mask column names the candidates (few set bits); those that really follow
+        // this leader are ranked by position with a warp scan of per-word popcounts
         const int nlead = s_cnt;
         constexpr int kMaxW = GNMS_MAX_BOXES / 32 / 32;          // mask words per lane per column (8)
         for (int k = warp; k < nlead; k += kChainThreads / 32) {
@@ -1159,7 +1179,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
 #pragma unroll
             for (int u = 0; u < kMaxW; ++u) {
                 const int jw = base0 + u * 32 + lane;
-                mw[u] = jw < nw ? mask[(size_t)jw * N + l] : 0u;
+                mw[u] = jw < nw ? mask[(size_t)l * NW + jw] : 0u;
             }
             int carry = 0;
 #pragma unroll
@@ -1189,7 +1209,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             }
         }
     }
-    __syncthreads(); GNMS_PHASE(17);
+    __syncthreads();
     const int gs = P.group_size;
     for (int pos = tid; pos < n; pos += kChainThreads) {
         if (lead[pos] >= 0 && lead[pos] != pos && grank[pos] > gs) lead[pos] = -1;
@@ -1651,7 +1671,7 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
 #undef GNMS_TILE
         GNMS_LAUNCH_CHECK();
         if (need_groups) {
-            has_earlier_kernel<<<dim3(NW, batch), 256, 0, s>>>(N, npi, ws, L.total);
+            has_earlier_kernel<<<dim3(gnms_div_up(N, 256), batch), 1024, 0, s>>>(N, npi, ws, L.total);
             GNMS_LAUNCH_CHECK();
         }
     }
