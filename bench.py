@@ -221,13 +221,20 @@ def run_ours(args, rank, world):
             ms = float(t.item())
         return ms
 
+    if args.splits > 1:
+        from groomed_nms_b200.hostapi import SplitPlan
+        for name, mat in (("materialised", True), ("fused", False)):
+            sp = SplitPlan(B, N, dev, params, materialise=mat, splits=args.splits)
+            sp.load(torch.from_numpy(boxes).to(dev), torch.from_numpy(scores).to(dev), torch.from_numpy(grads).to(dev))
+            plans[name + "_split"] = sp
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    head = plans[args.path]
+    sfx = "_split" if args.splits > 1 else ""
+    head = plans[args.path + sfx]
     ms_total = timed_steps(head, args.steps, args.warmup)
     other_name = "fused" if args.path == "materialised" else "materialised"
-    ms_other = timed_steps(plans[other_name], args.steps, args.warmup)
+    ms_other = timed_steps(plans[other_name + sfx], args.steps, args.warmup)
 
     # e2e: same step through the host-buffer API (pinned host inputs/outputs, copies inside the timed region)
     runner = HostRunner(B, N, dev, params, materialise=False)   # run_host returns no matrix: fused matrix-free pipeline
@@ -287,7 +294,7 @@ def run_ours(args, rank, world):
             "data": "synthetic",
             "config": {"workload": "C3: N=4096 7-DoF boxes/image, 32 objects x 128 proposals, overlap 0.5*(1+GIoU3D approx), "
                                    "group+mask, linear pruning, group_size 100, fwd+bwd (grad wrt scores)",
-                       "images_per_step_per_gpu": B, "path": args.path, "cuda_graph": True,
+                       "images_per_step_per_gpu": B, "path": args.path, "cuda_graph": True, "graph_branches": args.splits,
                        "l2": "no flush: per-step working set %.0f MiB of overlap matrices vs 126 MB L2" % (B * N * N * 4 / 2 ** 20)
                              if args.path == "materialised" else "matrix-free path: no N^2 HBM traffic; inputs are O(N)",
                        "parallelism": "per-image shard, %d rank(s), no data-path collective" % world},
@@ -325,6 +332,7 @@ def main():
     ap.add_argument("--images", type=int, default=8, help="images (of N=4096 boxes) per GPU per step")
     ap.add_argument("--path", default="materialised", choices=["materialised", "fused"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--splits", type=int, default=1, help="issue the batch as this many sub-batches on parallel graph branches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))

@@ -4,8 +4,8 @@
 // lib/nms/nms_kernel.cu:24-144 (+ cpu_nms.pyx, py_cpu_nms.py, nms_others.py:119-150).
 //
 // Pipeline per image (all on one stream, no host sync, no allocation):
-//   1. sort_kernel        one CTA: bitonic argsort of the scores (descending, stable by index) in shared memory;
-//                         writes order / rank / sorted scores (+ box records gathered into sorted order).
+//   1. rank_kernel        rank by counting (multi-CTA): order / rank / sorted scores (+ box records gathered into
+//                         sorted order); zeroes the bitmask and partials.
 //   2. mask_*_kernel      whole grid: the "suppression bitmask" in SORTED space,
 //                             mask[l][jw] bit r  <=>  box at sorted position j = 32*jw + r leaves the pool when
 //                                                     the box at sorted position l < j is picked as a leader,
@@ -59,90 +59,6 @@ __host__ __device__ inline WsLayout ws_layout(int N) {
 }
 
 enum BoxSrc { kSrcMatrix = 0, kSrcBox2d = 1, kSrcBox3d = 2, kSrcBoxShift = 3 };
-
-// ------------------------------------------------------------------------------------------ 1. sort
-// boxes (optional): kSrcBox2d  float[N,4]; kSrcBox3d float[N,8] records; kSrcBoxShift float[N,5] dets.
-// scores come from `scores` (stride sstride floats; dets use column 4 with stride 5).
-__global__ void __launch_bounds__(kChainThreads)
-sort_kernel(const float* __restrict__ scores, int64_t sstride, int64_t score_img_stride, int N,
-            const int32_t* __restrict__ n_per_image, int32_t* __restrict__ order_out, float* __restrict__ ss_out,
-            char* __restrict__ ws, size_t ws_img_stride, const float* __restrict__ boxes, int box_src,
-            int64_t box_img_stride, float shift, int presorted) {
-    extern __shared__ unsigned long long keys[];
-    const int b = blockIdx.x;
-    const int n = n_per_image ? min(n_per_image[b], N) : N;
-    const WsLayout L = ws_layout(N);
-    char* w = ws + (size_t)b * ws_img_stride;
-    int32_t* rank = reinterpret_cast<int32_t*>(w + L.rank);
-    float* sbox = reinterpret_cast<float*>(w + L.sbox);
-    uint32_t* has_earlier = reinterpret_cast<uint32_t*>(w + L.has_earlier);
-    const float* sc = scores + (size_t)b * score_img_stride;
-    int32_t* order = order_out + (size_t)b * N;
-    float* ss = ss_out + (size_t)b * N;
-    const int tid = threadIdx.x;
-
-    int P = 1;
-    while (P < n) P <<= 1;
-    for (int i = tid; i < P; i += kChainThreads) {
-        unsigned long long k = ~0ull;
-        if (i < n) {
-            uint32_t hi = presorted ? (uint32_t)0 : desc_key(sc[(int64_t)i * sstride]);
-            k = ((unsigned long long)hi << 32) | (uint32_t)i;
-        }
-        keys[i] = k;
-    }
-    const int nw = (N + 31) / 32;
-    for (int i = tid; i < nw * L.he_slots; i += kChainThreads) has_earlier[i] = 0u;
-    __syncthreads();
-    if (!presorted) {
-        for (int k = 2; k <= P; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < (P >> 1); t += kChainThreads) {
-                    int i = 2 * t - (t & (j - 1));
-                    int l = i + j;
-                    unsigned long long a = keys[i], c = keys[l];
-                    bool up = ((i & k) == 0);
-                    if ((a > c) == up) { keys[i] = c; keys[l] = a; }
-                }
-                __syncthreads();
-            }
-        }
-    }
-    const float* bx = boxes ? boxes + (size_t)b * box_img_stride : nullptr;
-    for (int pos = tid; pos < N; pos += kChainThreads) {
-        if (pos < n) {
-            int idx = (int)(uint32_t)(keys[pos] & 0xffffffffull);
-            order[pos] = idx;
-            rank[idx] = pos;
-            ss[pos] = sc[(int64_t)idx * sstride];
-            if (box_src == kSrcBox2d) {
-                float4 v = __ldg(reinterpret_cast<const float4*>(bx) + idx);
-                Box2 q = make_box2(v);
-                float4* o = reinterpret_cast<float4*>(sbox + (size_t)pos * 8);
-                o[0] = v;
-                o[1] = make_float4(q.area, 0.f, 0.f, 0.f);
-            } else if (box_src == kSrcBox3d) {
-                const float4* src = reinterpret_cast<const float4*>(bx + (size_t)idx * 8);
-                float4* o = reinterpret_cast<float4*>(sbox + (size_t)pos * 8);
-                o[0] = __ldg(src);
-                o[1] = __ldg(src + 1);
-            } else if (box_src == kSrcBoxShift) {
-                const float* d = bx + (size_t)idx * 5;
-                BoxS q = make_boxs(d[0], d[1], d[2], d[3], shift);
-                float4* o = reinterpret_cast<float4*>(sbox + (size_t)pos * 8);
-                o[0] = make_float4(q.x1, q.y1, q.x2, q.y2);
-                o[1] = make_float4(q.area, 0.f, 0.f, 0.f);
-            }
-        } else {
-            order[pos] = -1;
-            ss[pos] = 0.f;
-        }
-    }
-    // live boxes beyond n (padding) never get a rank; give them one past the end so mask builders skip them
-    for (int i = n + tid; i < N; i += kChainThreads) {
-        if (n_per_image) rank[i] = INT_MAX;
-    }
-}
 
 // ------------------------------------------------------------------------------------------ 1b. rank by counting
 // Multi-CTA replacement of the one-CTA bitonic sort: rank[i] = #{j : score_j > score_i or (== and j < i)}.
@@ -877,7 +793,7 @@ struct ChainArgs {
     int generalized, affine;       // kSrcBox3d
     gnms_params p;
     // outputs
-    int32_t* order;                // [batch,N] in (written by sort_kernel)
+    int32_t* order;                // [batch,N] in (written by rank_kernel)
     float* sorted_scores;          // [batch,N] in
     float* prob;                   // [batch,N]
     int64_t* valid_idx;
@@ -1507,7 +1423,6 @@ static int configure_once() {
     GNMS_CUDA_TRY(cudaGetDevice(&dev));
     bool& done = done_dev[dev & 63];
     if (done) return 0;
-    GNMS_CUDA_TRY(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     GNMS_CUDA_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)chain_smem_bytes(GNMS_MAX_BOXES)));
     GNMS_CUDA_TRY(cudaFuncSetAttribute(backward_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * GNMS_MAX_BOXES + 64));
@@ -1526,12 +1441,6 @@ static int32_t* tile_list_ptr(void* workspace, int N, int batch) {
 }
 
 static size_t rank_smem_bytes(int N) { return (size_t)((N + 15) & ~15) * 4; }
-
-static size_t sort_smem_bytes(int N) {
-    size_t P = 1;
-    while ((int)P < N) P <<= 1;
-    return P * 8;
-}
 
 template <int kSrc, int kCmp>
 static void launch_mask_boxes(dim3 grid, cudaStream_t s, int generalized, int affine, int N, const int32_t* npi,

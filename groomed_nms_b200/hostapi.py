@@ -103,6 +103,51 @@ class Nms3dPlan(object):
         return g
 
 
+class SplitPlan(object):
+    """The same step over `batch` images, issued as `splits` independent sub-batches on parallel graph branches.
+    Images are independent, and every stage except the tile kernel is a small-grid, latency-bound launch (one CTA
+    per image): with two or more branches the grouping / backward kernels of one sub-batch run under the tile kernel
+    of another instead of leaving the GPU idle."""
+
+    def __init__(self, batch, n, device, params, materialise=True, splits=2):
+        assert batch % splits == 0
+        self.dev = device
+        self.parts = [Nms3dPlan(batch // splits, n, device, params, materialise=materialise) for _ in range(splits)]
+        self.B, self.N = batch, n
+        self.launches_per_step = sum(p.launches_per_step for p in self.parts)
+        self.streams = [torch.cuda.Stream(device) for _ in range(splits)]
+
+    def load(self, boxes7, scores, grad_prob):
+        k = self.B // len(self.parts)
+        for i, p in enumerate(self.parts):
+            p.boxes7.copy_(boxes7[i * k:(i + 1) * k]); p.scores.copy_(scores[i * k:(i + 1) * k]); p.grad_prob.copy_(grad_prob[i * k:(i + 1) * k])
+
+    def step(self, stream=None):
+        main = stream if stream is not None else torch.cuda.current_stream(self.dev)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        done = []
+        for p, st in zip(self.parts, self.streams):
+            st.wait_event(ev)
+            p.step(st)
+            e = torch.cuda.Event()
+            e.record(st)
+            done.append(e)
+        for e in done:
+            main.wait_event(e)
+
+    def capture(self):
+        for p, st in zip(self.parts, self.streams):
+            st.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(st):
+                p.step(st)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step(torch.cuda.current_stream(self.dev))
+        return g
+
+
 class HostRunner(object):
     """End-to-end entry for HOST buffers: pinned staging + an Nms3dPlan.  run_host(...) returns host tensors."""
 
