@@ -175,3 +175,57 @@ class HostRunner(object):
         self.h_counts.copy_(p.counts, non_blocking=True)
         torch.cuda.current_stream(p.dev).synchronize()
         return self.h_prob, self.h_grad, self.h_valid, self.h_counts
+
+
+class HostPipeline(object):
+    """Streaming version of HostRunner for back-to-back calls with HOST buffers: `depth` slots, each with its own
+    device plan, pinned result buffers, stream and CUDA graph of the kernel sequence.  submit() enqueues H2D ->
+    graph -> D2H for one batch on the next slot and returns immediately, so the PCIe copies of one call overlap the
+    kernels of its neighbours; wait(ticket) (or drain()) makes a call's results readable.  Every call still moves
+    all of its inputs and outputs across PCIe."""
+
+    def __init__(self, batch, n, device, params, depth=2):
+        self.dev = device
+        self.slots = []
+        for _ in range(depth):
+            r = HostRunner(batch, n, device, params, materialise=False)
+            st = torch.cuda.Stream(device)
+            with torch.cuda.stream(st):
+                r.plan.step(st)
+            st.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                r.plan.step(st)
+            self.slots.append(dict(r=r, st=st, g=g, ev=torch.cuda.Event(), busy=False))
+        self.k = 0
+        self.h2d_bytes, self.d2h_bytes = self.slots[0]["r"].h2d_bytes, self.slots[0]["r"].d2h_bytes
+
+    def submit(self, boxes7_host, scores_host, grad_prob_host):
+        s = self.slots[self.k % len(self.slots)]
+        if s["busy"]:
+            s["ev"].synchronize()                 # the slot's previous results must have been produced (and are now overwritten)
+        r, p = s["r"], s["r"].plan
+        with torch.cuda.stream(s["st"]):
+            p.boxes7.copy_(boxes7_host, non_blocking=True)
+            p.scores.copy_(scores_host, non_blocking=True)
+            p.grad_prob.copy_(grad_prob_host, non_blocking=True)
+            s["g"].replay()
+            r.h_prob.copy_(p.prob, non_blocking=True)
+            r.h_grad.copy_(p.grad_scores, non_blocking=True)
+            r.h_valid.copy_(p.valid_idx, non_blocking=True)
+            r.h_counts.copy_(p.counts, non_blocking=True)
+            s["ev"].record(s["st"])
+        s["busy"] = True
+        self.k += 1
+        return self.k - 1
+
+    def wait(self, ticket):
+        s = self.slots[ticket % len(self.slots)]
+        s["ev"].synchronize()
+        r = s["r"]
+        return r.h_prob, r.h_grad, r.h_valid, r.h_counts
+
+    def drain(self):
+        for s in self.slots:
+            if s["busy"]:
+                s["ev"].synchronize()
