@@ -38,6 +38,19 @@ def algorithmic_bytes(n, d):
     return 8 * n * n + (4 * d + 24) * n
 
 
+def ncu_traffic(images):
+    """DRAM bytes (read + write) of one tile-kernel launch from the committed `ncu --set full` capture of this command
+    (profiles/r1_tile_kernel_traffic.json), or None if no capture exists for this batch size."""
+    path = os.path.join(ROOT, "profiles", "r1_tile_kernel_traffic.json")
+    try:
+        d = json.load(open(path))
+        if int(d["images_per_launch"]) == int(images):
+            return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -177,7 +190,7 @@ def run_ours(args, rank, world):
     from groomed_nms_b200.hostapi import HostRunner, Nms3dPlan
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
-    _lib.load()
+    lib = _lib.load()
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -278,6 +291,13 @@ def run_ours(args, rank, world):
         stages["corners"] = time_stage(torch, pl.stage_corners, st, it)
         stages["records"] = time_stage(torch, pl.stage_records, st, it)
         stages["forward_boxes+matrix_out(rank+tile+has_earlier+chain)"] = time_stage(torch, pl.stage_forward, st, it)
+        # the kernels of that forward one by one (debug stage mask of the library: the same launches, in isolation)
+        for bit, name in ((1, "rank_kernel"), (4, "tile_kernel(matrix out)"), (8, "has_earlier_kernel"), (16, "chain_kernel")):
+            lib.gnms_debug_stage_mask(bit)
+            stages[name] = time_stage(torch, pl.stage_forward, st, it)
+        lib.gnms_debug_stage_mask(4)
+        stages["tile_kernel(matrix-free, culled)"] = time_stage(torch, plans["fused"].stage_forward, st, it)
+        lib.gnms_debug_stage_mask(0xff)
         stages["backward"] = time_stage(torch, pl.stage_backward, st, it)
         stages["forward_boxes_no_matrix(rank+tile+has_earlier+chain)"] = time_stage(torch, plans["fused"].stage_forward, st, it)
         tk = Nms3dPlan(B, N, dev, params, materialise=True, two_kernel=True)
@@ -297,8 +317,8 @@ def run_ours(args, rank, world):
         step_bytes = algorithmic_bytes(N, BOX_DOF) * B
         # dominant kernel of the materialised path: the N x N overlap tile kernel (writes 4 N^2 per image) or the
         # matrix -> bitmask stream (reads 4 N^2 per image); algorithmic bytes per launch stated in DESIGN.md
-        k_ms = stages["forward_boxes+matrix_out(rank+tile+has_earlier+chain)"]
-        k_bytes = B * (4 * N * N + 2 * 32 * N)
+        k_ms = stages["tile_kernel(matrix out)"]
+        k_bytes = B * (4 * N * N + 36 * N)      # matrix written once + box records and ranks read
         ach = k_bytes / (k_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "boxes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -316,9 +336,13 @@ def run_ours(args, rank, world):
                     "blocking_call_api": "groomed_nms_b200.hostapi.HostRunner.run_host (one synchronous call per step)"},
             "gpu_launches": head.launches_per_step * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "overlap3d_kernel<generalized,affine> (N x N tile, batched)",
+            "roofline": {"bound": "hbm", "kernel": "gnms::tile_kernel<3D records, generalized, affine, matrix out> "
+                                                   "(symmetric 64x64 overlap tiles + suppression bits, %d images per launch)" % B,
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": k_bytes, "avg_launch_ms": k_ms, "traffic": None},
+                         "algorithmic_bytes_per_launch": k_bytes, "avg_launch_ms": k_ms, "traffic": ncu_traffic(B),
+                         "timing": "CUDA events around %d back-to-back launches of this kernel alone on the launching stream" % max(10, args.steps),
+                         "note": "the kernel is fp32-issue bound (about 67 issue slots per pair, FMNMX at half rate), "
+                                 "not HBM bound: see DESIGN.md section 5 and profiles/"},
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "effective_GBps": step_bytes / (ms_step * 1e-3) / 1e9,
                               "frac_of_peak": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
                               "note": "section 8(d) byte model 8N^2+(4D+24)N per image over the whole fwd+bwd step"},

@@ -31,8 +31,24 @@ constexpr int kWin = 64;                 // candidates resolved per window
 constexpr int kMaskThreads = 256;
 
 // ------------------------------------------------------------------------------------------ workspace
+constexpr int kBlkWords = 9 * 64;        // one 64-box block of the blocked SoA copy: 8 fields + rank
+constexpr int kBlkBytes = kBlkWords * 4;
+
+// Store record `src` (nf floats; nullptr: a harmless unit box) and `rank` as element e of a 64-box block.
+__device__ __forceinline__ void blk_store(float* blk, int e, const float* src, int nf, int rank) {
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+        // dummy: (ymin,ymax,bx1,bx2,bz1,bz2,vol,abev) = (0,1,0,1,0,1,1,1) in 3D, (x1,y1,x2,y2) = (0,0,1,1) in 2D
+        const float dummy = nf == 8 ? ((f & 1) || f >= 6 ? 1.f : 0.f) : (f >= 2 ? 1.f : 0.f);
+        if (f < nf) blk[f * 64 + e] = src ? src[f] : dummy;
+    }
+    // 2D: field 4 carries the area (x2-x1)*(y2-y1) for the tile kernel's range check
+    if (nf == 4) blk[4 * 64 + e] = src ? __fmul_rn(__fsub_rn(src[2], src[0]), __fsub_rn(src[3], src[1])) : 1.f;
+    reinterpret_cast<int32_t*>(blk)[8 * 64 + e] = rank;
+}
+
 struct WsLayout {
-    size_t rank, sbox, mask, has_earlier, gbeg, members, ngroups, prec, prank, total;   // byte offsets inside one image's slice
+    size_t rank, sbox, mask, has_earlier, gbeg, members, ngroups, blk, total;   // byte offsets inside one image's slice
     int he_slots;                                   // partial has-earlier words per row word (one per column-chunk CTA)
 };
 __host__ __device__ inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -51,9 +67,9 @@ __host__ __device__ inline WsLayout ws_layout(int N) {
     L.gbeg = off;        off += align_up(((size_t)N + 1) * 4);
     L.members = off;     off += align_up((size_t)N * 4);
     L.ngroups = off;     off += 256;
-    // spatially ordered copies of the box records / ranks for the culled tile pass (fused, matrix-free path)
-    L.prec = off;        off += align_up((size_t)N * 8 * 4);
-    L.prank = off;       off += align_up((size_t)N * 4);
+    // blocked structure-of-arrays copy of the boxes for the tile kernel: per run of 64 boxes, 8 field arrays + the rank
+    // array of 64 words each (2304 contiguous bytes = one bulk copy); input order, or spatial order in the culled pass
+    L.blk = off;         off += align_up((size_t)((N + 63) / 64) * kBlkWords * 4);
     L.total = off;
     return L;
 }
@@ -98,12 +114,21 @@ rank_kernel(const float* __restrict__ scores, int64_t sstride, int64_t score_img
     }
     if (blockIdx.x == 0) {
         for (int pos = n + tid; pos < N; pos += 256) { order[pos] = -1; ss[pos] = 0.f; rank[pos] = INT_MAX; }
-        if (tile_count && b == 0 && tid == 0) *tile_count = 0;
+        if (tile_count && b == 0 && tid == 0) { tile_count[0] = 0; tile_count[1] = 0; tile_count[2] = 0; }   // culled-tile count, work counters
     }
     __syncthreads();
     const int e = tid >> 2, q = tid & 3;
     const int i = blockIdx.x * kRankElems + e;
-    if (i >= n) return;                                               // whole quads leave together
+    // this CTA's 64 elements are exactly one block of the blocked SoA copy the tile kernel stages with bulk copies
+    const bool want_blk = zero_mask && boxes && (box_src == kSrcBox2d || box_src == kSrcBox3d);
+    float* blk = reinterpret_cast<float*>(w + L.blk) + (size_t)blockIdx.x * kBlkWords;
+    const int blk_nf = box_src == kSrcBox3d ? 8 : 4;
+    if (i >= n) {                                                     // whole quads leave together
+        // dead slots: boxes past the live count keep their record (rank INT_MAX: never emit), slots past N a unit box
+        if (want_blk && q == 0)
+            blk_store(blk, e, i < N ? boxes + (size_t)b * box_img_stride + (size_t)i * blk_nf : nullptr, blk_nf, INT_MAX);
+        return;
+    }
     int r;
     if (presorted) {
         r = i;
@@ -162,7 +187,9 @@ rank_kernel(const float* __restrict__ scores, int64_t sstride, int64_t score_img
         const float4* src = reinterpret_cast<const float4*>(bx + (size_t)i * 8);
         o[0] = __ldg(src);
         o[1] = __ldg(src + 1);
-    } else if (box_src == kSrcBoxShift) {
+    }
+    if (want_blk) blk_store(blk, e, bx + (size_t)i * blk_nf, blk_nf, r);
+    if (box_src == kSrcBoxShift) {
         const float* d = bx + (size_t)i * 5;
         const BoxS qb = make_boxs(d[0], d[1], d[2], d[3], shift);
         o[0] = make_float4(qb.x1, qb.y1, qb.x2, qb.y2);
@@ -322,14 +349,28 @@ mask_boxes_kernel(int N, const int32_t* __restrict__ n_per_image, char* __restri
 }
 
 // ------------------------------------------------------------------------------------------ 2c. fused overlap + mask tiles
-// The north-star kernel: every unordered pair of boxes of an image is evaluated ONCE (symmetric 64 x 64 tiles in
-// INPUT index space, values register-resident) and feeds two consumers:
-//   * the API-visible overlap matrix (optional): the tile is streamed to HBM directly and transposed (16-byte
-//     stores, algorithmic 4 N^2 bytes, never read back), and
+// The north-star kernel: every unordered pair of boxes of an image is evaluated ONCE (symmetric 64 x 64 tiles, values
+// register-resident) and feeds two consumers:
+//   * the API-visible overlap matrix (optional): the tile and its mirror image are streamed to HBM straight from
+//     registers with 16-byte stores (algorithmic 4 N^2 bytes, never read back), and
 //   * the grouping stage: for a pair with !(v <= thr) the later-ranked box gets its bit set in the earlier box's
 //     mask column (sorted space) with a fire-and-forget atomic OR -- ~3 % of the pairs on clustered boxes.
-// Persistent CTAs walk the tile list; the next tile's 128 box records + ranks are prefetched with cp.async into the
-// other half of a double buffer while the current tile is computed.  ALU bound (~55 issue slots per pair).
+// Design notes (each measured on B200, see profiles/ and tools/exp/):
+//   * persistent CTAs walk the tile list; the two 64-box blocks of the next tile are prefetched with 16-byte cp.async
+//     into a double buffer from the blocked structure-of-arrays copy the rank / spatial kernel wrote (2304 contiguous
+//     bytes per block: 8 field arrays + the rank array), so a thread fetches the 4 rows and 4 columns of a sub-tile
+//     with conflict-free 16-byte shared loads, one per field;
+//   * a thread owns 4 CONSECUTIVE rows x 4 consecutive columns: both the direct row segment and the mirrored one are
+//     16-byte register vectors, so the transposed tile needs no shared-memory round trip and no second barrier
+//     (warp = 8 column quads x 4 row quads: a direct store covers 4 rows x 128 B, a mirrored store 8 rows x 64 B);
+//   * the 16 pair evaluations of a sub-tile are one straight-line block (the rare exact-division fallback and the
+//     hits are handled after it), so independent division chains interleave; hits become mask bits in a short
+//     divergent loop run by the lanes that found them;
+//   * matrix-producing launches use 128-thread CTAs (a thread owns two sub-tiles, 4 CTAs per SM): the per-tile barrier
+//     joins 4 warps instead of 8, which was worth 10 % over the 256-thread shape; 64-thread CTAs, several tiles per
+//     barrier, a warp-autonomous mbarrier/bulk-copy variant and a shared-memory ring drained by bulk stores
+//     (cp.async.bulk shared -> global) were all slower and are not kept.
+// One barrier per tile.  fp32-issue bound: ~67 issue slots per pair, 16 of them FMNMX at half rate.
 struct TileArgs {
     int N, batch, nt, tiles_per_image, vec;
     const int32_t* n_per_image;
@@ -338,7 +379,8 @@ struct TileArgs {
     size_t ws_img_stride;
     float* out;                  // [batch, N, N] or nullptr
     float thr;
-    const int32_t* tile_list;    // culled pass: [0] = count, [64..] = entries; records/ranks are read from prec/prank
+    const int32_t* tile_list;    // culled pass: [0] = count, [64..] = entries (blocks are then in spatial order)
+    float inv_tpi, inv_w;        // 1 / tiles_per_image, 1 / (nt + 1): tile index decode without integer division
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -352,7 +394,6 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 constexpr int kTT = 64;              // tile edge
-constexpr int kTS = kTT + 1;         // transposed-tile row stride
 
 __device__ __forceinline__ void tile_decode(int t, int nt, int& I, int& J) {
     float fn = 2.0f * nt + 1.0f;
@@ -362,6 +403,20 @@ __device__ __forceinline__ void tile_decode(int t, int nt, int& I, int& J) {
     while ((i + 1) * nt - (i + 1) * i / 2 <= t) ++i;
     I = i;
     J = i + (t - (i * nt - i * (i - 1) / 2));
+}
+
+// Division-light enumeration of the nt(nt+1)/2 upper-triangle tiles: row i (nt - i tiles) is paired with row nt-1-i
+// (i + 1 tiles) into one line of nt + 1 entries, so a flat index decodes with one reciprocal multiply (inv_w = 1/(nt+1)).
+__device__ __forceinline__ int div_small(int t, int d, float inv_d) {      // t / d for t < 2^24-ish, d > 0
+    int q = __float2int_rd(__int2float_rn(t) * inv_d);
+    const int rem = t - q * d;
+    q += (rem >= d) - (rem < 0);
+    return q;
+}
+__device__ __forceinline__ void tile_decode_folded(int t, int nt, float inv_w, int& I, int& J) {
+    const int i = div_small(t, nt + 1, inv_w), j = t - i * (nt + 1);
+    if (j < nt - i) { I = i; J = i + j; }
+    else { I = nt - 1 - i; J = I + (j - (nt - i)); }
 }
 
 template <int kSrc> struct RecOf;
@@ -386,151 +441,165 @@ template <> struct RecOf<kSrcBox2d> {
     }
 };
 
-template <int kSrc, bool kGen, bool kAffine, bool kHasOut, bool kList>
-__global__ void __launch_bounds__(256, 3) tile_kernel(TileArgs A) {
+// Records of 4 consecutive boxes from a staged block ([field][64] arrays).
+template <int kSrc> struct SoaOf;
+template <> struct SoaOf<kSrcBox3d> {
+    static constexpr int kFields = 8;
+    // records of boxes first..first+3 from the SoA staging area (abev, field 7, is not needed by the 3D overlap)
+    static __device__ __forceinline__ void load4(const float* soa, int first, Rec3 (&o)[4]) {
+        float4 f[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) f[q] = *reinterpret_cast<const float4*>(soa + q * kTT + first);
+        const float* p = reinterpret_cast<const float*>(f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            o[k].ymin = p[0 * 4 + k]; o[k].ymax = p[1 * 4 + k]; o[k].bx1 = p[2 * 4 + k]; o[k].bx2 = p[3 * 4 + k];
+            o[k].bz1 = p[4 * 4 + k]; o[k].bz2 = p[5 * 4 + k]; o[k].vol = p[6 * 4 + k]; o[k].abev = 0.f;
+        }
+    }
+};
+template <> struct SoaOf<kSrcBox2d> {
+    static constexpr int kFields = 4;
+    static __device__ __forceinline__ void load4(const float* soa, int first, Box2 (&o)[4]) {
+        float4 f[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) f[q] = *reinterpret_cast<const float4*>(soa + q * kTT + first);
+        const float* p = reinterpret_cast<const float*>(f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = make_box2(make_float4(p[0 * 4 + k], p[1 * 4 + k], p[2 * 4 + k], p[3 * 4 + k]));
+    }
+};
+
+template <int kSrc, bool kGen, bool kAffine, bool kHasOut, bool kList, int kRB>
+__global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
+    constexpr int kThreads = 256 / kRB;                               // kRB row blocks of 64 / kRB rows per thread
     static_assert(!(kHasOut && kList), "the culled pass does not produce the matrix");
-    constexpr int kRecF = (kSrc == kSrcBox3d) ? 8 : 4;             // floats per staged record
-    __shared__ __align__(16) float s_rec[2][2][kTT * kRecF];       // [buffer][row/col][record]
-    __shared__ int s_rank[2][2][kTT];
-    __shared__ int s_ij[2][4];                                     // decoded (image, I, J) of the staged tile
-    __shared__ float s_tile[kHasOut ? kTT * kTS : 1];
-    __shared__ uint16_t s_hit[256 * 4];                            // queued (row, column quad, hit mask) of this tile
-    __shared__ int s_nhit[2];                                      // per staging buffer (reset one tile ahead)
+    typedef typename RecOf<kSrc>::type RecT;
+    constexpr int kChunks = kBlkBytes / 16;                           // 16-byte chunks of one staged block (144)
+    __shared__ __align__(16) float s_blk[2][2][kBlkWords];          // [buffer][row/col][8 field arrays + rank array][64]
+    __shared__ int s_ij[2][4];
     const int N = A.N, tid = threadIdx.x;
     const int NWt = (N + 31) / 32;
-    const int tx = tid & 15, ty = tid >> 4;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int tx = (lane & 7) + 8 * (warp & 1), ty = (lane >> 3) + 4 * (warp >> 1);      // 16 column quads x 16/kRB row quads
     const WsLayout L = ws_layout(N);
     const int total = kList ? A.tile_list[0] : A.tiles_per_image * A.batch;
 
+    // Every thread decodes the tile (a handful of instructions) and copies 288 / kThreads 16-byte chunks of the two
+    // 64-box blocks (blocked structure-of-arrays copies written by the rank / spatial kernel: 2304 contiguous bytes per
+    // block, so staging is a few wide coalesced cp.async per thread and all warps carry the same work into the barrier).
     auto prefetch = [&](int t, int buf) {
         int b, I, J;
         if (kList) {
             const int e = A.tile_list[64 + t];
             b = e >> 16; I = (e >> 8) & 255; J = e & 255;
         } else {
-            b = t / A.tiles_per_image;
-            tile_decode(t - b * A.tiles_per_image, A.nt, I, J);
+            b = div_small(t, A.tiles_per_image, A.inv_tpi);
+            tile_decode_folded(t - b * A.tiles_per_image, A.nt, A.inv_w, I, J);
         }
-        // culled pass: spatially ordered copies (3D: 8-float records, 2D: 4-float boxes) and their ranks
-        const float* bx = kList ? reinterpret_cast<const float*>(A.ws + (size_t)b * A.ws_img_stride + L.prec)
-                                : A.boxes + (size_t)b * N * kRecF;
-        const int32_t* rank = reinterpret_cast<const int32_t*>(A.ws + (size_t)b * A.ws_img_stride + (kList ? L.prank : L.rank));
-        if (tid < 2 * kTT) {                                       // thread = one record (rows first, then columns)
-            const int side = tid >> 6, k = tid & 63;
-            const int idx = min((side ? J : I) * kTT + k, N - 1);
-            const float* src = bx + (size_t)idx * kRecF;
-            float* dst = &s_rec[buf][side][k * kRecF];
-            cp_async16(dst, src);
-            if (kRecF == 8) cp_async16(dst + 4, src + 4);
-            cp_async4(&s_rank[buf][side][k], rank + idx);
-            if (tid == 0) { s_ij[buf][0] = b; s_ij[buf][1] = I; s_ij[buf][2] = J; }
+        const char* blk = A.ws + (size_t)b * A.ws_img_stride + L.blk;
+#pragma unroll
+        for (int c = tid; c < 2 * kChunks; c += kThreads) {
+            const int side = c >= kChunks ? 1 : 0, cc = c - side * kChunks;
+            cp_async16(reinterpret_cast<char*>(s_blk[buf][side]) + cc * 16, blk + (size_t)(side ? J : I) * kBlkBytes + cc * 16);
         }
+        if (tid == 0) { s_ij[buf][0] = b; s_ij[buf][1] = I; s_ij[buf][2] = J; }
+    };
+    // preconditions of the straight-line division, checked on the chunks this thread staged itself (visible after
+    // wait_all): coordinates |x| <= 2^19 (3D), volume / area within [2^-60, 2^60]
+    auto own_bad = [&](int buf) -> bool {
+        bool bad = false;
+#pragma unroll
+        for (int c = tid; c < 2 * kChunks; c += kThreads) {
+            const int side = c >= kChunks ? 1 : 0, cc = c - side * kChunks, f = cc >> 4;
+            const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(s_blk[buf][side]) + cc * 16);
+            if (kSrc == kSrcBox3d) {
+                if (f < 6) bad = bad || !(fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fmaxf(fabsf(q.z), fabsf(q.w))) <= 524288.0f);
+                else if (f == 6) bad = bad || outside_safe(q.x) || outside_safe(q.y) || outside_safe(q.z) || outside_safe(q.w);
+            } else {
+                if (f == 4) bad = bad || outside_safe(q.x) || outside_safe(q.y) || outside_safe(q.z) || outside_safe(q.w);
+            }
+        }
+        return bad;
     };
 
     int t = blockIdx.x, buf = 0;
-    if (tid < 2) s_nhit[tid] = 0;
     if (t < total) prefetch(t, 0);
     for (; t < total; t += gridDim.x, buf ^= 1) {
         cp_async_wait_all();
-        // box-level preconditions of the straight-line division: every thread checks the record it copied
-        bool bad = false;
-        if (tid < 2 * kTT) {
-            const float* p = &s_rec[buf][tid >> 6][(tid & 63) * kRecF];
-            if (kSrc == kSrcBox3d) {
-                const Rec3 r = {p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7]};
-                bad = !rec3_sane(r);
-            } else {
-                bad = !box2_sane(make_box2(make_float4(p[0], p[1], p[2], p[3])));
-            }
-        }
-        const bool tile_unsafe = __syncthreads_or(bad);              // also publishes the staged records
+        const bool bad = own_bad(buf);
+        // publishes the staged blocks; every thread is also done with the other buffer (previous tile) here
+        const bool tile_unsafe = __syncthreads_or(bad);
         const int b = s_ij[buf][0], I = s_ij[buf][1], J = s_ij[buf][2];
-        uint32_t* mask = reinterpret_cast<uint32_t*>(A.ws + (size_t)b * A.ws_img_stride + L.mask);
-        float* out = kHasOut ? A.out + (size_t)b * N * N : nullptr;
         if (t + (int)gridDim.x < total) prefetch(t + gridDim.x, buf ^ 1);
 
-        const int i0 = I * kTT, j0 = J * kTT;
-        const bool transposed = kHasOut && (I != J);
-        // whole tile inside the matrix and 16-byte stores legal -> no per-row bounds tests
-        const bool full_tile = kHasOut && A.vec && (i0 + kTT <= N) && (j0 + kTT <= N);
-        typename RecOf<kSrc>::type cr[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) cr[k] = RecOf<kSrc>::load(&s_rec[buf][1][(4 * tx + k) * kRecF]);
-        float* drow = kHasOut ? out + (int64_t)(i0 + ty) * N + (j0 + 4 * tx) : nullptr;
-        float* trow = s_tile + (4 * tx) * kTS + ty;
+        const float* rsoa = s_blk[buf][0];
+        const float* csoa = s_blk[buf][1];
+        const int* rrank = reinterpret_cast<const int*>(rsoa) + 8 * kTT;
+        const int* crank = reinterpret_cast<const int*>(csoa) + 8 * kTT;
+        RecT cr[4];
+        SoaOf<kSrc>::load4(csoa, 4 * tx, cr);
         const float thr = A.thr;
-        // one row of the thread's 4 x 4 sub-tile at a time keeps the live registers low (3 CTAs per SM)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const typename RecOf<kSrc>::type rr = RecOf<kSrc>::load(&s_rec[buf][0][(ty + 16 * r) * kRecF]);
-            float v[4];
+        float* out = kHasOut ? A.out + (size_t)b * N * N : nullptr;
+        uint32_t* mask = reinterpret_cast<uint32_t*>(A.ws + (size_t)b * A.ws_img_stride + L.mask);
+        const bool full_tile = kHasOut && A.vec && (I * kTT + kTT <= N) && (J * kTT + kTT <= N);
+#pragma unroll 1
+        for (int h = 0; h < kRB; ++h) {
+            const int rl = (kTT / kRB) * h + 4 * ty;                 // first of this thread's 4 rows inside the tile
+            RecT rr[4];
+            SoaOf<kSrc>::load4(rsoa, rl, rr);
+            float v[4][4];
             bool unsafe = tile_unsafe;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = RecOf<kSrc>::template fast<kGen, kAffine>(rr, cr[k], unsafe);
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template fast<kGen, kAffine>(rr[r], cr[k], unsafe);
             if (__builtin_expect(unsafe, 0)) {      // rare: outside div_rn_fast's proven range -> exact IEEE path
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = RecOf<kSrc>::template exact<kGen, kAffine>(rr, cr[k]);
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template exact<kGen, kAffine>(rr[r], cr[k]);
             }
-            // ---- consumer 1: threshold tests; rows with a hit are queued (row, column quad, 4-bit mask) and turned
-            //      into mask bits after the tile by all threads together (hits are ~3 % of the pairs: doing the bit
-            //      arithmetic inline would cost every warp ~12 issue slots per pair for the sake of a few lanes)
-            const uint32_t hits = (uint32_t)(!(v[0] <= thr)) | ((uint32_t)(!(v[1] <= thr)) << 1) |
-                                  ((uint32_t)(!(v[2] <= thr)) << 2) | ((uint32_t)(!(v[3] <= thr)) << 3);
-            if (hits) s_hit[atomicAdd(&s_nhit[buf], 1)] = (uint16_t)(((ty + 16 * r) << 8) | (tx << 4) | hits);
-            // ---- consumer 2: the overlap matrix (optional): direct row now, transposed tile via shared memory
+            uint32_t hits = 0u;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) hits |= (uint32_t)(!(v[r][k] <= thr)) << (4 * r + k);
+
+            // ---- consumer 2: the overlap matrix (optional), direct and mirrored, straight from registers
             if (kHasOut) {
+                const int i0 = I * kTT + rl, j0 = J * kTT + 4 * tx;
                 if (full_tile) {
-                    st_cs_f4(drow + (int64_t)(16 * r) * N, make_float4(v[0], v[1], v[2], v[3]));
-                } else {
-                    const int i = i0 + ty + 16 * r, j = j0 + 4 * tx;
-                    if (i < N) {
+                    float* drow = out + (int64_t)i0 * N + j0;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) if (j + k < N) drow[(int64_t)(16 * r) * N + k] = v[k];
+                    for (int r = 0; r < 4; ++r) st_cs_f4(drow + (int64_t)r * N, make_float4(v[r][0], v[r][1], v[r][2], v[r][3]));
+                    if (I != J) {
+                        float* dcol = out + (int64_t)j0 * N + i0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) st_cs_f4(dcol + (int64_t)k * N, make_float4(v[0][k], v[1][k], v[2][k], v[3][k]));
                     }
-                }
-                if (transposed) {
+                } else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) trow[k * kTS + 16 * r] = v[k];
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (i0 + r < N && j0 + k < N) {
+                                out[(int64_t)(i0 + r) * N + (j0 + k)] = v[r][k];
+                                if (I != J) out[(int64_t)(j0 + k) * N + (i0 + r)] = v[r][k];
+                            }
+                        }
                 }
             }
-        }
-        __syncthreads();
-        // ---- queued hits -> suppression bits (sorted space).  Off-diagonal tiles see every unordered pair once; the
-        //      diagonal tile sees (i,j) and (j,i): only the orientation "row is the later box" emits.
-        {
-            const int nh = s_nhit[buf];
-            if (tid == 0) s_nhit[buf ^ 1] = 0;                       // next tile appends only after its top barrier
-            for (int h = tid; h < nh; h += 256) {
-                const uint32_t e = s_hit[h];
-                const int ri = s_rank[buf][0][e >> 8];
-                const int cbase = ((e >> 4) & 15) * 4;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if ((e >> k) & 1u) {
-                        const int rj = s_rank[buf][1][cbase + k];
-                        const int later = max(ri, rj), earlier = min(ri, rj);
-                        // padded boxes (index >= n) carry rank INT_MAX; ri == rj only for a box with itself
-                        if (later != INT_MAX && ri != rj && (I != J || ri > rj))
-                            atomicOr(mask + ((unsigned)earlier * (unsigned)NWt + (unsigned)(later >> 5)), 1u << (later & 31));
-                    }
-                }
-            }
-        }
-        if (transposed) {
-            float* dcol = out + (int64_t)(j0 + ty) * N + (i0 + 4 * tx);
-            const float* src = s_tile + ty * kTS + 4 * tx;
-#pragma unroll
-            for (int pass = 0; pass < 4; ++pass) {
-                const float* sp = src + (16 * pass) * kTS;
-                if (full_tile) {
-                    st_cs_f4(dcol + (int64_t)(16 * pass) * N, make_float4(sp[0], sp[1], sp[2], sp[3]));
-                } else {
-                    const int i = j0 + ty + 16 * pass, j = i0 + 4 * tx;
-                    if (i < N) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) if (j + k < N) dcol[(int64_t)(16 * pass) * N + k] = sp[k];
-                    }
-                }
+            // ---- consumer 1: hits -> suppression bits (sorted space).  Off-diagonal tiles see every unordered pair
+            //      once; the diagonal tile sees (i,j) and (j,i): only the orientation "row is the later box" emits.
+            while (hits) {
+                const int bit = __ffs(hits) - 1;
+                hits &= hits - 1u;
+                const int ri = rrank[rl + (bit >> 2)], rj = crank[4 * tx + (bit & 3)];
+                const int later = max(ri, rj), earlier = min(ri, rj);
+                // dead slots (box index >= live count, padding) carry rank INT_MAX; ri == rj only for a box with itself
+                if (later != INT_MAX && ri != rj && (I != J || ri > rj))
+                    atomicOr(mask + ((unsigned)earlier * (unsigned)NWt + (unsigned)(later >> 5)), 1u << (later & 31));
             }
         }
     }
@@ -544,8 +613,8 @@ __global__ void __launch_bounds__(256, 3) tile_kernel(TileArgs A) {
 //   0.5 * (1 + GIoU):           v = 0.5 (1 - h), h = (hull - V) / hull >= gap / (w_a + w_b + gap) along the disjoint
 //                               axis, so v <= thr as soon as gap >= c (w_a + w_b), c = (1 - 2 thr + eps) / (2 thr - eps)
 // (eps = 1e-4 swallows the fp32 rounding of hull, V and the division, which is < 1e-6 relative).  One CTA per image
-// buckets the boxes by a 12-bit Morton code of their centre (counting sort in shared memory), writes spatially
-// ordered copies of the records and ranks, reduces each run of 64 boxes to an AABB + max extents, and lists the
+// buckets the boxes by a 12-bit Morton code of their centre (counting sort in shared memory), writes the blocked
+// structure-of-arrays copy of the records and ranks in that spatial order, reduces each run of 64 boxes to an AABB + max extents, and lists the
 // tile pairs whose groups are NOT provably out of reach.  Groups holding a degenerate / non-finite box are never
 // culled (0/0 = NaN counts as a hit, lib/groomed_nms.py:249-250).  On clustered boxes ~90 % of the tiles disappear.
 struct SpatialArgs {
@@ -568,8 +637,7 @@ __global__ void __launch_bounds__(1024) spatial_kernel(SpatialArgs A) {
     const WsLayout L = ws_layout(N);
     char* w = A.ws + (size_t)b * A.ws_img_stride;
     const int32_t* rank = reinterpret_cast<const int32_t*>(w + L.rank);
-    float* prec = reinterpret_cast<float*>(w + L.prec);
-    int32_t* prank = reinterpret_cast<int32_t*>(w + L.prank);
+    float* blk = reinterpret_cast<float*>(w + L.blk);               // blocked SoA copy, here in SPATIAL order
     const bool is3d = A.src == kSrcBox3d;
     const int recf = is3d ? 8 : 4;
     const float* bx = A.boxes + (size_t)b * N * recf;
@@ -665,16 +733,11 @@ __global__ void __launch_bounds__(1024) spatial_kernel(SpatialArgs A) {
         const int i = tid + q * 1024;
         if (i < N) {
             const int pos = s_hist[bucket[q]] + off[q];
-            if (is3d) {
-                const float4* src = reinterpret_cast<const float4*>(bx + (size_t)i * 8);
-                float4* dst = reinterpret_cast<float4*>(prec + (size_t)pos * 8);
-                dst[0] = src[0]; dst[1] = src[1];
-            } else {
-                reinterpret_cast<float4*>(prec)[pos] = reinterpret_cast<const float4*>(bx)[i];
-            }
-            prank[pos] = i < n ? rank[i] : INT_MAX;
+            blk_store(blk + (size_t)(pos >> 6) * kBlkWords, pos & 63, bx + (size_t)i * recf, recf, i < n ? rank[i] : INT_MAX);
         }
     }
+    for (int pos = N + tid; pos < ((N + 63) & ~63); pos += 1024)        // padding slots of the last block
+        blk_store(blk + (size_t)(pos >> 6) * kBlkWords, pos & 63, nullptr, recf, INT_MAX);
     __threadfence_block();
     __syncthreads();
     // AABB + max extents of every run of 64 boxes (padded boxes, rank INT_MAX, do not count)
@@ -685,17 +748,18 @@ __global__ void __launch_bounds__(1024) spatial_kernel(SpatialArgs A) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int pos = g * 64 + lane + 32 * h;
-            if (pos < N && prank[pos] != INT_MAX) {
+            const float* bg = blk + (size_t)g * kBlkWords + (lane + 32 * h);      // element of block g: field f at bg[f * 64]
+            if (pos < N && reinterpret_cast<const int32_t*>(bg)[8 * 64] != INT_MAX) {
                 float a[3][2];
                 if (is3d) {
-                    const Rec3 r = load_rec3(prec + (size_t)pos * 8);
+                    const Rec3 r = {bg[0], bg[64], bg[128], bg[192], bg[256], bg[320], bg[384], bg[448]};
                     a[0][0] = r.bx1; a[0][1] = r.bx2; a[1][0] = r.ymin; a[1][1] = r.ymax; a[2][0] = r.bz1; a[2][1] = r.bz2;
                     // the gap bound assumes vol = (BEV x extent)(y extent)(BEV z extent), true for y-rotated cuboids
                     // (lib/math_3d.py:364-435); records built from other corner sets are simply never culled
                     bad = bad || !rec3_sane(r) ||
                           r.vol != __fmul_rn(__fmul_rn(__fsub_rn(r.bx2, r.bx1), __fsub_rn(r.ymax, r.ymin)), __fsub_rn(r.bz2, r.bz1));
                 } else {
-                    const float4 q4 = reinterpret_cast<const float4*>(prec)[pos];
+                    const float4 q4 = make_float4(bg[0], bg[64], bg[128], bg[192]);
                     a[0][0] = q4.x; a[0][1] = q4.z; a[1][0] = q4.y; a[1][1] = q4.w; a[2][0] = 0.f; a[2][1] = 0.f;
                     bad = bad || !box2_sane(make_box2(q4)) || !(fabsf(q4.x) <= 1e18f && fabsf(q4.y) <= 1e18f && fabsf(q4.z) <= 1e18f && fabsf(q4.w) <= 1e18f);
                 }
@@ -1472,6 +1536,10 @@ using namespace gnms;
 
 extern "C" int gnms_version(void) { return GNMS_VERSION; }
 
+// debug only (not part of the public header): which stages of the forward run (bench.py times kernels in isolation)
+static int g_stage_mask = 0xff;            // bit 0 rank, 1 spatial order, 2 tile (or matrix -> mask), 3 has_earlier, 4 chain / solves
+extern "C" int gnms_debug_stage_mask(int m) { int old = g_stage_mask; if (m >= 0) g_stage_mask = m; return old; }
+
 // debug only (not part of the public header): phase clock of chain_kernel, see GNMS_PHASE
 extern "C" int gnms_debug_chain_clock(int on) {
     return (int)cudaMemcpyToSymbol(g_chain_clk_on, &on, sizeof(int));
@@ -1520,27 +1588,32 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     const int mode = p->mode;
     const bool need_groups = mode != GNMS_MODE_NOGROUP;
     const bool tiles = need_groups && src != kSrcMatrix;              // fused overlap + mask tile kernel
+    if (g_stage_mask & 1)
     rank_kernel<<<dim3(gnms_div_up(N, kRankElems), batch), 256, rank_smem_bytes(N), s>>>(
         scores, 1, N, N, npi, sv.order, sv.sorted_scores, ws, L.total, src == kSrcMatrix ? nullptr : boxes, src,
-        (int64_t)N * box_stride, 0.f, 0, tiles ? 1 : 0, tile_list_ptr(workspace, N, batch));
+        (int64_t)N * box_stride, 0.f, 0, (tiles || (src != kSrcMatrix && overlap_out)) ? 1 : 0, tile_list_ptr(workspace, N, batch));
     GNMS_LAUNCH_CHECK();
     if (src == kSrcMatrix && (!iou || ld < N)) return GNMS_E_BADARG;
     if (src != kSrcMatrix && !boxes) return GNMS_E_BADARG;
     if (need_groups && src == kSrcMatrix) {
         dim3 grid(gnms_div_up(N, kMaskThreads * 4), NW, batch);
         bool vec = ((reinterpret_cast<uintptr_t>(iou) & 15u) == 0) && (ld % 4 == 0) && (((int64_t)N * ld) % 4 == 0);
-        if (vec) mask_matrix_kernel<true><<<grid, kMaskThreads, 0, s>>>(iou, ld, (int64_t)N * ld, N, npi, sv.order, ws, L.total, p->nms_threshold);
+        if (!(g_stage_mask & 4)) {}
+        else if (vec) mask_matrix_kernel<true><<<grid, kMaskThreads, 0, s>>>(iou, ld, (int64_t)N * ld, N, npi, sv.order, ws, L.total, p->nms_threshold);
         else mask_matrix_kernel<false><<<grid, kMaskThreads, 0, s>>>(iou, ld, (int64_t)N * ld, N, npi, sv.order, ws, L.total, p->nms_threshold);
         GNMS_LAUNCH_CHECK();
     } else if (src != kSrcMatrix && (need_groups || overlap_out)) {
         // (mode NOGROUP needs no mask; the tile kernel still runs if the caller wants the overlap matrix)
         TileArgs T = {};
         T.N = N; T.batch = batch; T.nt = gnms_div_up(N, kTT); T.tiles_per_image = T.nt * (T.nt + 1) / 2;
+        T.inv_tpi = 1.0f / (float)T.tiles_per_image; T.inv_w = 1.0f / (float)(T.nt + 1);
         T.vec = overlap_out && ((reinterpret_cast<uintptr_t>(overlap_out) & 15u) == 0) && (N % 4 == 0);
         T.n_per_image = npi; T.boxes = boxes; T.ws = ws; T.ws_img_stride = L.total; T.out = overlap_out;
         T.thr = need_groups ? p->nms_threshold : INFINITY;             // no bits wanted: nothing is > +inf ... NaN aside
         const int total = T.tiles_per_image * batch;
-        const int grid = total < 148 * 3 ? total : 148 * 3;            // persistent: 3 CTAs per SM
+        const int grid_out = total < 148 * 4 ? total : 148 * 4;        // persistent: 128-thread CTAs, 4 per SM
+        const int grid_bits = total < 148 * 2 ? total : 148 * 2;       // matrix-free: 256-thread CTAs, 2 per SM
+        T.tile_list = tile_list_ptr(workspace, N, batch);
         const bool ho = overlap_out != nullptr;
         // matrix-free pass: spatial order + culling of tile pairs that provably hold no pair above the threshold
         float cull_c = -1.f;                                           // < 0: culling not applicable
@@ -1556,17 +1629,18 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
             SpatialArgs SA = {};
             SA.N = N; SA.batch = batch; SA.nt = T.nt; SA.src = src; SA.n_per_image = npi; SA.boxes = boxes; SA.ws = ws;
             SA.ws_img_stride = L.total; SA.tile_list = tile_list_ptr(workspace, N, batch); SA.cull_c = cull_c;
-            spatial_kernel<<<batch, 1024, 0, s>>>(SA);
+            if (g_stage_mask & 2) spatial_kernel<<<batch, 1024, 0, s>>>(SA);
             GNMS_LAUNCH_CHECK();
             T.tile_list = SA.tile_list;
         }
 #define GNMS_TILE(SRC, G, AF)                                                              \
     do {                                                                                   \
-        if (ho) tile_kernel<SRC, G, AF, true, false><<<grid, 256, 0, s>>>(T);              \
-        else if (culled) tile_kernel<SRC, G, AF, false, true><<<grid, 256, 0, s>>>(T);     \
-        else tile_kernel<SRC, G, AF, false, false><<<grid, 256, 0, s>>>(T);                \
+        if (ho) tile_kernel<SRC, G, AF, true, false, 2><<<grid_out, 128, 0, s>>>(T);       \
+        else if (culled) tile_kernel<SRC, G, AF, false, true, 1><<<grid_bits, 256, 0, s>>>(T); \
+        else tile_kernel<SRC, G, AF, false, false, 1><<<grid_bits, 256, 0, s>>>(T);        \
     } while (0)
-        if (src == kSrcBox3d) {
+        if (!(g_stage_mask & 4)) {
+        } else if (src == kSrcBox3d) {
             if (generalized) {
                 if (affine) GNMS_TILE(kSrcBox3d, true, true);
                 else GNMS_TILE(kSrcBox3d, true, false);
@@ -1579,7 +1653,7 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
         }
 #undef GNMS_TILE
         GNMS_LAUNCH_CHECK();
-        if (need_groups) {
+        if (need_groups && (g_stage_mask & 8)) {
             has_earlier_kernel<<<dim3(gnms_div_up(N, 256), batch), 1024, 0, s>>>(N, npi, ws, L.total);
             GNMS_LAUNCH_CHECK();
         }
@@ -1591,6 +1665,7 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     A.order = sv.order; A.sorted_scores = sv.sorted_scores; A.prob = prob; A.valid_idx = valid_idx;
     A.invalid_idx = invalid_idx; A.counts = counts; A.lead = sv.lead; A.pval = sv.pval; A.dpval = sv.dpval;
     A.pre = sv.pre; A.slot = slot;
+    if (!(g_stage_mask & 16)) return 0;
     if (mode == GNMS_MODE_GROUP_MASK) {
         A.stage = 0;
         chain_kernel<<<batch, kChainThreads, chain_smem_bytes(N), s>>>(A);

@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Per-kernel device times of the forward on the bench workload (run on the GPU box):
+    python tools/stage_times.py [--images 16] [--n 4096]
+Every stage of gnms_forward_boxes_f32 is launched back to back on its own (debug stage mask of the library), for the
+matrix-producing and the matrix-free pipeline, and the two pipelines are checked against each other."""
+import argparse
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from groomed_nms_b200 import _lib, ops, synthetic          # noqa: E402
+from groomed_nms_b200.hostapi import Nms3dPlan             # noqa: E402
+
+STAGES = {1: "rank", 3: "rank+spatial", 4: "tile", 8: "has_earlier", 16: "chain", 0xff: "forward (all)"}
+
+
+def time_call(fn, stream, iters=20, warm=3):
+    s = ctypes.c_void_p(stream.cuda_stream)
+    for _ in range(warm):
+        fn(s)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream.synchronize()
+    e0.record(stream)
+    for _ in range(iters):
+        fn(s)
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--images", type=int, default=16)
+    ap.add_argument("--n", type=int, default=4096)
+    args = ap.parse_args()
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    B, N = args.images, args.n
+    params = ops.make_params()
+    boxes = np.stack([synthetic.config_c3(seed=3 + 10 * i, n=N)[0] for i in range(B)])
+    scores = np.stack([synthetic.config_c3(seed=3 + 10 * i, n=N)[1] for i in range(B)])
+    st = torch.cuda.current_stream(dev)
+    s = ctypes.c_void_p(st.cuda_stream)
+    res = {}
+    for mat in (True, False):
+        lib.gnms_debug_stage_mask(0xff)
+        pl = Nms3dPlan(B, N, dev, params, materialise=mat)
+        pl.boxes7.copy_(torch.from_numpy(boxes)); pl.scores.copy_(torch.from_numpy(scores))
+        pl.grad_prob.normal_()
+        pl.stage_corners(s); pl.stage_records(s); pl.stage_forward(s)
+        torch.cuda.synchronize()
+        res[mat] = dict(prob=pl.prob.clone(), counts=pl.counts.clone(), lead=pl.lead.clone())
+        for m, nm in STAGES.items():
+            if m == 3 and mat:
+                continue
+            lib.gnms_debug_stage_mask(m)
+            us = time_call(pl.stage_forward, st)
+            extra = "  -> %.0f GB/s of matrix written" % (B * 4.0 * N * N / us / 1e3) if (m == 4 and mat) else ""
+            print("matrix=%d  %-14s %9.1f us%s" % (mat, nm, us, extra))
+        lib.gnms_debug_stage_mask(0xff)
+        del pl
+    print("matrix vs matrix-free:", " ".join("%s=%s" % (k, torch.equal(res[True][k], res[False][k])) for k in ("prob", "counts", "lead")))
+
+
+if __name__ == "__main__":
+    main()
