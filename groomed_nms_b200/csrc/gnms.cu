@@ -102,18 +102,22 @@ rank_kernel(const float* __restrict__ scores, int64_t sstride, int64_t score_img
     float* ss = ss_out + (size_t)b * N;
     const int tid = threadIdx.x;
     const int npad = (N + 15) & ~15;
-    for (int j = tid; j < npad; j += 256) skeys[j] = (j < n && !presorted) ? desc_key(sc[(int64_t)j * sstride]) : 0xffffffffu;
+    if (presorted == 0)                                              // (the other modes do not count)
+        for (int j = tid; j < npad; j += 256) skeys[j] = j < n ? desc_key(sc[(int64_t)j * sstride]) : 0xffffffffu;
     // chores, split over the CTAs of this image
     const int nw = (N + 31) / 32;
     const size_t ncta = gridDim.x, me = blockIdx.x;
-    for (size_t i = me * 256 + tid; i < (size_t)nw * L.he_slots; i += ncta * 256) has_earlier[i] = 0u;
-    if (zero_mask) {
+    if (presorted != 2)                                              // (sort_kernel's helper CTAs did the zeroing)
+        for (size_t i = me * 256 + tid; i < (size_t)nw * L.he_slots; i += ncta * 256) has_earlier[i] = 0u;
+    if (zero_mask && presorted != 2) {
         uint4* m4 = reinterpret_cast<uint4*>(mask);
         const size_t tot4 = ((size_t)nw * N + 3) / 4;                  // the mask slice is 256-byte aligned and padded
         for (size_t i = me * 256 + tid; i < tot4; i += ncta * 256) m4[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    if (blockIdx.x == 0) {
+    if (blockIdx.x == 0 && presorted != 2) {
         for (int pos = n + tid; pos < N; pos += 256) { order[pos] = -1; ss[pos] = 0.f; rank[pos] = INT_MAX; }
+    }
+    if (blockIdx.x == 0) {
         if (tile_count && b == 0 && tid == 0) { tile_count[0] = 0; tile_count[1] = 0; tile_count[2] = 0; }   // culled-tile count, work counters
     }
     __syncthreads();
@@ -130,7 +134,9 @@ rank_kernel(const float* __restrict__ scores, int64_t sstride, int64_t score_img
         return;
     }
     int r;
-    if (presorted) {
+    if (presorted == 2) {
+        r = rank[i];                                                  // sort_kernel ran first
+    } else if (presorted) {
         r = i;
     } else {
         // count keys that sort before (key_i, i): key_j < key_i, or key_j == key_i with j < i.  The four threads of
@@ -174,9 +180,11 @@ rank_kernel(const float* __restrict__ scores, int64_t sstride, int64_t score_img
         r = cnt;
     }
     if (q != 0) return;
-    order[r] = i;
-    rank[i] = r;
-    ss[r] = sc[(int64_t)i * sstride];
+    if (presorted != 2) {
+        order[r] = i;
+        rank[i] = r;
+        ss[r] = sc[(int64_t)i * sstride];
+    }
     const float* bx = boxes ? boxes + (size_t)b * box_img_stride : nullptr;
     float4* o = reinterpret_cast<float4*>(sbox + (size_t)r * 8);
     if (box_src == kSrcBox2d) {
@@ -194,6 +202,139 @@ rank_kernel(const float* __restrict__ scores, int64_t sstride, int64_t score_img
         const BoxS qb = make_boxs(d[0], d[1], d[2], d[3], shift);
         o[0] = make_float4(qb.x1, qb.y1, qb.x2, qb.y2);
         o[1] = make_float4(qb.area, 0.f, 0.f, 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ 1c. rank by sorting
+// One CTA per image: stable LSD radix sort (4 passes of 8 bits) of the (descending-order key, index) pairs in shared
+// memory.  The counting kernel above does batch * N^2 compares spread over the whole chip (~2.8 us per image at
+// N = 4096, ALU-pipe bound); this one takes ~10 us whatever the batch size because images sort side by side on
+// different SMs, so it wins as soon as a launch holds more than a few images.  Writes order / rank / sorted scores
+// (and the dead tail); rank_kernel then runs in gather-only mode (presorted = 2) for its other chores.
+// Per pass: keys are read striped per warp (element = warp base + 32 k + lane), ranked inside the warp among the lanes
+// holding the same digit (8 ballots), warp-private digit counters in shared memory, one CTA-wide exclusive scan over
+// (digit, warp), then a scatter into the other buffer.  Stable: ties keep the lower input index first.
+// CTAs past the first `batch` ones zero the suppression masks and has-earlier partials of all images meanwhile.
+constexpr int kSortThreads = 1024;
+__host__ __device__ inline int sort_npad(int N) { return (N + kSortThreads - 1) / kSortThreads * kSortThreads; }
+static size_t sort_smem_bytes(int N) { return (size_t)sort_npad(N) * 12 + 32 * 256 * 2 + 256; }
+
+__global__ void __launch_bounds__(kSortThreads)
+sort_kernel(const float* __restrict__ scores, int64_t score_img_stride, int N, int batch, const int32_t* __restrict__ n_per_image,
+            int32_t* __restrict__ order_out, float* __restrict__ ss_out, char* __restrict__ ws, size_t ws_img_stride,
+            int zero_mask) {
+    extern __shared__ __align__(16) unsigned char s_sort[];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (b >= batch) {                                                // helper CTAs: zero the per-image scratch
+        const WsLayout L = ws_layout(N);
+        const size_t nw = (size_t)((N + 31) / 32);
+        const size_t he4 = (nw * L.he_slots * 4 + 15) / 16, mk4 = zero_mask ? (nw * N * 4 + 15) / 16 : 0;   // slices are 256-byte padded
+        const size_t per_img = he4 + mk4, total = per_img * batch;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (size_t i = (size_t)(b - batch) * kSortThreads + tid; i < total; i += (size_t)(gridDim.x - batch) * kSortThreads) {
+            const size_t img = i / per_img, o = i - img * per_img;
+            char* base = ws + img * ws_img_stride;
+            uint4* dst = o < he4 ? reinterpret_cast<uint4*>(base + L.has_earlier) + o : reinterpret_cast<uint4*>(base + L.mask) + (o - he4);
+            *dst = z;
+        }
+        return;
+    }
+    const int n = n_per_image ? min(n_per_image[b], N) : N;
+    const int npad = sort_npad(N), kper = npad / kSortThreads;
+    uint32_t* keyA = reinterpret_cast<uint32_t*>(s_sort);
+    uint32_t* keyB = keyA + npad;
+    uint16_t* idxA = reinterpret_cast<uint16_t*>(keyB + npad);
+    uint16_t* idxB = idxA + npad;
+    uint16_t* cnt = idxB + npad;                                     // [32 warps][256 digits]
+    __shared__ int s_wsum[32];
+    const float* sc = scores + (size_t)b * score_img_stride;
+    const WsLayout L = ws_layout(N);
+    int32_t* rank = reinterpret_cast<int32_t*>(ws + (size_t)b * ws_img_stride + L.rank);
+    for (int j = tid; j < npad; j += kSortThreads) { keyA[j] = j < n ? desc_key(sc[j]) : 0xffffffffu; idxA[j] = (uint16_t)j; }
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 8 * pass;
+        uint32_t* c32 = reinterpret_cast<uint32_t*>(cnt);
+        for (int j = tid; j < 32 * 256 / 2; j += kSortThreads) c32[j] = 0u;
+        __syncthreads();
+        // rank of every key among the keys of its warp that carry the same digit, in (k, lane) order
+        int myrank[8];
+        uint16_t* wc = cnt + w * 256;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            myrank[k] = 0;
+            if (k < kper) {
+                const uint32_t d = (keyA[w * 32 * kper + k * 32 + lane] >> shift) & 255u;
+                // lanes holding the same digit: 8 ballots (MATCH.ANY measured ~43 cycles per warp instruction per SM)
+                unsigned peers = 0xffffffffu;
+#pragma unroll
+                for (int bit = 0; bit < 8; ++bit) {
+                    const bool one = (d >> bit) & 1u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, one);
+                    peers &= one ? bal : ~bal;
+                }
+                const int leader = __ffs(peers) - 1;
+                int base = 0;
+                if (lane == leader) { base = wc[d]; wc[d] = (uint16_t)(base + __popc(peers)); }
+                base = __shfl_sync(0xffffffffu, base, leader);
+                myrank[k] = base + __popc(peers & lt_mask);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the counters in (digit, warp) order: thread t owns digit t / 4, warps 8 (t % 4) .. + 7
+        {
+            const int d = tid >> 2, w0 = (tid & 3) * 8;
+            int loc[8], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { loc[q] = cnt[(w0 + q) * 256 + d]; sum += loc[q]; }
+            int incl = sum;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const int t2 = __shfl_up_sync(0xffffffffu, incl, dd);
+                if (lane >= dd) incl += t2;
+            }
+            if (lane == 31) s_wsum[w] = incl;
+            __syncthreads();
+            if (w == 0) {
+                const int v = s_wsum[lane];
+                int iv = v;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const int t2 = __shfl_up_sync(0xffffffffu, iv, dd);
+                    if (lane >= dd) iv += t2;
+                }
+                s_wsum[lane] = iv - v;
+            }
+            __syncthreads();
+            int run = s_wsum[w] + incl - sum;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { cnt[(w0 + q) * 256 + d] = (uint16_t)run; run += loc[q]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k < kper) {
+                const int e = w * 32 * kper + k * 32 + lane;
+                const uint32_t key = keyA[e];
+                const int pos = wc[(key >> shift) & 255u] + myrank[k];
+                keyB[pos] = key;
+                idxB[pos] = idxA[e];
+            }
+        }
+        __syncthreads();
+        uint32_t* tk = keyA; keyA = keyB; keyB = tk;
+        uint16_t* ti = idxA; idxA = idxB; idxB = ti;
+    }
+    int32_t* order = order_out + (size_t)b * N;
+    float* ss = ss_out + (size_t)b * N;
+    for (int r = tid; r < N; r += kSortThreads) {
+        if (r < n) {
+            const int i = idxA[r];
+            order[r] = i; rank[i] = r; ss[r] = sc[i];
+        } else {
+            order[r] = -1; ss[r] = 0.f; rank[r] = INT_MAX;          // dead tail: input index r >= n
+        }
     }
 }
 
@@ -632,6 +773,7 @@ __global__ void __launch_bounds__(1024) spatial_kernel(SpatialArgs A) {
     __shared__ float s_red[4][32];
     __shared__ float s_gt[128][10];      // per group: xlo,xhi,ylo,yhi,zlo,zhi, wx,wy,wz (max extents), bad
     __shared__ int s_wsum[32];
+    __shared__ uint16_t s_perm[GNMS_MAX_BOXES];                      // spatial position -> input index
     const int b = blockIdx.x, N = A.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = A.n_per_image ? min(A.n_per_image[b], N) : N;
     const WsLayout L = ws_layout(N);
@@ -727,17 +869,47 @@ __global__ void __launch_bounds__(1024) spatial_kernel(SpatialArgs A) {
         for (int q = 0; q < 4; ++q) { s_hist[tid * 4 + q] = run; run += loc[q]; }
     }
     __syncthreads();
-    // scatter the records / ranks into spatial order
+    // spatial order: position -> input index in shared memory first, so that the blocked copy can be written with
+    // 16-byte stores (a thread fills 4 consecutive slots of every field array)
 #pragma unroll
     for (int q = 0; q < kPer; ++q) {
         const int i = tid + q * 1024;
-        if (i < N) {
-            const int pos = s_hist[bucket[q]] + off[q];
-            blk_store(blk + (size_t)(pos >> 6) * kBlkWords, pos & 63, bx + (size_t)i * recf, recf, i < n ? rank[i] : INT_MAX);
-        }
+        if (i < N) s_perm[s_hist[bucket[q]] + off[q]] = (uint16_t)i;
     }
-    for (int pos = N + tid; pos < ((N + 63) & ~63); pos += 1024)        // padding slots of the last block
-        blk_store(blk + (size_t)(pos >> 6) * kBlkWords, pos & 63, nullptr, recf, INT_MAX);
+    __syncthreads();
+    for (int p4 = tid * 4; p4 < ((N + 63) & ~63); p4 += 4096) {
+        float fld[8][4];
+        int rk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int pos = p4 + e;
+            if (pos < N) {
+                const int i = s_perm[pos];
+                if (is3d) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(bx + (size_t)i * 8));
+                    const float4 c = __ldg(reinterpret_cast<const float4*>(bx + (size_t)i * 8) + 1);
+                    fld[0][e] = a.x; fld[1][e] = a.y; fld[2][e] = a.z; fld[3][e] = a.w;
+                    fld[4][e] = c.x; fld[5][e] = c.y; fld[6][e] = c.z; fld[7][e] = c.w;
+                } else {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(bx) + i);
+                    fld[0][e] = a.x; fld[1][e] = a.y; fld[2][e] = a.z; fld[3][e] = a.w;
+                    fld[4][e] = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));      // area, for the range check
+                    fld[5][e] = 0.f; fld[6][e] = 0.f; fld[7][e] = 0.f;
+                }
+                rk[e] = i < n ? rank[i] : INT_MAX;
+            } else {                                                   // padding slots of the last block: a unit box
+#pragma unroll
+                for (int f = 0; f < 8; ++f) fld[f][e] = is3d ? (((f & 1) || f >= 6) ? 1.f : 0.f) : ((f >= 2 && f <= 4) ? 1.f : 0.f);
+                rk[e] = INT_MAX;
+            }
+        }
+        float* bg = blk + (size_t)(p4 >> 6) * kBlkWords + (p4 & 63);
+        const int nf = is3d ? 8 : 5;
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+            if (f < nf) *reinterpret_cast<float4*>(bg + f * 64) = make_float4(fld[f][0], fld[f][1], fld[f][2], fld[f][3]);
+        *reinterpret_cast<int4*>(bg + 8 * 64) = make_int4(rk[0], rk[1], rk[2], rk[3]);
+    }
     __threadfence_block();
     __syncthreads();
     // AABB + max extents of every run of 64 boxes (padded boxes, rank INT_MAX, do not count)
@@ -1490,6 +1662,7 @@ static int configure_once() {
     GNMS_CUDA_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)chain_smem_bytes(GNMS_MAX_BOXES)));
     GNMS_CUDA_TRY(cudaFuncSetAttribute(backward_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * GNMS_MAX_BOXES + 64));
+    GNMS_CUDA_TRY(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(GNMS_MAX_BOXES)));
     done = true;
     return 0;
 }
@@ -1537,6 +1710,8 @@ using namespace gnms;
 extern "C" int gnms_version(void) { return GNMS_VERSION; }
 
 // debug only (not part of the public header): which stages of the forward run (bench.py times kernels in isolation)
+static int g_rank_by_sort = -1;            // -1 heuristic, 0 always count, 1 always sort
+extern "C" int gnms_debug_rank_by_sort(int v) { int old = g_rank_by_sort; g_rank_by_sort = v; return old; }
 static int g_stage_mask = 0xff;            // bit 0 rank, 1 spatial order, 2 tile (or matrix -> mask), 3 has_earlier, 4 chain / solves
 extern "C" int gnms_debug_stage_mask(int m) { int old = g_stage_mask; if (m >= 0) g_stage_mask = m; return old; }
 
@@ -1588,10 +1763,20 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     const int mode = p->mode;
     const bool need_groups = mode != GNMS_MODE_NOGROUP;
     const bool tiles = need_groups && src != kSrcMatrix;              // fused overlap + mask tile kernel
-    if (g_stage_mask & 1)
-    rank_kernel<<<dim3(gnms_div_up(N, kRankElems), batch), 256, rank_smem_bytes(N), s>>>(
-        scores, 1, N, N, npi, sv.order, sv.sorted_scores, ws, L.total, src == kSrcMatrix ? nullptr : boxes, src,
-        (int64_t)N * box_stride, 0.f, 0, (tiles || (src != kSrcMatrix && overlap_out)) ? 1 : 0, tile_list_ptr(workspace, N, batch));
+    // rank by counting costs batch * N^2 compares over the whole chip, the per-image radix sort a constant ~10 us
+    const bool by_sort = g_rank_by_sort == 1 || (g_rank_by_sort < 0 && (double)batch * N * N >= 10.0 * 4096 * 4096);
+    if (g_stage_mask & 1) {
+        if (by_sort) {
+            const int zm = (tiles || (src != kSrcMatrix && overlap_out)) ? 1 : 0;
+            sort_kernel<<<batch + (zm ? 4 * batch : 1), kSortThreads, sort_smem_bytes(N), s>>>(scores, N, N, batch, npi, sv.order,
+                                                                                              sv.sorted_scores, ws, L.total, zm);
+            GNMS_LAUNCH_CHECK();
+        }
+        rank_kernel<<<dim3(gnms_div_up(N, kRankElems), batch), 256, by_sort ? 0 : rank_smem_bytes(N), s>>>(
+            scores, 1, N, N, npi, sv.order, sv.sorted_scores, ws, L.total, src == kSrcMatrix ? nullptr : boxes, src,
+            (int64_t)N * box_stride, 0.f, by_sort ? 2 : 0, (tiles || (src != kSrcMatrix && overlap_out)) ? 1 : 0,
+            tile_list_ptr(workspace, N, batch));
+    }
     GNMS_LAUNCH_CHECK();
     if (src == kSrcMatrix && (!iou || ld < N)) return GNMS_E_BADARG;
     if (src != kSrcMatrix && !boxes) return GNMS_E_BADARG;

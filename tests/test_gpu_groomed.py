@@ -240,6 +240,51 @@ def test_batched_ragged_equals_per_image():
         assert (gs[b, n:] == 0).all() and (st.prob[b, n:] == 0).all()
 
 
+@pytest.mark.parametrize("N,ns", [(640, [640, 1, 333, 0, 500]), (4096, [4096, 4000]), (1100, [1100, 1024, 1025]), (8192, [8192])])
+@pytest.mark.parametrize("src", ["matrix", "boxes2d"])
+def test_rank_by_radix_sort_equals_rank_by_counting(N, ns, src):
+    """The per-image radix sort (chosen for large batches) and the counting kernel give the same stable order, also with
+    tied scores, ragged batches and the padded tail: every output of the forward is identical."""
+    from groomed_nms_b200 import _lib, ops, synthetic
+    if src == "matrix" and N > 2048:
+        pytest.skip("matrix inputs of that size are covered by the box path")
+    lib = _lib.load()
+    B = len(ns)
+    rng = np.random.default_rng(N)
+    sc = np.zeros((B, N), np.float32)
+    boxes = np.zeros((B, N, 4), np.float32)
+    for b in range(B):
+        bx, s, _ = synthetic.clustered_boxes_2d(N, 7, seed=N + b, jitter=0.08)
+        s[rng.integers(0, N, N // 3)] = s[rng.integers(0, N, N // 3)]          # many exact ties
+        s[rng.integers(0, N, 5)] = -0.0
+        sc[b], boxes[b] = s, bx
+    npi = torch.tensor(ns, dtype=torch.int32, device="cuda")
+    p = ops.make_params(group_size=40)
+    outs = []
+    try:
+        for by_sort in (0, 1):
+            lib.gnms_debug_rank_by_sort(by_sort)
+            if src == "matrix":
+                iou = torch.stack([ops.overlap2d(cuda(boxes[b]), cuda(boxes[b])) for b in range(B)])
+                st = ops.forward_matrix(cuda(sc), iou, p, n_per_image=npi)
+            else:
+                st = ops.forward_boxes(cuda(sc), cuda(boxes), _lib.BOX_2D, p, n_per_image=npi)
+            torch.cuda.synchronize()
+            outs.append(st)
+    finally:
+        lib.gnms_debug_rank_by_sort(-1)
+    a, c = outs
+    assert torch.equal(a.order, c.order) and torch.equal(a.counts, c.counts) and torch.equal(a.lead, c.lead)
+    assert torch.equal(a.prob, c.prob) and torch.equal(a.sorted_scores, c.sorted_scores)
+    for b, n in enumerate(ns):
+        nv = int(a.counts[b, 0])
+        assert torch.equal(a.valid_idx[b, :nv], c.valid_idx[b, :nv])
+        # stable: ties keep the lower input index first
+        o = a.order[b, :n].cpu().numpy()
+        want = np.argsort(-sc[b, :n], kind="stable")
+        assert np.array_equal(o, want)
+
+
 def test_config_c1_one_group(G):
     from groomed_nms_b200 import synthetic
     from groomed_nms_b200.lib import core
