@@ -10,6 +10,12 @@ code (INTEGRATION.md shows the patch):
     fg_idx, scores_after, best = branch.image(scores_to_nms_img, fg_inds_tensor, boxes7_raw, coords_2d_512_img,
                                               p2, scale_factor, gts_2d, gts_3d)        # replaces :731-825
     loss = branch.after_nms_loss(scores_after_nms, targets_after_nms, bbox_weights)    # replaces :1091-1137
+
+or, for the whole batch in one launch sequence and without the reference's three host syncs per image
+(SURVEY.md section 8(f) rank 1):
+
+    scores_after_nms, targets_after_nms = branch.batch(scores_to_nms, fg_mask, boxes7_raw, coords_2d_512, p2s,
+                                                       scale_factors, gts_2d_list, gts_3d_list)   # replaces the loop body
 """
 import numpy as np
 import torch
@@ -101,6 +107,74 @@ class GroomedNMSLossBranch(object):
         best, max_idx = torch.max(score_gt, dim=0)                                              # :818
         max_idx = max_idx[best > self.best_target_box_beta].flatten()                           # :820-822
         return fg_index_for_nms, prob, fg_index_for_nms[max_idx]
+
+    # ---------------------------------------------------------------------------------------------- :721-828, whole batch
+    def batch(self, scores_to_nms, fg_mask, boxes7_raw, coords_2d_512, p2s, scale_factors, gts_2d_list, gts_3d_list):
+        """All images of the batch at once (ragged: every image has its own number of foreground anchors and of GTs).
+
+        scores_to_nms [B,A] (requires grad)   fg_mask [B,A] bool   boxes7_raw [B,A,7]   coords_2d_512 [B,A,4]
+        p2s [B,4,4] and scale_factors [B] (only read when diff_nms_boxes_2d == "projected")
+        gts_2d_list / gts_3d_list: per image [G_b,4] / [G_b,16] tensors or arrays (G_b may be 0)
+        Returns (scores_after_nms [B,A] -- zero outside the boxes that went through NMS, differentiable wrt the scores --
+                 targets_after_nms [B,A] float, 1 at the best box of every ground truth that clears best_target_box_beta).
+        Same arithmetic as image() per image; the top-500 selection, corners, records, NMS forward and backward are single
+        launches over the batch (n_per_image carries the ragged counts on the device: no .cpu() / .item() anywhere)."""
+        dev = scores_to_nms.device
+        B, A = scores_to_nms.shape
+        K = min(self.max_boxes, A)
+        fg_mask = fg_mask.to(dev).bool()
+        # :731-737  foreground anchors by descending score, at most 500 (stable: ties keep the lower anchor index)
+        masked = torch.where(fg_mask, scores_to_nms.detach().float(), torch.full_like(scores_to_nms, -float("inf"), dtype=torch.float32))
+        _, sorted_index = torch.sort(masked, dim=1, descending=True, stable=True)
+        top = sorted_index[:, :K].contiguous()                                                   # [B,K] anchor ids
+        n_img = torch.clamp(fg_mask.sum(dim=1), max=K).to(torch.int32)                           # live boxes per image
+        live = torch.arange(K, device=dev)[None, :] < n_img[:, None]
+        b7 = torch.gather(boxes7_raw.detach().float(), 1, top[:, :, None].expand(B, K, 7)).contiguous()
+        box2d = torch.gather(coords_2d_512.detach().float(), 1, top[:, :, None].expand(B, K, 4)).contiguous()
+        corners = ops.corners_from_boxes7(b7.view(B * K, 7))                                     # :746-752
+        if self.diff_nms_boxes_2d == "projected":                                               # :754-768,774
+            nms_box2d = torch.empty_like(box2d)
+            for b in range(B):
+                pts = corners[b * K:(b + 1) * K].transpose(1, 2).reshape((-1, 3)).transpose(0, 1).contiguous()
+                pr = ops.project_points(p2s[b].to(dev), pts, True).transpose(0, 1).reshape((-1, 8, 4)).transpose(1, 2)
+                nms_box2d[b] = torch.stack([pr[:, 0].min(dim=1)[0], pr[:, 1].min(dim=1)[0], pr[:, 0].max(dim=1)[0],
+                                            pr[:, 1].max(dim=1)[0]], dim=1) * float(scale_factors[b])
+        else:
+            nms_box2d = box2d                                                                   # :772
+        scores_in = torch.gather(scores_to_nms, 1, top)                                         # keeps the graph
+        params = self.params()
+        if self.overlap_in_nms == "2d":                                                         # :776-777
+            prob = ops.GroomedNMSBatchFunction.apply(scores_in, nms_box2d, _lib.BOX_2D, params, False, False, n_img)[0]
+            rec = ops.box3d_records(corners, mutate_input=False)
+        else:
+            rec = ops.box3d_records(corners, mutate_input=True)                                 # :780 Y <- Z quirk
+            if self.overlap_in_nms == "3d":                                                     # :782-783
+                prob = ops.GroomedNMSBatchFunction.apply(scores_in, rec.view(B, K, 8), _lib.BOX_3D_REC, params, True, True, n_img)[0]
+            else:                                                                               # "product" :784-786
+                ov = torch.empty((B, K, K), dtype=torch.float32, device=dev)
+                for b in range(B):
+                    iou2d = ops.overlap2d(nms_box2d[b], nms_box2d[b])
+                    ov[b] = ops.overlap3d(rec[b * K:(b + 1) * K], rec[b * K:(b + 1) * K], False, True, generalized=True, affine=True, mul2d=iou2d)[1]
+                prob = ops.GroomedNMSBatchFunction.apply(scores_in, ov, None, params, False, False, n_img)[0]
+            rec = ops.box3d_records(corners, mutate_input=False)                                # GT matching sees the mutated corners (:813)
+        scores_after_nms = torch.zeros((B, A), dtype=prob.dtype, device=dev).scatter(1, top, prob * live)      # :793
+        # ---- best box per ground truth (:801-825): per image, enqueued back to back (G_b is known on the host)
+        targets_after_nms = torch.zeros((B, A), dtype=torch.float32, device=dev)
+        neg = torch.full((1,), -float("inf"), device=dev)
+        for b in range(B):
+            g3 = torch.as_tensor(gts_3d_list[b], device=dev).float().reshape(-1, 16)
+            if g3.shape[0] == 0:
+                continue
+            g2 = torch.as_tensor(gts_2d_list[b], device=dev).float().reshape(g3.shape[0], -1)
+            gt7 = torch.stack([g3[:, 7], g3[:, 8], g3[:, 9], g3[:, 3], g3[:, 4], g3[:, 5], g3[:, 10]], dim=1).contiguous()
+            rec_b2 = ops.box3d_records(ops.corners_from_boxes7(gt7), mutate_input=False)
+            iou2d_gt = ops.overlap2d(box2d[b], g2[:, :4].contiguous())                          # :814
+            _, score_gt = ops.overlap3d(rec[b * K:(b + 1) * K], rec_b2, False, True, generalized=True, affine=True, mul2d=iou2d_gt)  # :813,817
+            score_gt = torch.where(live[b][:, None], score_gt, neg)                             # dead slots never win
+            best, max_idx = torch.max(score_gt, dim=0)                                          # :818
+            hit = (best > self.best_target_box_beta).float()                                    # :820-822
+            targets_after_nms[b].scatter_reduce_(0, top[b][max_idx], hit, reduce="amax")
+        return scores_after_nms, targets_after_nms
 
     # ---------------------------------------------------------------------------------------------- :1091-1137
     def after_nms_loss(self, scores_after_nms, targets_after_nms, bbox_weights):

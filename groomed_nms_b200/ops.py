@@ -318,6 +318,27 @@ class GroomedNMSBoxesFunction(torch.autograd.Function):
         return gs[0], None, None, None, None, None
 
 
+class GroomedNMSBatchFunction(torch.autograd.Function):
+    """Batched, ragged form of the two functions above: scores [B,N] (slots past n_per_image[b] are dead and come back
+    as 0 with zero gradient), data = boxes [B,N,4] / records [B,N,8] (box_kind BOX_2D / BOX_3D_REC) or an overlap
+    matrix [B,N,N] (box_kind None).  One forward call and one backward call for the whole batch, no host sync."""
+
+    @staticmethod
+    def forward(ctx, scores, data, box_kind, params, generalized, affine, n_per_image):
+        if box_kind is None:
+            st = forward_matrix(scores.detach(), data.detach(), params, n_per_image=n_per_image)
+        else:
+            st = forward_boxes(scores.detach(), data.detach(), box_kind, params, generalized, affine, n_per_image=n_per_image)
+        ctx.st = st
+        ctx.mark_non_differentiable(st.valid_idx, st.invalid_idx, st.counts)
+        return st.prob, st.valid_idx, st.invalid_idx, st.counts
+
+    @staticmethod
+    def backward(ctx, g_prob, g_valid, g_invalid, g_counts):
+        gs, _ = backward(ctx.st, g_prob.contiguous(), need_grad_iou=False)
+        return gs, None, None, None, None, None, None
+
+
 def prune(x, nms_threshold, temperature, pruning_method):
     """Elementwise pruning function (lib/groomed_nms.py:167-189)."""
     _require_cuda(x, "iou")
