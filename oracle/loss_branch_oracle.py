@@ -60,3 +60,34 @@ def after_nms_rank_loss(scores_after, targets_after, weights, lam=1.0):
     if cnt:
         tot, grad = tot / cnt, grad / cnt
     return F32(lam) * tot, (F32(lam) * grad).astype(F32)
+
+
+def inference_site(coords_2d, scores, coords_3d, coords_3d_raw, cls_pred, tracker, use_diff, overlap_in_nms="2d", nms_thres=0.4,
+                   topn_pre=3000, temperature=1.0, valid_thr=0.3, group_size=100, max_boxes=500, corners=None):
+    """lib/rpn_util.py:1258-1341 composed from the pinned pieces -> (aboxes rows as the reference stacks them, keep_inds).
+    corners: optionally the CUDA path's corners of the first 500 sorted boxes (parity is defined from the corners onward)."""
+    order = O.stable_sort_desc(scores.astype(F32))[:min(topn_pre, len(scores))]          # :1260-1290
+    if use_diff:                                                                         # :1293-1320
+        sel = order[:max_boxes]
+        box2d = coords_2d[sel].astype(F32)
+        iou2d = O.iou(box2d, box2d)
+        if overlap_in_nms == "2d":
+            ov = iou2d
+        else:
+            if corners is None:
+                r = coords_3d_raw[sel].astype(F32)
+                corners = O.get_corners_of_cuboid(*[r[:, i] for i in range(7)])
+            _, g3 = O.iou3d_approximate(corners.astype(F32).copy(), corners.astype(F32).copy(), "combinations", "generalized")
+            ov3 = (F32(0.5) * (F32(1) + g3)).astype(F32)
+            ov = ov3 if overlap_in_nms == "3d" else (iou2d * ov3).astype(F32)
+        fwd = O.differentiable_nms(scores[sel].astype(F32), ov, nms_threshold=nms_thres, temperature=temperature,
+                                   valid_box_prob_threshold=valid_thr, group_size=group_size, dense=False)
+        keep = fwd["valid"]
+        base = sel
+    else:                                                                                # :1334
+        dets = np.concatenate([coords_2d[order], scores[order, None]], 1).astype(F32)
+        keep = np.asarray(O.hard_nms(dets, nms_thres, shift=1.0), dtype=np.int64)
+        base = order
+    rows = base[keep]
+    out = np.concatenate([coords_2d[rows], scores[rows, None], cls_pred[rows, None], coords_3d[rows], tracker[rows, None]], 1)
+    return out.astype(F32), keep
