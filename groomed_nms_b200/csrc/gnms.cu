@@ -611,14 +611,17 @@ template <> struct SoaOf<kSrcBox2d> {
     }
 };
 
-template <int kSrc, bool kGen, bool kAffine, bool kHasOut, bool kList, int kRB>
+template <int kSrc, bool kGen, bool kAffine, bool kHasOut, bool kList, int kRB, bool kQueue>
 __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
     constexpr int kThreads = 256 / kRB;                               // kRB row blocks of 64 / kRB rows per thread
     static_assert(!(kHasOut && kList), "the culled pass does not produce the matrix");
     typedef typename RecOf<kSrc>::type RecT;
     constexpr int kChunks = kBlkBytes / 16;                           // 16-byte chunks of one staged block (144)
-    __shared__ __align__(16) float s_blk[2][2][kBlkWords];          // [buffer][row/col][8 field arrays + rank array][64]
-    __shared__ int s_ij[2][4];
+    constexpr int kBufs = kQueue ? 3 : 2;                             // queued hits read the previous tile's rank arrays
+    __shared__ __align__(16) float s_blk[kBufs][2][kBlkWords];      // [buffer][row/col][8 field arrays + rank array][64]
+    __shared__ int s_ij[kBufs][4];
+    __shared__ uint32_t s_q[kQueue ? 3 : 1][kQueue ? 256 : 1];      // hit queue of a tile: (row quad, column quad, 16 hit bits)
+    __shared__ int s_nq[3];
     const int N = A.N, tid = threadIdx.x;
     const int NWt = (N + 31) / 32;
     const int lane = tid & 31, warp = tid >> 5;
@@ -663,16 +666,51 @@ __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
         }
         return bad;
     };
+    // hits -> suppression bits (sorted space).  Off-diagonal tiles see every unordered pair once; the diagonal tile sees
+    // (i,j) and (j,i): only the orientation "row is the later box" emits.  Dead slots (box index >= live count, padding)
+    // carry rank INT_MAX; ri == rj only for a box with itself.
+    auto emit = [&](uint32_t hits, const int* rrank4, const int* crank4, bool mirror, uint32_t* mask) {
+        while (hits) {
+            const int bit = __ffs(hits) - 1;
+            hits &= hits - 1u;
+            const int ri = rrank4[bit >> 2], rj = crank4[bit & 3];
+            const int later = max(ri, rj), earlier = min(ri, rj);
+            if (later != INT_MAX && ri != rj && (mirror || ri > rj))
+                atomicOr(mask + ((unsigned)earlier * (unsigned)NWt + (unsigned)(later >> 5)), 1u << (later & 31));
+        }
+    };
+    // queued hits of the tile staged in buffer qb (its rank arrays are still there: three staging buffers): one entry per
+    // thread, so the work is spread evenly over the CTA instead of following the lanes that happened to find the hits
+    auto drain = [&](int qb) {
+        const int nq = s_nq[qb];
+        if (nq == 0) return;
+        const int b = s_ij[qb][0];
+        const bool mirror = s_ij[qb][1] != s_ij[qb][2];
+        uint32_t* mask = reinterpret_cast<uint32_t*>(A.ws + (size_t)b * A.ws_img_stride + L.mask);
+        const int* rrank = reinterpret_cast<const int*>(s_blk[qb][0]) + 8 * kTT;
+        const int* crank = reinterpret_cast<const int*>(s_blk[qb][1]) + 8 * kTT;
+        for (int e = tid; e < nq; e += kThreads) {
+            const uint32_t ent = s_q[qb][e];
+            emit(ent & 0xffffu, rrank + ((ent >> 20) & 15u) * 4, crank + ((ent >> 16) & 15u) * 4, mirror, mask);
+        }
+    };
 
     int t = blockIdx.x, buf = 0;
+    if (kQueue && tid < 3) s_nq[tid] = 0;
     if (t < total) prefetch(t, 0);
-    for (; t < total; t += gridDim.x, buf ^= 1) {
+    for (; t < total; t += gridDim.x) {
         cp_async_wait_all();
         const bool bad = own_bad(buf);
-        // publishes the staged blocks; every thread is also done with the other buffer (previous tile) here
+        // publishes the staged blocks (and the previous tile's hit queue); every thread is done with the previous tile
         const bool tile_unsafe = __syncthreads_or(bad);
+        const int nbuf = buf + 1 == kBufs ? 0 : buf + 1;              // next tile's buffer
+        if (kQueue) {
+            const int pbuf = buf == 0 ? 2 : buf - 1;                  // previous tile's buffer == next-next tile's buffer
+            drain(pbuf);
+            if (tid == 0) s_nq[nbuf] = 0;                             // last read one barrier ago; pushed to after the next one
+        }
         const int b = s_ij[buf][0], I = s_ij[buf][1], J = s_ij[buf][2];
-        if (t + (int)gridDim.x < total) prefetch(t + gridDim.x, buf ^ 1);
+        if (t + (int)gridDim.x < total) prefetch(t + gridDim.x, nbuf);
 
         const float* rsoa = s_blk[buf][0];
         const float* csoa = s_blk[buf][1];
@@ -731,18 +769,26 @@ __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
                         }
                 }
             }
-            // ---- consumer 1: hits -> suppression bits (sorted space).  Off-diagonal tiles see every unordered pair
-            //      once; the diagonal tile sees (i,j) and (j,i): only the orientation "row is the later box" emits.
-            while (hits) {
-                const int bit = __ffs(hits) - 1;
-                hits &= hits - 1u;
-                const int ri = rrank[rl + (bit >> 2)], rj = crank[4 * tx + (bit & 3)];
-                const int later = max(ri, rj), earlier = min(ri, rj);
-                // dead slots (box index >= live count, padding) carry rank INT_MAX; ri == rj only for a box with itself
-                if (later != INT_MAX && ri != rj && (I != J || ri > rj))
-                    atomicOr(mask + ((unsigned)earlier * (unsigned)NWt + (unsigned)(later >> 5)), 1u << (later & 31));
+            // ---- consumer 1: threshold hits (~3 % of the pairs)
+            if (kQueue) {
+                // warp-aggregated append: one shared-memory atomic per warp and sub-tile
+                const unsigned who = __ballot_sync(0xffffffffu, hits != 0u);
+                if (who) {
+                    const int leader = __ffs(who) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(&s_nq[buf], __popc(who));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (hits) s_q[buf][base + __popc(who & ((1u << lane) - 1u))] = ((uint32_t)(rl >> 2) << 20) | ((uint32_t)tx << 16) | hits;
+                }
+            } else {
+                emit(hits, rrank + rl, crank + 4 * tx, I != J, mask);
             }
         }
+        buf = nbuf;
+    }
+    if (kQueue) {
+        __syncthreads();
+        drain(buf == 0 ? 2 : buf - 1);                               // the last tile's queue
     }
 }
 
@@ -1712,6 +1758,8 @@ extern "C" int gnms_version(void) { return GNMS_VERSION; }
 // debug only (not part of the public header): which stages of the forward run (bench.py times kernels in isolation)
 static int g_rank_by_sort = -1;            // -1 heuristic, 0 always count, 1 always sort
 extern "C" int gnms_debug_rank_by_sort(int v) { int old = g_rank_by_sort; g_rank_by_sort = v; return old; }
+static int g_tile_queue = 1;
+extern "C" int gnms_debug_tile_queue(int v) { int old = g_tile_queue; g_tile_queue = v; return old; }
 static int g_stage_mask = 0xff;            // bit 0 rank, 1 spatial order, 2 tile (or matrix -> mask), 3 has_earlier, 4 chain / solves
 extern "C" int gnms_debug_stage_mask(int m) { int old = g_stage_mask; if (m >= 0) g_stage_mask = m; return old; }
 
@@ -1820,9 +1868,10 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
         }
 #define GNMS_TILE(SRC, G, AF)                                                              \
     do {                                                                                   \
-        if (ho) tile_kernel<SRC, G, AF, true, false, 2><<<grid_out, 128, 0, s>>>(T);       \
-        else if (culled) tile_kernel<SRC, G, AF, false, true, 1><<<grid_bits, 256, 0, s>>>(T); \
-        else tile_kernel<SRC, G, AF, false, false, 1><<<grid_bits, 256, 0, s>>>(T);        \
+        if (ho && g_tile_queue) tile_kernel<SRC, G, AF, true, false, 2, true><<<grid_out, 128, 0, s>>>(T);   \
+        else if (ho) tile_kernel<SRC, G, AF, true, false, 2, false><<<grid_out, 128, 0, s>>>(T);             \
+        else if (culled) tile_kernel<SRC, G, AF, false, true, 1, false><<<grid_bits, 256, 0, s>>>(T);        \
+        else tile_kernel<SRC, G, AF, false, false, 1, false><<<grid_bits, 256, 0, s>>>(T);                   \
     } while (0)
         if (!(g_stage_mask & 4)) {
         } else if (src == kSrcBox3d) {

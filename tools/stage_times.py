@@ -37,8 +37,10 @@ def main():
     ap.add_argument("--images", type=int, default=16)
     ap.add_argument("--n", type=int, default=4096)
     ap.add_argument("--rank-by-sort", type=int, default=-1, help="-1 library heuristic, 0 counting kernel, 1 per-image radix sort")
+    ap.add_argument("--tile-queue", type=int, default=1, help="1: hits go through a shared-memory queue drained by the whole CTA; 0: inline loop")
     args = ap.parse_args()
     lib = _lib.load()
+    lib.gnms_debug_tile_queue(args.tile_queue)
     lib.gnms_debug_rank_by_sort(args.rank_by_sort)
     dev = torch.device("cuda", 0)
     B, N = args.images, args.n
