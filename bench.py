@@ -277,7 +277,7 @@ def run_ours(args, rank, world):
         return dt
 
     e2e_blocking_s = time_host(lambda: runner.run_host(hb, hs, hg), lambda: None)
-    pipe = HostPipeline(B, N, dev, params, depth=2)
+    pipe = HostPipeline(B, N, dev, params, depth=args.e2e_depth)
     e2e_s = time_host(lambda: pipe.submit(hb, hs, hg), pipe.drain)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -331,7 +331,7 @@ def run_ours(args, rank, world):
                              if args.path == "materialised" else "matrix-free path: no N^2 HBM traffic; inputs are O(N)",
                        "parallelism": "per-image shard, %d rank(s), no data-path collective" % world},
             "e2e": {"value": boxes_per_step * e2e_steps / e2e_s, "unit": "boxes/s", "h2d_bytes_per_step": runner.h2d_bytes,
-                    "d2h_bytes_per_step": runner.d2h_bytes, "api": "groomed_nms_b200.hostapi.HostPipeline.submit/drain (pinned host buffers, 2 slots: copies of one call overlap the kernels of the next; fused matrix-free pipeline: returns probabilities, score gradients and keep lists)",
+                    "d2h_bytes_per_step": runner.d2h_bytes, "api": "groomed_nms_b200.hostapi.HostPipeline.submit/drain (pinned host buffers, %d slots: copies of one call overlap the kernels of the next; fused matrix-free pipeline: returns probabilities, score gradients and keep lists)" % args.e2e_depth,
                     "blocking_call_value": boxes_per_step * e2e_steps / e2e_blocking_s,
                     "blocking_call_api": "groomed_nms_b200.hostapi.HostRunner.run_host (one synchronous call per step)"},
             "gpu_launches": head.launches_per_step * args.steps,
@@ -367,7 +367,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--images", type=int, default=16, help="images (of N=4096 boxes) per GPU per step")
+    ap.add_argument("--images", type=int, default=64, help="images (of N=4096 boxes) per GPU per step")
+    ap.add_argument("--e2e-depth", type=int, default=2, help="slots of the host pipeline (copies of one call overlap the kernels of the others)")
     ap.add_argument("--path", default="materialised", choices=["materialised", "fused"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--splits", type=int, default=1, help="issue the batch as this many sub-batches on parallel graph branches")

@@ -505,11 +505,14 @@ mask_boxes_kernel(int N, const int32_t* __restrict__ n_per_image, char* __restri
 //     16-byte register vectors, so the transposed tile needs no shared-memory round trip and no second barrier
 //     (warp = 8 column quads x 4 row quads: a direct store covers 4 rows x 128 B, a mirrored store 8 rows x 64 B);
 //   * the 16 pair evaluations of a sub-tile are one straight-line block (the rare exact-division fallback and the
-//     hits are handled after it), so independent division chains interleave; hits become mask bits in a short
-//     divergent loop run by the lanes that found them;
+//     hits are handled after it), so independent division chains interleave;
+//   * hits: matrix-producing launches append (row quad, column quad, 16 hit bits) to a shared-memory queue (one
+//     warp-aggregated atomic per warp and sub-tile) that the whole CTA drains one tile later, one entry per thread --
+//     the work no longer follows the lanes that happened to find the hits, which took 8 % off the kernel and halved
+//     the time at the per-tile barrier; the hit-dense culled pass keeps the inline loop (the queue is slower there);
 //   * matrix-producing launches use 128-thread CTAs (a thread owns two sub-tiles, 4 CTAs per SM): the per-tile barrier
-//     joins 4 warps instead of 8, which was worth 10 % over the 256-thread shape; 64-thread CTAs, several tiles per
-//     barrier, a warp-autonomous mbarrier/bulk-copy variant and a shared-memory ring drained by bulk stores
+//     joins 4 warps instead of 8, which was worth 10 % over the 256-thread shape; 64-thread CTAs, 5 or 6 CTAs per SM at 96 / 80
+//     registers, several tiles per barrier, a warp-autonomous mbarrier/bulk-copy variant and a shared-memory ring drained by bulk stores
 //     (cp.async.bulk shared -> global) were all slower and are not kept.
 // One barrier per tile.  fp32-issue bound: ~67 issue slots per pair, 16 of them FMNMX at half rate.
 struct TileArgs {
