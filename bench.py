@@ -368,7 +368,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=64, help="images (of N=4096 boxes) per GPU per step")
-    ap.add_argument("--e2e-depth", type=int, default=2, help="slots of the host pipeline (copies of one call overlap the kernels of the others)")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="slots of the host pipeline (copies of one call overlap the kernels of the others)")
     ap.add_argument("--path", default="materialised", choices=["materialised", "fused"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--splits", type=int, default=1, help="issue the batch as this many sub-batches on parallel graph branches")

@@ -48,7 +48,7 @@ __device__ __forceinline__ void blk_store(float* blk, int e, const float* src, i
 }
 
 struct WsLayout {
-    size_t rank, sbox, mask, has_earlier, gbeg, members, ngroups, blk, total;   // byte offsets inside one image's slice
+    size_t rank, sbox, mask, has_earlier, gbeg, members, ngroups, blk, gtab, dleader, dfsup, dflag, total;   // byte offsets inside one image's slice
     int he_slots;                                   // partial has-earlier words per row word (one per column-chunk CTA)
 };
 __host__ __device__ inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -70,11 +70,26 @@ __host__ __device__ inline WsLayout ws_layout(int N) {
     // blocked structure-of-arrays copy of the boxes for the tile kernel: per run of 64 boxes, 8 field arrays + the rank
     // array of 64 words each (2304 contiguous bytes = one bulk copy); input order, or spatial order in the culled pass
     L.blk = off;         off += align_up((size_t)((N + 63) / 64) * kBlkWords * 4);
+    // per 64-box group of the spatial order: AABB, max extents, bad flag (10 floats), written by the spatial kernel
+    L.gtab = off;        off += align_up((size_t)((N + 63) / 64) * 10 * 4);
+    // direct leader election (elect_kernel): leader bitset, first suppressor per sorted position, 1 = "gave up" flag
+    L.dleader = off;     off += align_up(nw * 4);
+    L.dfsup = off;       off += align_up((size_t)N * 4);
+    L.dflag = off;       off += 256;
     L.total = off;
     return L;
 }
 
 enum BoxSrc { kSrcMatrix = 0, kSrcBox2d = 1, kSrcBox3d = 2, kSrcBoxShift = 3 };
+
+// bits of word w that belong to boxes below n
+__device__ __forceinline__ uint32_t valid_word(int w, int n) {
+    int lo = w * 32;
+    if (n >= lo + 32) return 0xffffffffu;
+    if (n <= lo) return 0u;
+    return (1u << (n - lo)) - 1u;
+}
+
 
 // ------------------------------------------------------------------------------------------ 1b. rank by counting
 // Multi-CTA replacement of the one-CTA bitonic sort: rank[i] = #{j : score_j > score_i or (== and j < i)}.
@@ -807,6 +822,24 @@ __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
 // structure-of-arrays copy of the records and ranks in that spatial order, reduces each run of 64 boxes to an AABB + max extents, and lists the
 // tile pairs whose groups are NOT provably out of reach.  Groups holding a degenerate / non-finite box are never
 // culled (0/0 = NaN counts as a hit, lib/groomed_nms.py:249-250).  On clustered boxes ~90 % of the tiles disappear.
+// gt: [nt][10] group table (lo/hi per axis, max extents, bad flag); appends the tile pairs that are not provably out of reach
+__device__ __forceinline__ void list_tiles(const float* gt, int nt, int naxes, float c, int b, int32_t* tile_list, int tid, int nthreads) {
+    const int tpi = nt * (nt + 1) / 2;
+    for (int t = tid; t < tpi; t += nthreads) {
+        int I, J;
+        tile_decode(t, nt, I, J);
+        bool cull = false;
+        if (I != J && gt[I * 10 + 9] == 0.f && gt[J * 10 + 9] == 0.f) {
+            for (int ax = 0; ax < naxes; ++ax) {
+                const float gap = fmaxf(gt[J * 10 + 2 * ax] - gt[I * 10 + 2 * ax + 1], gt[I * 10 + 2 * ax] - gt[J * 10 + 2 * ax + 1]);
+                // empty groups have lo = +inf, hi = -inf: gap = +inf -> culled
+                if (gap > 0.f && gap > c * (gt[I * 10 + 6 + ax] + gt[J * 10 + 6 + ax])) cull = true;
+            }
+        }
+        if (!cull) tile_list[64 + atomicAdd(&tile_list[0], 1)] = (b << 16) | (I << 8) | J;
+    }
+}
+
 struct SpatialArgs {
     int N, batch, nt, src;
     const int32_t* n_per_image;
@@ -815,6 +848,7 @@ struct SpatialArgs {
     size_t ws_img_stride;
     int32_t* tile_list;          // [0] = count (zeroed by the rank kernel), [64..] = entries
     float cull_c;                // gap factor c (0: any positive gap)
+    int defer_list;              // direct-election flow: store the group table, list_failed_kernel lists tiles later
 };
 
 __global__ void __launch_bounds__(1024) spatial_kernel(SpatialArgs A) {
@@ -1008,37 +1042,29 @@ __global__ void __launch_bounds__(1024) spatial_kernel(SpatialArgs A) {
         }
     }
     __syncthreads();
-    // tile pairs that survive
-    const int tpi = nt * (nt + 1) / 2;
-    const int naxes = is3d ? 3 : 2;
-    const float c = A.cull_c;
-    for (int t = tid; t < tpi; t += 1024) {
-        int I, J;
-        tile_decode(t, nt, I, J);
-        bool cull = false;
-        if (I != J && s_gt[I][9] == 0.f && s_gt[J][9] == 0.f) {
-            for (int ax = 0; ax < naxes; ++ax) {
-                const float gap = fmaxf(s_gt[J][2 * ax] - s_gt[I][2 * ax + 1], s_gt[I][2 * ax] - s_gt[J][2 * ax + 1]);
-                // empty groups have lo = +inf, hi = -inf: gap = +inf -> culled
-                if (gap > 0.f && gap > c * (s_gt[I][6 + ax] + s_gt[J][6 + ax])) cull = true;
-            }
-        }
-        if (!cull) A.tile_list[64 + atomicAdd(&A.tile_list[0], 1)] = (b << 16) | (I << 8) | J;
+    if (A.defer_list) {                                               // direct-election flow: keep the table, list later if needed
+        float* gtab = reinterpret_cast<float*>(w + L.gtab);
+        for (int i = tid; i < nt * 10; i += 1024) gtab[i] = s_gt[i / 10][i % 10];
+        return;
     }
+    list_tiles(&s_gt[0][0], nt, is3d ? 3 : 2, A.cull_c, b, A.tile_list, tid, 1024);
+}
+
+// tile pairs of the images elect_kernel gave up on (grid batch x 256)
+__global__ void __launch_bounds__(256) list_failed_kernel(SpatialArgs A) {
+    const int b = blockIdx.x;
+    const WsLayout L = ws_layout(A.N);
+    char* w = A.ws + (size_t)b * A.ws_img_stride;
+    if (*reinterpret_cast<const int32_t*>(w + L.dflag) == 0) return;
+    list_tiles(reinterpret_cast<const float*>(w + L.gtab), A.nt, A.src == kSrcBox3d ? 3 : 2, A.cull_c, b, A.tile_list, threadIdx.x, 256);
 }
 
 // has-earlier partials from the finished mask (column-major): CTA = 256 columns; work item = (row word, 32-column
 // part): 32 independent coalesced loads per thread, parts combined in shared memory   (grid (ceil(N/256), batch) x 1024)
-__global__ void __launch_bounds__(1024) has_earlier_kernel(int N, const int32_t* __restrict__ n_per_image, char* __restrict__ ws,
-                                                           size_t ws_img_stride) {
-    __shared__ uint32_t s_acc[GNMS_MAX_BOXES / 32];
-    const int b = blockIdx.y, NW = (N + 31) / 32;
-    const int n = n_per_image ? min(n_per_image[b], N) : N;
-    const WsLayout L = ws_layout(N);
-    char* w = ws + (size_t)b * ws_img_stride;
-    const uint32_t* mask = reinterpret_cast<const uint32_t*>(w + L.mask);
-    uint32_t* has_earlier = reinterpret_cast<uint32_t*>(w + L.has_earlier);
-    const int l0 = blockIdx.x * 256;
+__device__ __forceinline__ void has_earlier_item(int N, int n, int chunk, const uint32_t* __restrict__ mask, uint32_t* __restrict__ has_earlier,
+                                                 int he_slots, uint32_t* s_acc) {
+    const int NW = (N + 31) / 32;
+    const int l0 = chunk * 256;
     for (int jw = threadIdx.x; jw < NW; jw += 1024) s_acc[jw] = 0u;
     __syncthreads();
     for (int item = threadIdx.x; item < NW * 8; item += 1024) {
@@ -1052,7 +1078,204 @@ __global__ void __launch_bounds__(1024) has_earlier_kernel(int N, const int32_t*
         if (acc) atomicOr(&s_acc[jw], acc);
     }
     __syncthreads();
-    for (int jw = threadIdx.x; jw < NW; jw += 1024) has_earlier[(size_t)jw * L.he_slots + blockIdx.x] = s_acc[jw];
+    for (int jw = threadIdx.x; jw < NW; jw += 1024) has_earlier[(size_t)jw * he_slots + chunk] = s_acc[jw];
+}
+
+__global__ void __launch_bounds__(1024) has_earlier_kernel(int N, const int32_t* __restrict__ n_per_image, char* __restrict__ ws,
+                                                           size_t ws_img_stride) {
+    __shared__ uint32_t s_acc[GNMS_MAX_BOXES / 32];
+    const int b = blockIdx.y;
+    const int n = n_per_image ? min(n_per_image[b], N) : N;
+    const WsLayout L = ws_layout(N);
+    char* w = ws + (size_t)b * ws_img_stride;
+    has_earlier_item(N, n, blockIdx.x, reinterpret_cast<const uint32_t*>(w + L.mask), reinterpret_cast<uint32_t*>(w + L.has_earlier),
+                     L.he_slots, s_acc);
+}
+
+// Direct-election flow: only the images elect_kernel gave up on need this; the grid is small and loops over
+// (image, 256-column chunk) items, so that a launch in which every image was elected costs next to nothing.
+__global__ void __launch_bounds__(1024) has_earlier_failed_kernel(int N, int batch, const int32_t* __restrict__ n_per_image,
+                                                                  char* __restrict__ ws, size_t ws_img_stride) {
+    __shared__ uint32_t s_acc[GNMS_MAX_BOXES / 32];
+    const int nchunks = (N + 255) / 256;
+    const WsLayout L = ws_layout(N);
+    for (int item0 = blockIdx.x; item0 < batch * nchunks; item0 += gridDim.x) {
+        const int b = item0 / nchunks, chunk = item0 - b * nchunks;
+        char* w = ws + (size_t)b * ws_img_stride;
+        if (*reinterpret_cast<const int32_t*>(w + L.dflag) == 0) continue;
+        __syncthreads();                                               // s_acc of the previous item has been written out
+        has_earlier_item(N, n_per_image ? min(n_per_image[b], N) : N, chunk, reinterpret_cast<const uint32_t*>(w + L.mask),
+                         reinterpret_cast<uint32_t*>(w + L.has_earlier), L.he_slots, s_acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ 2e. direct leader election
+// Matrix-free path.  The greedy election only ever needs the overlap COLUMNS of the leaders (a few dozen per image on
+// detector outputs), not all N^2 pairs: this kernel runs the reference's loop (lib/groomed_nms.py:247-262) as it is
+// written -- pick the best box still in the pool, evaluate its overlap with the boxes still in the pool, take those with
+// !(v <= thr) out (their first suppressor is this leader) -- with one CTA per image, all in shared memory:
+//   * the image's blocked copy in SPATIAL order (blk, written by the spatial kernel just before: records + ranks) is
+//     copied into shared memory once; the pool is a bitset over sorted positions that every warp scans redundantly, so a
+//     step costs ONE barrier;
+//   * per step every warp tests all 64-box groups against the leader with the conservative gap bound of the tile
+//     culling (group table of the spatial kernel; a lane owns two groups) and gets the same 64-bit "near" mask; only
+//     the boxes of the near groups are evaluated, one pair per thread, spread over the whole CTA -- so the critical
+//     path of a step is one pair evaluation, not a warp's worth of them;
+//   * a box that leaves the pool gets its first suppressor written straight to global memory (once per box).
+// ~0.5 us per leader; images run side by side on different SMs.  If an image needs more than kElectMaxLeaders steps
+// (boxes that barely overlap) the kernel gives up for that image and sets its flag: the list / tile / has-earlier
+// kernels then do the work for it (they skip the images whose flag is clear) and chain_kernel takes the mask route.
+constexpr int kElectMaxBoxes = 4096;
+constexpr int kElectMaxLeaders = 384;
+struct ElectArgs {
+    int N, batch;
+    const int32_t* n_per_image;
+    char* ws;
+    size_t ws_img_stride;
+    float thr, cull_c;
+};
+static size_t elect_smem_bytes(int N) {
+    const size_t nt = (size_t)((N + 63) / 64);
+    return nt * kBlkBytes + nt * 64 * 2 + 3 * 128 * 4 + 64;           // blocks, rank -> slot map, alive / leader / bad bitsets
+}
+
+constexpr int kElectThreads = 256;
+
+template <int kSrc, bool kGen, bool kAffine>
+__global__ void __launch_bounds__(kElectThreads) elect_kernel(ElectArgs A) {
+    typedef typename RecOf<kSrc>::type RecT;
+    constexpr int kAxes = kSrc == kSrcBox3d ? 3 : 2;
+    constexpr int kWarps = kElectThreads / 32;
+    extern __shared__ __align__(16) unsigned char s_el[];
+    const int b = blockIdx.x, N = A.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = A.n_per_image ? min(A.n_per_image[b], N) : N;
+    const int nw = (n + 31) / 32, nt = (N + 63) / 64;
+    const WsLayout L = ws_layout(N);
+    char* w = A.ws + (size_t)b * A.ws_img_stride;
+    const float* gtab = reinterpret_cast<const float*>(w + L.gtab);
+    int32_t* dfsup = reinterpret_cast<int32_t*>(w + L.dfsup);
+    float* s_blk = reinterpret_cast<float*>(s_el);                           // [group][8 fields + rank][64], spatial order
+    uint16_t* s_slot = reinterpret_cast<uint16_t*>(s_blk + (size_t)nt * kBlkWords);   // sorted position -> spatial slot
+    uint32_t* alive = reinterpret_cast<uint32_t*>(s_slot + (size_t)nt * 64); // boxes still in the pool, by sorted position
+    uint32_t* leaderb = alive + 128;
+    uint32_t* badb = leaderb + 128;                                          // by slot: record outside div_rn_fast's proven range
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(w + L.blk);
+        uint4* dst = reinterpret_cast<uint4*>(s_blk);
+        for (int i = tid; i < nt * (kBlkBytes / 16); i += kElectThreads) dst[i] = src[i];
+    }
+    if (tid < 128) { alive[tid] = tid < nw ? valid_word(tid, n) : 0u; leaderb[tid] = 0u; badb[tid] = 0u; }
+    for (int pos = tid; pos < n; pos += kElectThreads) dfsup[pos] = INT_MAX;
+    // work items of a step: the 2 nt half-groups (32 spatial slots each); warp w owns items w, w + 8, w + 16, ... and
+    // lane j keeps the reach of the group of item w + 8 j (lo / hi per axis, largest extents; a group holding an odd
+    // box is never skipped).  Neighbouring items belong to different warps, so the few groups near a leader spread out.
+    const int my_item = warp + kWarps * lane;
+    const int my_group = my_item >> 1;
+    float glo[kAxes], ghi[kAxes], gext[kAxes];
+    bool gok = false;
+    const bool item_valid = lane < 16 && my_group < nt;                      // 2 * 64 / 8 = 16 items per warp at most
+#pragma unroll
+    for (int ax = 0; ax < kAxes; ++ax) { glo[ax] = 0.f; ghi[ax] = 0.f; gext[ax] = 0.f; }
+    if (item_valid) {
+#pragma unroll
+        for (int ax = 0; ax < kAxes; ++ax) { glo[ax] = gtab[my_group * 10 + 2 * ax]; ghi[ax] = gtab[my_group * 10 + 2 * ax + 1]; gext[ax] = gtab[my_group * 10 + 6 + ax]; }
+        gok = A.cull_c >= 0.f && gtab[my_group * 10 + 9] == 0.f;
+    }
+    __shared__ uint32_t s_gbad[4];                                           // groups that may not be skipped
+    if (tid < 4) s_gbad[tid] = 0u;
+    __syncthreads();
+    if (tid < nt && !(A.cull_c >= 0.f && gtab[tid * 10 + 9] == 0.f)) atomicOr(&s_gbad[tid >> 5], 1u << (tid & 31));
+    for (int slot = tid; slot < nt * 64; slot += kElectThreads) {
+        const float* bg = s_blk + (size_t)(slot >> 6) * kBlkWords + (slot & 63);
+        const int r = reinterpret_cast<const int32_t*>(bg)[8 * 64];
+        if (r == INT_MAX) continue;                                          // dead slot (padding / past the live count)
+        s_slot[r] = (uint16_t)slot;
+        bool bad;
+        if constexpr (kSrc == kSrcBox3d) bad = !rec3_sane(Rec3{bg[0], bg[64], bg[128], bg[192], bg[256], bg[320], bg[384], 0.f});
+        else bad = !box2_sane(make_box2(make_float4(bg[0], bg[64], bg[128], bg[192])));
+        if (bad) atomicOr(&badb[slot >> 5], 1u << (slot & 31));
+    }
+    __syncthreads();
+    auto record = [&](int slot) -> RecT {
+        const float* bg = s_blk + (size_t)(slot >> 6) * kBlkWords + (slot & 63);
+        if constexpr (kSrc == kSrcBox3d) return Rec3{bg[0], bg[64], bg[128], bg[192], bg[256], bg[320], bg[384], 0.f};
+        else return make_box2(make_float4(bg[0], bg[64], bg[128], bg[192]));
+    };
+    int steps = 0;
+    bool failed = false;
+    while (true) {
+        // first box still in the pool: every warp scans the bitset itself (no barrier, same answer everywhere)
+        int l = -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t wv = alive[u * 32 + lane];
+            const unsigned any = __ballot_sync(0xffffffffu, wv != 0u);
+            if (any) {
+                const int fl = __ffs(any) - 1;
+                const uint32_t bits = __shfl_sync(0xffffffffu, wv, fl);
+                l = (u * 32 + fl) * 32 + __ffs(bits) - 1;
+                break;
+            }
+        }
+        if (l < 0) break;
+        if (++steps > kElectMaxLeaders) { failed = true; break; }
+        const int lslot = s_slot[l];
+        const RecT ldr = record(lslot);
+        const bool lbad = (badb[lslot >> 5] >> (lslot & 31)) & 1u;
+        const bool lok = !lbad && !((s_gbad[lslot >> 11] >> ((lslot >> 6) & 31)) & 1u);
+        // which of my warp's items are within the leader's reach (gap along an axis > c * (leader extent + largest
+        // extent in the group) => every overlap <= thr, see the tile culling; exact zeros when c == 0)
+        bool is_near = item_valid;
+        if (is_near && lok && gok) {
+            float llo[3], lhi[3];
+            if constexpr (kSrc == kSrcBox3d) { llo[0] = ldr.bx1; lhi[0] = ldr.bx2; llo[1] = ldr.ymin; lhi[1] = ldr.ymax; llo[2] = ldr.bz1; lhi[2] = ldr.bz2; }
+            else { llo[0] = ldr.x1; lhi[0] = ldr.x2; llo[1] = ldr.y1; lhi[1] = ldr.y2; llo[2] = 0.f; lhi[2] = 0.f; }
+#pragma unroll
+            for (int ax = 0; ax < kAxes; ++ax) {
+                const float gap = fmaxf(glo[ax] - lhi[ax], llo[ax] - ghi[ax]);
+                if (gap > 0.f && gap > A.cull_c * ((lhi[ax] - llo[ax]) + gext[ax])) is_near = false;
+            }
+        }
+        unsigned near = __ballot_sync(0xffffffffu, is_near);
+        while (near) {                                                       // usually zero or one item per warp
+            const int j = __ffs(near) - 1;
+            near &= near - 1u;
+            const int item = warp + kWarps * j;
+            const int slot = (item >> 1) * 64 + 32 * (item & 1) + lane;      // one pair per lane
+            const int r = reinterpret_cast<const int32_t*>(s_blk + (size_t)(item >> 1) * kBlkWords)[8 * 64 + (slot & 63)];
+            if (r == INT_MAX || !((alive[r >> 5] >> (r & 31)) & 1u)) continue;
+            bool out = false;
+            if (r == l) {
+                out = true;
+                atomicOr(&leaderb[l >> 5], 1u << (l & 31));
+            } else {
+                const RecT mine = record(slot);
+                bool unsafe = lbad || ((badb[slot >> 5] >> (slot & 31)) & 1u);
+                float v = RecOf<kSrc>::template fast<kGen, kAffine>(mine, ldr, unsafe);
+                if (__builtin_expect(unsafe, 0)) v = RecOf<kSrc>::template exact<kGen, kAffine>(mine, ldr);
+                if (!(v <= A.thr)) { out = true; dfsup[r] = l; }             // NaN leaves the pool too (:249-250)
+            }
+            if (out) atomicAnd(&alive[r >> 5], ~(1u << (r & 31)));
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *reinterpret_cast<int32_t*>(w + L.dflag) = failed ? 1 : 0;
+    if (failed) return;
+    uint32_t* dleader = reinterpret_cast<uint32_t*>(w + L.dleader);
+    if (tid < (N + 31) / 32) dleader[tid] = tid < 128 ? leaderb[tid] : 0u;
+}
+
+// zero the suppression mask of the images elect_kernel gave up on (small grid that loops over (image, eighth) items)
+__global__ void __launch_bounds__(256) zero_failed_kernel(int N, int batch, char* __restrict__ ws, size_t ws_img_stride) {
+    const WsLayout L = ws_layout(N);
+    const size_t tot4 = ((size_t)((N + 31) / 32) * N * 4 + 15) / 16, per = (tot4 + 7) / 8;
+    for (int item = blockIdx.x; item < batch * 8; item += gridDim.x) {
+        char* w = ws + (size_t)(item >> 3) * ws_img_stride;
+        if (*reinterpret_cast<const int32_t*>(w + L.dflag) == 0) continue;
+        uint4* m4 = reinterpret_cast<uint4*>(w + L.mask);
+        const size_t lo = (size_t)(item & 7) * per, hi = lo + per < tot4 ? lo + per : tot4;
+        for (size_t i = lo + threadIdx.x; i < hi; i += 256) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ 3. chain
@@ -1096,17 +1319,12 @@ struct ChainArgs {
     int32_t* keep;                 // hard NMS: kept input indices in score order
     int32_t* n_keep;
     int leaders_only;              // hard NMS: stop after leader election
+    int direct;                    // leaders / first suppressors come from elect_kernel (unless it gave up for this image)
     int stage;                     // 0: grouping + closed-form rescore + lists (mode GROUP_MASK)
                                    // 1: grouping only, exports the group structure (mode GROUP_NOMASK, before the solve)
                                    // 2: lists only, from pre[] / lead[] already in global memory (after the solve)
 };
 
-__device__ __forceinline__ uint32_t valid_word(int w, int n) {
-    int lo = w * 32;
-    if (n >= lo + 32) return 0xffffffffu;
-    if (n <= lo) return 0u;
-    return (1u << (n - lo)) - 1u;
-}
 
 // warp 0 only: list the positions of the first `limit` set bits of bits[0..nw) into out[], return the count
 __device__ int warp_list_bits(const uint32_t* bits, int nw, int limit, int32_t* out) {
@@ -1179,6 +1397,13 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             dpval[pos] = 0.f;
         }
         __syncthreads(); GNMS_PHASE(1);
+    } else {
+    const bool direct = A.direct && *reinterpret_cast<const int32_t*>(w + L.dflag) == 0;
+    if (direct) {
+        const uint32_t* dleader = reinterpret_cast<const uint32_t*>(w + L.dleader);
+        const int32_t* dfsup = reinterpret_cast<const int32_t*>(w + L.dfsup);
+        for (int i = tid; i < NW; i += kChainThreads) { removed[i] = 0u; leader[i] = i < nw ? dleader[i] : 0u; }
+        for (int i = tid; i < N; i += kChainThreads) fsup[i] = i < n ? dfsup[i] : INT_MAX;
     } else {
     for (int i = tid; i < NW; i += kChainThreads) {
         removed[i] = 0u;
@@ -1271,6 +1496,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             }
         }
     }
+    }   // mask route
     __syncthreads(); GNMS_PHASE(9);
 
     // ---- hard NMS: the leaders are the keep set
@@ -1373,6 +1599,20 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
         // this leader are ranked by position with a warp scan of per-word popcounts
         const int nlead = s_cnt;
         constexpr int kMaxW = GNMS_MAX_BOXES / 32 / 32;          // mask words per lane per column (8)
+        if (direct) {
+            // no mask on the direct route: one warp per listed leader walks lead[] from the leader on, 32 positions a step
+            for (int k = warp; k < nlead; k += kChainThreads / 32) {
+                const int l = llist[k];
+                int before = 0;
+                for (int base = l & ~31; base < n; base += 32) {
+                    const int pos = base + lane;
+                    const bool memb = pos < n && pos != l && lead[pos] == l;
+                    const unsigned bal = __ballot_sync(0xffffffffu, memb);
+                    if (memb) grank[pos] = 1 + before + __popc(bal & ((1u << lane) - 1u));
+                    before += __popc(bal);
+                }
+            }
+        } else
         for (int k = warp; k < nlead; k += kChainThreads / 32) {
             const int l = llist[k];
             const int base0 = l >> 5;
@@ -1761,6 +2001,8 @@ extern "C" int gnms_version(void) { return GNMS_VERSION; }
 // debug only (not part of the public header): which stages of the forward run (bench.py times kernels in isolation)
 static int g_rank_by_sort = -1;            // -1 heuristic, 0 always count, 1 always sort
 extern "C" int gnms_debug_rank_by_sort(int v) { int old = g_rank_by_sort; g_rank_by_sort = v; return old; }
+static int g_direct = 1;                   // direct leader election on the matrix-free path
+extern "C" int gnms_debug_direct_election(int v) { int old = g_direct; g_direct = v; return old; }
 static int g_tile_queue = 1;
 extern "C" int gnms_debug_tile_queue(int v) { int old = g_tile_queue; g_tile_queue = v; return old; }
 static int g_stage_mask = 0xff;            // bit 0 rank, 1 spatial order, 2 tile (or matrix -> mask), 3 has_earlier, 4 chain / solves
@@ -1814,23 +2056,72 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     const int mode = p->mode;
     const bool need_groups = mode != GNMS_MODE_NOGROUP;
     const bool tiles = need_groups && src != kSrcMatrix;              // fused overlap + mask tile kernel
+    // matrix-free pass: spatial order + culling of tile pairs that provably hold no pair above the threshold
+    float cull_c = -1.f;                                               // < 0: culling not applicable
+    if (src != kSrcMatrix && !overlap_out && need_groups && N <= 128 * kTT && batch < 32768 && p->nms_threshold >= 0.f) {
+        const float thr = p->nms_threshold;
+        if (src == kSrcBox2d) cull_c = 0.f;                            // disjoint -> IoU = 0 <= thr
+        else if (!affine) cull_c = 0.f;                                // IoU3D = 0 or GIoU <= 0 <= thr
+        else if (thr >= 0.5f) cull_c = 0.f;                            // 0.5 (1 + v) <= 0.5 <= thr
+        else if (generalized && thr > 0.05f) cull_c = (1.f - 2.f * thr + 1e-4f) / (2.f * thr - 1e-4f);
+    }
+    const bool culled = cull_c >= 0.f;
+    // direct leader election first (elect_kernel): the mask kernels below then only work for the images it gave up on
+    const bool direct = g_direct && culled && mode == GNMS_MODE_GROUP_MASK && N <= kElectMaxBoxes;
     // rank by counting costs batch * N^2 compares over the whole chip, the per-image radix sort a constant ~10 us
     const bool by_sort = g_rank_by_sort == 1 || (g_rank_by_sort < 0 && (double)batch * N * N >= 10.0 * 4096 * 4096);
     if (g_stage_mask & 1) {
         if (by_sort) {
-            const int zm = (tiles || (src != kSrcMatrix && overlap_out)) ? 1 : 0;
+            const int zm = ((tiles && !direct) || (src != kSrcMatrix && overlap_out)) ? 1 : 0;
             sort_kernel<<<batch + (zm ? 4 * batch : 1), kSortThreads, sort_smem_bytes(N), s>>>(scores, N, N, batch, npi, sv.order,
                                                                                               sv.sorted_scores, ws, L.total, zm);
             GNMS_LAUNCH_CHECK();
         }
         rank_kernel<<<dim3(gnms_div_up(N, kRankElems), batch), 256, by_sort ? 0 : rank_smem_bytes(N), s>>>(
             scores, 1, N, N, npi, sv.order, sv.sorted_scores, ws, L.total, src == kSrcMatrix ? nullptr : boxes, src,
-            (int64_t)N * box_stride, 0.f, by_sort ? 2 : 0, (tiles || (src != kSrcMatrix && overlap_out)) ? 1 : 0,
+            (int64_t)N * box_stride, 0.f, by_sort ? 2 : 0, ((tiles && !direct) || (src != kSrcMatrix && overlap_out)) ? 1 : 0,
             tile_list_ptr(workspace, N, batch));
     }
     GNMS_LAUNCH_CHECK();
-    if (src == kSrcMatrix && (!iou || ld < N)) return GNMS_E_BADARG;
     if (src != kSrcMatrix && !boxes) return GNMS_E_BADARG;
+    SpatialArgs SA = {};
+    SA.N = N; SA.batch = batch; SA.nt = gnms_div_up(N, kTT); SA.src = src; SA.n_per_image = npi; SA.boxes = boxes; SA.ws = ws;
+    SA.ws_img_stride = L.total; SA.tile_list = tile_list_ptr(workspace, N, batch); SA.cull_c = cull_c; SA.defer_list = direct ? 1 : 0;
+    if (direct) {
+        if (g_stage_mask & 2) spatial_kernel<<<batch, 1024, 0, s>>>(SA);     // spatial order + group table, no tile list yet
+        GNMS_LAUNCH_CHECK();
+    }
+    if (direct && (g_stage_mask & 32)) {
+        ElectArgs E = {};
+        E.N = N; E.batch = batch; E.n_per_image = npi; E.ws = ws; E.ws_img_stride = L.total; E.thr = p->nms_threshold; E.cull_c = cull_c;
+        const size_t esm = elect_smem_bytes(N);
+#define GNMS_ELECT(SRC, G, AF)                                                                                       \
+    do {                                                                                                             \
+        static bool attr_done[64] = {false};                                                                         \
+        int dev_ = 0;                                                                                                \
+        GNMS_CUDA_TRY(cudaGetDevice(&dev_));                                                                         \
+        if (!attr_done[dev_ & 63]) {                                                                                 \
+            GNMS_CUDA_TRY(cudaFuncSetAttribute(elect_kernel<SRC, G, AF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               (int)elect_smem_bytes(kElectMaxBoxes)));                              \
+            attr_done[dev_ & 63] = true;                                                                             \
+        }                                                                                                            \
+        elect_kernel<SRC, G, AF><<<batch, kElectThreads, esm, s>>>(E);                                                       \
+    } while (0)
+        if (src == kSrcBox3d) {
+            if (generalized) { if (affine) GNMS_ELECT(kSrcBox3d, true, true); else GNMS_ELECT(kSrcBox3d, true, false); }
+            else { if (affine) GNMS_ELECT(kSrcBox3d, false, true); else GNMS_ELECT(kSrcBox3d, false, false); }
+        } else {
+            GNMS_ELECT(kSrcBox2d, false, false);
+        }
+#undef GNMS_ELECT
+        GNMS_LAUNCH_CHECK();
+        // images the election gave up on: zero their suppression masks (the sort / rank kernels skipped that), list their tiles
+        zero_failed_kernel<<<(batch * 8 < 296 ? batch * 8 : 296), 256, 0, s>>>(N, batch, ws, L.total);
+        GNMS_LAUNCH_CHECK();
+        list_failed_kernel<<<batch, 256, 0, s>>>(SA);
+        GNMS_LAUNCH_CHECK();
+    }
+    if (src == kSrcMatrix && (!iou || ld < N)) return GNMS_E_BADARG;
     if (need_groups && src == kSrcMatrix) {
         dim3 grid(gnms_div_up(N, kMaskThreads * 4), NW, batch);
         bool vec = ((reinterpret_cast<uintptr_t>(iou) & 15u) == 0) && (ld % 4 == 0) && (((int64_t)N * ld) % 4 == 0);
@@ -1851,23 +2142,9 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
         const int grid_bits = total < 148 * 2 ? total : 148 * 2;       // matrix-free: 256-thread CTAs, 2 per SM
         T.tile_list = tile_list_ptr(workspace, N, batch);
         const bool ho = overlap_out != nullptr;
-        // matrix-free pass: spatial order + culling of tile pairs that provably hold no pair above the threshold
-        float cull_c = -1.f;                                           // < 0: culling not applicable
-        const float thr = p->nms_threshold;
-        if (!ho && need_groups && N <= 128 * kTT && batch < 32768 && thr >= 0.f) {
-            if (src == kSrcBox2d) cull_c = 0.f;                        // disjoint -> IoU = 0 <= thr
-            else if (!affine) cull_c = 0.f;                            // IoU3D = 0 or GIoU <= 0 <= thr
-            else if (thr >= 0.5f) cull_c = 0.f;                        // 0.5 (1 + v) <= 0.5 <= thr
-            else if (generalized && thr > 0.05f) cull_c = (1.f - 2.f * thr + 1e-4f) / (2.f * thr - 1e-4f);
-        }
-        const bool culled = cull_c >= 0.f;
-        if (culled) {
-            SpatialArgs SA = {};
-            SA.N = N; SA.batch = batch; SA.nt = T.nt; SA.src = src; SA.n_per_image = npi; SA.boxes = boxes; SA.ws = ws;
-            SA.ws_img_stride = L.total; SA.tile_list = tile_list_ptr(workspace, N, batch); SA.cull_c = cull_c;
+        if (culled && !direct) {
             if (g_stage_mask & 2) spatial_kernel<<<batch, 1024, 0, s>>>(SA);
             GNMS_LAUNCH_CHECK();
-            T.tile_list = SA.tile_list;
         }
 #define GNMS_TILE(SRC, G, AF)                                                              \
     do {                                                                                   \
@@ -1891,7 +2168,9 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
 #undef GNMS_TILE
         GNMS_LAUNCH_CHECK();
         if (need_groups && (g_stage_mask & 8)) {
-            has_earlier_kernel<<<dim3(gnms_div_up(N, 256), batch), 1024, 0, s>>>(N, npi, ws, L.total);
+            const int he_items = gnms_div_up(N, 256) * batch;
+            if (direct) has_earlier_failed_kernel<<<(he_items < 148 ? he_items : 148), 1024, 0, s>>>(N, batch, npi, ws, L.total);
+            else has_earlier_kernel<<<dim3(gnms_div_up(N, 256), batch), 1024, 0, s>>>(N, npi, ws, L.total);
             GNMS_LAUNCH_CHECK();
         }
     }
@@ -1901,7 +2180,7 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     A.generalized = generalized; A.affine = affine; A.p = *p;
     A.order = sv.order; A.sorted_scores = sv.sorted_scores; A.prob = prob; A.valid_idx = valid_idx;
     A.invalid_idx = invalid_idx; A.counts = counts; A.lead = sv.lead; A.pval = sv.pval; A.dpval = sv.dpval;
-    A.pre = sv.pre; A.slot = slot;
+    A.pre = sv.pre; A.slot = slot; A.direct = direct ? 1 : 0;
     if (!(g_stage_mask & 16)) return 0;
     if (mode == GNMS_MODE_GROUP_MASK) {
         A.stage = 0;

@@ -483,3 +483,68 @@ def test_culled_fused_pass_equals_matrix_path_on_unclustered_boxes(kind, n, seed
         assert torch.equal(getattr(st1, f), getattr(st2, f)), f
     nv = int(st1.counts[0, 0])
     assert torch.equal(st1.valid_idx[0, :nv], st2.valid_idx[0, :nv])
+
+
+@pytest.mark.parametrize("kind", ["2d", "3d"])
+def test_direct_election_mixed_batch_and_fallback(kind):
+    """Matrix-free path: elect_kernel finds the leaders directly for images with few groups and gives up (flag) for
+    images that need too many steps, which then go through the spatial tile list / mask route INSIDE THE SAME LAUNCH
+    SEQUENCE.  A ragged batch mixing both kinds of image -- clustered detector-like boxes, uniformly scattered boxes with
+    well over 384 leaders, an empty image, a single box -- must equal the matrix path bit for bit, with the direct
+    election switched on and off."""
+    from groomed_nms_b200 import _lib, ops, synthetic
+    lib = _lib.load()
+    N = 2048
+    rng = np.random.default_rng(77)
+    ns = [2048, 2048, 0, 1, 1500, 2048]
+    sc = np.zeros((len(ns), N), np.float32)
+    if kind == "2d":
+        data = np.zeros((len(ns), N, 4), np.float32)
+        for b, n in enumerate(ns):
+            if b in (0, 4):                                              # clustered: a handful of groups
+                bx, s, _ = synthetic.clustered_boxes_2d(N, 9, seed=50 + b, jitter=0.06)
+            else:                                                        # scattered: thousands of leaders -> fallback
+                c = rng.uniform(0, 2000, (N, 2)); wh = rng.uniform(10, 40, (N, 2))
+                bx = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+                s = (rng.uniform(0.05, 1.0, N) + np.arange(N) * 1e-7).astype(np.float32)
+            sc[b], data[b] = s, bx
+        dev_data = cuda(data)
+        iou = torch.stack([ops.overlap2d(dev_data[b], dev_data[b]) for b in range(len(ns))])
+        kw = dict(box_kind=_lib.BOX_2D)
+    else:
+        recs = []
+        for b, n in enumerate(ns):
+            if b in (0, 4):
+                b7, s = synthetic.config_c3(seed=60 + b, n=N, k=12)
+            else:
+                b7 = np.stack([rng.uniform(-60, 60, N), 1.6 + 0.2 * rng.standard_normal(N), rng.uniform(5, 120, N),
+                               1.6 + 0.2 * rng.standard_normal(N), 1.5 + 0.1 * rng.standard_normal(N),
+                               4 + 0.5 * rng.standard_normal(N), rng.uniform(-np.pi, np.pi, N)], 1).astype(np.float32)
+                s = (rng.uniform(0.05, 1.0, N) + np.arange(N) * 1e-7).astype(np.float32)
+            sc[b] = s
+            recs.append(ops.box3d_records(ops.corners_from_boxes7(cuda(b7))))
+        dev_data = torch.stack(recs)
+        iou = torch.stack([ops.overlap3d(r, r, False, True, generalized=True, affine=True)[1] for r in recs])
+        kw = dict(box_kind=_lib.BOX_3D_REC, generalized=True, affine=True)
+    npi = torch.tensor(ns, dtype=torch.int32, device="cuda")
+    p = ops.make_params(group_size=25)
+    ref = ops.forward_matrix(cuda(sc), iou, p, n_per_image=npi)
+    n_lead = [(int((ref.lead[b, :n] == torch.arange(n, device="cuda")).sum())) for b, n in enumerate(ns)]
+    assert n_lead[0] < 100 and n_lead[1] > 384 and n_lead[5] > 384      # both routes are really exercised
+    try:
+        for direct in (1, 0):
+            lib.gnms_debug_direct_election(direct)
+            st = ops.forward_boxes(cuda(sc), dev_data, kw.pop("box_kind") if False else kw["box_kind"], p,
+                                   kw.get("generalized", False), kw.get("affine", False), n_per_image=npi)
+            torch.cuda.synchronize()
+            for f in ("order", "lead", "prob", "pre", "counts"):
+                assert torch.equal(getattr(ref, f), getattr(st, f)), (direct, f)
+            for b in range(len(ns)):
+                nv = int(ref.counts[b, 0])
+                assert torch.equal(ref.valid_idx[b, :nv], st.valid_idx[b, :nv])
+            up = torch.randn(len(ns), N, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+            g1, _ = ops.backward(ref, up)
+            g2, _ = ops.backward(st, up)
+            assert torch.allclose(g1, g2, rtol=1e-6, atol=1e-7)
+    finally:
+        lib.gnms_debug_direct_election(1)

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from groomed_nms_b200 import _lib, ops, synthetic          # noqa: E402
 from groomed_nms_b200.hostapi import Nms3dPlan             # noqa: E402
 
-STAGES = {1: "rank", 3: "rank+spatial", 4: "tile", 8: "has_earlier", 16: "chain", 0xff: "forward (all)"}
+STAGES = {1: "rank", 32: "elect", 3: "rank+spatial", 4: "tile", 8: "has_earlier", 16: "chain", 0xff: "forward (all)"}
 
 
 def time_call(fn, stream, iters=20, warm=3):
@@ -58,8 +58,11 @@ def main():
         pl.stage_corners(s); pl.stage_records(s); pl.stage_forward(s)
         torch.cuda.synchronize()
         res[mat] = dict(prob=pl.prob.clone(), counts=pl.counts.clone(), lead=pl.lead.clone())
+        if not mat:
+            nl = (pl.lead == torch.arange(N, device=dev)[None, :]).sum(dim=1)
+            print("leaders per image: min %d mean %.1f max %d" % (int(nl.min()), float(nl.float().mean()), int(nl.max())))
         for m, nm in STAGES.items():
-            if m == 3 and mat:
+            if m in (3, 32) and mat:
                 continue
             lib.gnms_debug_stage_mask(m)
             us = time_call(pl.stage_forward, st)
