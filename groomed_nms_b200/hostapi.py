@@ -49,8 +49,11 @@ class Nms3dPlan(object):
         self.fl = torch.empty((4, batch, n), **f)
         self.ws = torch.empty((int(self.lib.gnms_workspace_bytes(n, batch)),), dtype=torch.uint8, device=device)
         self.saved = Saved(_vp(self.order), _vp(self.fl[0]), _vp(self.lead), _vp(self.fl[1]), _vp(self.fl[2]), _vp(self.fl[3]))
-        # corners, records, rank, tile, has_earlier, chain, backward  (two_kernel: + overlap, mask instead of tile/has_earlier)
-        self.launches_per_step = 7
+        # matrix produced: corners, records, sort, rank (gather), tile, has_earlier, chain, backward
+        # matrix-free:     corners, records, sort, rank, spatial, elect, zero_failed, list_failed, tile (culled list, empty
+        #                  unless the election gave up on an image), has_earlier_failed, chain, backward
+        # (batches below ~10 images rank by counting: one launch fewer; two_kernel: overlap + mask instead of tile/has_earlier)
+        self.launches_per_step = 8 if materialise else 12
 
     # -- individual stages (each is one C-ABI call = one kernel launch unless noted)
     def stage_corners(self, s):
