@@ -629,8 +629,11 @@ template <> struct SoaOf<kSrcBox2d> {
     }
 };
 
-template <int kSrc, bool kGen, bool kAffine, bool kHasOut, bool kList, int kRB, bool kQueue>
+template <int kSrc, bool kGen, bool kAffine, bool kHasOut, bool kList, int kRB, bool kQueue, bool kMatrixOnly = false>
 __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
+    // kMatrixOnly: the overlap matrix and nothing else -- no suppression bits, no ranks, no workspace: the boxes are staged
+    // straight from the caller's records (one record per thread, scattered into the field arrays by 4-byte cp.async)
+    static_assert(!kMatrixOnly || (kHasOut && !kList && !kQueue && kRB == 2), "matrix-only launches are 128-thread, matrix-producing");
     constexpr int kThreads = 256 / kRB;                               // kRB row blocks of 64 / kRB rows per thread
     static_assert(!(kHasOut && kList), "the culled pass does not produce the matrix");
     typedef typename RecOf<kSrc>::type RecT;
@@ -659,11 +662,21 @@ __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
             b = div_small(t, A.tiles_per_image, A.inv_tpi);
             tile_decode_folded(t - b * A.tiles_per_image, A.nt, A.inv_w, I, J);
         }
-        const char* blk = A.ws + (size_t)b * A.ws_img_stride + L.blk;
+        if (kMatrixOnly) {
+            constexpr int kNF = SoaOf<kSrc>::kFields;
+            const int side = tid >> 6, k = tid & 63;                  // 128 threads: one record each
+            const int idx = min((side ? J : I) * kTT + k, N - 1);
+            const float* src = A.boxes + ((size_t)b * N + idx) * kNF;
+            float* dst = &s_blk[buf][side][k];
 #pragma unroll
-        for (int c = tid; c < 2 * kChunks; c += kThreads) {
-            const int side = c >= kChunks ? 1 : 0, cc = c - side * kChunks;
-            cp_async16(reinterpret_cast<char*>(s_blk[buf][side]) + cc * 16, blk + (size_t)(side ? J : I) * kBlkBytes + cc * 16);
+            for (int q = 0; q < kNF; ++q) cp_async4(dst + q * kTT, src + q);
+        } else {
+            const char* blk = A.ws + (size_t)b * A.ws_img_stride + L.blk;
+#pragma unroll
+            for (int c = tid; c < 2 * kChunks; c += kThreads) {
+                const int side = c >= kChunks ? 1 : 0, cc = c - side * kChunks;
+                cp_async16(reinterpret_cast<char*>(s_blk[buf][side]) + cc * 16, blk + (size_t)(side ? J : I) * kBlkBytes + cc * 16);
+            }
         }
         if (tid == 0) { s_ij[buf][0] = b; s_ij[buf][1] = I; s_ij[buf][2] = J; }
     };
@@ -671,6 +684,11 @@ __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
     // wait_all): coordinates |x| <= 2^19 (3D), volume / area within [2^-60, 2^60]
     auto own_bad = [&](int buf) -> bool {
         bool bad = false;
+        if (kMatrixOnly) {                                            // the record this thread staged
+            const float* f = &s_blk[buf][tid >> 6][tid & 63];
+            if constexpr (kSrc == kSrcBox3d) return !rec3_sane(Rec3{f[0], f[64], f[128], f[192], f[256], f[320], f[384], 0.f});
+            else return !box2_sane(make_box2(make_float4(f[0], f[64], f[128], f[192])));
+        }
 #pragma unroll
         for (int c = tid; c < 2 * kChunks; c += kThreads) {
             const int side = c >= kChunks ? 1 : 0, cc = c - side * kChunks, f = cc >> 4;
@@ -758,10 +776,12 @@ __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
                     for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template exact<kGen, kAffine>(rr[r], cr[k]);
             }
             uint32_t hits = 0u;
+            if (!kMatrixOnly) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+                for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) hits |= (uint32_t)(!(v[r][k] <= thr)) << (4 * r + k);
+                    for (int k = 0; k < 4; ++k) hits |= (uint32_t)(!(v[r][k] <= thr)) << (4 * r + k);
+            }
 
             // ---- consumer 2: the overlap matrix (optional), direct and mirrored, straight from registers
             if (kHasOut) {
@@ -788,7 +808,8 @@ __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
                 }
             }
             // ---- consumer 1: threshold hits (~3 % of the pairs)
-            if (kQueue) {
+            if (kMatrixOnly) {
+            } else if (kQueue) {
                 // warp-aggregated append: one shared-memory atomic per warp and sub-tile
                 const unsigned who = __ballot_sync(0xffffffffu, hits != 0u);
                 if (who) {
@@ -2003,6 +2024,8 @@ static int g_rank_by_sort = -1;            // -1 heuristic, 0 always count, 1 al
 extern "C" int gnms_debug_rank_by_sort(int v) { int old = g_rank_by_sort; g_rank_by_sort = v; return old; }
 static int g_direct = 1;                   // direct leader election on the matrix-free path
 extern "C" int gnms_debug_direct_election(int v) { int old = g_direct; g_direct = v; return old; }
+static int g_split_matrix = 1;             // matrix requested + direct election possible: matrix-only kernel + matrix-free path
+extern "C" int gnms_debug_split_matrix(int v) { int old = g_split_matrix; g_split_matrix = v; return old; }
 static int g_tile_queue = 1;
 extern "C" int gnms_debug_tile_queue(int v) { int old = g_tile_queue; g_tile_queue = v; return old; }
 static int g_stage_mask = 0xff;            // bit 0 rank, 1 spatial order, 2 tile (or matrix -> mask), 3 has_earlier, 4 chain / solves
@@ -2035,6 +2058,34 @@ extern "C" size_t gnms_workspace_bytes(int N, int batch) {
            tile_list_bytes(N, batch);
 }
 
+// Overlap matrices only (no bits, no workspace): the matrix-only instantiation of the tile kernel.  Used by the batched
+// overlap entry points of overlap.cu and by the forward when the caller asks for the matrix.
+int gnms_launch_overlap_tiles(const float* boxes, int src, int generalized, int affine, int N, int batch, float* out, cudaStream_t s) {
+    if (N <= 0 || batch <= 0) return 0;
+    if (!boxes || !out) return GNMS_E_BADARG;
+    TileArgs T = {};
+    T.N = N; T.batch = batch; T.nt = gnms_div_up(N, kTT); T.tiles_per_image = T.nt * (T.nt + 1) / 2;
+    T.inv_tpi = 1.0f / (float)T.tiles_per_image; T.inv_w = 1.0f / (float)(T.nt + 1);
+    T.vec = ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && (N % 4 == 0);
+    T.boxes = boxes; T.out = out; T.thr = INFINITY;
+    const long long total = (long long)T.tiles_per_image * batch;
+    if (total > 0x7fffffffLL) return GNMS_E_TOOLARGE;
+    const int grid = total < 148 * 4 ? (int)total : 148 * 4;
+    if (src == kSrcBox3d) {
+        if (generalized) {
+            if (affine) tile_kernel<kSrcBox3d, true, true, true, false, 2, false, true><<<grid, 128, 0, s>>>(T);
+            else tile_kernel<kSrcBox3d, true, false, true, false, 2, false, true><<<grid, 128, 0, s>>>(T);
+        } else {
+            if (affine) tile_kernel<kSrcBox3d, false, true, true, false, 2, false, true><<<grid, 128, 0, s>>>(T);
+            else tile_kernel<kSrcBox3d, false, false, true, false, 2, false, true><<<grid, 128, 0, s>>>(T);
+        }
+    } else {
+        tile_kernel<kSrcBox2d, false, false, true, false, 2, false, true><<<grid, 128, 0, s>>>(T);
+    }
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
+
 static int run_forward(const float* scores, int src, const float* iou, int64_t ld, const float* boxes,
                        float* overlap_out, int generalized, int affine, int N, int batch, const int32_t* npi,
                        const gnms_params* p,
@@ -2058,6 +2109,18 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     const bool tiles = need_groups && src != kSrcMatrix;              // fused overlap + mask tile kernel
     // matrix-free pass: spatial order + culling of tile pairs that provably hold no pair above the threshold
     float cull_c = -1.f;                                               // < 0: culling not applicable
+    // The caller wants the overlap matrix AND the leaders can be elected directly: the matrix then comes from the
+    // matrix-only tile kernel (no bits, no ranks -- it does not depend on anything else in this call) and the rest of the
+    // call is the matrix-free path.
+    if (overlap_out && src != kSrcMatrix && g_direct && g_split_matrix && mode == GNMS_MODE_GROUP_MASK && N <= kElectMaxBoxes &&
+        N <= 128 * kTT && batch < 32768 && p->nms_threshold >= 0.f &&
+        (src == kSrcBox2d || !affine || p->nms_threshold >= 0.5f || (generalized && p->nms_threshold > 0.05f))) {
+        if (g_stage_mask & 4) {
+            rc = gnms_launch_overlap_tiles(boxes, src, generalized, affine, N, batch, overlap_out, s);
+            if (rc) return rc;
+        }
+        overlap_out = nullptr;
+    }
     if (src != kSrcMatrix && !overlap_out && need_groups && N <= 128 * kTT && batch < 32768 && p->nms_threshold >= 0.f) {
         const float thr = p->nms_threshold;
         if (src == kSrcBox2d) cull_c = 0.f;                            // disjoint -> IoU = 0 <= thr
