@@ -206,7 +206,8 @@ def run_ours(args, rank, world):
 
     plans = {}
     for name, mat in (("materialised", True), ("fused", False)):
-        pl = Nms3dPlan(B, N, dev, params, materialise=mat)
+        pl = Nms3dPlan(B, N, dev, params, materialise=mat, overlap_branch=(mat and not args.no_overlap_branch))
+        pl.tiles_per_cta = args.tiles_per_cta
         pl.boxes7.copy_(torch.from_numpy(boxes)); pl.scores.copy_(torch.from_numpy(scores)); pl.grad_prob.copy_(torch.from_numpy(grads))
         plans[name] = pl
     torch.cuda.synchronize()
@@ -290,16 +291,17 @@ def run_ours(args, rank, world):
         it = max(10, args.steps)
         stages["corners"] = time_stage(torch, pl.stage_corners, st, it)
         stages["records"] = time_stage(torch, pl.stage_records, st, it)
-        stages["forward_boxes+matrix_out(rank+tile+has_earlier+chain)"] = time_stage(torch, pl.stage_forward, st, it)
+        stages["forward_boxes+matrix_out(all kernels, one stream)"] = time_stage(torch, pl.stage_forward, st, it)
         # the kernels of that forward one by one (debug stage mask of the library: the same launches, in isolation)
-        for bit, name in ((1, "rank_kernel"), (4, "tile_kernel(matrix out)"), (8, "has_earlier_kernel"), (16, "chain_kernel")):
+        old_tpc = lib.gnms_debug_tiles_per_cta(args.tiles_per_cta if not args.no_overlap_branch else 0)   # as launched in the step
+        for bit, name in ((1, "sort_kernel+rank_kernel"), (2, "spatial_kernel"), (32, "elect_kernel(+zero/list of failed images)"),
+                          (4, "tile_kernel(matrix only)"), (16, "chain_kernel")):
             lib.gnms_debug_stage_mask(bit)
             stages[name] = time_stage(torch, pl.stage_forward, st, it)
-        lib.gnms_debug_stage_mask(4)
-        stages["tile_kernel(matrix-free, culled)"] = time_stage(torch, plans["fused"].stage_forward, st, it)
+        lib.gnms_debug_tiles_per_cta(old_tpc)
         lib.gnms_debug_stage_mask(0xff)
         stages["backward"] = time_stage(torch, pl.stage_backward, st, it)
-        stages["forward_boxes_no_matrix(rank+tile+has_earlier+chain)"] = time_stage(torch, plans["fused"].stage_forward, st, it)
+        stages["forward_boxes_no_matrix(all kernels)"] = time_stage(torch, plans["fused"].stage_forward, st, it)
         tk = Nms3dPlan(B, N, dev, params, materialise=True, two_kernel=True)
         tk.boxes7.copy_(pl.boxes7); tk.scores.copy_(pl.scores); tk.grad_prob.copy_(pl.grad_prob)
         tk.stage_corners(__import__("ctypes").c_void_p(st.cuda_stream)); tk.stage_records(__import__("ctypes").c_void_p(st.cuda_stream))
@@ -317,8 +319,8 @@ def run_ours(args, rank, world):
         step_bytes = algorithmic_bytes(N, BOX_DOF) * B
         # dominant kernel of the materialised path: the N x N overlap tile kernel (writes 4 N^2 per image) or the
         # matrix -> bitmask stream (reads 4 N^2 per image); algorithmic bytes per launch stated in DESIGN.md
-        k_ms = stages["tile_kernel(matrix out)"]
-        k_bytes = B * (4 * N * N + 36 * N)      # matrix written once + box records and ranks read
+        k_ms = stages["tile_kernel(matrix only)"]
+        k_bytes = B * (4 * N * N + 32 * N)      # matrix written once + box records read
         ach = k_bytes / (k_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "boxes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -326,7 +328,7 @@ def run_ours(args, rank, world):
             "data": "synthetic",
             "config": {"workload": "C3: N=4096 7-DoF boxes/image, 32 objects x 128 proposals, overlap 0.5*(1+GIoU3D approx), "
                                    "group+mask, linear pruning, group_size 100, fwd+bwd (grad wrt scores)",
-                       "images_per_step_per_gpu": B, "path": args.path, "cuda_graph": True, "graph_branches": args.splits,
+                       "images_per_step_per_gpu": B, "path": args.path, "cuda_graph": True, "graph_branches": (2 if (args.path == "materialised" and not args.no_overlap_branch) else 1) * args.splits,
                        "l2": "no flush: per-step working set %.0f MiB of overlap matrices vs 126 MB L2" % (B * N * N * 4 / 2 ** 20)
                              if args.path == "materialised" else "matrix-free path: no N^2 HBM traffic; inputs are O(N)",
                        "parallelism": "per-image shard, %d rank(s), no data-path collective" % world},
@@ -336,12 +338,12 @@ def run_ours(args, rank, world):
                     "blocking_call_api": "groomed_nms_b200.hostapi.HostRunner.run_host (one synchronous call per step)"},
             "gpu_launches": head.launches_per_step * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "gnms::tile_kernel<3D records, generalized, affine, matrix out> "
-                                                   "(symmetric 64x64 overlap tiles + suppression bits, %d images per launch)" % B,
+            "roofline": {"bound": "hbm", "kernel": "gnms::tile_kernel<3D records, generalized, affine, matrix only> "
+                                                   "(symmetric 64x64 overlap tiles written direct + mirrored, %d images per launch)" % B,
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k_bytes, "avg_launch_ms": k_ms, "traffic": ncu_traffic(B),
                          "timing": "CUDA events around %d back-to-back launches of this kernel alone on the launching stream" % max(10, args.steps),
-                         "note": "the kernel is fp32-issue bound (about 67 issue slots per pair, FMNMX at half rate), "
+                         "note": "the kernel is fp32-issue bound (about 60 issue slots per pair, FMNMX at half rate), "
                                  "not HBM bound: see DESIGN.md section 5 and profiles/"},
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "effective_GBps": step_bytes / (ms_step * 1e-3) / 1e9,
                               "frac_of_peak": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
@@ -371,6 +373,8 @@ def main():
     ap.add_argument("--e2e-depth", type=int, default=3, help="slots of the host pipeline (copies of one call overlap the kernels of the others)")
     ap.add_argument("--path", default="materialised", choices=["materialised", "fused"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap-branch", action="store_true", help="matrix kernel and NMS kernels on one stream instead of two graph branches")
+    ap.add_argument("--tiles-per-cta", type=int, default=8, help="matrix-only tile kernel on its branch: tiles per CTA (0 = persistent)")
     ap.add_argument("--splits", type=int, default=1, help="issue the batch as this many sub-batches on parallel graph branches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

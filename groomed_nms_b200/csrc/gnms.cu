@@ -540,6 +540,7 @@ struct TileArgs {
     float thr;
     const int32_t* tile_list;    // culled pass: [0] = count, [64..] = entries (blocks are then in spatial order)
     float inv_tpi, inv_w;        // 1 / tiles_per_image, 1 / (nt + 1): tile index decode without integer division
+    int tiles_per_cta;           // matrix-only launches: > 0 = CTA c takes tiles [c k, (c+1) k) and retires (not persistent)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -731,10 +732,16 @@ __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
         }
     };
 
-    int t = blockIdx.x, buf = 0;
+    // persistent CTAs stride over the tile list; matrix-only launches may instead give every CTA a short run of
+    // consecutive tiles, so that CTAs retire all the time and kernels of another (higher-priority) stream -- the NMS half
+    // of the step -- get SM slots while the matrix is being written
+    const bool chunked = kMatrixOnly && A.tiles_per_cta > 0;
+    const int t_step = chunked ? 1 : (int)gridDim.x;
+    const int t_end = chunked ? min(total, ((int)blockIdx.x + 1) * A.tiles_per_cta) : total;
+    int t = chunked ? (int)blockIdx.x * A.tiles_per_cta : (int)blockIdx.x, buf = 0;
     if (kQueue && tid < 3) s_nq[tid] = 0;
-    if (t < total) prefetch(t, 0);
-    for (; t < total; t += gridDim.x) {
+    if (t < t_end) prefetch(t, 0);
+    for (; t < t_end; t += t_step) {
         cp_async_wait_all();
         const bool bad = own_bad(buf);
         // publishes the staged blocks (and the previous tile's hit queue); every thread is done with the previous tile
@@ -746,7 +753,7 @@ __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
             if (tid == 0) s_nq[nbuf] = 0;                             // last read one barrier ago; pushed to after the next one
         }
         const int b = s_ij[buf][0], I = s_ij[buf][1], J = s_ij[buf][2];
-        if (t + (int)gridDim.x < total) prefetch(t + gridDim.x, nbuf);
+        if (t + t_step < t_end) prefetch(t + t_step, nbuf);
 
         const float* rsoa = s_blk[buf][0];
         const float* csoa = s_blk[buf][1];
@@ -2024,6 +2031,8 @@ static int g_rank_by_sort = -1;            // -1 heuristic, 0 always count, 1 al
 extern "C" int gnms_debug_rank_by_sort(int v) { int old = g_rank_by_sort; g_rank_by_sort = v; return old; }
 static int g_direct = 1;                   // direct leader election on the matrix-free path
 extern "C" int gnms_debug_direct_election(int v) { int old = g_direct; g_direct = v; return old; }
+static int g_tiles_per_cta = 0;            // matrix-only tile kernel: 0 = persistent CTAs, k = k consecutive tiles per CTA
+extern "C" int gnms_debug_tiles_per_cta(int v) { int old = g_tiles_per_cta; g_tiles_per_cta = v; return old; }
 static int g_split_matrix = 1;             // matrix requested + direct election possible: matrix-only kernel + matrix-free path
 extern "C" int gnms_debug_split_matrix(int v) { int old = g_split_matrix; g_split_matrix = v; return old; }
 static int g_tile_queue = 1;
@@ -2070,7 +2079,9 @@ int gnms_launch_overlap_tiles(const float* boxes, int src, int generalized, int 
     T.boxes = boxes; T.out = out; T.thr = INFINITY;
     const long long total = (long long)T.tiles_per_image * batch;
     if (total > 0x7fffffffLL) return GNMS_E_TOOLARGE;
-    const int grid = total < 148 * 4 ? (int)total : 148 * 4;
+    int grid = total < 148 * 4 ? (int)total : 148 * 4;
+    T.tiles_per_cta = g_tiles_per_cta;
+    if (T.tiles_per_cta > 0) grid = (int)((total + T.tiles_per_cta - 1) / T.tiles_per_cta);
     if (src == kSrcBox3d) {
         if (generalized) {
             if (affine) tile_kernel<kSrcBox3d, true, true, true, false, 2, false, true><<<grid, 128, 0, s>>>(T);

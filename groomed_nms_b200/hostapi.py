@@ -28,10 +28,21 @@ class Nms3dPlan(object):
     two_kernel=True   : the reference's call sequence instead: overlap kernel writes the matrix, then
                         gnms_forward_f32 streams it back (8*n^2 bytes of matrix traffic); kept for comparison."""
 
-    def __init__(self, batch, n, device, params, materialise=True, box_dof=7, two_kernel=False):
+    def __init__(self, batch, n, device, params, materialise=True, box_dof=7, two_kernel=False, overlap_branch=None):
         self.lib = _lib.load()
         self.B, self.N, self.dev, self.params, self.materialise = batch, n, device, params, materialise
         self.two_kernel = two_kernel and materialise
+        # overlap_branch: the matrix does not depend on the NMS half of the step (leaders are elected directly from the
+        # boxes), so it is written by the matrix-only tile kernel on its own stream / graph branch while the NMS kernels
+        # run on a higher-priority one.  tiles_per_cta > 0 makes the matrix kernel's CTAs retire continuously so that
+        # the NMS kernels find SM slots.
+        if overlap_branch is None:
+            overlap_branch = materialise and not two_kernel
+        self.overlap_branch = bool(overlap_branch) and materialise and not self.two_kernel
+        self.tiles_per_cta = 8
+        if self.overlap_branch:
+            self.side = torch.cuda.Stream(device, priority=0)       # matrix branch (default priority)
+            self.hi = torch.cuda.Stream(device, priority=-1)        # NMS branch
         f = dict(dtype=torch.float32, device=device)
         self.boxes7 = torch.zeros((batch, n, box_dof), **f)
         self.scores = torch.zeros((batch, n), **f)
@@ -49,11 +60,11 @@ class Nms3dPlan(object):
         self.fl = torch.empty((4, batch, n), **f)
         self.ws = torch.empty((int(self.lib.gnms_workspace_bytes(n, batch)),), dtype=torch.uint8, device=device)
         self.saved = Saved(_vp(self.order), _vp(self.fl[0]), _vp(self.lead), _vp(self.fl[1]), _vp(self.fl[2]), _vp(self.fl[3]))
-        # matrix produced: corners, records, sort, rank (gather), tile, has_earlier, chain, backward
         # matrix-free:     corners, records, sort, rank, spatial, elect, zero_failed, list_failed, tile (culled list, empty
         #                  unless the election gave up on an image), has_earlier_failed, chain, backward
+        # matrix produced: the same plus the matrix-only tile kernel
         # (batches below ~10 images rank by counting: one launch fewer; two_kernel: overlap + mask instead of tile/has_earlier)
-        self.launches_per_step = 8 if materialise else 12
+        self.launches_per_step = 13 if materialise else 12
 
     # -- individual stages (each is one C-ABI call = one kernel launch unless noted)
     def stage_corners(self, s):
@@ -64,6 +75,12 @@ class Nms3dPlan(object):
 
     def stage_overlap(self, s):          # one launch, grid.z = image
         check(self.lib.gnms_overlap3d_batched_f32(_vp(self.rec), self.N, self.B, _vp(self.overlap), 1, 1, s), "overlap3d_batched")
+
+    def stage_forward_no_matrix(self, s):
+        p = ctypes.byref(self.params)
+        check(self.lib.gnms_forward_boxes_f32(_vp(self.scores), _vp(self.rec), _lib.BOX_3D_REC, 1, 1, self.N, self.B, None, p,
+                                              None, _vp(self.prob), _vp(self.valid_idx), _vp(self.invalid_idx),
+                                              _vp(self.counts), self.saved, _vp(self.ws), s), "forward_boxes")
 
     def stage_forward(self, s):          # sort + mask + chain: 3 launches
         p = ctypes.byref(self.params)
@@ -87,6 +104,22 @@ class Nms3dPlan(object):
         s = ctypes.c_void_p(st.cuda_stream)
         self.stage_corners(s)
         self.stage_records(s)
+        if self.overlap_branch:
+            # fork: matrix on the side stream, NMS forward + backward on the high-priority stream, join on `st`
+            ev = torch.cuda.Event()
+            ev.record(st)
+            self.side.wait_event(ev)
+            self.hi.wait_event(ev)
+            old = self.lib.gnms_debug_tiles_per_cta(self.tiles_per_cta)
+            self.stage_overlap(ctypes.c_void_p(self.side.cuda_stream))
+            self.lib.gnms_debug_tiles_per_cta(old)
+            sh = ctypes.c_void_p(self.hi.cuda_stream)
+            self.stage_forward_no_matrix(sh)
+            self.stage_backward(sh)
+            e1, e2 = torch.cuda.Event(), torch.cuda.Event()
+            e1.record(self.side); e2.record(self.hi)
+            st.wait_event(e1); st.wait_event(e2)
+            return
         if self.two_kernel:
             self.stage_overlap(s)
         self.stage_forward(s)

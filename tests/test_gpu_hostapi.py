@@ -1,0 +1,85 @@
+"""GPU parity of the allocation-free runners behind bench.py (groomed_nms_b200.hostapi): the CUDA-graph plan with the
+matrix written on its own graph branch, the matrix-free plan, the blocking host-buffer call and the streaming host
+pipeline must all give what the plain C-ABI calls give -- and those are checked against the oracle elsewhere."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(B, N, seed=5):
+    from groomed_nms_b200 import synthetic
+    boxes = np.stack([synthetic.config_c3(seed=seed + 10 * i, n=N, k=max(2, N // 128))[0] for i in range(B)])
+    scores = np.stack([synthetic.config_c3(seed=seed + 10 * i, n=N, k=max(2, N // 128))[1] for i in range(B)])
+    grads = np.random.default_rng(seed).standard_normal((B, N)).astype(np.float32)
+    return boxes, scores, grads
+
+
+def _reference(boxes, scores, grads, params):
+    """Plain calls: corners -> records -> overlap matrix -> forward from the MATRIX -> backward."""
+    from groomed_nms_b200 import ops
+    B, N = scores.shape
+    dev = torch.device("cuda", 0)
+    rec = ops.box3d_records(ops.corners_from_boxes7(torch.from_numpy(boxes).to(dev).view(B * N, 7))).view(B, N, 8)
+    ov = torch.stack([ops.overlap3d(rec[b], rec[b], False, True, generalized=True, affine=True)[1] for b in range(B)])
+    st = ops.forward_matrix(torch.from_numpy(scores).to(dev), ov, params)
+    gs, _ = ops.backward(st, torch.from_numpy(grads).to(dev))
+    return ov, st, gs
+
+
+@pytest.mark.parametrize("B,N", [(3, 1024), (2, 1000), (5, 256)])
+@pytest.mark.parametrize("tiles_per_cta", [0, 3])
+def test_plans_match_plain_calls(B, N, tiles_per_cta):
+    from groomed_nms_b200 import ops
+    from groomed_nms_b200.hostapi import Nms3dPlan
+    dev = torch.device("cuda", 0)
+    params = ops.make_params()
+    boxes, scores, grads = _inputs(B, N)
+    ov, st, gs = _reference(boxes, scores, grads, params)
+    for mat, branch in ((True, True), (True, False), (False, False)):
+        pl = Nms3dPlan(B, N, dev, params, materialise=mat, overlap_branch=branch)
+        pl.tiles_per_cta = tiles_per_cta
+        pl.boxes7.copy_(torch.from_numpy(boxes)); pl.scores.copy_(torch.from_numpy(scores)); pl.grad_prob.copy_(torch.from_numpy(grads))
+        g = pl.capture()
+        for _ in range(3):                                  # replays must be idempotent
+            g.replay()
+        torch.cuda.synchronize()
+        if mat:
+            assert torch.equal(pl.overlap.view(torch.int32), ov.view(torch.int32))
+        assert torch.equal(pl.prob, st.prob) and torch.equal(pl.counts, st.counts) and torch.equal(pl.lead, st.lead)
+        for b in range(B):
+            nv = int(st.counts[b, 0])
+            assert torch.equal(pl.valid_idx[b, :nv], st.valid_idx[b, :nv])
+        assert torch.allclose(pl.grad_scores, gs, rtol=1e-6, atol=1e-7)
+
+
+def test_host_runner_and_pipeline_match_plain_calls():
+    from groomed_nms_b200 import ops
+    from groomed_nms_b200.hostapi import HostPipeline, HostRunner
+    dev = torch.device("cuda", 0)
+    params = ops.make_params()
+    B, N = 4, 768
+    batches = [_inputs(B, N, seed=20 + k) for k in range(5)]
+    want = [_reference(*x, params) for x in batches]
+    pinned = [[torch.from_numpy(a).pin_memory() for a in x] for x in batches]
+    runner = HostRunner(B, N, dev, params)
+    for x, (_, st, gs) in zip(pinned, want):
+        prob, grad, valid, counts = runner.run_host(*x)
+        assert torch.equal(prob, st.prob.cpu()) and torch.equal(counts, st.counts.cpu())
+        assert torch.allclose(grad, gs.cpu(), rtol=1e-6, atol=1e-7)
+    pipe = HostPipeline(B, N, dev, params, depth=3)
+    tickets = []
+    for k, x in enumerate(pinned):
+        tickets.append(pipe.submit(*x))
+        if k >= 2:                                          # read a result while later calls are in flight
+            j = k - 2
+            prob, grad, valid, counts = pipe.wait(tickets[j])
+            assert torch.equal(prob, want[j][1].prob.cpu()) and torch.equal(counts, want[j][1].counts.cpu())
+            assert torch.allclose(grad, want[j][2].cpu(), rtol=1e-6, atol=1e-7)
+    pipe.drain()
+    for j in (3, 4):
+        prob, grad, valid, counts = pipe.wait(tickets[j])
+        assert torch.equal(prob, want[j][1].prob.cpu())
+        nv = int(counts[0, 0])
+        assert torch.equal(valid[0, :nv], want[j][1].valid_idx[0, :nv].cpu())
