@@ -112,7 +112,8 @@ int gnms_box3d_records_f32(float* corners, int N, float* rec, int mutate_input, 
  * mul2d (NULL or [M,N] with ld_out): out_3d *= mul2d  (overlap_in_nms="product", lib/loss/rpn_3d.py:786). */
 int gnms_overlap3d_f32(const float* rec_a, int M, const float* rec_b, int N, float* out_bev, float* out_3d,
                        int64_t ld_out, int generalized, int affine, const float* mul2d, void* stream);
-/* Batched self-overlaps (one launch, grid.z = image): boxes[B,N,4] -> out[B,N,N] IoU; rec[B,N,8] -> out_3d[B,N,N]. */
+/* Batched self-overlaps (one launch): boxes[B,N,4] -> out[B,N,N] IoU; rec[B,N,8] -> out_3d[B,N,N].  Symmetric 64x64
+ * tiles, every unordered pair evaluated once, the tile and its mirror image stored straight from registers. */
 int gnms_overlap2d_batched_f32(const float* boxes, int N, int batch, float* out, void* stream);
 int gnms_overlap3d_batched_f32(const float* rec, int N, int batch, float* out_3d, int generalized, int affine,
                                void* stream);
@@ -146,12 +147,16 @@ int gnms_forward_f32(const float* scores, const float* iou, int64_t ld, int N, i
                      const int32_t* n_per_image, const gnms_params* p, float* prob, int64_t* valid_idx,
                      int64_t* invalid_idx, int32_t* counts, gnms_saved saved, void* workspace, void* stream);
 
-/* Forward from BOXES (the fused north-star path): every pair of boxes is evaluated once, register-resident, by
- * the symmetric tile kernel, which feeds the grouping stage directly (suppression bits) and -- if overlap_out is
- * not NULL -- also streams the API-visible overlap matrix [batch,N,N] to HBM (written once, never read back;
- * bitwise equal to gnms_overlap2d_f32 / gnms_overlap3d_f32).  boxes: box_kind GNMS_BOX_2D float[batch,N,4] or
- * GNMS_BOX_3D_REC float[batch,N,8] records; overlap3d flags as in gnms_overlap3d_f32 (generalized, affine).
- * Same outputs as gnms_forward_f32. */
+/* Forward from BOXES (the fused north-star path): no overlap matrix is read.  boxes: box_kind GNMS_BOX_2D
+ * float[batch,N,4] or GNMS_BOX_3D_REC float[batch,N,8] records; overlap3d flags as in gnms_overlap3d_f32 (generalized,
+ * affine).  Same outputs as gnms_forward_f32, bit for bit what it gives on the matrix of the same boxes.
+ *   mode GROUP_MASK, N <= 4096: the leaders are elected directly from the boxes (the reference's greedy loop,
+ *     lib/groomed_nms.py:247-262, one CTA per image, only the leaders' overlap columns are ever evaluated); an image
+ *     that needs more than 384 leaders falls back, inside the same call, to
+ *   the general route: every unordered pair of boxes is evaluated once, register-resident, by the symmetric tile
+ *     kernel (spatially culled when no matrix is wanted), which emits the suppression bits the greedy stage consumes.
+ * overlap_out (optional, [batch,N,N]): the API-visible overlap matrix is also streamed to HBM (written once, never
+ * read back; bitwise equal to gnms_overlap2d_f32 / gnms_overlap3d_f32). */
 int gnms_forward_boxes_f32(const float* scores, const float* boxes, int box_kind, int generalized, int affine,
                            int N, int batch, const int32_t* n_per_image, const gnms_params* p, float* overlap_out,
                            float* prob, int64_t* valid_idx, int64_t* invalid_idx, int32_t* counts, gnms_saved saved,
