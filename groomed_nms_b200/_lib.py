@@ -61,6 +61,8 @@ SIGNATURES = {
     "gnms_soft_nms_workspace_bytes": (sz, [i32]),
     "gnms_aploss_f32": (i32, [vp, vp, i32, vp, vp, vp, sz, vp]),
     "gnms_aploss_workspace_bytes": (sz, [i32]),
+    "gnms_targets_overlaps_workspace_bytes": (sz, [i32, i32]),
+    "gnms_targets_overlaps_f64": (i32, [vp, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
 }
 
 _lib = None

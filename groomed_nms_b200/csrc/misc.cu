@@ -238,6 +238,98 @@ __global__ void indices_copy_kernel(float* __restrict__ A, int64_t colsA, const 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------ target-assignment overlaps
+// lib/rpn_util.py:439-461 (compute_targets): ols = iou(rois, gts) [M,G] in float64 (numpy promotes the float32 rois
+// against the float64 ground truths; only area_a stays float32 arithmetic, flag area_f32), its row max / argmax
+// (first maximum, NaN counts as the maximum: np.amax / np.argmax) and, per ground truth, the best roi (first maximum
+// over the rows).  kind = 1: iou_ign (lib/core.py:535-575), intersection over the roi's own area.  A thread owns one
+// roi; the G <= 64 ground truths sit in shared memory; the per-column (value, row) maxima are reduced per CTA into
+// partials, finalised by col_finalize_kernel.
+constexpr int kTgtThreads = 256;
+constexpr int kTgtMaxG = 64;
+__device__ __forceinline__ bool better_max(double v, double best) {          // strict: the first maximum stays
+    return (v != v && best == best) || (best == best && v > best);
+}
+
+__global__ void __launch_bounds__(kTgtThreads)
+targets_overlaps_kernel(const double* __restrict__ rois, int64_t ld, int M, const double* __restrict__ gts, int G, int kind,
+                        int area_f32, double* __restrict__ ols, double* __restrict__ row_max, int64_t* __restrict__ row_arg,
+                        double* __restrict__ part_val, int32_t* __restrict__ part_idx) {
+    __shared__ double s_g[kTgtMaxG][5];
+    __shared__ double s_cv[kTgtThreads / 32][kTgtMaxG];
+    __shared__ int s_ci[kTgtThreads / 32][kTgtMaxG];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int g = tid; g < G; g += kTgtThreads) {
+        const double x1 = gts[g * 4 + 0], y1 = gts[g * 4 + 1], x2 = gts[g * 4 + 2], y2 = gts[g * 4 + 3];
+        s_g[g][0] = x1; s_g[g][1] = y1; s_g[g][2] = x2; s_g[g][3] = y2;
+        s_g[g][4] = __dmul_rn(__dsub_rn(x2, x1), __dsub_rn(y2, y1));
+    }
+    __syncthreads();
+    const int i = blockIdx.x * kTgtThreads + tid;
+    const bool live = i < M;
+    double x1 = 0, y1 = 0, x2 = 0, y2 = 0, area = 0;
+    if (live) {
+        x1 = rois[(int64_t)i * ld + 0]; y1 = rois[(int64_t)i * ld + 1]; x2 = rois[(int64_t)i * ld + 2]; y2 = rois[(int64_t)i * ld + 3];
+        if (area_f32) area = (double)__fmul_rn(__fsub_rn((float)x2, (float)x1), __fsub_rn((float)y2, (float)y1));
+        else area = __dmul_rn(__dsub_rn(x2, x1), __dsub_rn(y2, y1));
+    }
+    double best = -INFINITY;
+    int barg = 0;
+    for (int g = 0; g < G; ++g) {
+        double v = -INFINITY;
+        if (live) {
+            const double w = fmax(__dsub_rn(fmin(x2, s_g[g][2]), fmax(x1, s_g[g][0])), 0.0);     // lib/core.py:205-207
+            const double h = fmax(__dsub_rn(fmin(y2, s_g[g][3]), fmax(y1, s_g[g][1])), 0.0);
+            const double inter = __dmul_rn(w, h);                                                // :218
+            double uni;
+            if (kind == 0) uni = __dsub_rn(__dadd_rn(area, s_g[g][4]), inter);                   // :511
+            else uni = __dsub_rn(__dadd_rn(area, __dmul_rn(s_g[g][4], 0.0)), __dmul_rn(inter, 0.0));   // :564
+            v = __ddiv_rn(inter, uni);
+            if (ols) ols[(int64_t)i * G + g] = v;
+            if (g == 0 || better_max(v, best)) { best = v; barg = g; }
+        }
+        // column maximum over the rows of this CTA: (value, lowest row index)
+        double cv = v;
+        int ci = live ? i : INT_MAX;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, cv, d);
+            const int oi = __shfl_down_sync(0xffffffffu, ci, d);
+            if (oi != INT_MAX && (ci == INT_MAX || better_max(ov, cv) || (!(better_max(cv, ov)) && oi < ci))) { cv = ov; ci = oi; }
+        }
+        if (lane == 0) { s_cv[warp][g] = cv; s_ci[warp][g] = ci; }
+    }
+    if (live) { row_max[i] = best; row_arg[i] = barg; }
+    __syncthreads();
+    for (int g = tid; g < G; g += kTgtThreads) {
+        double cv = s_cv[0][g];
+        int ci = s_ci[0][g];
+        for (int w = 1; w < kTgtThreads / 32; ++w) {
+            const double ov = s_cv[w][g];
+            const int oi = s_ci[w][g];
+            if (oi != INT_MAX && (ci == INT_MAX || better_max(ov, cv) || (!(better_max(cv, ov)) && oi < ci))) { cv = ov; ci = oi; }
+        }
+        part_val[(size_t)blockIdx.x * G + g] = cv;
+        part_idx[(size_t)blockIdx.x * G + g] = ci;
+    }
+}
+
+__global__ void col_finalize_kernel(const double* __restrict__ part_val, const int32_t* __restrict__ part_idx, int nblocks, int G,
+                                    double* __restrict__ col_max, int64_t* __restrict__ col_arg) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    double cv = part_val[g];
+    int ci = part_idx[g];
+    for (int b = 1; b < nblocks; ++b) {                                     // blocks are in row order: strict keeps the first maximum
+        const double ov = part_val[(size_t)b * G + g];
+        const int oi = part_idx[(size_t)b * G + g];
+        if (oi != INT_MAX && (ci == INT_MAX || better_max(ov, cv))) { cv = ov; ci = oi; }
+    }
+    col_max[g] = cv;
+    col_arg[g] = ci == INT_MAX ? 0 : ci;
+}
+
 }  // namespace gnms
 
 using namespace gnms;
@@ -306,6 +398,30 @@ extern "C" int gnms_aploss_f32(const float* logits, const float* targets, int n,
     float* fg_prec = reinterpret_cast<float*>(w + al256((size_t)n * 4) + al256((size_t)n * 8));
     unsigned long long* fg_keys = reinterpret_cast<unsigned long long*>(w + al256((size_t)n * 4) + al256((size_t)n * 8) + al256((size_t)n * 4));
     aploss_kernel<<<1, kT, 0, s>>>(logits, targets, n, loss, grad, fg_list, fg_ab, fg_prec, fg_keys);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" size_t gnms_targets_overlaps_workspace_bytes(int M, int G) {
+    if (M <= 0 || G <= 0) return 256;
+    const size_t nb = (size_t)((M + kTgtThreads - 1) / kTgtThreads);
+    return nb * G * (sizeof(double) + sizeof(int32_t)) + 512;
+}
+
+extern "C" int gnms_targets_overlaps_f64(const double* rois, int64_t ld_rois, int M, const double* gts, int G, int kind, int area_f32,
+                                         double* ols, double* row_max, int64_t* row_arg, double* col_max, int64_t* col_arg,
+                                         void* workspace, void* stream) {
+    if (M < 0 || G < 0 || ld_rois < 4 || kind < 0 || kind > 1) return GNMS_E_BADARG;
+    if (G > kTgtMaxG) return GNMS_E_TOOLARGE;
+    if (M == 0 || G == 0) return 0;
+    if (!rois || !gts || !row_max || !row_arg || !col_max || !col_arg || !workspace) return GNMS_E_BADARG;
+    const int nb = (M + kTgtThreads - 1) / kTgtThreads;
+    double* pv = reinterpret_cast<double*>(workspace);
+    int32_t* pi = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + (((size_t)nb * G * sizeof(double) + 255) & ~(size_t)255));
+    cudaStream_t s = (cudaStream_t)stream;
+    targets_overlaps_kernel<<<nb, kTgtThreads, 0, s>>>(rois, ld_rois, M, gts, G, kind, area_f32, ols, row_max, row_arg, pv, pi);
+    GNMS_LAUNCH_CHECK();
+    col_finalize_kernel<<<(G + 63) / 64, 64, 0, s>>>(pv, pi, nb, G, col_max, col_arg);
     GNMS_LAUNCH_CHECK();
     return 0;
 }

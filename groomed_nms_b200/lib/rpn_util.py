@@ -75,3 +75,45 @@ def nms_after_detection(coords_2d, scores, coords_3d, coords_3d_raw, cls_pred, t
     rows = sorted_inds[:num_boxes][keep]                                                        # :1337-1340
     out = torch.cat([c2[rows], sc[rows, None], cls[rows], c3[rows], trk[rows]], dim=1)
     return (out.cpu().numpy(), keep.cpu().numpy()) if as_numpy else (out, keep)
+
+
+def targets_overlaps(rois, gts_val, gts_ign):
+    """The overlap part of the reference's compute_targets (lib/rpn_util.py:439-461) on the GPU, in float64 with the call
+    site's numpy promotion rules (float32 rois keep a float32 area_a).  rois [M,>=4], gts_val [G,4], gts_ign [Gi,4]
+    (numpy or tensors; G, Gi <= 64, either may be empty).
+    -> dict with what the reference derives right there: ols [M,G], ols_max = amax(ols, 1), targets = argmax(ols, 1),
+       gt_best_rois = argmax(ols, 0), gt_best_ols = amax(ols, 0) (absent when there is no valid ground truth) and
+       ols_ign_max = amax(iou_ign(rois, gts_ign), 1) (zeros when there is no ignore region, :443).
+    numpy in -> numpy out."""
+    as_numpy = not torch.is_tensor(rois)
+    dev = rois.device if torch.is_tensor(rois) and rois.is_cuda else device()
+    area_f32 = int((rois.dtype == torch.float32) if torch.is_tensor(rois) else (np.asarray(rois).dtype == np.float32))
+    r = _to_dev(rois, dev, torch.float64).contiguous()
+    M = r.shape[0]
+    lib = _lib.load()
+
+    def run(gts, kind, want_ols):
+        g = _to_dev(gts, dev, torch.float64).reshape(-1, 4).contiguous()
+        G = g.shape[0]
+        ols = torch.empty((M, G), dtype=torch.float64, device=dev) if want_ols else None
+        rmax = torch.empty((M,), dtype=torch.float64, device=dev); rarg = torch.empty((M,), dtype=torch.int64, device=dev)
+        cmax = torch.empty((G,), dtype=torch.float64, device=dev); carg = torch.empty((G,), dtype=torch.int64, device=dev)
+        if M and G:
+            ws = torch.empty((int(lib.gnms_targets_overlaps_workspace_bytes(M, G)),), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.gnms_targets_overlaps_f64(ops._p(r), r.stride(0), M, ops._p(g), G, kind, area_f32, ops._p(ols), ops._p(rmax),
+                                                         ops._p(rarg), ops._p(cmax), ops._p(carg), ops._p(ws), ops._stream(dev)),
+                           "gnms_targets_overlaps_f64")
+        return ols, rmax, rarg, cmax, carg
+
+    out = {}
+    if (gts_val.shape[0] if hasattr(gts_val, "shape") else len(gts_val)) > 0:
+        ols, rmax, rarg, cmax, carg = run(gts_val, 0, True)
+        out.update(ols=ols, ols_max=rmax, targets=rarg, gt_best_rois=carg, gt_best_ols=cmax)
+    if (gts_ign.shape[0] if hasattr(gts_ign, "shape") else len(gts_ign)) > 0:
+        out["ols_ign_max"] = run(gts_ign, 1, False)[1]
+    else:
+        out["ols_ign_max"] = torch.zeros((M,), dtype=torch.float32, device=dev)
+    if as_numpy:
+        out = {k: v.cpu().numpy() for k, v in out.items()}
+    return out

@@ -20,6 +20,7 @@
  *                                              -> gnms_hard_nms_f32 and the host-pointer `gnms_nms_host`
  *   lib/nms_others.py:6-116 navneeth_soft_nms  -> gnms_soft_nms_f64
  *   lib/loss/aploss.py:14-97 backpropAPLoss    -> gnms_aploss_f32
+ *   lib/rpn_util.py:439-461 compute_targets overlaps (lib/core.py iou / iou_ign, numpy branch) -> gnms_targets_overlaps_f64
  */
 #ifndef GROOMED_NMS_B200_H_
 #define GROOMED_NMS_B200_H_
@@ -214,6 +215,17 @@ size_t gnms_soft_nms_workspace_bytes(int N);
 int gnms_aploss_f32(const float* logits, const float* targets, int n, float* loss, float* grad,
                     void* workspace, size_t workspace_bytes, void* stream);
 size_t gnms_aploss_workspace_bytes(int n);
+
+/* ---------------------------------------------------------------- target-assignment overlaps (next to the path) */
+/* lib/rpn_util.py:439-461 compute_targets: ols = iou(rois, gts) (kind GNMS_KIND_IOU, lib/core.py:480-513 numpy branch)
+ * or iou_ign(rois, gts) (kind 1, lib/core.py:535-575), float64 like numpy's promotion at the call site (rois float32,
+ * ground truths float64; area_f32 != 0 keeps the rois' own area in float32 arithmetic as numpy does there).
+ * rois[M, ld_rois >= 4] and gts[G <= 64, 4] are device float64.  Outputs: ols[M,G] (optional), row_max[M] / row_arg[M]
+ * (np.amax / np.argmax over axis 1: first maximum, NaN is the maximum), col_max[G] / col_arg[G] (axis 0). */
+size_t gnms_targets_overlaps_workspace_bytes(int M, int G);
+int gnms_targets_overlaps_f64(const double* rois, int64_t ld_rois, int M, const double* gts, int G, int kind, int area_f32,
+                              double* ols, double* row_max, int64_t* row_arg, double* col_max, int64_t* col_arg,
+                              void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -526,3 +526,42 @@ def aploss(logits, targets, delta=1.0):
     grad /= F32(nfg)
     metric = prec.sum(dtype=F32) / F32(nfg)
     return F32(1) - metric, grad
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Target-assignment overlaps                              reference: lib/rpn_util.py:439-461 (compute_targets)
+# ---------------------------------------------------------------------------------------------------------
+def targets_overlaps(rois, gts_val, gts_ign):
+    """numpy restatement of the overlap part of compute_targets with the call site's dtypes: rois float32 [M,>=4],
+    ground truths float64.  lib/core.py:205-207,218 (intersect), :497-513 (iou), :556-564 (iou_ign): min / max / clip and
+    the union are evaluated after numpy's promotion to float64, but area_a = (x2-x1)*(y2-y1) of the rois stays float32.
+    -> dict(ols [M,G] f64, ols_max, targets, gt_best_rois, gt_best_ols, ols_ign_max)"""
+    a32 = np.asarray(rois)[:, :4]
+    a = a32.astype(np.float64)
+
+    def inter(b):
+        hi = np.minimum(a[None, :, 2:4], b[:, None, 2:4])
+        lo = np.maximum(a[None, :, 0:2], b[:, None, 0:2])
+        d = np.clip(hi - lo, 0, None)
+        return d[:, :, 0] * d[:, :, 1]                                                   # [G,M]
+
+    area_a = ((a32[:, 2] - a32[:, 0]) * (a32[:, 3] - a32[:, 1])).astype(np.float64)      # float32 arithmetic when rois are float32
+    out = {}
+    g = np.asarray(gts_val, dtype=np.float64).reshape(-1, 4)
+    if g.shape[0]:
+        it = inter(g)
+        area_b = (g[:, 2] - g[:, 0]) * (g[:, 3] - g[:, 1])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ols = (it / (area_a[None, :] + area_b[:, None] - it)).T
+        out.update(ols=ols, ols_max=np.amax(ols, axis=1), targets=np.argmax(ols, axis=1),
+                   gt_best_rois=np.argmax(ols, axis=0), gt_best_ols=np.amax(ols, axis=0))
+    gi = np.asarray(gts_ign, dtype=np.float64).reshape(-1, 4)
+    if gi.shape[0]:
+        it = inter(gi)
+        area_b = (gi[:, 2] - gi[:, 0]) * (gi[:, 3] - gi[:, 1])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ols_ign = (it / (area_a[None, :] + area_b[:, None] * 0 - it * 0)).T
+        out["ols_ign_max"] = np.amax(ols_ign, axis=1)
+    else:
+        out["ols_ign_max"] = np.zeros(a.shape[0], dtype=np.float32)                     # lib/rpn_util.py:443
+    return out
