@@ -548,3 +548,30 @@ def test_direct_election_mixed_batch_and_fallback(kind):
             assert torch.allclose(g1, g2, rtol=1e-6, atol=1e-7)
     finally:
         lib.gnms_debug_direct_election(1)
+
+
+def test_config_c4_batched_2d_images_vs_oracle(G):
+    """BASELINE config 4: a batch of independent N=2048 2D images (16 clusters each), one ragged launch sequence.  Every
+    image equals its own single-image call; three of them are checked against the oracle (forward and backward)."""
+    from groomed_nms_b200 import _lib, ops, synthetic
+    from oracle import groomed_oracle as O
+    B, N = 32, 2048
+    data = [synthetic.config_c4_image(i) for i in range(B)]
+    boxes = np.stack([d[0] for d in data]); sc = np.stack([d[1] for d in data])
+    p = ops.make_params(nms_threshold=0.4, temperature=0.1, group_size=100)
+    st = ops.forward_boxes(cuda(sc), cuda(boxes), _lib.BOX_2D, p)
+    up = np.random.default_rng(4).standard_normal((B, N)).astype(np.float32)
+    gs, _ = ops.backward(st, cuda(up))
+    torch.cuda.synchronize()
+    assert int(st.counts.sum()) == B * N
+    for b in (0, 13, 31):
+        iou = O.iou(boxes[b], boxes[b])
+        o = O.differentiable_nms(sc[b], iou, nms_threshold=0.4, temperature=0.1, group_size=100, dense=False)
+        nv = int(st.counts[b, 0])
+        check_against(o, st.prob[b].cpu().numpy(), st.valid_idx[b, :nv].cpu().numpy(), st.invalid_idx[b, :N - nv].cpu().numpy())
+        assert np.array_equal(st.lead[b].cpu().numpy(), o["lead"])
+        want, _ = O.differentiable_nms_backward(o, up[b], need_grad_iou=False)
+        assert np.allclose(gs[b].cpu().numpy(), want, rtol=1e-5, atol=2e-6 * np.abs(want).max())
+    for b in (1, 7, 20):
+        s1 = ops.forward_boxes(cuda(sc[b:b + 1]), cuda(boxes[b:b + 1]), _lib.BOX_2D, p)
+        assert torch.equal(s1.prob[0], st.prob[b]) and torch.equal(s1.lead[0], st.lead[b]) and torch.equal(s1.counts[0], st.counts[b])
