@@ -289,8 +289,7 @@ def run_ours(args, rank, world):
         st = torch.cuda.current_stream(dev)
         pl = plans["materialised"]
         it = max(10, args.steps)
-        stages["corners"] = time_stage(torch, pl.stage_corners, st, it)
-        stages["records"] = time_stage(torch, pl.stage_records, st, it)
+        stages["records_from_boxes7(corners in registers)"] = time_stage(torch, pl.stage_front, st, it)
         stages["forward_boxes+matrix_out(all kernels, one stream)"] = time_stage(torch, pl.stage_forward, st, it)
         # the kernels of that forward one by one (debug stage mask of the library: the same launches, in isolation)
         old_tpc = lib.gnms_debug_tiles_per_cta(args.tiles_per_cta if not args.no_overlap_branch else 0)   # as launched in the step

@@ -69,10 +69,8 @@ __global__ void overlap2d_list_kernel(const float* __restrict__ a, const float* 
 
 // 7-DoF -> 8 corners.  Template corners (l on x for idx {1,3,5,6}; h on y for {2,3,6,7}; w on z for {4,5,6,7},
 // centred), rotation about y, translation                                     lib/math_3d.py:369-435
-__global__ void corners_kernel(const float* __restrict__ boxes7, int64_t ld, int N, float* __restrict__ corners) {
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const float* p = boxes7 + (int64_t)n * ld;
+// corners of one cuboid (lib/math_3d.py:364-435), x / y / z of the 8 corners
+__device__ __forceinline__ void corners_of(const float* __restrict__ p, float (&ox)[8], float (&oy)[8], float (&oz)[8]) {
     float x = p[0], y = p[1], z = p[2], w = p[3], h = p[4], l = p[5], ry = p[6];
     float cs = cosf(ry), sn = sinf(ry);
     float hl = __fdiv_rn(l, 2.0f), hh = __fdiv_rn(h, 2.0f), hw = __fdiv_rn(w, 2.0f);
@@ -81,7 +79,6 @@ __global__ void corners_kernel(const float* __restrict__ boxes7, int64_t ld, int
     float cz[2] = {__fsub_rn(0.0f, hw), __fsub_rn(w, hw)};
     // corner k uses: x-high for k in {1,3,5,6}; y-high for {2,3,6,7}; z-high for {4,5,6,7}
     const unsigned xmask = 0x6Au, ymask = 0xCCu, zmask = 0xF0u;
-    float ox[8], oy[8], oz[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         float px = cx[(xmask >> k) & 1], py = cy[(ymask >> k) & 1], pz = cz[(zmask >> k) & 1];
@@ -90,21 +87,9 @@ __global__ void corners_kernel(const float* __restrict__ boxes7, int64_t ld, int
         oy[k] = __fadd_rn(py, y);
         oz[k] = __fadd_rn(__fadd_rn(__fmul_rn(-sn, px), __fmul_rn(cs, pz)), z);
     }
-    float4* o = reinterpret_cast<float4*>(corners + (int64_t)n * 24);
-    o[0] = make_float4(ox[0], ox[1], ox[2], ox[3]);
-    o[1] = make_float4(ox[4], ox[5], ox[6], ox[7]);
-    o[2] = make_float4(oy[0], oy[1], oy[2], oy[3]);
-    o[3] = make_float4(oy[4], oy[5], oy[6], oy[7]);
-    o[4] = make_float4(oz[0], oz[1], oz[2], oz[3]);
-    o[5] = make_float4(oz[4], oz[5], oz[6], oz[7]);
 }
-
-// corners[N,3,8] -> rec[N,8]                                                   lib/core.py:354-388,434-477
-__global__ void records_kernel(float* __restrict__ corners, int N, float* __restrict__ rec, int mutate) {
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    float4* c = reinterpret_cast<float4*>(corners + (int64_t)n * 24);
-    float4 x0 = c[0], x1 = c[1], y0 = c[2], y1 = c[3], z0 = c[4], z1 = c[5];
+// per-box record iou3d_approximate derives from the corners (lib/core.py:354-388)
+__device__ __forceinline__ void record_of(float4 x0, float4 x1, float4 y0, float4 y1, float4 z0, float4 z1, float4& o0, float4& o1) {
     float xmin = fminf(fminf(fminf(x0.x, x0.y), fminf(x0.z, x0.w)), fminf(fminf(x1.x, x1.y), fminf(x1.z, x1.w)));
     float xmax = fmaxf(fmaxf(fmaxf(x0.x, x0.y), fmaxf(x0.z, x0.w)), fmaxf(fmaxf(x1.x, x1.y), fmaxf(x1.z, x1.w)));
     float ymin = fminf(fminf(fminf(y0.x, y0.y), fminf(y0.z, y0.w)), fminf(fminf(y1.x, y1.y), fminf(y1.z, y1.w)));
@@ -116,12 +101,49 @@ __global__ void records_kernel(float* __restrict__ corners, int N, float* __rest
     float bz1 = fminf(fminf(z0.z, z0.w), fminf(z1.z, z1.w)), bz2 = fmaxf(fmaxf(z0.z, z0.w), fmaxf(z1.z, z1.w));
     float vol = __fmul_rn(__fmul_rn(__fsub_rn(xmax, xmin), __fsub_rn(ymax, ymin)), __fsub_rn(zmax, zmin));  // :448
     float abev = __fmul_rn(__fsub_rn(bx2, bx1), __fsub_rn(bz2, bz1));
+    o0 = make_float4(ymin, ymax, bx1, bx2);
+    o1 = make_float4(bz1, bz2, vol, abev);
+}
+
+__global__ void corners_kernel(const float* __restrict__ boxes7, int64_t ld, int N, float* __restrict__ corners) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float ox[8], oy[8], oz[8];
+    corners_of(boxes7 + (int64_t)n * ld, ox, oy, oz);
+    float4* o = reinterpret_cast<float4*>(corners + (int64_t)n * 24);
+    o[0] = make_float4(ox[0], ox[1], ox[2], ox[3]);
+    o[1] = make_float4(ox[4], ox[5], ox[6], ox[7]);
+    o[2] = make_float4(oy[0], oy[1], oy[2], oy[3]);
+    o[3] = make_float4(oy[4], oy[5], oy[6], oy[7]);
+    o[4] = make_float4(oz[0], oz[1], oz[2], oz[3]);
+    o[5] = make_float4(oz[4], oz[5], oz[6], oz[7]);
+}
+__global__ void records_kernel(float* __restrict__ corners, int N, float* __restrict__ rec, int mutate) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float4* c = reinterpret_cast<float4*>(corners + (int64_t)n * 24);
+    float4 x0 = c[0], x1 = c[1], y0 = c[2], y1 = c[3], z0 = c[4], z1 = c[5];
     float4* o = reinterpret_cast<float4*>(rec + (int64_t)n * 8);
-    o[0] = make_float4(ymin, ymax, bx1, bx2);
-    o[1] = make_float4(bz1, bz2, vol, abev);
+    record_of(x0, x1, y0, y1, z0, z1, o[0], o[1]);
     if (mutate) {  // the reference overwrites Y with Z in the caller's storage (lib/core.py:379-380)
         c[2] = z0;
         c[3] = z1;
+    }
+}
+// both in one pass: 7-DoF boxes -> records (and, if asked, the corners as well); same arithmetic, same bits
+__global__ void records7_kernel(const float* __restrict__ boxes7, int64_t ld, int N, float* __restrict__ rec, float* __restrict__ corners) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float ox[8], oy[8], oz[8];
+    corners_of(boxes7 + (int64_t)n * ld, ox, oy, oz);
+    const float4 x0 = make_float4(ox[0], ox[1], ox[2], ox[3]), x1 = make_float4(ox[4], ox[5], ox[6], ox[7]);
+    const float4 y0 = make_float4(oy[0], oy[1], oy[2], oy[3]), y1 = make_float4(oy[4], oy[5], oy[6], oy[7]);
+    const float4 z0 = make_float4(oz[0], oz[1], oz[2], oz[3]), z1 = make_float4(oz[4], oz[5], oz[6], oz[7]);
+    float4* o = reinterpret_cast<float4*>(rec + (int64_t)n * 8);
+    record_of(x0, x1, y0, y1, z0, z1, o[0], o[1]);
+    if (corners) {
+        float4* c = reinterpret_cast<float4*>(corners + (int64_t)n * 24);
+        c[0] = x0; c[1] = x1; c[2] = y0; c[3] = y1; c[4] = z0; c[5] = z1;
     }
 }
 
@@ -480,6 +502,16 @@ extern "C" int gnms_project_points_f32(const float* p2, const float* pts, int64_
     if (n == 0) return 0;
     if (!p2 || !pts || !out) return GNMS_E_BADARG;
     project_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p2, pts, n, pad_ones, out);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gnms_box3d_records_from_boxes7_f32(const float* boxes7, int64_t ld, int N, float* rec, float* corners, void* stream) {
+    if (N < 0 || ld < 7) return GNMS_E_BADARG;
+    if (N == 0) return 0;
+    if (!boxes7 || !rec) return GNMS_E_BADARG;
+    if (!aligned16(rec) || (corners && !aligned16(corners))) return GNMS_E_ALIGN;
+    records7_kernel<<<gnms_div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(boxes7, ld, N, rec, corners);
     GNMS_LAUNCH_CHECK();
     return 0;
 }

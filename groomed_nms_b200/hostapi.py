@@ -60,11 +60,11 @@ class Nms3dPlan(object):
         self.fl = torch.empty((4, batch, n), **f)
         self.ws = torch.empty((int(self.lib.gnms_workspace_bytes(n, batch)),), dtype=torch.uint8, device=device)
         self.saved = Saved(_vp(self.order), _vp(self.fl[0]), _vp(self.lead), _vp(self.fl[1]), _vp(self.fl[2]), _vp(self.fl[3]))
-        # matrix-free:     corners, records, sort, rank, spatial, elect, zero_failed, list_failed, tile (culled list, empty
+        # matrix-free:     records (from the 7-DoF boxes), sort, rank, spatial, elect, zero_failed, list_failed, tile (culled list, empty
         #                  unless the election gave up on an image), has_earlier_failed, chain, backward
         # matrix produced: the same plus the matrix-only tile kernel
         # (batches below ~10 images rank by counting: one launch fewer; two_kernel: overlap + mask instead of tile/has_earlier)
-        self.launches_per_step = 13 if materialise else 12
+        self.launches_per_step = 12 if materialise else 11
 
     # -- individual stages (each is one C-ABI call = one kernel launch unless noted)
     def stage_corners(self, s):
@@ -98,12 +98,19 @@ class Nms3dPlan(object):
                                          ctypes.byref(self.params), self.saved, _vp(self.grad_scores), None, self.N,
                                          _vp(self.ws), s), "backward")
 
+    def stage_front(self, s):            # 7-DoF boxes -> records in one launch (the corners stay in registers)
+        check(self.lib.gnms_box3d_records_from_boxes7_f32(_vp(self.boxes7), self.boxes7.stride(1), self.B * self.N, _vp(self.rec),
+                                                          None, s), "records_from_boxes7")
+
     def step(self, stream=None):
         """Enqueue one forward+backward pass over the batch on `stream` (default: torch's current stream)."""
         st = stream if stream is not None else torch.cuda.current_stream(self.dev)
         s = ctypes.c_void_p(st.cuda_stream)
-        self.stage_corners(s)
-        self.stage_records(s)
+        if self.two_kernel:
+            self.stage_corners(s)
+            self.stage_records(s)
+        else:
+            self.stage_front(s)
         if self.overlap_branch:
             # fork: matrix on the side stream, NMS forward + backward on the high-priority stream, join on `st`
             ev = torch.cuda.Event()
@@ -196,15 +203,18 @@ class HostRunner(object):
         self.h_counts = torch.empty((batch, 2), dtype=torch.int32, **pin)
         self.h2d_bytes = batch * n * (7 + 1 + 1) * 4
         self.d2h_bytes = batch * n * (4 + 4 + 8) + batch * 8
+        self.graph = None                        # the kernel sequence as a CUDA graph, captured on first use
 
     def run_host(self, boxes7_host, scores_host, grad_prob_host):
         """boxes7 [B,N,7], scores [B,N], dL/dprob [B,N] (pinned host fp32) -> (prob, grad_scores, valid_idx, counts)
-        on the host.  One H2D per input, the kernels, one D2H per output, one stream sync."""
+        on the host.  One H2D per input, the kernels (one graph launch), one D2H per output, one stream sync."""
         p = self.plan
+        if self.graph is None:
+            self.graph = p.capture()
         p.boxes7.copy_(boxes7_host, non_blocking=True)
         p.scores.copy_(scores_host, non_blocking=True)
         p.grad_prob.copy_(grad_prob_host, non_blocking=True)
-        p.step()
+        self.graph.replay()
         self.h_prob.copy_(p.prob, non_blocking=True)
         self.h_grad.copy_(p.grad_scores, non_blocking=True)
         self.h_valid.copy_(p.valid_idx, non_blocking=True)

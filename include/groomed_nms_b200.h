@@ -107,6 +107,9 @@ int gnms_project_points_f32(const float* p2, const float* pts, int64_t n, int pa
 /* corners[N,3,8] -> rec[N,8] = (ymin,ymax,bx1,bx2,bz1,bz2,vol,area_bev) exactly as iou3d_approximate derives
  * them (lib/core.py:354-388).  mutate_input!=0 reproduces the reference's in-place Y<-Z write (:379-380). */
 int gnms_box3d_records_f32(float* corners, int N, float* rec, int mutate_input, void* stream);
+/* Both steps in one launch: boxes7[N,7] (row stride ld) -> rec[N,8], and corners[N,3,8] too if not NULL.  Same bits as
+ * gnms_corners_from_boxes7_f32 followed by gnms_box3d_records_f32 (mutate_input = 0). */
+int gnms_box3d_records_from_boxes7_f32(const float* boxes7, int64_t ld, int N, float* rec, float* corners, void* stream);
 
 /* rec_a[M,8], rec_b[N,8] -> out_bev / out_3d [M,N] (either may be NULL).  generalized!=0: GIoU hull term
  * (lib/core.py:390-419).  affine!=0 additionally maps out_3d to 0.5*(1+x) (lib/loss/rpn_3d.py:781).
