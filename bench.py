@@ -191,6 +191,8 @@ def run_ours(args, rank, world):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
     lib = _lib.load()
+    if args.tall >= 0:
+        lib.gnms_debug_tall_tiles(args.tall)
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -374,7 +376,8 @@ def main():
     ap.add_argument("--path", default="materialised", choices=["materialised", "fused"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap-branch", action="store_true", help="matrix kernel and NMS kernels on one stream instead of two graph branches")
-    ap.add_argument("--tiles-per-cta", type=int, default=8, help="matrix-only tile kernel on its branch: tiles per CTA (0 = persistent)")
+    ap.add_argument("--tiles-per-cta", type=int, default=4, help="matrix-only tile kernel on its branch: tiles per CTA (0 = persistent)")
+    ap.add_argument("--tall", type=int, default=-1, help="debug: rows of the matrix-only tiles in units of 64 (0, 2 or 4; -1 = library default)")
     ap.add_argument("--splits", type=int, default=1, help="issue the batch as this many sub-batches on parallel graph branches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

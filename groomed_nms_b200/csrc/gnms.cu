@@ -838,6 +838,146 @@ __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ 2c-tall. matrix-only, tall tiles
+// The matrix-only launch with tiles of 64 kQ rows x 64 columns (kQ = 4: 256 x 64 is the default): a thread evaluates
+// 2 kQ sub-tiles of 4 x 4 pairs per tile against the same four column boxes, so the per-tile barrier, decode and column
+// staging are spread over kQ times the pairs of the 64 x 64 shape (measured per 64 images of N = 4096: 1200 us with
+// 64-row tiles, 1118 with 128, 1094 with 256).  Row block R meets the column blocks C >= kQ R.  With c = C - kQ R, a tile
+// with c < kQ touches the diagonal: its 64-row quarters before quarter c are ordinary off-diagonal 64 x 64 tiles
+// (mirrored), quarter c is a diagonal tile (not mirrored) and the quarters after it are skipped (they are the mirror
+// images of quarters of the neighbouring tiles); every other tile is mirrored whole.
+// kQ = 64-row quarters per row block (2: 128 x 64 tiles, 4: 256 x 64 tiles)
+template <int kQ>
+__device__ __forceinline__ void tall_decode(int t, int ntc, int& R, int& C) {
+    // rows of the tile triangle have ntc - kQ R tiles: S(R) = R ntc - kQ R (R - 1) / 2 tiles come before row R
+    const float bq = (float)ntc + 0.5f * kQ;
+    int r = (int)((bq - sqrtf(fmaxf(bq * bq - 2.0f * kQ * (float)t, 0.f))) / (float)kQ);
+    r = max(0, r);
+    while (r > 0 && r * ntc - kQ * r * (r - 1) / 2 > t) --r;
+    while ((r + 1) * ntc - kQ * (r + 1) * r / 2 <= t) ++r;
+    R = r;
+    C = kQ * r + (t - (r * ntc - kQ * r * (r - 1) / 2));
+}
+static inline int tall_tiles_per_image(int N, int kQ) {
+    const int ntc = (N + 63) / 64, ntr = (N + 64 * kQ - 1) / (64 * kQ);
+    int n = 0;
+    for (int R = 0; R < ntr; ++R) n += ntc - kQ * R;
+    return n;
+}
+
+template <int kSrc, bool kGen, bool kAffine, int kQ>
+__global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
+    typedef typename RecOf<kSrc>::type RecT;
+    constexpr int kNF = SoaOf<kSrc>::kFields;
+    constexpr int kRows = 64 * kQ;
+    __shared__ __align__(16) float s_row[2][kNF * kRows];            // [buffer][field][row box]
+    __shared__ __align__(16) float s_col[2][kNF * kTT];             // [buffer][field][column box]
+    __shared__ int s_ij[2][4];
+    const int N = A.N, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int tx = (lane & 7) + 8 * (warp & 1), ty = (lane >> 3) + 4 * (warp >> 1);      // 16 column quads x 8 row quads
+    const int total = A.tiles_per_image * A.batch;
+    auto prefetch = [&](int t, int buf) {
+        const int b = div_small(t, A.tiles_per_image, A.inv_tpi);
+        int R, C;
+        tall_decode<kQ>(t - b * A.tiles_per_image, A.nt, R, C);
+        const float* bx = A.boxes + (size_t)b * N * kNF;
+#pragma unroll
+        for (int k = tid; k < kRows; k += 128) {                                 // kRows / 128 row records per thread
+            const float* src = bx + (size_t)min(R * kRows + k, N - 1) * kNF;
+            float* dst = &s_row[buf][k];
+#pragma unroll
+            for (int q = 0; q < kNF; ++q) cp_async4(dst + q * kRows, src + q);
+        }
+        if (tid < kTT) {                                                         // ... and one column record
+            const float* src = bx + (size_t)min(C * kTT + tid, N - 1) * kNF;
+            float* dst = &s_col[buf][tid];
+#pragma unroll
+            for (int q = 0; q < kNF; ++q) cp_async4(dst + q * kTT, src + q);
+        }
+        if (tid == 0) { s_ij[buf][0] = b; s_ij[buf][1] = R; s_ij[buf][2] = C; }
+    };
+    auto record_ok = [&](const float* f, int stride) -> bool {
+        if constexpr (kSrc == kSrcBox3d)
+            return rec3_sane(Rec3{f[0], f[stride], f[2 * stride], f[3 * stride], f[4 * stride], f[5 * stride], f[6 * stride], 0.f});
+        else return box2_sane(make_box2(make_float4(f[0], f[stride], f[2 * stride], f[3 * stride])));
+    };
+    const bool chunked = A.tiles_per_cta > 0;
+    const int t_step = chunked ? 1 : (int)gridDim.x;
+    const int t_end = chunked ? min(total, ((int)blockIdx.x + 1) * A.tiles_per_cta) : total;
+    int t = chunked ? (int)blockIdx.x * A.tiles_per_cta : (int)blockIdx.x, buf = 0;
+    if (t < t_end) prefetch(t, 0);
+    for (; t < t_end; t += t_step, buf ^= 1) {
+        cp_async_wait_all();
+        bool bad = false;
+#pragma unroll
+        for (int k = tid; k < kRows; k += 128) bad = bad || !record_ok(&s_row[buf][k], kRows);
+        if (tid < kTT) bad = bad || !record_ok(&s_col[buf][tid], kTT);
+        const bool tile_unsafe = __syncthreads_or(bad);
+        const int b = s_ij[buf][0], R = s_ij[buf][1], C = s_ij[buf][2];
+        if (t + t_step < t_end) prefetch(t + t_step, buf ^ 1);
+        RecT cr[4];
+        SoaOf<kSrc>::load4(s_col[buf], 4 * tx, cr);
+        float* out = A.out + (size_t)b * N * N;
+        const bool full_tile = A.vec && (R * kRows + kRows <= N) && (C * kTT + kTT <= N);
+        const int c = C - kQ * R;                                     // < kQ: the tile touches the diagonal in quarter c
+        const int h_end = c < kQ ? 2 * (c + 1) : 2 * kQ;              // quarters past the diagonal one are mirrors of other tiles
+        const int j0 = C * kTT + 4 * tx;
+#pragma unroll 1
+        for (int h = 0; h < h_end; ++h) {
+            const int rl = 32 * h + 4 * ty;
+            if (R * kRows + 32 * h >= N) break;
+            const bool mirror = (h >> 1) != c;                        // the diagonal 64 x 64 quarter is not mirrored
+            RecT rr[4];
+            {
+                float4 f[7];
+                constexpr int kUse = kSrc == kSrcBox3d ? 7 : 4;
+#pragma unroll
+                for (int q = 0; q < kUse; ++q) f[q] = *reinterpret_cast<const float4*>(&s_row[buf][q * kRows + rl]);
+                const float* pf = reinterpret_cast<const float*>(f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if constexpr (kSrc == kSrcBox3d) rr[k] = Rec3{pf[k], pf[4 + k], pf[8 + k], pf[12 + k], pf[16 + k], pf[20 + k], pf[24 + k], 0.f};
+                    else rr[k] = make_box2(make_float4(pf[k], pf[4 + k], pf[8 + k], pf[12 + k]));
+                }
+            }
+            float v[4][4];
+            bool unsafe = tile_unsafe;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template fast<kGen, kAffine>(rr[r], cr[k], unsafe);
+            if (__builtin_expect(unsafe, 0)) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template exact<kGen, kAffine>(rr[r], cr[k]);
+            }
+            const int i0 = R * kRows + rl;
+            if (full_tile) {
+                float* drow = out + (int64_t)i0 * N + j0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) st_cs_f4(drow + (int64_t)r * N, make_float4(v[r][0], v[r][1], v[r][2], v[r][3]));
+                if (mirror) {
+                    float* dcol = out + (int64_t)j0 * N + i0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) st_cs_f4(dcol + (int64_t)k * N, make_float4(v[0][k], v[1][k], v[2][k], v[3][k]));
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (i0 + r < N && j0 + k < N) {
+                            out[(int64_t)(i0 + r) * N + (j0 + k)] = v[r][k];
+                            if (mirror) out[(int64_t)(j0 + k) * N + (i0 + r)] = v[r][k];
+                        }
+                    }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ 2d. spatial order + tile culling
 // Matrix-free path only.  Suppression needs a pair's overlap only when it can exceed the threshold, and boxes that
 // are far apart cannot: if two boxes are disjoint along an axis their intersection is EXACTLY 0 in fp32, so
@@ -2031,6 +2171,8 @@ static int g_rank_by_sort = -1;            // -1 heuristic, 0 always count, 1 al
 extern "C" int gnms_debug_rank_by_sort(int v) { int old = g_rank_by_sort; g_rank_by_sort = v; return old; }
 static int g_direct = 1;                   // direct leader election on the matrix-free path
 extern "C" int gnms_debug_direct_election(int v) { int old = g_direct; g_direct = v; return old; }
+static int g_tall_tiles = 4;               // matrix-only launches: 0 = 64 x 64 tiles, 2 = 128 x 64, 4 = 256 x 64
+extern "C" int gnms_debug_tall_tiles(int v) { int old = g_tall_tiles; g_tall_tiles = v; return old; }
 static int g_tiles_per_cta = 0;            // matrix-only tile kernel: 0 = persistent CTAs, k = k consecutive tiles per CTA
 extern "C" int gnms_debug_tiles_per_cta(int v) { int old = g_tiles_per_cta; g_tiles_per_cta = v; return old; }
 static int g_split_matrix = 1;             // matrix requested + direct election possible: matrix-only kernel + matrix-free path
@@ -2077,6 +2219,30 @@ int gnms_launch_overlap_tiles(const float* boxes, int src, int generalized, int 
     T.inv_tpi = 1.0f / (float)T.tiles_per_image; T.inv_w = 1.0f / (float)(T.nt + 1);
     T.vec = ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && (N % 4 == 0);
     T.boxes = boxes; T.out = out; T.thr = INFINITY;
+    if (g_tall_tiles == 2 || g_tall_tiles == 4) {                      // 128 x 64 or 256 x 64 tiles
+        const int kq = g_tall_tiles;
+        T.tiles_per_image = tall_tiles_per_image(N, kq);
+        T.inv_tpi = 1.0f / (float)T.tiles_per_image;
+        const long long tot = (long long)T.tiles_per_image * batch;
+        if (tot > 0x7fffffffLL) return GNMS_E_TOOLARGE;
+        int grid = tot < 148 * 4 ? (int)tot : 148 * 4;
+        T.tiles_per_cta = g_tiles_per_cta > 0 ? (g_tiles_per_cta + kq - 1) / kq : 0;
+        if (T.tiles_per_cta > 0) grid = (int)((tot + T.tiles_per_cta - 1) / T.tiles_per_cta);
+#define GNMS_TALL(SRC, G, AF)                                                           \
+    do {                                                                                \
+        if (kq == 2) tile_tall_kernel<SRC, G, AF, 2><<<grid, 128, 0, s>>>(T);           \
+        else tile_tall_kernel<SRC, G, AF, 4><<<grid, 128, 0, s>>>(T);                   \
+    } while (0)
+        if (src == kSrcBox3d) {
+            if (generalized) { if (affine) GNMS_TALL(kSrcBox3d, true, true); else GNMS_TALL(kSrcBox3d, true, false); }
+            else { if (affine) GNMS_TALL(kSrcBox3d, false, true); else GNMS_TALL(kSrcBox3d, false, false); }
+        } else {
+            GNMS_TALL(kSrcBox2d, false, false);
+        }
+#undef GNMS_TALL
+        GNMS_LAUNCH_CHECK();
+        return 0;
+    }
     const long long total = (long long)T.tiles_per_image * batch;
     if (total > 0x7fffffffLL) return GNMS_E_TOOLARGE;
     int grid = total < 148 * 4 ? (int)total : 148 * 4;

@@ -39,7 +39,7 @@ class Nms3dPlan(object):
         if overlap_branch is None:
             overlap_branch = materialise and not two_kernel
         self.overlap_branch = bool(overlap_branch) and materialise and not self.two_kernel
-        self.tiles_per_cta = 8
+        self.tiles_per_cta = 4
         if self.overlap_branch:
             self.side = torch.cuda.Stream(device, priority=0)       # matrix branch (default priority)
             self.hi = torch.cuda.Stream(device, priority=-1)        # NMS branch
