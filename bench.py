@@ -193,6 +193,8 @@ def run_ours(args, rank, world):
     lib = _lib.load()
     if args.tall >= 0:
         lib.gnms_debug_tall_tiles(args.tall)
+    if args.packed >= 0:
+        lib.gnms_debug_packed(args.packed)
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -377,6 +379,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap-branch", action="store_true", help="matrix kernel and NMS kernels on one stream instead of two graph branches")
     ap.add_argument("--tiles-per-cta", type=int, default=4, help="matrix-only tile kernel on its branch: tiles per CTA (0 = persistent)")
+    ap.add_argument("--packed", type=int, default=-1, help="debug: packed fp32x2 arithmetic in the matrix-only kernel (0/1; -1 = library default)")
     ap.add_argument("--tall", type=int, default=-1, help="debug: rows of the matrix-only tiles in units of 64 (0, 2 or 4; -1 = library default)")
     ap.add_argument("--splits", type=int, default=1, help="issue the batch as this many sub-batches on parallel graph branches")
     args = ap.parse_args()

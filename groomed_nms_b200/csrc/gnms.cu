@@ -865,7 +865,7 @@ static inline int tall_tiles_per_image(int N, int kQ) {
     return n;
 }
 
-template <int kSrc, bool kGen, bool kAffine, int kQ>
+template <int kSrc, bool kGen, bool kAffine, int kQ, bool kPacked = false>
 __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
     typedef typename RecOf<kSrc>::type RecT;
     constexpr int kNF = SoaOf<kSrc>::kFields;
@@ -943,10 +943,20 @@ __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
             }
             float v[4][4];
             bool unsafe = tile_unsafe;
+            if constexpr (kPacked && kSrc == kSrcBox3d) {             // two column boxes per instruction (fp32x2)
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+                for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template fast<kGen, kAffine>(rr[r], cr[k], unsafe);
+                    for (int k = 0; k < 4; k += 2) {
+                        const F2 pv = iou3_fast2<kGen, kAffine>(rr[r], cr[k], cr[k + 1], unsafe);
+                        v[r][k] = pv.x; v[r][k + 1] = pv.y;
+                    }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template fast<kGen, kAffine>(rr[r], cr[k], unsafe);
+            }
             if (__builtin_expect(unsafe, 0)) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
@@ -2171,6 +2181,8 @@ static int g_rank_by_sort = -1;            // -1 heuristic, 0 always count, 1 al
 extern "C" int gnms_debug_rank_by_sort(int v) { int old = g_rank_by_sort; g_rank_by_sort = v; return old; }
 static int g_direct = 1;                   // direct leader election on the matrix-free path
 extern "C" int gnms_debug_direct_election(int v) { int old = g_direct; g_direct = v; return old; }
+static int g_packed = 1;                   // matrix-only tall tiles: packed fp32x2 arithmetic for 3D records
+extern "C" int gnms_debug_packed(int v) { int old = g_packed; g_packed = v; return old; }
 static int g_tall_tiles = 4;               // matrix-only launches: 0 = 64 x 64 tiles, 2 = 128 x 64, 4 = 256 x 64
 extern "C" int gnms_debug_tall_tiles(int v) { int old = g_tall_tiles; g_tall_tiles = v; return old; }
 static int g_tiles_per_cta = 0;            // matrix-only tile kernel: 0 = persistent CTAs, k = k consecutive tiles per CTA
@@ -2231,6 +2243,7 @@ int gnms_launch_overlap_tiles(const float* boxes, int src, int generalized, int 
 #define GNMS_TALL(SRC, G, AF)                                                           \
     do {                                                                                \
         if (kq == 2) tile_tall_kernel<SRC, G, AF, 2><<<grid, 128, 0, s>>>(T);           \
+        else if (g_packed) tile_tall_kernel<SRC, G, AF, 4, true><<<grid, 128, 0, s>>>(T); \
         else tile_tall_kernel<SRC, G, AF, 4><<<grid, 128, 0, s>>>(T);                   \
     } while (0)
         if (src == kSrcBox3d) {
