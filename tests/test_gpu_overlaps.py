@@ -131,3 +131,42 @@ def test_iou3d_c3_full_size_bitwise_vs_oracle(L):
     got = got.cpu().numpy()
     assert nbits_diff(got, want) == 0
     assert bits_equal(got, got.T)
+
+
+@pytest.mark.parametrize("kind,n,batch", [("2d", 2051, 1), ("3d", 2051, 1), ("2d", 700, 3), ("3d", 1029, 2), ("3d", 4096, 2), ("2d", 8192, 1)])
+def test_batched_self_overlap_tall_tiles_bitwise(kind, n, batch):
+    """The batched self-overlap entry points run the matrix-only tile kernel (256 x 64 tiles, mirrored stores straight from
+    registers, packed fp32x2 arithmetic for 3D): odd sizes (partial tiles, scalar store path when N % 4 != 0), several
+    images per launch, degenerate boxes (exact-division fallback) -- bitwise equal to the oracle, and symmetric."""
+    import ctypes
+    from groomed_nms_b200 import _lib, ops
+    from oracle import groomed_oracle as O
+    lib = _lib.load()
+    rng = np.random.default_rng(n + batch)
+    outs, wants = [], []
+    if kind == "2d":
+        c = rng.uniform(0, 1500, (batch, n, 2)); wh = rng.uniform(5, 200, (batch, n, 2))
+        boxes = np.concatenate([c - wh / 2, c + wh / 2], 2).astype(np.float32)
+        boxes[:, 7, 2:] = boxes[:, 7, :2]; boxes[:, 11] = boxes[:, 7]          # zero-area twins: 0/0 = NaN
+        d = cuda(boxes)
+        out = torch.empty((batch, n, n), dtype=torch.float32, device="cuda")
+        _lib.check(lib.gnms_overlap2d_batched_f32(ops._p(d), n, batch, ops._p(out), ops._stream(d.device)), "overlap2d_batched")
+        for b in range(batch if n <= 2100 else 1):
+            wants.append(O.iou(boxes[b], boxes[b])); outs.append(out[b].cpu().numpy())
+    else:
+        b7 = np.stack([rng.uniform(-30, 30, (batch, n)), 1.6 + 0.2 * rng.standard_normal((batch, n)), rng.uniform(5, 70, (batch, n)),
+                       1.6 + 0.2 * rng.standard_normal((batch, n)), 1.5 + 0.1 * rng.standard_normal((batch, n)),
+                       4 + 0.5 * rng.standard_normal((batch, n)), rng.uniform(-np.pi, np.pi, (batch, n))], 2).astype(np.float32)
+        corners = ops.corners_from_boxes7(cuda(b7).view(batch * n, 7))
+        rec = ops.box3d_records(corners).view(batch, n, 8).contiguous()
+        out = torch.empty((batch, n, n), dtype=torch.float32, device="cuda")
+        _lib.check(lib.gnms_overlap3d_batched_f32(ops._p(rec), n, batch, ops._p(out), 1, 1, ops._stream(rec.device)), "overlap3d_batched")
+        cn = corners.view(batch, n, 3, 8).cpu().numpy()
+        for b in range(batch if n <= 2100 else 1):
+            g3 = O.iou3d_approximate(cn[b], cn[b], "combinations", "generalized")[1]
+            wants.append((np.float32(0.5) * (np.float32(1) + g3)).astype(np.float32)); outs.append(out[b].cpu().numpy())
+    torch.cuda.synchronize()
+    for got, want in zip(outs, wants):
+        assert bits_equal(got, want)
+    last = out[batch - 1]
+    assert torch.equal(torch.nan_to_num(last, nan=-7.0), torch.nan_to_num(last.t(), nan=-7.0))          # mirror image
