@@ -246,7 +246,8 @@ class HostPipeline(object):
         self.k = 0
         self.h2d_bytes, self.d2h_bytes = self.slots[0]["r"].h2d_bytes, self.slots[0]["r"].d2h_bytes
 
-    def submit(self, boxes7_host, scores_host, grad_prob_host):
+    def submit(self, boxes7_host, scores_host, grad_prob_host, copies_only=False):
+        """copies_only: skip the kernels (measures what the PCIe link alone allows for this call pattern)."""
         s = self.slots[self.k % len(self.slots)]
         if s["busy"]:
             s["ev"].synchronize()                 # the slot's previous results must have been produced (and are now overwritten)
@@ -255,7 +256,8 @@ class HostPipeline(object):
             p.boxes7.copy_(boxes7_host, non_blocking=True)
             p.scores.copy_(scores_host, non_blocking=True)
             p.grad_prob.copy_(grad_prob_host, non_blocking=True)
-            s["g"].replay()
+            if not copies_only:
+                s["g"].replay()
             r.h_prob.copy_(p.prob, non_blocking=True)
             r.h_grad.copy_(p.grad_scores, non_blocking=True)
             r.h_valid.copy_(p.valid_idx, non_blocking=True)
