@@ -630,11 +630,8 @@ template <> struct SoaOf<kSrcBox2d> {
     }
 };
 
-template <int kSrc, bool kGen, bool kAffine, bool kHasOut, bool kList, int kRB, bool kQueue, bool kMatrixOnly = false>
+template <int kSrc, bool kGen, bool kAffine, bool kHasOut, bool kList, int kRB, bool kQueue>
 __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
-    // kMatrixOnly: the overlap matrix and nothing else -- no suppression bits, no ranks, no workspace: the boxes are staged
-    // straight from the caller's records (one record per thread, scattered into the field arrays by 4-byte cp.async)
-    static_assert(!kMatrixOnly || (kHasOut && !kList && !kQueue && kRB == 2), "matrix-only launches are 128-thread, matrix-producing");
     constexpr int kThreads = 256 / kRB;                               // kRB row blocks of 64 / kRB rows per thread
     static_assert(!(kHasOut && kList), "the culled pass does not produce the matrix");
     typedef typename RecOf<kSrc>::type RecT;
@@ -663,21 +660,11 @@ __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
             b = div_small(t, A.tiles_per_image, A.inv_tpi);
             tile_decode_folded(t - b * A.tiles_per_image, A.nt, A.inv_w, I, J);
         }
-        if (kMatrixOnly) {
-            constexpr int kNF = SoaOf<kSrc>::kFields;
-            const int side = tid >> 6, k = tid & 63;                  // 128 threads: one record each
-            const int idx = min((side ? J : I) * kTT + k, N - 1);
-            const float* src = A.boxes + ((size_t)b * N + idx) * kNF;
-            float* dst = &s_blk[buf][side][k];
+        const char* blk = A.ws + (size_t)b * A.ws_img_stride + L.blk;
 #pragma unroll
-            for (int q = 0; q < kNF; ++q) cp_async4(dst + q * kTT, src + q);
-        } else {
-            const char* blk = A.ws + (size_t)b * A.ws_img_stride + L.blk;
-#pragma unroll
-            for (int c = tid; c < 2 * kChunks; c += kThreads) {
-                const int side = c >= kChunks ? 1 : 0, cc = c - side * kChunks;
-                cp_async16(reinterpret_cast<char*>(s_blk[buf][side]) + cc * 16, blk + (size_t)(side ? J : I) * kBlkBytes + cc * 16);
-            }
+        for (int c = tid; c < 2 * kChunks; c += kThreads) {
+            const int side = c >= kChunks ? 1 : 0, cc = c - side * kChunks;
+            cp_async16(reinterpret_cast<char*>(s_blk[buf][side]) + cc * 16, blk + (size_t)(side ? J : I) * kBlkBytes + cc * 16);
         }
         if (tid == 0) { s_ij[buf][0] = b; s_ij[buf][1] = I; s_ij[buf][2] = J; }
     };
@@ -685,11 +672,6 @@ __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
     // wait_all): coordinates |x| <= 2^19 (3D), volume / area within [2^-60, 2^60]
     auto own_bad = [&](int buf) -> bool {
         bool bad = false;
-        if (kMatrixOnly) {                                            // the record this thread staged
-            const float* f = &s_blk[buf][tid >> 6][tid & 63];
-            if constexpr (kSrc == kSrcBox3d) return !rec3_sane(Rec3{f[0], f[64], f[128], f[192], f[256], f[320], f[384], 0.f});
-            else return !box2_sane(make_box2(make_float4(f[0], f[64], f[128], f[192])));
-        }
 #pragma unroll
         for (int c = tid; c < 2 * kChunks; c += kThreads) {
             const int side = c >= kChunks ? 1 : 0, cc = c - side * kChunks, f = cc >> 4;
@@ -732,13 +714,10 @@ __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
         }
     };
 
-    // persistent CTAs stride over the tile list; matrix-only launches may instead give every CTA a short run of
-    // consecutive tiles, so that CTAs retire all the time and kernels of another (higher-priority) stream -- the NMS half
-    // of the step -- get SM slots while the matrix is being written
-    const bool chunked = kMatrixOnly && A.tiles_per_cta > 0;
-    const int t_step = chunked ? 1 : (int)gridDim.x;
-    const int t_end = chunked ? min(total, ((int)blockIdx.x + 1) * A.tiles_per_cta) : total;
-    int t = chunked ? (int)blockIdx.x * A.tiles_per_cta : (int)blockIdx.x, buf = 0;
+    // persistent CTAs stride over the tile list
+    const int t_step = (int)gridDim.x;
+    const int t_end = total;
+    int t = (int)blockIdx.x, buf = 0;
     if (kQueue && tid < 3) s_nq[tid] = 0;
     if (t < t_end) prefetch(t, 0);
     for (; t < t_end; t += t_step) {
@@ -783,12 +762,10 @@ __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
                     for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template exact<kGen, kAffine>(rr[r], cr[k]);
             }
             uint32_t hits = 0u;
-            if (!kMatrixOnly) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < 4; ++r)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) hits |= (uint32_t)(!(v[r][k] <= thr)) << (4 * r + k);
-            }
+                for (int k = 0; k < 4; ++k) hits |= (uint32_t)(!(v[r][k] <= thr)) << (4 * r + k);
 
             // ---- consumer 2: the overlap matrix (optional), direct and mirrored, straight from registers
             if (kHasOut) {
@@ -815,8 +792,7 @@ __global__ void __launch_bounds__(256 / kRB, 2 * kRB) tile_kernel(TileArgs A) {
                 }
             }
             // ---- consumer 1: threshold hits (~3 % of the pairs)
-            if (kMatrixOnly) {
-            } else if (kQueue) {
+            if (kQueue) {
                 // warp-aggregated append: one shared-memory atomic per warp and sub-tile
                 const unsigned who = __ballot_sync(0xffffffffu, hits != 0u);
                 if (who) {
@@ -2183,7 +2159,7 @@ static int g_direct = 1;                   // direct leader election on the matr
 extern "C" int gnms_debug_direct_election(int v) { int old = g_direct; g_direct = v; return old; }
 static int g_packed = 1;                   // matrix-only tall tiles: packed fp32x2 arithmetic for 3D records
 extern "C" int gnms_debug_packed(int v) { int old = g_packed; g_packed = v; return old; }
-static int g_tall_tiles = 4;               // matrix-only launches: 0 = 64 x 64 tiles, 2 = 128 x 64, 4 = 256 x 64
+static int g_tall_tiles = 4;               // matrix-only launches: 4 = 256 x 64 tiles, 2 = 128 x 64
 extern "C" int gnms_debug_tall_tiles(int v) { int old = g_tall_tiles; g_tall_tiles = v; return old; }
 static int g_tiles_per_cta = 0;            // matrix-only tile kernel: 0 = persistent CTAs, k = k consecutive tiles per CTA
 extern "C" int gnms_debug_tiles_per_cta(int v) { int old = g_tiles_per_cta; g_tiles_per_cta = v; return old; }
@@ -2231,8 +2207,8 @@ int gnms_launch_overlap_tiles(const float* boxes, int src, int generalized, int 
     T.inv_tpi = 1.0f / (float)T.tiles_per_image; T.inv_w = 1.0f / (float)(T.nt + 1);
     T.vec = ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && (N % 4 == 0);
     T.boxes = boxes; T.out = out; T.thr = INFINITY;
-    if (g_tall_tiles == 2 || g_tall_tiles == 4) {                      // 128 x 64 or 256 x 64 tiles
-        const int kq = g_tall_tiles;
+    {                                                                  // 256 x 64 tiles (128 x 64: debug switch)
+        const int kq = g_tall_tiles == 2 ? 2 : 4;
         T.tiles_per_image = tall_tiles_per_image(N, kq);
         T.inv_tpi = 1.0f / (float)T.tiles_per_image;
         const long long tot = (long long)T.tiles_per_image * batch;
@@ -2254,25 +2230,7 @@ int gnms_launch_overlap_tiles(const float* boxes, int src, int generalized, int 
         }
 #undef GNMS_TALL
         GNMS_LAUNCH_CHECK();
-        return 0;
     }
-    const long long total = (long long)T.tiles_per_image * batch;
-    if (total > 0x7fffffffLL) return GNMS_E_TOOLARGE;
-    int grid = total < 148 * 4 ? (int)total : 148 * 4;
-    T.tiles_per_cta = g_tiles_per_cta;
-    if (T.tiles_per_cta > 0) grid = (int)((total + T.tiles_per_cta - 1) / T.tiles_per_cta);
-    if (src == kSrcBox3d) {
-        if (generalized) {
-            if (affine) tile_kernel<kSrcBox3d, true, true, true, false, 2, false, true><<<grid, 128, 0, s>>>(T);
-            else tile_kernel<kSrcBox3d, true, false, true, false, 2, false, true><<<grid, 128, 0, s>>>(T);
-        } else {
-            if (affine) tile_kernel<kSrcBox3d, false, true, true, false, 2, false, true><<<grid, 128, 0, s>>>(T);
-            else tile_kernel<kSrcBox3d, false, false, true, false, 2, false, true><<<grid, 128, 0, s>>>(T);
-        }
-    } else {
-        tile_kernel<kSrcBox2d, false, false, true, false, 2, false, true><<<grid, 128, 0, s>>>(T);
-    }
-    GNMS_LAUNCH_CHECK();
     return 0;
 }
 
