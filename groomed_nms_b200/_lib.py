@@ -64,6 +64,7 @@ SIGNATURES = {
     "gnms_aploss_workspace_bytes": (sz, [i32]),
     "gnms_targets_overlaps_workspace_bytes": (sz, [i32, i32]),
     "gnms_targets_overlaps_f64": (i32, [vp, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "gnms_iou3d_exact_f64": (i32, [vp, i64, i32, vp, i64, i32, vp, i32, vp, vp, vp]),
 }
 
 _lib = None

@@ -1,6 +1,7 @@
 // Soft-NMS (lib/nms_others.py:6-116) and AP loss (lib/loss/aploss.py:14-97) for sm_100a.
 // Both are small, inherently sequential-over-rounds algorithms: one CTA per problem, block-wide reductions.
 #include "common.cuh"
+#include "polygon.cuh"
 
 namespace gnms {
 
@@ -422,6 +423,45 @@ extern "C" int gnms_targets_overlaps_f64(const double* rois, int64_t ld_rois, in
     targets_overlaps_kernel<<<nb, kTgtThreads, 0, s>>>(rois, ld_rois, M, gts, G, kind, area_f32, ols, row_max, row_arg, pv, pi);
     GNMS_LAUNCH_CHECK();
     col_finalize_kernel<<<(G + 63) / 64, 64, 0, s>>>(pv, pi, nb, G, col_max, col_arg);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- exact polygon iou3d (lib/core.py:246-302) --------------------------------------------------------------------
+// One thread per pair.  The per-box preparation (face, y range, volume) is a few dozen flops and is redone per pair; the
+// callers of the reference evaluate tens of detections against a handful of ground-truth boxes (lib/rpn_util.py:1776).
+namespace gnms {
+
+__global__ void __launch_bounds__(128)
+iou3d_exact_kernel(const double* __restrict__ ca, int64_t ld_a, int M, const double* __restrict__ cb, int64_t ld_b, int N,
+                   const double* __restrict__ vol, int list_mode, double* __restrict__ out_bev, double* __restrict__ out_3d) {
+    const int64_t total = list_mode ? (int64_t)M : (int64_t)M * N;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = list_mode ? p : p / N, j = list_mode ? p : p % N;
+        double a[24], b[24];
+        for (int k = 0; k < 24; ++k) { a[k] = ca[i * ld_a + k]; b[k] = cb[j * ld_b + k]; }
+        ExactBox b1, b2;
+        exact_box_from_corners(a, b1);
+        exact_box_from_corners(b, b2);
+        double bev, v3;
+        iou3d_exact_pair(b1, b2, vol != nullptr, vol ? vol[p] : 0.0, bev, v3);
+        if (out_bev) out_bev[p] = bev;
+        if (out_3d) out_3d[p] = v3;
+    }
+}
+
+}  // namespace gnms
+
+extern "C" int gnms_iou3d_exact_f64(const double* corners_a, int64_t ld_a, int M, const double* corners_b, int64_t ld_b, int N,
+                                    const double* vol, int list_mode, double* out_bev, double* out_3d, void* stream) {
+    if (M < 0 || N < 0 || ld_a < 24 || ld_b < 24) return GNMS_E_BADARG;
+    if (list_mode && M != N) return GNMS_E_BADARG;
+    if (M == 0 || N == 0) return 0;
+    if (!corners_a || !corners_b || (!out_bev && !out_3d)) return GNMS_E_BADARG;
+    const int64_t total = list_mode ? (int64_t)M : (int64_t)M * N;
+    const int64_t want = (total + 127) / 128;
+    const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+    iou3d_exact_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(corners_a, ld_a, M, corners_b, ld_b, N, vol, list_mode, out_bev, out_3d);
     GNMS_LAUNCH_CHECK();
     return 0;
 }

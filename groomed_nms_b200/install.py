@@ -6,7 +6,7 @@ import sys
 import types
 
 _MODULES = ["groomed_nms", "nms", "nms.gpu_nms", "nms.cpu_nms", "nms.py_cpu_nms", "nms_others", "loss.aploss"]
-_CORE_SYMBOLS = ["iou", "intersect", "iou3d_approximate", "get_volume", "get_hull", "remove_rotation_in_boxes"]
+_CORE_SYMBOLS = ["iou", "intersect", "iou3d", "iou3d_approximate", "get_volume", "get_hull", "remove_rotation_in_boxes"]
 _MATH3D_SYMBOLS = ["get_corners_of_cuboid", "project_3d_points_in_4D_format"]
 
 

@@ -1,12 +1,13 @@
 """Mirror of the overlap functions of the reference's lib/core.py:178-532 on the sm_100a tile kernels.
 
-Public names and argument meaning follow the reference: intersect, iou, iou3d_approximate, get_volume, get_hull,
-remove_rotation_in_boxes.  Results are bitwise equal to the reference's torch CPU ops (separately rounded fp32)."""
+Public names and argument meaning follow the reference: intersect, iou, iou3d, iou3d_approximate, get_volume, get_hull,
+remove_rotation_in_boxes (plus iou3d_batch, the many-pairs form of iou3d).  Results are bitwise equal to the reference's torch CPU ops (separately rounded fp32)."""
 import numpy as np
 import torch
 
 from .. import _lib, ops
 from ._util import Origin, to_cuda_f32
+from ._util import device as _device
 
 
 def _check_type(data_type, x):
@@ -79,6 +80,42 @@ def get_hull(y_min_b1, y_max_b1, y_min_b2, y_max_b2, mode="list"):
         lo = torch.min(y_min_b1, y_min_b2)
         hi = torch.max(y_max_b1, y_max_b2)
     return torch.clamp(hi - lo, min=0)
+
+
+def iou3d(corners_3d_b1, corners_3d_b2, vol=None):
+    """Exact (polygon) BEV IoU and 3D IoU of two cuboids given as (3, 8) corner arrays (reference lib/core.py:246-302,
+    which intersects two shapely polygons on the host).  Returns (iou_bev, iou_3d) as Python floats like the reference.
+    `vol` is the sum of the two volumes (default: the sum of the two get_volume values, :278-279).
+    The inputs are not modified (the reference works on copies, :273-274)."""
+    c1, c2 = _corners_f64(corners_3d_b1), _corners_f64(corners_3d_b2)
+    v = None if vol is None else torch.as_tensor(float(vol), dtype=torch.float64).reshape(1)
+    bev, v3d = ops.iou3d_exact(c1[None], c2[None], vol=v, list_mode=True)
+    out = torch.stack([bev[0], v3d[0]]).cpu()
+    return float(out[0]), float(out[1])
+
+
+def iou3d_batch(corners_3d_b1, corners_3d_b2, mode="combinations", vol=None):
+    """Batched form of `iou3d`: corners [M,3,8] against [N,3,8] -> (iou_bev, iou_3d), each [M,N] ("combinations") or [M]
+    ("list"), float64, in the container type of the first argument.  One launch instead of M*N shapely calls (the loops
+    at lib/rpn_util.py:1770-1780, test/get_oracle_nms.py:125-131)."""
+    if mode not in ("combinations", "list"):
+        raise ValueError('unknown mode {}'.format(mode))
+    origin = Origin(corners_3d_b1) if isinstance(corners_3d_b1, (np.ndarray, torch.Tensor)) else Origin(np.zeros(0))
+    c1, c2 = _corners_f64(corners_3d_b1), _corners_f64(corners_3d_b2)
+    if vol is not None and not isinstance(vol, torch.Tensor):
+        vol = torch.as_tensor(np.asarray(vol, dtype=np.float64))
+    bev, v3d = ops.iou3d_exact(c1, c2, vol=vol, list_mode=(mode == "list"))
+    return origin.back(bev), origin.back(v3d)
+
+
+def _corners_f64(c):
+    if isinstance(c, np.ndarray):
+        c = torch.from_numpy(np.ascontiguousarray(c, dtype=np.float64))
+    elif not isinstance(c, torch.Tensor):
+        c = torch.as_tensor(np.asarray(c, dtype=np.float64))
+    if not c.is_cuda:
+        c = c.to(_device())
+    return c.double()
 
 
 def iou3d_approximate(corners_3d_b1, corners_3d_b2, mode="list", method="normal"):

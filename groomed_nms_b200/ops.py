@@ -423,3 +423,31 @@ def aploss(logits, targets):
         with torch.cuda.device(dev):
             check(_lib.load().gnms_aploss_f32(_p(x), _p(t), n, _p(loss), _p(grad), _p(ws), nb, _stream(dev)), "gnms_aploss_f32")
     return loss, grad
+
+
+def iou3d_exact(corners_a, corners_b, vol=None, list_mode=False):
+    """corners_a [M,rows>=3,8], corners_b [N,rows>=3,8] cuda (any float dtype, computed in float64) ->
+    (iou_bev, iou_3d), each float64 [M,N] (or [M] in list mode): exact polygon overlap (lib/core.py:246-302).
+    vol: None or the per-pair volume sums, same shape as the result."""
+    _require_cuda(corners_a, "corners_a")
+    _require_cuda(corners_b, "corners_b")
+    a = corners_a.double().contiguous()
+    b = corners_b.double().contiguous()
+    if a.dim() != 3 or b.dim() != 3 or a.shape[1] < 3 or b.shape[1] < 3 or a.shape[2] != 8 or b.shape[2] != 8:
+        raise ValueError("corners must be [M, rows >= 3, 8]")
+    M, N = a.shape[0], b.shape[0]
+    if list_mode and M != N:
+        raise ValueError("list mode needs as many boxes in both sets")
+    dev = a.device
+    shape = (M,) if list_mode else (M, N)
+    bev = torch.empty(shape, dtype=torch.float64, device=dev)
+    v3d = torch.empty(shape, dtype=torch.float64, device=dev)
+    v = None
+    if vol is not None:
+        v = vol.to(dev).double().reshape(shape).contiguous()
+    if M and N:
+        with torch.cuda.device(dev):
+            check(_lib.load().gnms_iou3d_exact_f64(_p(a), a.shape[1] * 8, M, _p(b), b.shape[1] * 8, N,
+                                                   _p(v) if v is not None else None, int(bool(list_mode)), _p(bev), _p(v3d),
+                                                   _stream(dev)), "gnms_iou3d_exact_f64")
+    return bev, v3d

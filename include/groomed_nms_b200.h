@@ -21,6 +21,7 @@
  *   lib/nms_others.py:6-116 navneeth_soft_nms  -> gnms_soft_nms_f64
  *   lib/loss/aploss.py:14-97 backpropAPLoss    -> gnms_aploss_f32
  *   lib/rpn_util.py:439-461 compute_targets overlaps (lib/core.py iou / iou_ign, numpy branch) -> gnms_targets_overlaps_f64
+ *   lib/core.py:246-302   iou3d (exact polygon overlap, shapely in the reference) -> gnms_iou3d_exact_f64
  */
 #ifndef GROOMED_NMS_B200_H_
 #define GROOMED_NMS_B200_H_
@@ -229,6 +230,16 @@ size_t gnms_targets_overlaps_workspace_bytes(int M, int G);
 int gnms_targets_overlaps_f64(const double* rois, int64_t ld_rois, int M, const double* gts, int G, int kind, int area_f32,
                               double* ols, double* row_max, int64_t* row_arg, double* col_max, int64_t* col_arg,
                               void* workspace, void* stream);
+
+/* lib/core.py:246-302 iou3d: exact overlap of rotated cuboids -- the bottom faces (corners 7, 2, 3, 6 in the x-z plane)
+ * are intersected as polygons (the reference asks shapely/GEOS, one pair per host call; here the two convex quadrilaterals
+ * are clipped in fp64, one thread per pair), the height overlap comes from the y range of the 8 corners.
+ * corners_*: double[M][rows >= 3][8] (x row, y row, z row; ld_* = doubles between boxes, >= 24).  vol: NULL (the sum of
+ * the two get_volume values, :278-279) or one volume sum per pair.  list_mode: pair i with i (M == N), else all M x N
+ * combinations, a-major.  out_bev / out_3d: double[M*N] (or [M]); either may be NULL.  Zero-area boxes give NaN (0/0)
+ * where the reference's Python floats raise ZeroDivisionError. */
+int gnms_iou3d_exact_f64(const double* corners_a, int64_t ld_a, int M, const double* corners_b, int64_t ld_b, int N,
+                         const double* vol, int list_mode, double* out_bev, double* out_3d, void* stream);
 
 #ifdef __cplusplus
 }
