@@ -66,3 +66,25 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(d, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(lib, tmp_path):
+    """include/groomed_nms_b200.h compiles as strict C99 and a C program linked against the library reaches the entry
+    points (examples/c_abi_check.c: version, workspace sizes, argument validation -- nothing that needs a GPU)."""
+    import subprocess
+    libdir = os.path.join(ROOT, "groomed_nms_b200")
+    exe = os.path.join(str(tmp_path), "c_abi_check")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_abi_check.c"), "-L", libdir, "-lgroomed_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    assert "c abi ok: version 100" in out.stdout
+
+
+def test_exact_overlap_argument_errors_without_a_gpu(lib):
+    z = ctypes.c_void_p(0)
+    assert lib.gnms_iou3d_exact_f64(z, 24, 0, z, 24, 3, z, 0, z, z, z) == 0
+    assert lib.gnms_iou3d_exact_f64(z, 23, 2, z, 24, 3, z, 0, z, z, z) == -1          # fewer than 3 rows of 8
+    assert lib.gnms_iou3d_exact_f64(z, 24, 2, z, 24, 3, z, 1, z, z, z) == -1          # list mode needs M == N
+    assert lib.gnms_iou3d_exact_f64(z, 24, 2, z, 24, 2, z, 1, z, z, z) == -1          # null pointers
