@@ -899,8 +899,13 @@ __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
         const int c = C - kQ * R;                                     // < kQ: the tile touches the diagonal in quarter c
         const int h_end = c < kQ ? 2 * (c + 1) : 2 * kQ;              // quarters past the diagonal one are mirrors of other tiles
         const int j0 = C * kTT + 4 * tx;
+        // store addresses are carried from one 32-row step to the next (byte pointers; N <= 8192, so row offsets fit 32 bits):
+        // drow walks down 32 rows of the direct block, dcol walks 32 columns to the right in the mirrored block
+        const uint32_t row_bytes = (uint32_t)N * 4u;
+        char* drow = reinterpret_cast<char*>(out + (int64_t)(R * kRows + 4 * ty) * N + j0);
+        char* dcol = reinterpret_cast<char*>(out + (int64_t)j0 * N + (R * kRows + 4 * ty));
 #pragma unroll 1
-        for (int h = 0; h < h_end; ++h) {
+        for (int h = 0; h < h_end; ++h, drow += 32u * (size_t)row_bytes, dcol += 128) {
             const int rl = 32 * h + 4 * ty;
             if (R * kRows + 32 * h >= N) break;
             const bool mirror = (h >> 1) != c;                        // the diagonal 64 x 64 quarter is not mirrored
@@ -939,17 +944,17 @@ __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template exact<kGen, kAffine>(rr[r], cr[k]);
             }
-            const int i0 = R * kRows + rl;
             if (full_tile) {
-                float* drow = out + (int64_t)i0 * N + j0;
 #pragma unroll
-                for (int r = 0; r < 4; ++r) st_cs_f4(drow + (int64_t)r * N, make_float4(v[r][0], v[r][1], v[r][2], v[r][3]));
+                for (int r = 0; r < 4; ++r)
+                    st_cs_f4(reinterpret_cast<float*>(drow + r * row_bytes), make_float4(v[r][0], v[r][1], v[r][2], v[r][3]));
                 if (mirror) {
-                    float* dcol = out + (int64_t)j0 * N + i0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) st_cs_f4(dcol + (int64_t)k * N, make_float4(v[0][k], v[1][k], v[2][k], v[3][k]));
+                    for (int k = 0; k < 4; ++k)
+                        st_cs_f4(reinterpret_cast<float*>(dcol + k * row_bytes), make_float4(v[0][k], v[1][k], v[2][k], v[3][k]));
                 }
             } else {
+                const int i0 = R * kRows + rl;
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
 #pragma unroll
