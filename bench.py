@@ -346,13 +346,13 @@ def run_ours(args, rank, world):
                     "blocking_call_api": "groomed_nms_b200.hostapi.HostRunner.run_host (one synchronous call per step)"},
             "gpu_launches": head.launches_per_step * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "gnms::tile_kernel<3D records, generalized, affine, matrix only> "
-                                                   "(symmetric 64x64 overlap tiles written direct + mirrored, %d images per launch)" % B,
+            "roofline": {"bound": "hbm", "kernel": "gnms::tile_tall_kernel<3D records, generalized, affine, packed fp32x2> "
+                                                   "(symmetric 256x64 overlap tiles written direct + mirrored, %d images per launch)" % B,
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k_bytes, "avg_launch_ms": k_ms, "traffic": ncu_traffic(B),
                          "timing": "CUDA events around %d back-to-back launches of this kernel alone on the launching stream" % max(10, args.steps),
-                         "note": "the kernel is fp32-issue bound (about 60 issue slots per pair, FMNMX at half rate), "
-                                 "not HBM bound: see DESIGN.md section 5 and profiles/"},
+                         "note": "fp32 instruction issue / latency limits the kernel (about 37 issue slots per pair at 4 warps per "
+                                 "sub-partition), not HBM: see DESIGN.md section 5 and profiles/"},
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "effective_GBps": step_bytes / (ms_step * 1e-3) / 1e9,
                               "frac_of_peak": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
                               "note": "section 8(d) byte model 8N^2+(4D+24)N per image over the whole fwd+bwd step"},
