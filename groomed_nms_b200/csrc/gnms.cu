@@ -969,6 +969,141 @@ __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ 2c-narrow. EXPERIMENT (not the default)
+// Same 256 x 64 tiles as tile_tall_kernel, but a thread evaluates 2 rows x 4 columns per step (16 steps of 16 rows per
+// tile) instead of 4 x 4: half the results and row records live, so that the kernel fits 80 registers and 6 CTAs (24
+// warps) stay resident per SM instead of 4 (16 warps).  Motivation: the 4 x 4 kernel issues one instruction per warp
+// every 6.6 cycles -- ptxas has no registers left to interleave the pair chains (each reciprocal is followed directly by
+// its five dependent FFMA2), and 4 warps per sub-partition do not cover that.  Warp = 4 column quads x 8 row pairs: the
+// direct stores of a warp are 16 rows x 64 B, the mirrored ones 16 rows x 64 B (8-byte stores).
+// Selected with gnms_debug_tall_tiles(8); written at the end of round 1 without GPU time left: NOT measured and NOT
+// verified on the device yet (tests/test_gpu_overlaps.py holds the bitwise test, enabled with GNMS_EXPERIMENTAL=1).
+template <int kSrc, bool kGen, bool kAffine>
+__global__ void __launch_bounds__(128, 6) tile_tall_narrow_kernel(TileArgs A) {
+    typedef typename RecOf<kSrc>::type RecT;
+    constexpr int kNF = SoaOf<kSrc>::kFields;
+    constexpr int kQ = 4, kRows = 64 * kQ;
+    __shared__ __align__(16) float s_row[2][kNF * kRows];
+    __shared__ __align__(16) float s_col[2][kNF * kTT];
+    __shared__ int s_ij[2][4];
+    const int N = A.N, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int tx = (lane & 3) + 4 * warp, ty = lane >> 2;             // 16 column quads x 8 row pairs
+    const int total = A.tiles_per_image * A.batch;
+    auto prefetch = [&](int t, int buf) {
+        const int b = div_small(t, A.tiles_per_image, A.inv_tpi);
+        int R, C;
+        tall_decode<kQ>(t - b * A.tiles_per_image, A.nt, R, C);
+        const float* bx = A.boxes + (size_t)b * N * kNF;
+#pragma unroll
+        for (int k = tid; k < kRows; k += 128) {
+            const float* src = bx + (size_t)min(R * kRows + k, N - 1) * kNF;
+            float* dst = &s_row[buf][k];
+#pragma unroll
+            for (int q = 0; q < kNF; ++q) cp_async4(dst + q * kRows, src + q);
+        }
+        if (tid < kTT) {
+            const float* src = bx + (size_t)min(C * kTT + tid, N - 1) * kNF;
+            float* dst = &s_col[buf][tid];
+#pragma unroll
+            for (int q = 0; q < kNF; ++q) cp_async4(dst + q * kTT, src + q);
+        }
+        if (tid == 0) { s_ij[buf][0] = b; s_ij[buf][1] = R; s_ij[buf][2] = C; }
+    };
+    auto record_ok = [&](const float* f, int stride) -> bool {
+        if constexpr (kSrc == kSrcBox3d)
+            return rec3_sane(Rec3{f[0], f[stride], f[2 * stride], f[3 * stride], f[4 * stride], f[5 * stride], f[6 * stride], 0.f});
+        else return box2_sane(make_box2(make_float4(f[0], f[stride], f[2 * stride], f[3 * stride])));
+    };
+    const bool chunked = A.tiles_per_cta > 0;
+    const int t_step = chunked ? 1 : (int)gridDim.x;
+    const int t_end = chunked ? min(total, ((int)blockIdx.x + 1) * A.tiles_per_cta) : total;
+    int t = chunked ? (int)blockIdx.x * A.tiles_per_cta : (int)blockIdx.x, buf = 0;
+    if (t < t_end) prefetch(t, 0);
+    for (; t < t_end; t += t_step, buf ^= 1) {
+        cp_async_wait_all();
+        bool bad = false;
+#pragma unroll
+        for (int k = tid; k < kRows; k += 128) bad = bad || !record_ok(&s_row[buf][k], kRows);
+        if (tid < kTT) bad = bad || !record_ok(&s_col[buf][tid], kTT);
+        const bool tile_unsafe = __syncthreads_or(bad);
+        const int b = s_ij[buf][0], R = s_ij[buf][1], C = s_ij[buf][2];
+        if (t + t_step < t_end) prefetch(t + t_step, buf ^ 1);
+        RecT cr[4];
+        SoaOf<kSrc>::load4(s_col[buf], 4 * tx, cr);
+        float* out = A.out + (size_t)b * N * N;
+        const bool full_tile = A.vec && (R * kRows + kRows <= N) && (C * kTT + kTT <= N);
+        const int c = C - kQ * R;                                     // < kQ: the tile touches the diagonal in quarter c
+        const int h_end = c < kQ ? 4 * (c + 1) : 4 * kQ;              // 16-row steps; quarters past the diagonal one are mirrors
+        const int j0 = C * kTT + 4 * tx;
+        const uint32_t row_bytes = (uint32_t)N * 4u;
+        char* drow = reinterpret_cast<char*>(out + (int64_t)(R * kRows + 2 * ty) * N + j0);
+        char* dcol = reinterpret_cast<char*>(out + (int64_t)j0 * N + (R * kRows + 2 * ty));
+#pragma unroll 1
+        for (int h = 0; h < h_end; ++h, drow += 16u * (size_t)row_bytes, dcol += 64) {
+            const int rl = 16 * h + 2 * ty;
+            if (R * kRows + 16 * h >= N) break;
+            const bool mirror = (h >> 2) != c;                        // the diagonal 64 x 64 quarter is not mirrored
+            RecT rr[2];
+            {
+                float2 f[7];
+                constexpr int kUse = kSrc == kSrcBox3d ? 7 : 4;
+#pragma unroll
+                for (int q = 0; q < kUse; ++q) f[q] = *reinterpret_cast<const float2*>(&s_row[buf][q * kRows + rl]);
+                const float* pf = reinterpret_cast<const float*>(f);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if constexpr (kSrc == kSrcBox3d) rr[k] = Rec3{pf[k], pf[2 + k], pf[4 + k], pf[6 + k], pf[8 + k], pf[10 + k], pf[12 + k], 0.f};
+                    else rr[k] = make_box2(make_float4(pf[k], pf[2 + k], pf[4 + k], pf[6 + k]));
+                }
+            }
+            float v[2][4];
+            bool unsafe = tile_unsafe;
+            if constexpr (kSrc == kSrcBox3d) {                        // two column boxes per instruction (fp32x2)
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int k = 0; k < 4; k += 2) {
+                        const F2 pv = iou3_fast2<kGen, kAffine>(rr[r], cr[k], cr[k + 1], unsafe);
+                        v[r][k] = pv.x; v[r][k + 1] = pv.y;
+                    }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template fast<kGen, kAffine>(rr[r], cr[k], unsafe);
+            }
+            if (__builtin_expect(unsafe, 0)) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template exact<kGen, kAffine>(rr[r], cr[k]);
+            }
+            if (full_tile) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                    st_cs_f4(reinterpret_cast<float*>(drow + r * row_bytes), make_float4(v[r][0], v[r][1], v[r][2], v[r][3]));
+                if (mirror) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        __stcs(reinterpret_cast<float2*>(dcol + k * row_bytes), make_float2(v[0][k], v[1][k]));
+                }
+            } else {
+                const int i0 = R * kRows + rl;
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (i0 + r < N && j0 + k < N) {
+                            out[(int64_t)(i0 + r) * N + (j0 + k)] = v[r][k];
+                            if (mirror) out[(int64_t)(j0 + k) * N + (i0 + r)] = v[r][k];
+                        }
+                    }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ 2d. spatial order + tile culling
 // Matrix-free path only.  Suppression needs a pair's overlap only when it can exceed the threshold, and boxes that
 // are far apart cannot: if two boxes are disjoint along an axis their intersection is EXACTLY 0 in fp32, so
@@ -2164,7 +2299,8 @@ static int g_direct = 1;                   // direct leader election on the matr
 extern "C" int gnms_debug_direct_election(int v) { int old = g_direct; g_direct = v; return old; }
 static int g_packed = 1;                   // matrix-only tall tiles: packed fp32x2 arithmetic for 3D records
 extern "C" int gnms_debug_packed(int v) { int old = g_packed; g_packed = v; return old; }
-static int g_tall_tiles = 4;               // matrix-only launches: 4 = 256 x 64 tiles, 2 = 128 x 64
+static int g_tall_tiles = 4;               // matrix-only launches: 4 = 256 x 64 tiles, 2 = 128 x 64, 8 = 256 x 64 with the
+                                           // experimental 2-rows-per-step kernel (tile_tall_narrow_kernel)
 extern "C" int gnms_debug_tall_tiles(int v) { int old = g_tall_tiles; g_tall_tiles = v; return old; }
 static int g_tiles_per_cta = 0;            // matrix-only tile kernel: 0 = persistent CTAs, k = k consecutive tiles per CTA
 extern "C" int gnms_debug_tiles_per_cta(int v) { int old = g_tiles_per_cta; g_tiles_per_cta = v; return old; }
@@ -2223,7 +2359,8 @@ int gnms_launch_overlap_tiles(const float* boxes, int src, int generalized, int 
         if (T.tiles_per_cta > 0) grid = (int)((tot + T.tiles_per_cta - 1) / T.tiles_per_cta);
 #define GNMS_TALL(SRC, G, AF)                                                           \
     do {                                                                                \
-        if (kq == 2) tile_tall_kernel<SRC, G, AF, 2><<<grid, 128, 0, s>>>(T);           \
+        if (g_tall_tiles == 8) tile_tall_narrow_kernel<SRC, G, AF><<<grid, 128, 0, s>>>(T); \
+        else if (kq == 2) tile_tall_kernel<SRC, G, AF, 2><<<grid, 128, 0, s>>>(T);      \
         else if (g_packed) tile_tall_kernel<SRC, G, AF, 4, true><<<grid, 128, 0, s>>>(T); \
         else tile_tall_kernel<SRC, G, AF, 4><<<grid, 128, 0, s>>>(T);                   \
     } while (0)

@@ -1,6 +1,8 @@
 """GPU parity: overlap kernels (through the C-ABI) vs the oracle and the reference's golden vectors.
 Bar: bitwise equal fp32 for every overlap computed from boxes / corners; 1e-6 relative for the cos/sin + rotation
 that produces corners from 7-DoF boxes (backend-defined op order in the reference)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -170,3 +172,21 @@ def test_batched_self_overlap_tall_tiles_bitwise(kind, n, batch):
         assert bits_equal(got, want)
     last = out[batch - 1]
     assert torch.equal(torch.nan_to_num(last, nan=-7.0), torch.nan_to_num(last.t(), nan=-7.0))          # mirror image
+
+
+@pytest.mark.skipif(not os.environ.get("GNMS_EXPERIMENTAL"),
+                    reason="tile_tall_narrow_kernel is an unmeasured experiment (DESIGN.md section 8); set GNMS_EXPERIMENTAL=1")
+@pytest.mark.parametrize("kind,n,batch", [("2d", 2051, 1), ("3d", 2051, 1), ("3d", 1029, 2), ("3d", 4096, 2)])
+def test_experimental_narrow_step_kernel_bitwise(kind, n, batch):
+    """The 2-rows-per-step variant of the matrix-only kernel (gnms_debug_tall_tiles(8)) must give the same bits as the
+    default one."""
+    import ctypes
+    from groomed_nms_b200 import _lib
+    lib = _lib.load()
+    lib.gnms_debug_tall_tiles.argtypes = [ctypes.c_int]
+    lib.gnms_debug_tall_tiles.restype = ctypes.c_int
+    old = lib.gnms_debug_tall_tiles(8)
+    try:
+        test_batched_self_overlap_tall_tiles_bitwise(kind, n, batch)
+    finally:
+        lib.gnms_debug_tall_tiles(old)
