@@ -841,7 +841,10 @@ static inline int tall_tiles_per_image(int N, int kQ) {
     return n;
 }
 
-template <int kSrc, bool kGen, bool kAffine, int kQ, bool kPacked = false>
+// kPipe (EXPERIMENT, not the default, not yet run on a device -- DESIGN.md section 8 lead (a)): the row records of the next
+// 32-row step are loaded before the stores of this one and the store pointers are advanced before, not after, the
+// stores, so that the instructions that follow the stores do not rewrite the registers the queued STG still read.
+template <int kSrc, bool kGen, bool kAffine, int kQ, bool kPacked = false, bool kPipe = false>
 __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
     typedef typename RecOf<kSrc>::type RecT;
     constexpr int kNF = SoaOf<kSrc>::kFields;
@@ -904,24 +907,30 @@ __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
         const uint32_t row_bytes = (uint32_t)N * 4u;
         char* drow = reinterpret_cast<char*>(out + (int64_t)(R * kRows + 4 * ty) * N + j0);
         char* dcol = reinterpret_cast<char*>(out + (int64_t)j0 * N + (R * kRows + 4 * ty));
+        auto load_rows = [&](int rl, RecT* rr) {
+            float4 f[7];
+            constexpr int kUse = kSrc == kSrcBox3d ? 7 : 4;
+#pragma unroll
+            for (int q = 0; q < kUse; ++q) f[q] = *reinterpret_cast<const float4*>(&s_row[buf][q * kRows + rl]);
+            const float* pf = reinterpret_cast<const float*>(f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if constexpr (kSrc == kSrcBox3d) rr[k] = Rec3{pf[k], pf[4 + k], pf[8 + k], pf[12 + k], pf[16 + k], pf[20 + k], pf[24 + k], 0.f};
+                else rr[k] = make_box2(make_float4(pf[k], pf[4 + k], pf[8 + k], pf[12 + k]));
+            }
+        };
+        RecT rr[4];
+        if constexpr (kPipe) {
+            load_rows(4 * ty, rr);
+            drow -= 32u * (size_t)row_bytes;
+            dcol -= 128;
+        }
 #pragma unroll 1
-        for (int h = 0; h < h_end; ++h, drow += 32u * (size_t)row_bytes, dcol += 128) {
+        for (int h = 0; h < h_end; ++h) {
             const int rl = 32 * h + 4 * ty;
             if (R * kRows + 32 * h >= N) break;
             const bool mirror = (h >> 1) != c;                        // the diagonal 64 x 64 quarter is not mirrored
-            RecT rr[4];
-            {
-                float4 f[7];
-                constexpr int kUse = kSrc == kSrcBox3d ? 7 : 4;
-#pragma unroll
-                for (int q = 0; q < kUse; ++q) f[q] = *reinterpret_cast<const float4*>(&s_row[buf][q * kRows + rl]);
-                const float* pf = reinterpret_cast<const float*>(f);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if constexpr (kSrc == kSrcBox3d) rr[k] = Rec3{pf[k], pf[4 + k], pf[8 + k], pf[12 + k], pf[16 + k], pf[20 + k], pf[24 + k], 0.f};
-                    else rr[k] = make_box2(make_float4(pf[k], pf[4 + k], pf[8 + k], pf[12 + k]));
-                }
-            }
+            if constexpr (!kPipe) load_rows(rl, rr);
             float v[4][4];
             bool unsafe = tile_unsafe;
             if constexpr (kPacked && kSrc == kSrcBox3d) {             // two column boxes per instruction (fp32x2)
@@ -944,6 +953,11 @@ __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template exact<kGen, kAffine>(rr[r], cr[k]);
             }
+            if constexpr (kPipe) {
+                if (h + 1 < h_end) load_rows(rl + 32, rr);            // next step's rows, before this step's stores
+                drow += 32u * (size_t)row_bytes;
+                dcol += 128;
+            }
             if (full_tile) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
@@ -964,6 +978,10 @@ __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
                             if (mirror) out[(int64_t)(j0 + k) * N + (i0 + r)] = v[r][k];
                         }
                     }
+            }
+            if constexpr (!kPipe) {
+                drow += 32u * (size_t)row_bytes;
+                dcol += 128;
             }
         }
     }
@@ -2300,7 +2318,8 @@ extern "C" int gnms_debug_direct_election(int v) { int old = g_direct; g_direct 
 static int g_packed = 1;                   // matrix-only tall tiles: packed fp32x2 arithmetic for 3D records
 extern "C" int gnms_debug_packed(int v) { int old = g_packed; g_packed = v; return old; }
 static int g_tall_tiles = 4;               // matrix-only launches: 4 = 256 x 64 tiles, 2 = 128 x 64, 8 = 256 x 64 with the
-                                           // experimental 2-rows-per-step kernel (tile_tall_narrow_kernel)
+                                           // experimental 2-rows-per-step kernel (tile_tall_narrow_kernel), 9 = 256 x 64 with
+                                           // the experimental kPipe ordering of tile_tall_kernel
 extern "C" int gnms_debug_tall_tiles(int v) { int old = g_tall_tiles; g_tall_tiles = v; return old; }
 static int g_tiles_per_cta = 0;            // matrix-only tile kernel: 0 = persistent CTAs, k = k consecutive tiles per CTA
 extern "C" int gnms_debug_tiles_per_cta(int v) { int old = g_tiles_per_cta; g_tiles_per_cta = v; return old; }
@@ -2360,6 +2379,7 @@ int gnms_launch_overlap_tiles(const float* boxes, int src, int generalized, int 
 #define GNMS_TALL(SRC, G, AF)                                                           \
     do {                                                                                \
         if (g_tall_tiles == 8) tile_tall_narrow_kernel<SRC, G, AF><<<grid, 128, 0, s>>>(T); \
+        else if (g_tall_tiles == 9) tile_tall_kernel<SRC, G, AF, 4, true, true><<<grid, 128, 0, s>>>(T); \
         else if (kq == 2) tile_tall_kernel<SRC, G, AF, 2><<<grid, 128, 0, s>>>(T);      \
         else if (g_packed) tile_tall_kernel<SRC, G, AF, 4, true><<<grid, 128, 0, s>>>(T); \
         else tile_tall_kernel<SRC, G, AF, 4><<<grid, 128, 0, s>>>(T);                   \

@@ -1,12 +1,13 @@
 #!/bin/bash
 # Run ON THE GPU BOX (under gpurun): first measurement of the experimental 2-rows-per-step matrix-only kernel
-# (tile_tall_narrow_kernel, DESIGN.md section 8 lead (b)) against the default one.
+# (tile_tall_narrow_kernel, --tall 8, DESIGN.md section 8 lead (b)) and of the kPipe ordering of tile_tall_kernel (--tall 9,
+# lead (a)) against the default one (--tall 4).
 #   gpurun --timeout 400 -- 'bash tools/ab_narrow.sh'
 # 1. its bitwise parity test (skipped unless GNMS_EXPERIMENTAL=1); 2. bench lines of both kernels (roofline.avg_launch_ms is
 # the kernel alone, ms_per_step the whole step); 3. if parity holds: one ncu --set full capture of the narrow kernel.
 mkdir -p gpurun_out
 GNMS_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_overlaps.py -q -k "narrow or tall" 2>&1 | tail -5 | tee gpurun_out/ab_narrow_parity.txt
-for tall in 4 8; do
+for tall in 4 8 9; do
     timeout 150 python bench.py --no-cpu --tall $tall > gpurun_out/ab_tall_$tall.json 2> gpurun_out/ab_tall_$tall.err
     python - <<PY
 import json
