@@ -841,7 +841,8 @@ static inline int tall_tiles_per_image(int N, int kQ) {
     return n;
 }
 
-// kPipe (EXPERIMENT, not the default, not yet run on a device -- DESIGN.md section 8 lead (a)): the row records of the next
+// kPipe (EXPERIMENT, not the default; 483.8 vs 509.4 us and bit-identical in the one run of tools/exp/ab_tall.cu, partial
+// tiles and persistent launch not yet run on a device -- DESIGN.md section 8 lead (a)): the row records of the next
 // 32-row step are loaded before the stores of this one and the store pointers are advanced before, not after, the
 // stores, so that the instructions that follow the stores do not rewrite the registers the queued STG still read.
 template <int kSrc, bool kGen, bool kAffine, int kQ, bool kPacked = false, bool kPipe = false>
@@ -994,8 +995,9 @@ __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
 // every 6.6 cycles -- ptxas has no registers left to interleave the pair chains (each reciprocal is followed directly by
 // its five dependent FFMA2), and 4 warps per sub-partition do not cover that.  Warp = 4 column quads x 8 row pairs: the
 // direct stores of a warp are 16 rows x 64 B, the mirrored ones 16 rows x 64 B (8-byte stores).
-// Selected with gnms_debug_tall_tiles(8); written at the end of round 1 without GPU time left: NOT measured and NOT
-// verified on the device yet (tests/test_gpu_overlaps.py holds the bitwise test, enabled with GNMS_EXPERIMENTAL=1).
+// Selected with gnms_debug_tall_tiles(8).  Measured once (tools/exp/ab_tall.cu, 32 images of N = 4096, one tile per CTA):
+// 474.5 us against 509.4 us of the default kernel, every output word identical.  Its partial-tile path and the persistent
+// launch have not run on a device yet (tests/test_gpu_overlaps.py holds the bitwise test, enabled with GNMS_EXPERIMENTAL=1).
 template <int kSrc, bool kGen, bool kAffine>
 __global__ void __launch_bounds__(128, 6) tile_tall_narrow_kernel(TileArgs A) {
     typedef typename RecOf<kSrc>::type RecT;
