@@ -386,7 +386,7 @@ def main():
     ap.add_argument("--tiles-per-cta", type=int, default=4, help="matrix-only tile kernel on its branch: tiles per CTA (0 = persistent)")
     ap.add_argument("--packed", type=int, default=-1, help="debug: packed fp32x2 arithmetic in the matrix-only kernel (0/1; -1 = library default)")
     ap.add_argument("--tall", type=int, default=-1, help="debug: rows of the matrix-only tiles in units of 64 (2 or 4; -1 = library default 4; 8 = the experimental "
-                         "2-rows-per-step kernel, 6 CTAs per SM; 9 = the experimental kPipe ordering)")
+                         "2-rows-per-step kernel, 6 CTAs per SM; 9 = the experimental kPipe ordering; 10 = both)")
     ap.add_argument("--splits", type=int, default=1, help="issue the batch as this many sub-batches on parallel graph branches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -998,7 +998,9 @@ __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
 // Selected with gnms_debug_tall_tiles(8).  Measured once (tools/exp/ab_tall.cu, 32 images of N = 4096, one tile per CTA):
 // 474.5 us against 509.4 us of the default kernel, every output word identical.  Its partial-tile path and the persistent
 // launch have not run on a device yet (tests/test_gpu_overlaps.py holds the bitwise test, enabled with GNMS_EXPERIMENTAL=1).
-template <int kSrc, bool kGen, bool kAffine>
+// kPipe: as in tile_tall_kernel (next rows loaded and store pointers advanced before the stores); gnms_debug_tall_tiles(10),
+// not yet run on a device.
+template <int kSrc, bool kGen, bool kAffine, bool kPipe = false>
 __global__ void __launch_bounds__(128, 6) tile_tall_narrow_kernel(TileArgs A) {
     typedef typename RecOf<kSrc>::type RecT;
     constexpr int kNF = SoaOf<kSrc>::kFields;
@@ -1059,24 +1061,30 @@ __global__ void __launch_bounds__(128, 6) tile_tall_narrow_kernel(TileArgs A) {
         const uint32_t row_bytes = (uint32_t)N * 4u;
         char* drow = reinterpret_cast<char*>(out + (int64_t)(R * kRows + 2 * ty) * N + j0);
         char* dcol = reinterpret_cast<char*>(out + (int64_t)j0 * N + (R * kRows + 2 * ty));
+        auto load_rows = [&](int rl, RecT* rr) {
+            float2 f[7];
+            constexpr int kUse = kSrc == kSrcBox3d ? 7 : 4;
+#pragma unroll
+            for (int q = 0; q < kUse; ++q) f[q] = *reinterpret_cast<const float2*>(&s_row[buf][q * kRows + rl]);
+            const float* pf = reinterpret_cast<const float*>(f);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if constexpr (kSrc == kSrcBox3d) rr[k] = Rec3{pf[k], pf[2 + k], pf[4 + k], pf[6 + k], pf[8 + k], pf[10 + k], pf[12 + k], 0.f};
+                else rr[k] = make_box2(make_float4(pf[k], pf[2 + k], pf[4 + k], pf[6 + k]));
+            }
+        };
+        RecT rr[2];
+        if constexpr (kPipe) {
+            load_rows(2 * ty, rr);
+            drow -= 16u * (size_t)row_bytes;
+            dcol -= 64;
+        }
 #pragma unroll 1
-        for (int h = 0; h < h_end; ++h, drow += 16u * (size_t)row_bytes, dcol += 64) {
+        for (int h = 0; h < h_end; ++h) {
             const int rl = 16 * h + 2 * ty;
             if (R * kRows + 16 * h >= N) break;
             const bool mirror = (h >> 2) != c;                        // the diagonal 64 x 64 quarter is not mirrored
-            RecT rr[2];
-            {
-                float2 f[7];
-                constexpr int kUse = kSrc == kSrcBox3d ? 7 : 4;
-#pragma unroll
-                for (int q = 0; q < kUse; ++q) f[q] = *reinterpret_cast<const float2*>(&s_row[buf][q * kRows + rl]);
-                const float* pf = reinterpret_cast<const float*>(f);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    if constexpr (kSrc == kSrcBox3d) rr[k] = Rec3{pf[k], pf[2 + k], pf[4 + k], pf[6 + k], pf[8 + k], pf[10 + k], pf[12 + k], 0.f};
-                    else rr[k] = make_box2(make_float4(pf[k], pf[2 + k], pf[4 + k], pf[6 + k]));
-                }
-            }
+            if constexpr (!kPipe) load_rows(rl, rr);
             float v[2][4];
             bool unsafe = tile_unsafe;
             if constexpr (kSrc == kSrcBox3d) {                        // two column boxes per instruction (fp32x2)
@@ -1099,6 +1107,11 @@ __global__ void __launch_bounds__(128, 6) tile_tall_narrow_kernel(TileArgs A) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template exact<kGen, kAffine>(rr[r], cr[k]);
             }
+            if constexpr (kPipe) {
+                if (h + 1 < h_end) load_rows(rl + 16, rr);            // next step's rows, before this step's stores
+                drow += 16u * (size_t)row_bytes;
+                dcol += 64;
+            }
             if (full_tile) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r)
@@ -1119,6 +1132,10 @@ __global__ void __launch_bounds__(128, 6) tile_tall_narrow_kernel(TileArgs A) {
                             if (mirror) out[(int64_t)(j0 + k) * N + (i0 + r)] = v[r][k];
                         }
                     }
+            }
+            if constexpr (!kPipe) {
+                drow += 16u * (size_t)row_bytes;
+                dcol += 64;
             }
         }
     }
@@ -2321,7 +2338,7 @@ static int g_packed = 1;                   // matrix-only tall tiles: packed fp3
 extern "C" int gnms_debug_packed(int v) { int old = g_packed; g_packed = v; return old; }
 static int g_tall_tiles = 4;               // matrix-only launches: 4 = 256 x 64 tiles, 2 = 128 x 64, 8 = 256 x 64 with the
                                            // experimental 2-rows-per-step kernel (tile_tall_narrow_kernel), 9 = 256 x 64 with
-                                           // the experimental kPipe ordering of tile_tall_kernel
+                                           // the experimental kPipe ordering of tile_tall_kernel, 10 = both
 extern "C" int gnms_debug_tall_tiles(int v) { int old = g_tall_tiles; g_tall_tiles = v; return old; }
 static int g_tiles_per_cta = 0;            // matrix-only tile kernel: 0 = persistent CTAs, k = k consecutive tiles per CTA
 extern "C" int gnms_debug_tiles_per_cta(int v) { int old = g_tiles_per_cta; g_tiles_per_cta = v; return old; }
@@ -2381,6 +2398,7 @@ int gnms_launch_overlap_tiles(const float* boxes, int src, int generalized, int 
 #define GNMS_TALL(SRC, G, AF)                                                           \
     do {                                                                                \
         if (g_tall_tiles == 8) tile_tall_narrow_kernel<SRC, G, AF><<<grid, 128, 0, s>>>(T); \
+        else if (g_tall_tiles == 10) tile_tall_narrow_kernel<SRC, G, AF, true><<<grid, 128, 0, s>>>(T); \
         else if (g_tall_tiles == 9) tile_tall_kernel<SRC, G, AF, 4, true, true><<<grid, 128, 0, s>>>(T); \
         else if (kq == 2) tile_tall_kernel<SRC, G, AF, 2><<<grid, 128, 0, s>>>(T);      \
         else if (g_packed) tile_tall_kernel<SRC, G, AF, 4, true><<<grid, 128, 0, s>>>(T); \

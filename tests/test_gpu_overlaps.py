@@ -176,11 +176,11 @@ def test_batched_self_overlap_tall_tiles_bitwise(kind, n, batch):
 
 @pytest.mark.skipif(not os.environ.get("GNMS_EXPERIMENTAL"),
                     reason="unmeasured experimental kernels (DESIGN.md section 8); set GNMS_EXPERIMENTAL=1")
-@pytest.mark.parametrize("variant", [8, 9])
+@pytest.mark.parametrize("variant", [8, 9, 10])
 @pytest.mark.parametrize("kind,n,batch", [("2d", 2051, 1), ("3d", 2051, 1), ("3d", 1029, 2), ("3d", 4096, 2)])
 def test_experimental_narrow_step_kernel_bitwise(kind, n, batch, variant):
     """The experimental variants of the matrix-only kernel -- gnms_debug_tall_tiles(8): 2 rows per step, 6 CTAs per SM;
-    (9): next rows loaded and store pointers advanced before the stores -- must give the same bits as the default one."""
+    (9): next rows loaded and store pointers advanced before the stores; (10): both -- must give the same bits as the default one."""
     import ctypes
     from groomed_nms_b200 import _lib
     lib = _lib.load()

@@ -7,7 +7,7 @@
 # the kernel alone, ms_per_step the whole step); 3. if parity holds: one ncu --set full capture of the narrow kernel.
 mkdir -p gpurun_out
 GNMS_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_overlaps.py -q -k "narrow or tall" 2>&1 | tail -5 | tee gpurun_out/ab_narrow_parity.txt
-for tall in 4 8 9; do
+for tall in 4 8 9 10; do
     timeout 150 python bench.py --no-cpu --tall $tall > gpurun_out/ab_tall_$tall.json 2> gpurun_out/ab_tall_$tall.err
     python - <<PY
 import json

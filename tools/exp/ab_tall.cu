@@ -2,7 +2,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../include -o ab_tall.bin ab_tall.cu \
 //        -L../../groomed_nms_b200 -lgroomed_b200 -Xlinker -rpath -Xlinker '$ORIGIN/../../groomed_nms_b200'
 //   ./ab_tall.bin [images=32]
-// For gnms_debug_tall_tiles = 4 (default), 8 (2 rows per step, 6 CTAs per SM), 9 (kPipe ordering): time of one launch over
+// For gnms_debug_tall_tiles = 4 (default), 8 (2 rows per step, 6 CTAs per SM), 9 (kPipe ordering), 10 (both): time of one launch over
 // `images` x N=4096 7-DoF boxes (CUDA events, 10 launches after 2 warm-ups) and the number of output words that differ
 // from the default kernel's (must be 0).
 #include <cstdint>
@@ -48,8 +48,8 @@ int main(int argc, char** argv) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     gnms_debug_tiles_per_cta(4);
-    const int variants[3] = {4, 8, 9};
-    for (int vi = 0; vi < 3; ++vi) {
+    const int variants[4] = {4, 8, 9, 10};
+    for (int vi = 0; vi < 4; ++vi) {
         gnms_debug_tall_tiles(variants[vi]);
         float* out = vi == 0 ? d_ref : d_out;
         CK(cudaMemset(out, 0xff, mat * 4));
