@@ -1,9 +1,11 @@
 """TEST INFRASTRUCTURE ONLY -- numpy restatement of the GrooMeD branch of the detection loss
 (reference lib/loss/rpn_3d.py:731-825 and :1117-1137, "rank" mode).
 
-PARITY UNPINNED against the reference's own run: RPN_3D_loss.forward hard-codes CUDA (54 .cuda() sites) and cannot be
-executed in the CPU build container, and /root/reference does not exist on the GPU box.  Every step below is a
-composition of functions that ARE pinned by golden vectors (oracle.groomed_oracle: corners, iou, iou3d_approximate,
+Pinned against the reference's own run: tests/golden/loss_branch_ref.npz holds what the UNMODIFIED RPN_3D_loss.forward
+consumed and produced on 8 synthetic cases (oracle/gen_golden_loss.py runs it in the build container with its `.cuda()`
+calls mapped to the CPU by oracle/ref_shim.fake_cuda); tests/test_oracle_loss_ref.py checks this restatement against
+it (selection / keep / target indices exact, scores 1e-5, loss and score gradients).  Every step below is a composition
+of functions pinned by their own golden vectors (oracle.groomed_oracle: corners, iou, iou3d_approximate,
 differentiable_nms, aploss), in the order of the reference lines cited."""
 import numpy as np
 
@@ -13,7 +15,8 @@ F32 = np.float32
 
 
 def branch_image(scores, fg_inds, boxes7, coords_2d, gts_2d, gts_3d, overlap_in_nms="2d", nms_thres=0.4, temperature=0.1,
-                 valid_thr=0.3, group_size=100, beta=0.3, max_boxes=500, corners_b1=None):
+                 valid_thr=0.3, group_size=100, beta=0.3, max_boxes=500, corners_b1=None, pruning_method="linear",
+                 group_boxes=True, mask_group_boxes=True, boxes_2d="normal", p2=None, scale_factor=1.0):
     """-> dict(fg_index_for_nms, scores_after_nms (in that order), best (anchor ids), fwd (oracle nms state)).
     corners_b1: optionally the CUDA path's corners (parity is defined from the corners onward)."""
     fg_scores = scores[fg_inds]
@@ -25,7 +28,11 @@ def branch_image(scores, fg_inds, boxes7, coords_2d, gts_2d, gts_3d, overlap_in_
         corners_b1 = O.get_corners_of_cuboid(*[b7[:, i] for i in range(7)])            # :746-752
     corners_b1 = corners_b1.astype(F32).copy()
     box2d = coords_2d[fg_idx].astype(F32)
-    iou2d = O.iou(box2d, box2d)                                                        # :772
+    if boxes_2d == "projected":                                                        # :756-768,774
+        nms_box2d = O.projected_boxes_from_corners(p2, corners_b1, scale_factor)
+    else:
+        nms_box2d = box2d
+    iou2d = O.iou(nms_box2d, nms_box2d)                                                # :772-774
     if overlap_in_nms == "2d":
         ov = iou2d
     else:
@@ -33,8 +40,9 @@ def branch_image(scores, fg_inds, boxes7, coords_2d, gts_2d, gts_3d, overlap_in_
         corners_b1 = O.mutated_corners(corners_b1)                                     # the reference's in-place Y<-Z
         ov3 = (F32(0.5) * (F32(1) + g3)).astype(F32)                                   # :781
         ov = ov3 if overlap_in_nms == "3d" else (iou2d * ov3).astype(F32)              # :783,786
-    fwd = O.differentiable_nms(scores[fg_idx], ov, nms_threshold=nms_thres, temperature=temperature,
-                               valid_box_prob_threshold=valid_thr, group_size=group_size, dense=False)   # :791
+    fwd = O.differentiable_nms(scores[fg_idx], ov, nms_threshold=nms_thres, temperature=temperature, pruning_method=pruning_method,
+                               valid_box_prob_threshold=valid_thr, group_size=group_size, group_boxes=group_boxes,
+                               mask_group_boxes=mask_group_boxes, dense=not (group_boxes and mask_group_boxes))   # :791
     gt7 = np.stack([gts_3d[:, 7], gts_3d[:, 8], gts_3d[:, 9], gts_3d[:, 3], gts_3d[:, 4], gts_3d[:, 5], gts_3d[:, 10]], 1).astype(F32)
     corners_b2 = O.get_corners_of_cuboid(*[gt7[:, i] for i in range(7)])               # :804-811
     _, g3gt = O.iou3d_approximate(corners_b1, corners_b2, "combinations", "generalized")   # :813
