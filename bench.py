@@ -272,10 +272,7 @@ def run_ours(args, rank, world):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
     lib = _lib.load()
-    if args.tall >= 0:
-        lib.gnms_debug_tall_tiles(args.tall)
-    if args.packed >= 0:
-        lib.gnms_debug_packed(args.packed)
+    matrix_kernel = {"auto": _lib.MATRIX_KERNEL_AUTO, "direct": _lib.MATRIX_KERNEL_DIRECT, "tma": _lib.MATRIX_KERNEL_TMA}[args.matrix_kernel]
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -292,7 +289,9 @@ def run_ours(args, rank, world):
     plans = {}
     for name, mat in (("materialised", True), ("fused", False)):
         pl = Nms3dPlan(B, N, dev, params, materialise=mat, overlap_branch=(mat and not args.no_overlap_branch))
-        pl.tiles_per_cta = args.tiles_per_cta
+        pl.matrix_opts = _lib.launch_opts(matrix_kernel=matrix_kernel, tiles_per_cta=args.tiles_per_cta if pl.overlap_branch else 0,
+                                          flags=0 if args.packed else _lib.OPT_SCALAR_MATH)
+        pl.forward_opts = _lib.launch_opts(matrix_kernel=matrix_kernel, flags=0 if args.packed else _lib.OPT_SCALAR_MATH)
         pl.boxes7.copy_(torch.from_numpy(boxes)); pl.scores.copy_(torch.from_numpy(scores)); pl.grad_prob.copy_(torch.from_numpy(grads))
         plans[name] = pl
     torch.cuda.synchronize()
@@ -379,13 +378,15 @@ def run_ours(args, rank, world):
         stages["records_from_boxes7(corners in registers)"] = time_stage(torch, pl.stage_front, st, it)
         stages["forward_boxes+matrix_out(all kernels, one stream)"] = time_stage(torch, pl.stage_forward, st, it)
         # the kernels of that forward one by one (debug stage mask of the library: the same launches, in isolation)
-        old_tpc = lib.gnms_debug_tiles_per_cta(args.tiles_per_cta if not args.no_overlap_branch else 0)   # as launched in the step
-        for bit, name in ((1, "sort_kernel+rank_kernel"), (2, "spatial_kernel"), (32, "elect_kernel(+zero/list of failed images)"),
-                          (4, "tile_kernel(matrix only)"), (16, "chain_kernel")):
-            lib.gnms_debug_stage_mask(bit)
+        keep = pl.forward_opts
+        for bit, name in ((_lib.STAGE_RANK, "sort_kernel+rank_kernel"), (_lib.STAGE_SPATIAL, "spatial_kernel"),
+                          (_lib.STAGE_ELECT, "elect_kernel(+zero/list of failed images)"),
+                          (_lib.STAGE_TILES, "tile_kernel(matrix only)"), (_lib.STAGE_CHAIN, "chain_kernel")):
+            # the same launches one at a time: a per-call stage mask (gnms_launch_opts), tiles_per_cta as in the step
+            pl.forward_opts = _lib.launch_opts(matrix_kernel=matrix_kernel, stage_mask=bit, flags=keep.flags,
+                                               tiles_per_cta=args.tiles_per_cta if pl.overlap_branch else 0)
             stages[name] = time_stage(torch, pl.stage_forward, st, it)
-        lib.gnms_debug_tiles_per_cta(old_tpc)
-        lib.gnms_debug_stage_mask(0xff)
+        pl.forward_opts = keep
         stages["backward"] = time_stage(torch, pl.stage_backward, st, it)
         stages["forward_boxes_no_matrix(all kernels)"] = time_stage(torch, plans["fused"].stage_forward, st, it)
         tk = Nms3dPlan(B, N, dev, params, materialise=True, two_kernel=True)
@@ -470,9 +471,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap-branch", action="store_true", help="matrix kernel and NMS kernels on one stream instead of two graph branches")
     ap.add_argument("--tiles-per-cta", type=int, default=4, help="matrix-only tile kernel on its branch: tiles per CTA (0 = persistent)")
-    ap.add_argument("--packed", type=int, default=-1, help="debug: packed fp32x2 arithmetic in the matrix-only kernel (0/1; -1 = library default)")
-    ap.add_argument("--tall", type=int, default=-1, help="debug: rows of the matrix-only tiles in units of 64 (2 or 4; -1 = library default 4; 8 = the experimental "
-                         "2-rows-per-step kernel, 6 CTAs per SM; 9 = the experimental kPipe ordering; 10 = both)")
+    ap.add_argument("--packed", type=int, default=1, help="packed fp32x2 arithmetic in the matrix-only kernel (0 = scalar)")
+    ap.add_argument("--matrix-kernel", default="auto", choices=["auto", "direct", "tma"],
+                    help="how the overlap matrix leaves the SM: register-direct STG or shared-memory staging + TMA tensor stores")
     ap.add_argument("--splits", type=int, default=1, help="issue the batch as this many sub-batches on parallel graph branches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -29,6 +29,33 @@ class Params(ctypes.Structure):
                 ("thresholded_output", ctypes.c_int32), ("sorted_output", ctypes.c_int32)]
 
 
+class LaunchOpts(ctypes.Structure):
+    """gnms_launch_opts (include/groomed_nms_b200.h): per-call tuning / profiling knobs; 0 = library default everywhere."""
+    _fields_ = [("struct_size", ctypes.c_uint32), ("matrix_kernel", ctypes.c_int32), ("tiles_per_cta", ctypes.c_int32),
+                ("rank_method", ctypes.c_int32), ("election", ctypes.c_int32), ("stage_mask", ctypes.c_uint32),
+                ("flags", ctypes.c_uint32)]
+
+
+MATRIX_KERNEL_AUTO, MATRIX_KERNEL_DIRECT, MATRIX_KERNEL_TMA = 0, 1, 2
+RANK_AUTO, RANK_COUNT, RANK_SORT = 0, 1, 2
+ELECT_AUTO, ELECT_DIRECT, ELECT_MASK = 0, 1, 2
+STAGE_RANK, STAGE_SPATIAL, STAGE_TILES, STAGE_EARLIER, STAGE_CHAIN, STAGE_ELECT = 1, 2, 4, 8, 16, 32
+OPT_SCALAR_MATH, OPT_INLINE_HITS, OPT_ONE_PASS = 1, 2, 4
+
+
+def launch_opts(matrix_kernel=0, tiles_per_cta=0, rank_method=0, election=0, stage_mask=0, flags=0):
+    o = LaunchOpts()
+    o.struct_size = ctypes.sizeof(LaunchOpts)
+    o.matrix_kernel, o.tiles_per_cta, o.rank_method, o.election = matrix_kernel, tiles_per_cta, rank_method, election
+    o.stage_mask, o.flags = stage_mask, flags
+    return o
+
+
+def opts_ref(o):
+    """ctypes argument for an optional LaunchOpts (None -> NULL)."""
+    return ctypes.byref(o) if o is not None else None
+
+
 class Saved(ctypes.Structure):
     _fields_ = [("order", vp), ("sorted_scores", vp), ("lead", vp), ("pval", vp), ("dpval", vp), ("pre", vp)]
 
@@ -48,10 +75,16 @@ SIGNATURES = {
     "gnms_overlap2d_batched_f32": (i32, [vp, i32, i32, vp, vp]),
     "gnms_overlap3d_batched_f32": (i32, [vp, i32, i32, vp, i32, i32, vp]),
     "gnms_overlap3d_list_f32": (i32, [vp, vp, i32, vp, vp, i32, i32, vp]),
+    "gnms_overlap2d_batched_ex_f32": (i32, [vp, i32, i32, vp, ctypes.POINTER(LaunchOpts), vp]),
+    "gnms_overlap3d_batched_ex_f32": (i32, [vp, i32, i32, vp, i32, i32, ctypes.POINTER(LaunchOpts), vp]),
     "gnms_workspace_bytes": (sz, [i32, i32]),
     "gnms_forward_f32": (i32, [vp, vp, i64, i32, i32, vp, ctypes.POINTER(Params), vp, vp, vp, vp, Saved, vp, vp]),
     "gnms_forward_boxes_f32": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, ctypes.POINTER(Params), vp, vp, vp, vp, vp,
                                      Saved, vp, vp]),
+    "gnms_forward_ex_f32": (i32, [vp, vp, i64, i32, i32, vp, ctypes.POINTER(Params), vp, vp, vp, vp, Saved, vp,
+                                  ctypes.POINTER(LaunchOpts), vp]),
+    "gnms_forward_boxes_ex_f32": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, ctypes.POINTER(Params), vp, vp, vp, vp, vp,
+                                        Saved, vp, ctypes.POINTER(LaunchOpts), vp]),
     "gnms_backward_f32": (i32, [vp, vp, vp, i64, i32, i32, vp, ctypes.POINTER(Params), Saved, vp, vp, i64, vp, vp]),
     "gnms_get_groups_f32": (i32, [vp, vp, i64, i32, f32, i32, vp, vp, vp, vp, vp]),
     "gnms_prune_f32": (i32, [vp, i64, i32, f32, f32, vp, vp]),

@@ -22,7 +22,9 @@
 //   4. backward_kernel    one CTA: analytic vector-Jacobian product.
 #include "common.cuh"
 
+#include <cuda.h>
 #include <limits.h>
+#include <atomic>
 
 namespace gnms {
 
@@ -988,30 +990,63 @@ __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
     }
 }
 
-// ------------------------------------------------------------------------------------------ 2c-narrow. EXPERIMENT (not the default)
-// Same 256 x 64 tiles as tile_tall_kernel, but a thread evaluates 2 rows x 4 columns per step (16 steps of 16 rows per
-// tile) instead of 4 x 4: half the results and row records live, so that the kernel fits 80 registers and 6 CTAs (24
-// warps) stay resident per SM instead of 4 (16 warps).  Motivation: the 4 x 4 kernel issues one instruction per warp
-// every 6.6 cycles -- ptxas has no registers left to interleave the pair chains (each reciprocal is followed directly by
-// its five dependent FFMA2), and 4 warps per sub-partition do not cover that.  Warp = 4 column quads x 8 row pairs: the
-// direct stores of a warp are 16 rows x 64 B, the mirrored ones 16 rows x 64 B (8-byte stores).
-// Selected with gnms_debug_tall_tiles(8).  Measured once (tools/exp/ab_tall.cu, 32 images of N = 4096, one tile per CTA):
-// 474.5 us against 509.4 us of the default kernel, every output word identical.  Its partial-tile path and the persistent
-// launch have not run on a device yet (tests/test_gpu_overlaps.py holds the bitwise test, enabled with GNMS_EXPERIMENTAL=1).
-// kPipe: as in tile_tall_kernel (next rows loaded and store pointers advanced before the stores); gnms_debug_tall_tiles(10),
-// not yet run on a device.
-template <int kSrc, bool kGen, bool kAffine, bool kPipe = false>
-__global__ void __launch_bounds__(128, 6) tile_tall_narrow_kernel(TileArgs A) {
+// ------------------------------------------------------------------------------------------ 2d. matrix only, TMA tensor stores
+// Same 256 x 64 symmetric tiles, same arithmetic, same bits as tile_tall_kernel; what changes is how the results leave the
+// SM.  tile_tall_kernel stores every 4 x 4 sub-tile straight from registers (8 STG.128 + the address arithmetic they need)
+// and then stalls on the registers the queued stores still read (ncu: all of its long_scoreboard time).  Here a warp owns
+// a 32-row x 32-column block of the tile per step: its threads drop their 4 x 4 results into two shared-memory boxes of
+// 32 rows x 128 bytes -- the block itself and its transpose (the mirror image across the matrix diagonal), both in the
+// 128-byte-swizzled layout of the tensor map so that the row-wise and the transposed 16-byte writes spread over the banks
+// -- and one lane hands both boxes to the copy engine (cp.async.bulk.tensor.3d ... shared::cta -> global, SASS UTMASTG).
+// Registers are free right after the STS, the stores drain asynchronously while the warp evaluates its next block, there
+// is no per-store address arithmetic (shared offsets are per-thread constants), partial tiles are clipped by the tensor
+// map ([batch, N, N], so a tall tile never runs into the next image), and no barrier is added: a warp waits only for its
+// own previous bulk store to have read its staging area (cp.async.bulk.wait_group.read), one 32 x 32 block later.
+// Warp w of the 128-thread CTA takes column half w & 1 of the tile and the 32-row steps of parity w >> 1.
+// Lane -> (tx, ty) = 4-column quad x 4-row quad inside the 32 x 32 block, in two 16-row sub-steps; lane bits (t0 t1 y0 t2 y1)
+// make the direct writes conflict-free (a quarter warp covers 4 quads of 2 rows: 8 distinct swizzled chunks) and the
+// transposed ones 2-way (no lane order makes both conflict-free: each needs its own third bit next to t0 and y0).
+constexpr int kTmaStageBytes = 4 * 2 * 4096;                 // 4 warps x (direct box + mirror box) x 32 rows x 128 B
+
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_addr, int x, int y, int z, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;"
+                 :: "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_addr), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts_f4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int kSrc, bool kGen, bool kAffine, bool kPacked>
+__global__ void __launch_bounds__(128, 4) tile_tma_kernel(TileArgs A, const __grid_constant__ CUtensorMap tmap) {
     typedef typename RecOf<kSrc>::type RecT;
     constexpr int kNF = SoaOf<kSrc>::kFields;
     constexpr int kQ = 4, kRows = 64 * kQ;
-    __shared__ __align__(16) float s_row[2][kNF * kRows];
-    __shared__ __align__(16) float s_col[2][kNF * kTT];
-    __shared__ int s_ij[2][4];
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t sbase = ((uint32_t)__cvta_generic_to_shared(smem_dyn) + 1023u) & ~1023u;        // swizzle atoms are 1 KB
+    unsigned char* gbase = smem_dyn + (sbase - (uint32_t)__cvta_generic_to_shared(smem_dyn));
+    float* s_row = reinterpret_cast<float*>(gbase + kTmaStageBytes);                                // [2][kNF * kRows]
+    float* s_col = s_row + 2 * kNF * kRows;                                                         // [2][kNF * kTT]
+    int* s_ij = reinterpret_cast<int*>(s_col + 2 * kNF * kTT);                                      // [2][4]
     const int N = A.N, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int tx = (lane & 3) + 4 * warp, ty = lane >> 2;             // 16 column quads x 8 row pairs
+    const int half = warp & 1, hpar = warp >> 1;
+    const int tx = (lane & 3) | ((lane >> 1) & 4), ty = ((lane >> 2) & 1) | ((lane >> 3) & 2);
     const int total = A.tiles_per_image * A.batch;
+    // per-thread shared offsets (bytes) inside the warp's two boxes; sub-step 1 adds 16 rows (direct) / flips chunk bit 2 (mirror)
+    const uint32_t dbox = sbase + (uint32_t)warp * 8192u, mbox = dbox + 4096u;
+    uint32_t doff[4], moff[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int row = 4 * ty + r;                                        // + 16 * sub: (row & 7) is the same in both sub-steps
+        doff[r] = dbox + (uint32_t)(row * 128 + ((tx ^ (row & 7)) << 4));
+        const int mrow = 4 * tx + r;                                       // r plays k here: column k of the thread = mirror row
+        moff[r] = mbox + (uint32_t)(mrow * 128 + ((ty ^ (mrow & 7)) << 4));
+    }
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     auto prefetch = [&](int t, int buf) {
         const int b = div_small(t, A.tiles_per_image, A.inv_tpi);
         int R, C;
@@ -1020,17 +1055,17 @@ __global__ void __launch_bounds__(128, 6) tile_tall_narrow_kernel(TileArgs A) {
 #pragma unroll
         for (int k = tid; k < kRows; k += 128) {
             const float* src = bx + (size_t)min(R * kRows + k, N - 1) * kNF;
-            float* dst = &s_row[buf][k];
+            float* dst = s_row + buf * kNF * kRows + k;
 #pragma unroll
             for (int q = 0; q < kNF; ++q) cp_async4(dst + q * kRows, src + q);
         }
         if (tid < kTT) {
             const float* src = bx + (size_t)min(C * kTT + tid, N - 1) * kNF;
-            float* dst = &s_col[buf][tid];
+            float* dst = s_col + buf * kNF * kTT + tid;
 #pragma unroll
             for (int q = 0; q < kNF; ++q) cp_async4(dst + q * kTT, src + q);
         }
-        if (tid == 0) { s_ij[buf][0] = b; s_ij[buf][1] = R; s_ij[buf][2] = C; }
+        if (tid == 0) { s_ij[buf * 4 + 0] = b; s_ij[buf * 4 + 1] = R; s_ij[buf * 4 + 2] = C; }
     };
     auto record_ok = [&](const float* f, int stride) -> bool {
         if constexpr (kSrc == kSrcBox3d)
@@ -1044,101 +1079,84 @@ __global__ void __launch_bounds__(128, 6) tile_tall_narrow_kernel(TileArgs A) {
     if (t < t_end) prefetch(t, 0);
     for (; t < t_end; t += t_step, buf ^= 1) {
         cp_async_wait_all();
+        const float* srow = s_row + buf * kNF * kRows;
+        const float* scol = s_col + buf * kNF * kTT;
         bool bad = false;
 #pragma unroll
-        for (int k = tid; k < kRows; k += 128) bad = bad || !record_ok(&s_row[buf][k], kRows);
-        if (tid < kTT) bad = bad || !record_ok(&s_col[buf][tid], kTT);
+        for (int k = tid; k < kRows; k += 128) bad = bad || !record_ok(srow + k, kRows);
+        if (tid < kTT) bad = bad || !record_ok(scol + tid, kTT);
         const bool tile_unsafe = __syncthreads_or(bad);
-        const int b = s_ij[buf][0], R = s_ij[buf][1], C = s_ij[buf][2];
+        const int b = s_ij[buf * 4 + 0], R = s_ij[buf * 4 + 1], C = s_ij[buf * 4 + 2];
         if (t + t_step < t_end) prefetch(t + t_step, buf ^ 1);
         RecT cr[4];
-        SoaOf<kSrc>::load4(s_col[buf], 4 * tx, cr);
-        float* out = A.out + (size_t)b * N * N;
-        const bool full_tile = A.vec && (R * kRows + kRows <= N) && (C * kTT + kTT <= N);
+        SoaOf<kSrc>::load4(scol, 32 * half + 4 * tx, cr);
         const int c = C - kQ * R;                                     // < kQ: the tile touches the diagonal in quarter c
-        const int h_end = c < kQ ? 4 * (c + 1) : 4 * kQ;              // 16-row steps; quarters past the diagonal one are mirrors
-        const int j0 = C * kTT + 4 * tx;
-        const uint32_t row_bytes = (uint32_t)N * 4u;
-        char* drow = reinterpret_cast<char*>(out + (int64_t)(R * kRows + 2 * ty) * N + j0);
-        char* dcol = reinterpret_cast<char*>(out + (int64_t)j0 * N + (R * kRows + 2 * ty));
-        auto load_rows = [&](int rl, RecT* rr) {
-            float2 f[7];
-            constexpr int kUse = kSrc == kSrcBox3d ? 7 : 4;
-#pragma unroll
-            for (int q = 0; q < kUse; ++q) f[q] = *reinterpret_cast<const float2*>(&s_row[buf][q * kRows + rl]);
-            const float* pf = reinterpret_cast<const float*>(f);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                if constexpr (kSrc == kSrcBox3d) rr[k] = Rec3{pf[k], pf[2 + k], pf[4 + k], pf[6 + k], pf[8 + k], pf[10 + k], pf[12 + k], 0.f};
-                else rr[k] = make_box2(make_float4(pf[k], pf[2 + k], pf[4 + k], pf[6 + k]));
-            }
-        };
-        RecT rr[2];
-        if constexpr (kPipe) {
-            load_rows(2 * ty, rr);
-            drow -= 16u * (size_t)row_bytes;
-            dcol -= 64;
-        }
+        const int h_end = c < kQ ? 2 * (c + 1) : 2 * kQ;              // quarters past the diagonal one are mirrors of other tiles
+        const int col0 = C * kTT + 32 * half;                         // first column of this warp's blocks
 #pragma unroll 1
-        for (int h = 0; h < h_end; ++h) {
-            const int rl = 16 * h + 2 * ty;
-            if (R * kRows + 16 * h >= N) break;
-            const bool mirror = (h >> 2) != c;                        // the diagonal 64 x 64 quarter is not mirrored
-            if constexpr (!kPipe) load_rows(rl, rr);
-            float v[2][4];
-            bool unsafe = tile_unsafe;
-            if constexpr (kSrc == kSrcBox3d) {                        // two column boxes per instruction (fp32x2)
+        for (int h = hpar; h < h_end; h += 2) {
+            const int row0 = R * kRows + 32 * h;                      // first row of this block
+            if (row0 >= N) break;
+            const bool mirror = (h >> 1) != c;                        // the diagonal 64 x 64 quarter is not mirrored
 #pragma unroll
-                for (int r = 0; r < 2; ++r)
+            for (int sub = 0; sub < 2; ++sub) {
+                const int rl = 32 * h + 16 * sub + 4 * ty;
+                RecT rr[4];
+                {
+                    float4 f[7];
+                    constexpr int kUse = kSrc == kSrcBox3d ? 7 : 4;
 #pragma unroll
-                    for (int k = 0; k < 4; k += 2) {
-                        const F2 pv = iou3_fast2<kGen, kAffine>(rr[r], cr[k], cr[k + 1], unsafe);
-                        v[r][k] = pv.x; v[r][k + 1] = pv.y;
-                    }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template fast<kGen, kAffine>(rr[r], cr[k], unsafe);
-            }
-            if (__builtin_expect(unsafe, 0)) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template exact<kGen, kAffine>(rr[r], cr[k]);
-            }
-            if constexpr (kPipe) {
-                if (h + 1 < h_end) load_rows(rl + 16, rr);            // next step's rows, before this step's stores
-                drow += 16u * (size_t)row_bytes;
-                dcol += 64;
-            }
-            if (full_tile) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-                    st_cs_f4(reinterpret_cast<float*>(drow + r * row_bytes), make_float4(v[r][0], v[r][1], v[r][2], v[r][3]));
-                if (mirror) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        __stcs(reinterpret_cast<float2*>(dcol + k * row_bytes), make_float2(v[0][k], v[1][k]));
-                }
-            } else {
-                const int i0 = R * kRows + rl;
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
+                    for (int q = 0; q < kUse; ++q) f[q] = *reinterpret_cast<const float4*>(srow + q * kRows + rl);
+                    const float* pf = reinterpret_cast<const float*>(f);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (i0 + r < N && j0 + k < N) {
-                            out[(int64_t)(i0 + r) * N + (j0 + k)] = v[r][k];
-                            if (mirror) out[(int64_t)(j0 + k) * N + (i0 + r)] = v[r][k];
-                        }
+                        if constexpr (kSrc == kSrcBox3d) rr[k] = Rec3{pf[k], pf[4 + k], pf[8 + k], pf[12 + k], pf[16 + k], pf[20 + k], pf[24 + k], 0.f};
+                        else rr[k] = make_box2(make_float4(pf[k], pf[4 + k], pf[8 + k], pf[12 + k]));
                     }
+                }
+                float v[4][4];
+                bool unsafe = tile_unsafe;
+                if constexpr (kPacked && kSrc == kSrcBox3d) {         // two column boxes per instruction (fp32x2)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int k = 0; k < 4; k += 2) {
+                            const F2 pv = iou3_fast2<kGen, kAffine>(rr[r], cr[k], cr[k + 1], unsafe);
+                            v[r][k] = pv.x; v[r][k + 1] = pv.y;
+                        }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template fast<kGen, kAffine>(rr[r], cr[k], unsafe);
+                }
+                if (__builtin_expect(unsafe, 0)) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template exact<kGen, kAffine>(rr[r], cr[k]);
+                }
+                if (sub == 0) {                                       // the previous block's bulk stores must have read the boxes
+                    if (lane == 0) bulk_wait_read0();
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) sts_f4(doff[r] + (uint32_t)sub * 2048u, v[r][0], v[r][1], v[r][2], v[r][3]);
+                if (mirror) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) sts_f4(moff[k] ^ ((uint32_t)sub << 6), v[0][k], v[1][k], v[2][k], v[3][k]);
+                }
             }
-            if constexpr (!kPipe) {
-                drow += 16u * (size_t)row_bytes;
-                dcol += 64;
+            fence_async_smem();                                       // generic-proxy writes -> visible to the copy engine
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_3d(&tmap, dbox, col0, row0, b, policy);
+                if (mirror) tma_store_3d(&tmap, mbox, row0, col0, b, policy);
+                bulk_commit();
             }
         }
     }
+    if (lane == 0) bulk_wait_read0();                                 // the staging area must outlive the copy engine's reads
 }
 
 // ------------------------------------------------------------------------------------------ 2d. spatial order + tile culling
@@ -1684,9 +1702,13 @@ __device__ int warp_list_bits(const uint32_t* bits, int nw, int limit, int32_t* 
 
 // Optional phase clock (debug): thread 0 of image 0 stamps SM clock values at phase boundaries when enabled through
 // gnms_debug_chain_clock(1); read back with gnms_debug_chain_clock_read.  Costs one predicated branch per phase.
+#ifdef GNMS_DEBUG
 __device__ long long g_chain_clk[64];
 __device__ int g_chain_clk_on = 0;
 #define GNMS_PHASE(k) do { if (g_chain_clk_on && threadIdx.x == 0 && blockIdx.x == 0) g_chain_clk[k] = clock64(); } while (0)
+#else
+#define GNMS_PHASE(k) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
     GNMS_PHASE(0);
@@ -2273,17 +2295,19 @@ __global__ void __launch_bounds__(kChainThreads) backward_mask_kernel(BwdArgs A)
 
 static size_t chain_smem_bytes(int N) { return chain_wcol_end(N) + (((size_t)N + 3) & ~(size_t)3) * 4 + 16; }
 
+// One-time function attributes per device.  Idempotent, so a race between two first callers is harmless; the flag is
+// atomic so that the store is never torn or reordered before the attribute calls.
 static int configure_once() {
-    static bool done_dev[64] = {false};
+    static std::atomic<bool> done_dev[64];
     int dev = 0;
     GNMS_CUDA_TRY(cudaGetDevice(&dev));
-    bool& done = done_dev[dev & 63];
-    if (done) return 0;
+    std::atomic<bool>& done = done_dev[dev & 63];
+    if (done.load(std::memory_order_acquire)) return 0;
     GNMS_CUDA_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)chain_smem_bytes(GNMS_MAX_BOXES)));
     GNMS_CUDA_TRY(cudaFuncSetAttribute(backward_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * GNMS_MAX_BOXES + 64));
     GNMS_CUDA_TRY(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(GNMS_MAX_BOXES)));
-    done = true;
+    done.store(true, std::memory_order_release);
     return 0;
 }
 
@@ -2329,33 +2353,15 @@ using namespace gnms;
 
 extern "C" int gnms_version(void) { return GNMS_VERSION; }
 
-// debug only (not part of the public header): which stages of the forward run (bench.py times kernels in isolation)
-static int g_rank_by_sort = -1;            // -1 heuristic, 0 always count, 1 always sort
-extern "C" int gnms_debug_rank_by_sort(int v) { int old = g_rank_by_sort; g_rank_by_sort = v; return old; }
-static int g_direct = 1;                   // direct leader election on the matrix-free path
-extern "C" int gnms_debug_direct_election(int v) { int old = g_direct; g_direct = v; return old; }
-static int g_packed = 1;                   // matrix-only tall tiles: packed fp32x2 arithmetic for 3D records
-extern "C" int gnms_debug_packed(int v) { int old = g_packed; g_packed = v; return old; }
-static int g_tall_tiles = 4;               // matrix-only launches: 4 = 256 x 64 tiles, 2 = 128 x 64, 8 = 256 x 64 with the
-                                           // experimental 2-rows-per-step kernel (tile_tall_narrow_kernel), 9 = 256 x 64 with
-                                           // the experimental kPipe ordering of tile_tall_kernel, 10 = both
-extern "C" int gnms_debug_tall_tiles(int v) { int old = g_tall_tiles; g_tall_tiles = v; return old; }
-static int g_tiles_per_cta = 0;            // matrix-only tile kernel: 0 = persistent CTAs, k = k consecutive tiles per CTA
-extern "C" int gnms_debug_tiles_per_cta(int v) { int old = g_tiles_per_cta; g_tiles_per_cta = v; return old; }
-static int g_split_matrix = 1;             // matrix requested + direct election possible: matrix-only kernel + matrix-free path
-extern "C" int gnms_debug_split_matrix(int v) { int old = g_split_matrix; g_split_matrix = v; return old; }
-static int g_tile_queue = 1;
-extern "C" int gnms_debug_tile_queue(int v) { int old = g_tile_queue; g_tile_queue = v; return old; }
-static int g_stage_mask = 0xff;            // bit 0 rank, 1 spatial order, 2 tile (or matrix -> mask), 3 has_earlier, 4 chain / solves
-extern "C" int gnms_debug_stage_mask(int m) { int old = g_stage_mask; if (m >= 0) g_stage_mask = m; return old; }
-
-// debug only (not part of the public header): phase clock of chain_kernel, see GNMS_PHASE
+#ifdef GNMS_DEBUG
+// phase clock of chain_kernel (see GNMS_PHASE); only in -DGNMS_DEBUG builds, not part of the public header
 extern "C" int gnms_debug_chain_clock(int on) {
     return (int)cudaMemcpyToSymbol(g_chain_clk_on, &on, sizeof(int));
 }
 extern "C" int gnms_debug_chain_clock_read(long long* out64) {
     return (int)cudaMemcpyFromSymbol(out64, g_chain_clk, sizeof(long long) * 64);
 }
+#endif
 
 extern "C" const char* gnms_error_string(int rc) {
     if (rc == 0) return "success";
@@ -2376,9 +2382,35 @@ extern "C" size_t gnms_workspace_bytes(int N, int batch) {
            tile_list_bytes(N, batch);
 }
 
+// Tensor map of the [batch, N, N] fp32 overlap matrix for tile_tma_kernel: boxes of 32 rows x 32 columns (128 bytes per
+// row), 128-byte swizzle.  The encoder is the driver's cuTensorMapEncodeTiled, looked up through the runtime so that the
+// library does not link against libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int encode_matrix_tmap(CUtensorMap* m, float* out, int N, int batch) {
+    static std::atomic<EncodeTiledFn> cached{nullptr};
+    EncodeTiledFn fn = cached.load(std::memory_order_acquire);
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        GNMS_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !p) return GNMS_E_UNSUPPORTED;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+        cached.store(fn, std::memory_order_release);
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)N, (cuuint64_t)batch};
+    const cuuint64_t gstr[2] = {(cuuint64_t)N * 4, (cuuint64_t)N * (cuuint64_t)N * 4};
+    const cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : GNMS_E_UNSUPPORTED;
+}
+
 // Overlap matrices only (no bits, no workspace): the matrix-only instantiation of the tile kernel.  Used by the batched
 // overlap entry points of overlap.cu and by the forward when the caller asks for the matrix.
-int gnms_launch_overlap_tiles(const float* boxes, int src, int generalized, int affine, int N, int batch, float* out, cudaStream_t s) {
+int gnms_launch_overlap_tiles(const float* boxes, int src, int generalized, int affine, int N, int batch, float* out,
+                              const GnmsLaunchOpts& O, cudaStream_t s) {
     if (N <= 0 || batch <= 0) return 0;
     if (!boxes || !out) return GNMS_E_BADARG;
     TileArgs T = {};
@@ -2386,23 +2418,46 @@ int gnms_launch_overlap_tiles(const float* boxes, int src, int generalized, int 
     T.inv_tpi = 1.0f / (float)T.tiles_per_image; T.inv_w = 1.0f / (float)(T.nt + 1);
     T.vec = ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && (N % 4 == 0);
     T.boxes = boxes; T.out = out; T.thr = INFINITY;
-    {                                                                  // 256 x 64 tiles (128 x 64: debug switch)
-        const int kq = g_tall_tiles == 2 ? 2 : 4;
+    {                                                                  // 256 x 64 tiles
+        constexpr int kq = 4;
         T.tiles_per_image = tall_tiles_per_image(N, kq);
         T.inv_tpi = 1.0f / (float)T.tiles_per_image;
         const long long tot = (long long)T.tiles_per_image * batch;
         if (tot > 0x7fffffffLL) return GNMS_E_TOOLARGE;
         int grid = tot < 148 * 4 ? (int)tot : 148 * 4;
-        T.tiles_per_cta = g_tiles_per_cta > 0 ? (g_tiles_per_cta + kq - 1) / kq : 0;
+        T.tiles_per_cta = O.tiles_per_cta > 0 ? (O.tiles_per_cta + kq - 1) / kq : 0;
         if (T.tiles_per_cta > 0) grid = (int)((tot + T.tiles_per_cta - 1) / T.tiles_per_cta);
+        const bool scalar = (O.flags & GNMS_OPT_SCALAR_MATH) != 0;
+        // TMA tensor stores need a 16-byte aligned matrix with rows that are multiples of 16 bytes (T.vec) and the driver's
+        // tensor-map encoder; anything else takes the register-direct kernel (same bits).
+        bool use_tma = O.matrix_kernel != GNMS_MATRIX_KERNEL_DIRECT && T.vec;
+        CUtensorMap tmap;
+        if (use_tma) {
+            const int erc = encode_matrix_tmap(&tmap, out, N, batch);
+            if (erc != 0) {
+                if (O.matrix_kernel == GNMS_MATRIX_KERNEL_TMA) return erc;       // asked for explicitly: report
+                use_tma = false;
+            }
+        }
+        const size_t tma_smem = 1024 + kTmaStageBytes + (size_t)2 * (src == kSrcBox3d ? 8 : 4) * (256 + kTT) * 4 + 64;
 #define GNMS_TALL(SRC, G, AF)                                                           \
     do {                                                                                \
-        if (g_tall_tiles == 8) tile_tall_narrow_kernel<SRC, G, AF><<<grid, 128, 0, s>>>(T); \
-        else if (g_tall_tiles == 10) tile_tall_narrow_kernel<SRC, G, AF, true><<<grid, 128, 0, s>>>(T); \
-        else if (g_tall_tiles == 9) tile_tall_kernel<SRC, G, AF, 4, true, true><<<grid, 128, 0, s>>>(T); \
-        else if (kq == 2) tile_tall_kernel<SRC, G, AF, 2><<<grid, 128, 0, s>>>(T);      \
-        else if (g_packed) tile_tall_kernel<SRC, G, AF, 4, true><<<grid, 128, 0, s>>>(T); \
-        else tile_tall_kernel<SRC, G, AF, 4><<<grid, 128, 0, s>>>(T);                   \
+        if (use_tma) {                                                                  \
+            if (scalar) { GNMS_TMA_ATTR((tile_tma_kernel<SRC, G, AF, false>)); tile_tma_kernel<SRC, G, AF, false><<<grid, 128, tma_smem, s>>>(T, tmap); } \
+            else { GNMS_TMA_ATTR((tile_tma_kernel<SRC, G, AF, true>)); tile_tma_kernel<SRC, G, AF, true><<<grid, 128, tma_smem, s>>>(T, tmap); } \
+        }                                                                               \
+        else if (scalar) tile_tall_kernel<SRC, G, AF, 4><<<grid, 128, 0, s>>>(T);       \
+        else tile_tall_kernel<SRC, G, AF, 4, true><<<grid, 128, 0, s>>>(T);             \
+    } while (0)
+#define GNMS_TMA_ATTR(KERNEL)                                                                                       \
+    do {                                                                                                            \
+        static std::atomic<bool> attr_done[64];                                                                     \
+        int dev_ = 0;                                                                                               \
+        GNMS_CUDA_TRY(cudaGetDevice(&dev_));                                                                        \
+        if (!attr_done[dev_ & 63].load(std::memory_order_acquire)) {                                                \
+            GNMS_CUDA_TRY(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem)); \
+            attr_done[dev_ & 63].store(true, std::memory_order_release);                                            \
+        }                                                                                                           \
     } while (0)
         if (src == kSrcBox3d) {
             if (generalized) { if (affine) GNMS_TALL(kSrcBox3d, true, true); else GNMS_TALL(kSrcBox3d, true, false); }
@@ -2410,6 +2465,7 @@ int gnms_launch_overlap_tiles(const float* boxes, int src, int generalized, int 
         } else {
             GNMS_TALL(kSrcBox2d, false, false);
         }
+#undef GNMS_TMA_ATTR
 #undef GNMS_TALL
         GNMS_LAUNCH_CHECK();
     }
@@ -2420,8 +2476,15 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
                        float* overlap_out, int generalized, int affine, int N, int batch, const int32_t* npi,
                        const gnms_params* p,
                        float* prob, int64_t* valid_idx, int64_t* invalid_idx, int32_t* counts, gnms_saved sv,
-                       int32_t* slot, void* workspace, cudaStream_t s) {
-    int rc = check_common(N, batch, p);
+                       int32_t* slot, void* workspace, const gnms_launch_opts* opts, cudaStream_t s) {
+    GnmsLaunchOpts O;
+    int rc = gnms_resolve_opts(opts, &O);
+    if (rc) return rc;
+    const bool g_direct = O.election != GNMS_ELECT_MASK, g_split_matrix = !(O.flags & GNMS_OPT_ONE_PASS),
+               g_tile_queue = !(O.flags & GNMS_OPT_INLINE_HITS);
+    const unsigned g_stage_mask = O.stage_mask;
+    const int g_rank_by_sort = O.rank_method == GNMS_RANK_SORT ? 1 : O.rank_method == GNMS_RANK_COUNT ? 0 : -1;
+    rc = check_common(N, batch, p);
     if (rc) return rc;
     if (N == 0 || batch == 0) return 0;
     if (!scores || !prob || !valid_idx || !invalid_idx || !counts || !workspace || !sv.order || !sv.sorted_scores ||
@@ -2446,7 +2509,7 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
         N <= 128 * kTT && batch < 32768 && p->nms_threshold >= 0.f &&
         (src == kSrcBox2d || !affine || p->nms_threshold >= 0.5f || (generalized && p->nms_threshold > 0.05f))) {
         if (g_stage_mask & 4) {
-            rc = gnms_launch_overlap_tiles(boxes, src, generalized, affine, N, batch, overlap_out, s);
+            rc = gnms_launch_overlap_tiles(boxes, src, generalized, affine, N, batch, overlap_out, O, s);
             if (rc) return rc;
         }
         overlap_out = nullptr;
@@ -2490,13 +2553,13 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
         const size_t esm = elect_smem_bytes(N);
 #define GNMS_ELECT(SRC, G, AF)                                                                                       \
     do {                                                                                                             \
-        static bool attr_done[64] = {false};                                                                         \
+        static std::atomic<bool> attr_done[64];                                                                      \
         int dev_ = 0;                                                                                                \
         GNMS_CUDA_TRY(cudaGetDevice(&dev_));                                                                         \
-        if (!attr_done[dev_ & 63]) {                                                                                 \
+        if (!attr_done[dev_ & 63].load(std::memory_order_acquire)) {                                                 \
             GNMS_CUDA_TRY(cudaFuncSetAttribute(elect_kernel<SRC, G, AF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                (int)elect_smem_bytes(kElectMaxBoxes)));                              \
-            attr_done[dev_ & 63] = true;                                                                             \
+            attr_done[dev_ & 63].store(true, std::memory_order_release);                                             \
         }                                                                                                            \
         elect_kernel<SRC, G, AF><<<batch, kElectThreads, esm, s>>>(E);                                                       \
     } while (0)
@@ -2607,24 +2670,39 @@ static int32_t* slot_ptr(void* workspace, int N, int batch) {
     return reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + ws_layout(N).total * (size_t)batch);
 }
 
+extern "C" int gnms_forward_ex_f32(const float* scores, const float* iou, int64_t ld, int N, int batch,
+                                   const int32_t* n_per_image, const gnms_params* p, float* prob, int64_t* valid_idx,
+                                   int64_t* invalid_idx, int32_t* counts, gnms_saved saved, void* workspace,
+                                   const gnms_launch_opts* opts, void* stream) {
+    return run_forward(scores, kSrcMatrix, iou, ld, nullptr, nullptr, 0, 0, N, batch, n_per_image, p, prob, valid_idx,
+                       invalid_idx, counts, saved, workspace ? slot_ptr(workspace, N, batch) : nullptr, workspace, opts,
+                       (cudaStream_t)stream);
+}
 extern "C" int gnms_forward_f32(const float* scores, const float* iou, int64_t ld, int N, int batch,
                                 const int32_t* n_per_image, const gnms_params* p, float* prob, int64_t* valid_idx,
                                 int64_t* invalid_idx, int32_t* counts, gnms_saved saved, void* workspace,
                                 void* stream) {
-    return run_forward(scores, kSrcMatrix, iou, ld, nullptr, nullptr, 0, 0, N, batch, n_per_image, p, prob, valid_idx,
-                       invalid_idx, counts, saved, workspace ? slot_ptr(workspace, N, batch) : nullptr, workspace,
-                       (cudaStream_t)stream);
+    return gnms_forward_ex_f32(scores, iou, ld, N, batch, n_per_image, p, prob, valid_idx, invalid_idx, counts, saved, workspace,
+                               nullptr, stream);
 }
 
-extern "C" int gnms_forward_boxes_f32(const float* scores, const float* boxes, int box_kind, int generalized,
-                                      int affine, int N, int batch, const int32_t* n_per_image, const gnms_params* p,
-                                      float* overlap_out, float* prob, int64_t* valid_idx, int64_t* invalid_idx,
-                                      int32_t* counts, gnms_saved saved, void* workspace, void* stream) {
+extern "C" int gnms_forward_boxes_ex_f32(const float* scores, const float* boxes, int box_kind, int generalized,
+                                         int affine, int N, int batch, const int32_t* n_per_image, const gnms_params* p,
+                                         float* overlap_out, float* prob, int64_t* valid_idx, int64_t* invalid_idx,
+                                         int32_t* counts, gnms_saved saved, void* workspace, const gnms_launch_opts* opts,
+                                         void* stream) {
     if (box_kind != GNMS_BOX_2D && box_kind != GNMS_BOX_3D_REC) return GNMS_E_BADARG;
     if (boxes && (reinterpret_cast<uintptr_t>(boxes) & 15u)) return GNMS_E_ALIGN;
     return run_forward(scores, box_kind == GNMS_BOX_2D ? kSrcBox2d : kSrcBox3d, nullptr, 0, boxes, overlap_out, generalized, affine,
                        N, batch, n_per_image, p, prob, valid_idx, invalid_idx, counts, saved,
-                       workspace ? slot_ptr(workspace, N, batch) : nullptr, workspace, (cudaStream_t)stream);
+                       workspace ? slot_ptr(workspace, N, batch) : nullptr, workspace, opts, (cudaStream_t)stream);
+}
+extern "C" int gnms_forward_boxes_f32(const float* scores, const float* boxes, int box_kind, int generalized,
+                                      int affine, int N, int batch, const int32_t* n_per_image, const gnms_params* p,
+                                      float* overlap_out, float* prob, int64_t* valid_idx, int64_t* invalid_idx,
+                                      int32_t* counts, gnms_saved saved, void* workspace, void* stream) {
+    return gnms_forward_boxes_ex_f32(scores, boxes, box_kind, generalized, affine, N, batch, n_per_image, p, overlap_out, prob,
+                                     valid_idx, invalid_idx, counts, saved, workspace, nullptr, stream);
 }
 
 extern "C" int gnms_backward_f32(const float* grad_prob, const float* prob, const float* iou, int64_t ld, int N,

@@ -562,15 +562,22 @@ extern "C" int gnms_overlap3d_f32(const float* rec_a, int M, const float* rec_b,
 
 // Batched self-overlap: image z of boxes[B,N,4] / rec[B,N,8] -> out[B,N,N] in one launch (grid.z = image).
 // (the large cases go to the matrix-only instantiation of the tile kernel in gnms.cu: same values bit for bit, faster stores)
-int gnms_launch_overlap_tiles(const float* boxes, int src, int generalized, int affine, int N, int batch, float* out, cudaStream_t s);
+int gnms_launch_overlap_tiles(const float* boxes, int src, int generalized, int affine, int N, int batch, float* out,
+                              const GnmsLaunchOpts& O, cudaStream_t s);
 static const int kTileSrcBox2d = 1, kTileSrcBox3d = 2;                // gnms::BoxSrc
 
 extern "C" int gnms_overlap2d_batched_f32(const float* boxes, int N, int batch, float* out, void* stream) {
+    return gnms_overlap2d_batched_ex_f32(boxes, N, batch, out, nullptr, stream);
+}
+extern "C" int gnms_overlap2d_batched_ex_f32(const float* boxes, int N, int batch, float* out, const gnms_launch_opts* opts, void* stream) {
+    GnmsLaunchOpts O;
+    const int orc = gnms_resolve_opts(opts, &O);
+    if (orc) return orc;
     if (N < 0 || batch < 0) return GNMS_E_BADARG;
     if (N == 0 || batch == 0) return 0;
     if (!boxes || !out) return GNMS_E_BADARG;
     if (!aligned16(boxes)) return GNMS_E_ALIGN;
-    if ((long long)N * batch >= 2048) return gnms_launch_overlap_tiles(boxes, kTileSrcBox2d, 0, 0, N, batch, out, (cudaStream_t)stream);
+    if ((long long)N * batch >= 2048) return gnms_launch_overlap_tiles(boxes, kTileSrcBox2d, 0, 0, N, batch, out, O, (cudaStream_t)stream);
     const int nt = gnms_div_up(N, kST);
     const int vec = aligned16(out) && (N % 4 == 0);
     overlap2d_self_kernel<<<dim3(nt * (nt + 1) / 2, batch), 256, 0, (cudaStream_t)stream>>>(boxes, N, out, nt, vec);
@@ -580,11 +587,18 @@ extern "C" int gnms_overlap2d_batched_f32(const float* boxes, int N, int batch, 
 
 extern "C" int gnms_overlap3d_batched_f32(const float* rec, int N, int batch, float* out_3d, int generalized, int affine,
                                           void* stream) {
+    return gnms_overlap3d_batched_ex_f32(rec, N, batch, out_3d, generalized, affine, nullptr, stream);
+}
+extern "C" int gnms_overlap3d_batched_ex_f32(const float* rec, int N, int batch, float* out_3d, int generalized, int affine,
+                                             const gnms_launch_opts* opts, void* stream) {
+    GnmsLaunchOpts O;
+    const int orc = gnms_resolve_opts(opts, &O);
+    if (orc) return orc;
     if (N < 0 || batch < 0) return GNMS_E_BADARG;
     if (N == 0 || batch == 0) return 0;
     if (!rec || !out_3d) return GNMS_E_BADARG;
     if (!aligned16(rec)) return GNMS_E_ALIGN;
-    if ((long long)N * batch >= 2048) return gnms_launch_overlap_tiles(rec, kTileSrcBox3d, generalized, affine, N, batch, out_3d, (cudaStream_t)stream);
+    if ((long long)N * batch >= 2048) return gnms_launch_overlap_tiles(rec, kTileSrcBox3d, generalized, affine, N, batch, out_3d, O, (cudaStream_t)stream);
     const int nt = gnms_div_up(N, kST);
     const int vec = aligned16(out_3d) && (N % 4 == 0);
     dim3 grid(nt * (nt + 1) / 2, batch);

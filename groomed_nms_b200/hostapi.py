@@ -34,12 +34,14 @@ class Nms3dPlan(object):
         self.two_kernel = two_kernel and materialise
         # overlap_branch: the matrix does not depend on the NMS half of the step (leaders are elected directly from the
         # boxes), so it is written by the matrix-only tile kernel on its own stream / graph branch while the NMS kernels
-        # run on a higher-priority one.  tiles_per_cta > 0 makes the matrix kernel's CTAs retire continuously so that
-        # the NMS kernels find SM slots.
+        # run on a higher-priority one.  matrix_opts.tiles_per_cta > 0 makes the matrix kernel's CTAs retire continuously so
+        # that the NMS kernels find SM slots.
         if overlap_branch is None:
             overlap_branch = materialise and not two_kernel
         self.overlap_branch = bool(overlap_branch) and materialise and not self.two_kernel
-        self.tiles_per_cta = 4
+        # per-call launch options of the matrix kernel / the forward (gnms_launch_opts: nothing process-wide is touched)
+        self.matrix_opts = _lib.launch_opts(tiles_per_cta=4 if self.overlap_branch else 0)
+        self.forward_opts = None
         if self.overlap_branch:
             self.side = torch.cuda.Stream(device, priority=0)       # matrix branch (default priority)
             self.hi = torch.cuda.Stream(device, priority=-1)        # NMS branch
@@ -73,25 +75,28 @@ class Nms3dPlan(object):
     def stage_records(self, s):
         check(self.lib.gnms_box3d_records_f32(_vp(self.corners), self.B * self.N, _vp(self.rec), 0, s), "records")
 
-    def stage_overlap(self, s):          # one launch, grid.z = image
-        check(self.lib.gnms_overlap3d_batched_f32(_vp(self.rec), self.N, self.B, _vp(self.overlap), 1, 1, s), "overlap3d_batched")
+    def stage_overlap(self, s):          # one launch over all images
+        check(self.lib.gnms_overlap3d_batched_ex_f32(_vp(self.rec), self.N, self.B, _vp(self.overlap), 1, 1,
+                                                     _lib.opts_ref(self.matrix_opts), s), "overlap3d_batched")
 
     def stage_forward_no_matrix(self, s):
         p = ctypes.byref(self.params)
-        check(self.lib.gnms_forward_boxes_f32(_vp(self.scores), _vp(self.rec), _lib.BOX_3D_REC, 1, 1, self.N, self.B, None, p,
-                                              None, _vp(self.prob), _vp(self.valid_idx), _vp(self.invalid_idx),
-                                              _vp(self.counts), self.saved, _vp(self.ws), s), "forward_boxes")
+        check(self.lib.gnms_forward_boxes_ex_f32(_vp(self.scores), _vp(self.rec), _lib.BOX_3D_REC, 1, 1, self.N, self.B, None, p,
+                                                 None, _vp(self.prob), _vp(self.valid_idx), _vp(self.invalid_idx),
+                                                 _vp(self.counts), self.saved, _vp(self.ws), _lib.opts_ref(self.forward_opts), s),
+              "forward_boxes")
 
     def stage_forward(self, s):          # sort + mask + chain: 3 launches
         p = ctypes.byref(self.params)
         if self.two_kernel:
-            check(self.lib.gnms_forward_f32(_vp(self.scores), _vp(self.overlap), self.N, self.N, self.B, None, p, _vp(self.prob),
-                                            _vp(self.valid_idx), _vp(self.invalid_idx), _vp(self.counts), self.saved,
-                                            _vp(self.ws), s), "forward")
+            check(self.lib.gnms_forward_ex_f32(_vp(self.scores), _vp(self.overlap), self.N, self.N, self.B, None, p, _vp(self.prob),
+                                               _vp(self.valid_idx), _vp(self.invalid_idx), _vp(self.counts), self.saved,
+                                               _vp(self.ws), _lib.opts_ref(self.forward_opts), s), "forward")
         else:
-            check(self.lib.gnms_forward_boxes_f32(_vp(self.scores), _vp(self.rec), _lib.BOX_3D_REC, 1, 1, self.N, self.B, None, p,
-                                                  _vp(self.overlap), _vp(self.prob), _vp(self.valid_idx), _vp(self.invalid_idx),
-                                                  _vp(self.counts), self.saved, _vp(self.ws), s), "forward_boxes")
+            check(self.lib.gnms_forward_boxes_ex_f32(_vp(self.scores), _vp(self.rec), _lib.BOX_3D_REC, 1, 1, self.N, self.B, None, p,
+                                                     _vp(self.overlap), _vp(self.prob), _vp(self.valid_idx), _vp(self.invalid_idx),
+                                                     _vp(self.counts), self.saved, _vp(self.ws), _lib.opts_ref(self.forward_opts), s),
+                  "forward_boxes")
 
     def stage_backward(self, s):
         check(self.lib.gnms_backward_f32(_vp(self.grad_prob), _vp(self.prob), _vp(self.overlap), self.N, self.N, self.B, None,
@@ -117,9 +122,7 @@ class Nms3dPlan(object):
             ev.record(st)
             self.side.wait_event(ev)
             self.hi.wait_event(ev)
-            old = self.lib.gnms_debug_tiles_per_cta(self.tiles_per_cta)
             self.stage_overlap(ctypes.c_void_p(self.side.cuda_stream))
-            self.lib.gnms_debug_tiles_per_cta(old)
             sh = ctypes.c_void_p(self.hi.cuda_stream)
             self.stage_forward_no_matrix(sh)
             self.stage_backward(sh)

@@ -1,6 +1,7 @@
 """Drop-in installation: alias the mirrored modules into `sys.modules['lib.*']` so that reference code such as
 `from lib.groomed_nms import differentiable_nms` (lib/loss/rpn_3d.py:14), `from lib.nms.gpu_nms import gpu_nms`
 (lib/rpn_util.py:17) or `from lib.nms_others import *` picks up the sm_100a implementation unchanged."""
+import functools
 import importlib
 import sys
 import types
@@ -10,10 +11,38 @@ _CORE_SYMBOLS = ["iou", "intersect", "iou3d", "iou3d_approximate", "get_volume",
 _MATH3D_SYMBOLS = ["get_corners_of_cuboid", "project_3d_points_in_4D_format"]
 
 
+def _needs_autograd(args, kwargs):
+    import torch
+    if not torch.is_grad_enabled():
+        return False
+    return any(isinstance(a, torch.Tensor) and a.requires_grad for a in list(args) + list(kwargs.values()))
+
+
+def _grad_aware(mine, original):
+    """The kernel-backed mirrors of get_corners_of_cuboid / project_3d_points_in_4D_format / iou3d_approximate / intersect /
+    get_volume return plain tensors (no grad_fn); only `iou` and `differentiable_nms` carry an analytic backward.  The
+    reference's composites are differentiable, and its loss does differentiate them when the acceptance-probability
+    target is not detached (lib/loss/rpn_3d.py:663-679 with :1060).  So a call whose inputs require grad goes to the
+    reference's own function (same results, autograd intact); everything else -- in particular every call on the
+    GrooMeD-NMS path, whose overlaps are detached at lib/loss/rpn_3d.py:791 -- goes to the kernels."""
+    @functools.wraps(original)
+    def dispatch(*args, **kwargs):
+        if _needs_autograd(args, kwargs):
+            return original(*args, **kwargs)
+        return mine(*args, **kwargs)
+    dispatch.__wrapped_kernel__ = mine
+    dispatch.__wrapped_reference__ = original
+    return dispatch
+
+
+_HAS_BACKWARD = {"iou"}                 # mirrors that are torch.autograd.Functions themselves
+
+
 def install(patch_core=True):
     """Register lib.groomed_nms, lib.nms.*, lib.nms_others, lib.loss.aploss.  If the reference's own `lib.core` /
     `lib.math_3d` are importable and patch_core is set, their overlap/corner functions are rebound in place (the
-    rest of those modules -- config, checkpoints, LR policy -- is outside the hot path and stays the reference's)."""
+    rest of those modules -- config, checkpoints, LR policy -- is outside the hot path and stays the reference's).
+    Rebound functions without an analytic backward keep the reference's autograd: see _grad_aware."""
     from . import _lib
     _lib.load()                                   # fail loudly right here if the CUDA library is missing
     if "lib" not in sys.modules:
@@ -38,4 +67,7 @@ def install(patch_core=True):
                 sys.modules[modname] = mine
                 continue
             for sym in symbols:
-                setattr(ref, sym, getattr(mine, sym))
+                orig = getattr(ref, sym, None)
+                orig = getattr(orig, "__wrapped_reference__", orig)          # install() twice: keep the true original
+                new = getattr(mine, sym)
+                setattr(ref, sym, new if (sym in _HAS_BACKWARD or orig is None) else _grad_aware(new, orig))

@@ -38,3 +38,11 @@ def to_cuda_f32(x):
     if not x.is_cuda:
         x = x.to(device())
     return x.float() if x.dtype != torch.float32 else x
+
+
+def no_autograd(name, *tensors):
+    """The kernel behind `name` has no backward: refuse inputs that require grad instead of silently dropping it."""
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise RuntimeError("groomed_nms_b200.%s has no autograd backward: detach() its inputs (as the GrooMeD-NMS path does, "
+                           "lib/loss/rpn_3d.py:791) or call it through groomed_nms_b200.install(), which routes differentiable "
+                           "calls to the reference's own composite" % name)

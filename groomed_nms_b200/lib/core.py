@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from .. import _lib, ops
-from ._util import Origin, to_cuda_f32
+from ._util import Origin, no_autograd, to_cuda_f32
 from ._util import device as _device
 
 
@@ -22,6 +22,7 @@ def intersect(box_a, box_b, mode='combinations', data_type=None):
     """Intersection areas (reference lib/core.py:178-243).  combinations: box_a[M,4], box_b[N,4] -> [N,M]
     (b-major, like the reference :210-218); list: [M]."""
     _check_type(data_type, box_a)
+    no_autograd("lib.core.intersect", box_a, box_b)
     origin = Origin(box_a)
     a, b = to_cuda_f32(box_a), to_cuda_f32(box_b)
     if mode == 'combinations':
@@ -51,6 +52,7 @@ def iou(box_a, box_b, mode='combinations', data_type=None):
 
 def get_volume(corners_3d):
     """Axis-aligned volume of [N,3,8] (or [3,8]) corners (reference lib/core.py:434-451)."""
+    no_autograd("lib.core.get_volume", corners_3d)
     origin = Origin(corners_3d)
     c = to_cuda_f32(corners_3d)
     if c.dim() == 2:
@@ -126,6 +128,7 @@ def iou3d_approximate(corners_3d_b1, corners_3d_b2, mode="list", method="normal"
     they are contiguous fp32 CUDA tensors -- the training loss relies on that quirk (lib/loss/rpn_3d.py:813)."""
     if mode not in ("list", "combinations"):
         raise ValueError('unknown mode {}'.format(mode))
+    no_autograd("lib.core.iou3d_approximate", corners_3d_b1, corners_3d_b2)
     origin = Origin(corners_3d_b1)
     c1, c2 = to_cuda_f32(corners_3d_b1), to_cuda_f32(corners_3d_b2)
     if c1.dim() == 2:

@@ -3,7 +3,7 @@ import numpy as np
 import torch
 
 from .. import ops
-from ._util import Origin, to_cuda_f32
+from ._util import Origin, no_autograd, to_cuda_f32
 
 
 def get_corners_of_cuboid(x3d, y3d, z3d, w3d, h3d, l3d, ry3d, iou_3d_convention=True):
@@ -11,6 +11,7 @@ def get_corners_of_cuboid(x3d, y3d, z3d, w3d, h3d, l3d, ry3d, iou_3d_convention=
     iou_3d_convention docstring (:379-398).  torch in -> torch out on the same device, numpy in -> numpy out."""
     if not iou_3d_convention:
         raise NotImplementedError("only iou_3d_convention=True is on the GrooMeD-NMS path")
+    no_autograd("lib.math_3d.get_corners_of_cuboid", x3d, y3d, z3d, w3d, h3d, l3d, ry3d)
     origin = Origin(x3d)
     cols = [to_cuda_f32(v).reshape(-1) for v in (x3d, y3d, z3d, w3d, h3d, l3d, ry3d)]
     boxes7 = torch.stack(cols, dim=1)
@@ -20,6 +21,7 @@ def get_corners_of_cuboid(x3d, y3d, z3d, w3d, h3d, l3d, ry3d, iou_3d_convention=
 
 def project_3d_points_in_4D_format(p2, points_4d, pad_ones=False):
     """p2[4,4] @ [pts;1] with the x,y rows divided by z where |z| > 1e-2 (reference lib/math_3d.py:47-72)."""
+    no_autograd("lib.math_3d.project_3d_points_in_4D_format", p2, points_4d)
     origin = Origin(points_4d)
     pts = to_cuda_f32(points_4d)
     P = to_cuda_f32(p2)

@@ -215,7 +215,7 @@ def _alloc_state(dev, B, N, params, n_per_image, private_ws):
     return st
 
 
-def forward_matrix(scores, iou, params, n_per_image=None, private_ws=None):
+def forward_matrix(scores, iou, params, n_per_image=None, private_ws=None, opts=None):
     """scores [B,N] fp32 cuda, iou [B,N,N] fp32 cuda (unit column stride) -> ForwardState."""
     _require_cuda(scores, "scores")
     scores = _f32c(scores)
@@ -234,16 +234,16 @@ def forward_matrix(scores, iou, params, n_per_image=None, private_ws=None):
     if B and N:
         ld = iou.stride(-2)
         with torch.cuda.device(dev):
-            check(_lib.load().gnms_forward_f32(_p(scores), _p(iou), ld, N, B, _p(n_per_image), ctypes.byref(params),
-                                               _p(st.prob), _p(st.valid_idx), _p(st.invalid_idx), _p(st.counts),
-                                               st.saved(), _p(st.ws), _stream(dev)), "gnms_forward_f32")
+            check(_lib.load().gnms_forward_ex_f32(_p(scores), _p(iou), ld, N, B, _p(n_per_image), ctypes.byref(params),
+                                                  _p(st.prob), _p(st.valid_idx), _p(st.invalid_idx), _p(st.counts),
+                                                  st.saved(), _p(st.ws), _lib.opts_ref(opts), _stream(dev)), "gnms_forward_f32")
     else:
         st.counts.zero_()
     return st
 
 
 def forward_boxes(scores, boxes, box_kind, params, generalized=False, affine=False, n_per_image=None, private_ws=None,
-                  overlap_out=None):
+                  overlap_out=None, opts=None):
     """Fused forward from boxes [B,N,4] (box_kind BOX_2D) or records [B,N,8] (BOX_3D_REC); overlap_out: optional
     [B,N,N] fp32 tensor that receives the overlap matrix (written once by the tile kernel)."""
     _require_cuda(scores, "scores")
@@ -257,10 +257,10 @@ def forward_boxes(scores, boxes, box_kind, params, generalized=False, affine=Fal
     st = _alloc_state(dev, B, N, params, n_per_image, private_ws)
     if B and N:
         with torch.cuda.device(dev):
-            check(_lib.load().gnms_forward_boxes_f32(_p(scores), _p(boxes), box_kind, int(generalized), int(affine), N, B,
-                                                     _p(n_per_image), ctypes.byref(params), _p(overlap_out), _p(st.prob),
-                                                     _p(st.valid_idx), _p(st.invalid_idx), _p(st.counts), st.saved(),
-                                                     _p(st.ws), _stream(dev)), "gnms_forward_boxes_f32")
+            check(_lib.load().gnms_forward_boxes_ex_f32(_p(scores), _p(boxes), box_kind, int(generalized), int(affine), N, B,
+                                                        _p(n_per_image), ctypes.byref(params), _p(overlap_out), _p(st.prob),
+                                                        _p(st.valid_idx), _p(st.invalid_idx), _p(st.counts), st.saved(),
+                                                        _p(st.ws), _lib.opts_ref(opts), _stream(dev)), "gnms_forward_boxes_f32")
     else:
         st.counts.zero_()
     return st

@@ -2,8 +2,8 @@
  * groomed_nms_b200 -- C-ABI of the B200-native GrooMeD-NMS hot path (libgroomed_b200.so).
  *
  * Every entry point is `extern "C"`, takes plain pointers and sizes (no torch types), returns an int
- * (0 = success, >0 = cudaError_t, <0 = GNMS_E_* argument error), never throws, never prints, keeps no global
- * state and is re-entrant.  Unless stated otherwise all pointers are DEVICE pointers, outputs and workspaces
+ * (0 = success, >0 = cudaError_t, <0 = GNMS_E_* argument error), never throws, never prints, keeps no mutable
+ * process-wide state and is re-entrant (tuning knobs travel per call in a gnms_launch_opts, never in globals).  Unless stated otherwise all pointers are DEVICE pointers, outputs and workspaces
  * are caller-allocated, and work is enqueued on `stream` (a cudaStream_t passed as void*) without synchronising.
  *
  * Reference interfaces replaced (paths relative to abhi1kumar/groomed_nms @ ad10dbb):
@@ -80,6 +80,41 @@ typedef struct gnms_params {
 int gnms_version(void);
 const char* gnms_error_string(int rc);
 
+/* ---------------------------------------------------------------- per-call launch options ---------- */
+/* Optional tuning / profiling knobs of the `_ex` entry points.  Pass NULL for the library defaults (what the plain entry
+ * points do).  Versioned by struct_size: set it to sizeof(gnms_launch_opts); a library built against a longer struct reads
+ * only the fields the caller's size covers.  Every field's 0 means "library default".  Nothing here changes results: all
+ * variants are bit-identical, only the schedule differs. */
+#define GNMS_MATRIX_KERNEL_AUTO   0
+#define GNMS_MATRIX_KERNEL_DIRECT 1   /* 256x64 symmetric tiles stored straight from registers (16-byte STG, direct + mirrored) */
+#define GNMS_MATRIX_KERNEL_TMA    2   /* same tiles staged through swizzled shared memory, drained by 2-D TMA tensor stores */
+#define GNMS_RANK_AUTO   0
+#define GNMS_RANK_COUNT  1            /* rank by counting (small batches) */
+#define GNMS_RANK_SORT   2            /* per-image radix sort in shared memory */
+#define GNMS_ELECT_AUTO   0
+#define GNMS_ELECT_DIRECT 1           /* leaders elected directly from the boxes where applicable (default) */
+#define GNMS_ELECT_MASK   2           /* always through the all-pairs suppression bitmask */
+/* stage bits of gnms_launch_opts.stage_mask (profiling: run only some kernels of a forward) */
+#define GNMS_STAGE_RANK     1u
+#define GNMS_STAGE_SPATIAL  2u
+#define GNMS_STAGE_TILES    4u        /* tile kernel / matrix -> mask stream / matrix-only kernel */
+#define GNMS_STAGE_EARLIER  8u
+#define GNMS_STAGE_CHAIN   16u        /* chain kernel and triangular solves */
+#define GNMS_STAGE_ELECT   32u
+#define GNMS_OPT_SCALAR_MATH   1u     /* flags: scalar fp32 instead of packed fp32x2 arithmetic in the matrix-only kernel */
+#define GNMS_OPT_INLINE_HITS   2u     /* flags: threshold hits handled inline instead of through the CTA-drained queue */
+#define GNMS_OPT_ONE_PASS      4u     /* flags: matrix + suppression bits from one all-pairs pass (no separate matrix-only kernel) */
+typedef struct gnms_launch_opts {
+    uint32_t struct_size;          /* sizeof(gnms_launch_opts) */
+    int32_t  matrix_kernel;        /* GNMS_MATRIX_KERNEL_* : how the [N,N] overlap matrix is written */
+    int32_t  tiles_per_cta;        /* matrix-only kernel: 0 = persistent CTAs (one wave), k > 0 = each CTA takes k 64x64-column
+                                      tile units and retires (lets concurrent small kernels of another stream find SM slots) */
+    int32_t  rank_method;          /* GNMS_RANK_* */
+    int32_t  election;             /* GNMS_ELECT_* */
+    uint32_t stage_mask;           /* 0 = all stages, else an OR of GNMS_STAGE_* */
+    uint32_t flags;                /* OR of GNMS_OPT_* */
+} gnms_launch_opts;
+
 /* ---------------------------------------------------------------- pairwise overlaps ---------------- */
 /* out[i*ld_out + j] = overlap(a_i, b_j), i<M, j<N ("combinations"); a,b are [.,4] row-major boxes.
  * kind=IOU gives the LOGICAL [M,N] result of lib/core.py:480 iou (the reference returns it as a transposed
@@ -124,6 +159,10 @@ int gnms_overlap3d_batched_f32(const float* rec, int N, int batch, float* out_3d
                                void* stream);
 int gnms_overlap3d_list_f32(const float* rec_a, const float* rec_b, int M, float* out_bev, float* out_3d,
                             int generalized, int affine, void* stream);
+/* The batched self-overlaps with per-call launch options (matrix_kernel, tiles_per_cta, flags). */
+int gnms_overlap2d_batched_ex_f32(const float* boxes, int N, int batch, float* out, const gnms_launch_opts* opts, void* stream);
+int gnms_overlap3d_batched_ex_f32(const float* rec, int N, int batch, float* out_3d, int generalized, int affine,
+                                  const gnms_launch_opts* opts, void* stream);
 
 /* ---------------------------------------------------------------- GrooMeD-NMS ---------------------- */
 /* Bytes of scratch for a batch of `batch` images of up to N boxes each. */
@@ -166,6 +205,16 @@ int gnms_forward_boxes_f32(const float* scores, const float* boxes, int box_kind
                            int N, int batch, const int32_t* n_per_image, const gnms_params* p, float* overlap_out,
                            float* prob, int64_t* valid_idx, int64_t* invalid_idx, int32_t* counts, gnms_saved saved,
                            void* workspace, void* stream);
+
+/* The two forwards with per-call launch options (NULL = defaults = the plain entry points). */
+int gnms_forward_ex_f32(const float* scores, const float* iou, int64_t ld, int N, int batch,
+                        const int32_t* n_per_image, const gnms_params* p, float* prob, int64_t* valid_idx,
+                        int64_t* invalid_idx, int32_t* counts, gnms_saved saved, void* workspace,
+                        const gnms_launch_opts* opts, void* stream);
+int gnms_forward_boxes_ex_f32(const float* scores, const float* boxes, int box_kind, int generalized, int affine,
+                              int N, int batch, const int32_t* n_per_image, const gnms_params* p, float* overlap_out,
+                              float* prob, int64_t* valid_idx, int64_t* invalid_idx, int32_t* counts, gnms_saved saved,
+                              void* workspace, const gnms_launch_opts* opts, void* stream);
 
 /* Analytic backward.  grad_prob[batch,N] is dL/dprob for the prob the forward returned.
  * grad_scores[batch,N] (input order) is fully written.  grad_iou: NULL, or [batch,N,ld_gi] which must be

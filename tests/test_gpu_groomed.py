@@ -261,18 +261,15 @@ def test_rank_by_radix_sort_equals_rank_by_counting(N, ns, src):
     npi = torch.tensor(ns, dtype=torch.int32, device="cuda")
     p = ops.make_params(group_size=40)
     outs = []
-    try:
-        for by_sort in (0, 1):
-            lib.gnms_debug_rank_by_sort(by_sort)
-            if src == "matrix":
-                iou = torch.stack([ops.overlap2d(cuda(boxes[b]), cuda(boxes[b])) for b in range(B)])
-                st = ops.forward_matrix(cuda(sc), iou, p, n_per_image=npi)
-            else:
-                st = ops.forward_boxes(cuda(sc), cuda(boxes), _lib.BOX_2D, p, n_per_image=npi)
-            torch.cuda.synchronize()
-            outs.append(st)
-    finally:
-        lib.gnms_debug_rank_by_sort(-1)
+    for method in (_lib.RANK_COUNT, _lib.RANK_SORT):
+        o = _lib.launch_opts(rank_method=method)
+        if src == "matrix":
+            iou = torch.stack([ops.overlap2d(cuda(boxes[b]), cuda(boxes[b])) for b in range(B)])
+            st = ops.forward_matrix(cuda(sc), iou, p, n_per_image=npi, opts=o)
+        else:
+            st = ops.forward_boxes(cuda(sc), cuda(boxes), _lib.BOX_2D, p, n_per_image=npi, opts=o)
+        torch.cuda.synchronize()
+        outs.append(st)
     a, c = outs
     assert torch.equal(a.order, c.order) and torch.equal(a.counts, c.counts) and torch.equal(a.lead, c.lead)
     assert torch.equal(a.prob, c.prob) and torch.equal(a.sorted_scores, c.sorted_scores)
@@ -531,23 +528,19 @@ def test_direct_election_mixed_batch_and_fallback(kind):
     ref = ops.forward_matrix(cuda(sc), iou, p, n_per_image=npi)
     n_lead = [(int((ref.lead[b, :n] == torch.arange(n, device="cuda")).sum())) for b, n in enumerate(ns)]
     assert n_lead[0] < 100 and n_lead[1] > 384 and n_lead[5] > 384      # both routes are really exercised
-    try:
-        for direct in (1, 0):
-            lib.gnms_debug_direct_election(direct)
-            st = ops.forward_boxes(cuda(sc), dev_data, kw.pop("box_kind") if False else kw["box_kind"], p,
-                                   kw.get("generalized", False), kw.get("affine", False), n_per_image=npi)
-            torch.cuda.synchronize()
-            for f in ("order", "lead", "prob", "pre", "counts"):
-                assert torch.equal(getattr(ref, f), getattr(st, f)), (direct, f)
-            for b in range(len(ns)):
-                nv = int(ref.counts[b, 0])
-                assert torch.equal(ref.valid_idx[b, :nv], st.valid_idx[b, :nv])
-            up = torch.randn(len(ns), N, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
-            g1, _ = ops.backward(ref, up)
-            g2, _ = ops.backward(st, up)
-            assert torch.allclose(g1, g2, rtol=1e-6, atol=1e-7)
-    finally:
-        lib.gnms_debug_direct_election(1)
+    for direct in (_lib.ELECT_DIRECT, _lib.ELECT_MASK):
+        st = ops.forward_boxes(cuda(sc), dev_data, kw["box_kind"], p, kw.get("generalized", False), kw.get("affine", False),
+                               n_per_image=npi, opts=_lib.launch_opts(election=direct))
+        torch.cuda.synchronize()
+        for f in ("order", "lead", "prob", "pre", "counts"):
+            assert torch.equal(getattr(ref, f), getattr(st, f)), (direct, f)
+        for b in range(len(ns)):
+            nv = int(ref.counts[b, 0])
+            assert torch.equal(ref.valid_idx[b, :nv], st.valid_idx[b, :nv])
+        up = torch.randn(len(ns), N, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+        g1, _ = ops.backward(ref, up)
+        g2, _ = ops.backward(st, up)
+        assert torch.allclose(g1, g2, rtol=1e-6, atol=1e-7)
 
 
 def test_config_c4_batched_2d_images_vs_oracle(G):

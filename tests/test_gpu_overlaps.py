@@ -135,24 +135,34 @@ def test_iou3d_c3_full_size_bitwise_vs_oracle(L):
     assert bits_equal(got, got.T)
 
 
-@pytest.mark.parametrize("kind,n,batch", [("2d", 2051, 1), ("3d", 2051, 1), ("2d", 700, 3), ("3d", 1029, 2), ("3d", 4096, 2), ("2d", 8192, 1)])
-def test_batched_self_overlap_tall_tiles_bitwise(kind, n, batch):
-    """The batched self-overlap entry points run the matrix-only tile kernel (256 x 64 tiles, mirrored stores straight from
-    registers, packed fp32x2 arithmetic for 3D): odd sizes (partial tiles, scalar store path when N % 4 != 0), several
-    images per launch, degenerate boxes (exact-division fallback) -- bitwise equal to the oracle, and symmetric."""
-    import ctypes
+MATRIX_VARIANTS = {"auto": (0, 0), "direct": (1, 0), "direct_chunked": (1, 4), "tma": (2, 0), "tma_chunked": (2, 4), "direct_scalar": (1, 0)}
+
+
+@pytest.mark.parametrize("variant", sorted(MATRIX_VARIANTS))
+@pytest.mark.parametrize("kind,n,batch", [("2d", 2051, 1), ("3d", 2052, 1), ("2d", 700, 3), ("3d", 1028, 2), ("3d", 4096, 2), ("2d", 8192, 1),
+                                          ("3d", 300, 7), ("3d", 2051, 1)])
+def test_batched_self_overlap_tall_tiles_bitwise(kind, n, batch, variant):
+    """The batched self-overlap entry points run the matrix-only tile kernels (256 x 64 symmetric tiles, packed fp32x2
+    arithmetic for 3D) -- register-direct mirrored stores or shared-memory staging + TMA tensor stores, persistent or
+    chunked launches, selected per call through gnms_launch_opts: odd sizes (partial tiles clipped by the tensor map, scalar
+    store path when N % 4 != 0), several images per launch (a tall tile must not run into the next image), degenerate
+    boxes (exact-division fallback) -- bitwise equal to the oracle, and symmetric."""
     from groomed_nms_b200 import _lib, ops
     from oracle import groomed_oracle as O
     lib = _lib.load()
+    mk, tpc = MATRIX_VARIANTS[variant]
+    o = _lib.launch_opts(matrix_kernel=mk, tiles_per_cta=tpc, flags=_lib.OPT_SCALAR_MATH if variant.endswith("scalar") else 0)
     rng = np.random.default_rng(n + batch)
     outs, wants = [], []
+    guard = 64                                                                       # canary rows after the last image
     if kind == "2d":
         c = rng.uniform(0, 1500, (batch, n, 2)); wh = rng.uniform(5, 200, (batch, n, 2))
         boxes = np.concatenate([c - wh / 2, c + wh / 2], 2).astype(np.float32)
         boxes[:, 7, 2:] = boxes[:, 7, :2]; boxes[:, 11] = boxes[:, 7]          # zero-area twins: 0/0 = NaN
         d = cuda(boxes)
-        out = torch.empty((batch, n, n), dtype=torch.float32, device="cuda")
-        _lib.check(lib.gnms_overlap2d_batched_f32(ops._p(d), n, batch, ops._p(out), ops._stream(d.device)), "overlap2d_batched")
+        buf = torch.full((batch * n * n + guard * n,), -3.0, dtype=torch.float32, device="cuda")
+        out = buf[:batch * n * n].view(batch, n, n)
+        _lib.check(lib.gnms_overlap2d_batched_ex_f32(ops._p(d), n, batch, ops._p(out), _lib.opts_ref(o), ops._stream(d.device)), "overlap2d_batched")
         for b in range(batch if n <= 2100 else 1):
             wants.append(O.iou(boxes[b], boxes[b])); outs.append(out[b].cpu().numpy())
     else:
@@ -161,8 +171,9 @@ def test_batched_self_overlap_tall_tiles_bitwise(kind, n, batch):
                        4 + 0.5 * rng.standard_normal((batch, n)), rng.uniform(-np.pi, np.pi, (batch, n))], 2).astype(np.float32)
         corners = ops.corners_from_boxes7(cuda(b7).view(batch * n, 7))
         rec = ops.box3d_records(corners).view(batch, n, 8).contiguous()
-        out = torch.empty((batch, n, n), dtype=torch.float32, device="cuda")
-        _lib.check(lib.gnms_overlap3d_batched_f32(ops._p(rec), n, batch, ops._p(out), 1, 1, ops._stream(rec.device)), "overlap3d_batched")
+        buf = torch.full((batch * n * n + guard * n,), -3.0, dtype=torch.float32, device="cuda")
+        out = buf[:batch * n * n].view(batch, n, n)
+        _lib.check(lib.gnms_overlap3d_batched_ex_f32(ops._p(rec), n, batch, ops._p(out), 1, 1, _lib.opts_ref(o), ops._stream(rec.device)), "overlap3d_batched")
         cn = corners.view(batch, n, 3, 8).cpu().numpy()
         for b in range(batch if n <= 2100 else 1):
             g3 = O.iou3d_approximate(cn[b], cn[b], "combinations", "generalized")[1]
@@ -170,24 +181,22 @@ def test_batched_self_overlap_tall_tiles_bitwise(kind, n, batch):
     torch.cuda.synchronize()
     for got, want in zip(outs, wants):
         assert bits_equal(got, want)
-    last = out[batch - 1]
-    assert torch.equal(torch.nan_to_num(last, nan=-7.0), torch.nan_to_num(last.t(), nan=-7.0))          # mirror image
+    for b in range(batch):                                                            # every image is its own mirror image
+        img = out[b]
+        assert torch.equal(torch.nan_to_num(img, nan=-7.0), torch.nan_to_num(img.t(), nan=-7.0))
+    assert bool((buf[batch * n * n:] == -3.0).all())                                  # nothing written past the last image
 
 
-@pytest.mark.skipif(not os.environ.get("GNMS_EXPERIMENTAL"),
-                    reason="unmeasured experimental kernels (DESIGN.md section 8); set GNMS_EXPERIMENTAL=1")
-@pytest.mark.parametrize("variant", [8, 9, 10])
-@pytest.mark.parametrize("kind,n,batch", [("2d", 2051, 1), ("3d", 2051, 1), ("3d", 1029, 2), ("3d", 4096, 2)])
-def test_experimental_narrow_step_kernel_bitwise(kind, n, batch, variant):
-    """The experimental variants of the matrix-only kernel -- gnms_debug_tall_tiles(8): 2 rows per step, 6 CTAs per SM;
-    (9): next rows loaded and store pointers advanced before the stores; (10): both -- must give the same bits as the default one."""
+def test_launch_opts_are_validated_and_versioned():
+    """gnms_launch_opts: unknown enumerators are rejected, a shorter (older) struct is accepted (struct_size versioning)."""
     import ctypes
-    from groomed_nms_b200 import _lib
+    from groomed_nms_b200 import _lib, ops
     lib = _lib.load()
-    lib.gnms_debug_tall_tiles.argtypes = [ctypes.c_int]
-    lib.gnms_debug_tall_tiles.restype = ctypes.c_int
-    old = lib.gnms_debug_tall_tiles(variant)
-    try:
-        test_batched_self_overlap_tall_tiles_bitwise(kind, n, batch)
-    finally:
-        lib.gnms_debug_tall_tiles(old)
+    rec = torch.zeros((1, 64, 8), device="cuda"); out = torch.empty((1, 64, 64), device="cuda")
+    bad = _lib.launch_opts(matrix_kernel=7)
+    assert lib.gnms_overlap3d_batched_ex_f32(ops._p(rec), 64, 1, ops._p(out), 1, 1, ctypes.byref(bad), None) == -1
+    short = _lib.launch_opts(matrix_kernel=1, tiles_per_cta=4)
+    short.struct_size = 12                                                            # only matrix_kernel and tiles_per_cta are covered
+    short.rank_method = 99                                                            # beyond struct_size: must be ignored
+    assert lib.gnms_overlap3d_batched_ex_f32(ops._p(rec), 64, 1, ops._p(out), 1, 1, ctypes.byref(short), None) == 0
+    torch.cuda.synchronize()

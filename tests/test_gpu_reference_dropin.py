@@ -30,6 +30,10 @@ def _run(arm, out, extra):
 
 
 CONFIGS = {
+    # gradient reaches the raw 3D box parameters through get_corners_of_cuboid and iou3d_approximate (the acceptance-probability
+    # target is not detached, lib/loss/rpn_3d.py:663-679 with :1060): install() must not drop it
+    "accprob_regress_all": ["--seed", "8", "--batch", "2", "--feat", "16x56", "--set", "acceptance_prob_lambda=1.0", "--set",
+                            "acceptance_prob_mode=\"regress\"", "--set", "boxes_for_acceptance_prob=\"all\""],
     "default_2d": ["--seed", "0", "--batch", "2", "--feat", "24x80"],
     "product": ["--seed", "2", "--batch", "2", "--feat", "16x56", "--set", "overlap_in_nms=\"product\""],
     "3d_nomask_sigmoidal": ["--seed", "7", "--batch", "2", "--feat", "16x56", "--set", "overlap_in_nms=\"3d\"", "--set",

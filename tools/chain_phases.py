@@ -1,4 +1,6 @@
-"""Debug: per-phase time of chain_kernel (SM clock stamps at every barrier) for one C3 image."""
+"""Debug: per-phase time of chain_kernel (SM clock stamps at every barrier) for one C3 image.
+Needs a library built with -DGNMS_DEBUG (the phase clock is compiled out of the shipped build):
+    NVCC_EXTRA=-DGNMS_DEBUG python -m groomed_nms_b200.build --force"""
 import ctypes, sys
 import numpy as np, torch
 sys.path.insert(0, ".")

@@ -2,9 +2,10 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../include -o ab_tall.bin ab_tall.cu \
 //        -L../../groomed_nms_b200 -lgroomed_b200 -Xlinker -rpath -Xlinker '$ORIGIN/../../groomed_nms_b200'
 //   ./ab_tall.bin [images=32]
-// For gnms_debug_tall_tiles = 4 (default), 8 (2 rows per step, 6 CTAs per SM), 9 (kPipe ordering), 10 (both): time of one launch over
-// `images` x N=4096 7-DoF boxes (CUDA events, 10 launches after 2 warm-ups) and the number of output words that differ
-// from the default kernel's (must be 0).
+// For matrix_kernel = DIRECT (register-direct STG) and TMA (shared-memory staging + 2-D tensor stores), each with CTAs that take
+// one 256 x 64 tile and retire (tiles_per_cta = 4) and persistent CTAs (tiles_per_cta = 0): time of one launch over `images` x
+// N=4096 7-DoF boxes (CUDA events, 10 launches after 2 warm-ups) and the number of output words that differ from the first
+// variant's (must be 0).
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -13,8 +14,6 @@
 #include <cuda_runtime.h>
 #include "groomed_nms_b200.h"
 
-extern "C" int gnms_debug_tall_tiles(int v);
-extern "C" int gnms_debug_tiles_per_cta(int v);
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("cuda error %s at line %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
 #define RC(x) do { int rc = (x); if (rc) { printf("gnms rc %d at line %d\n", rc, __LINE__); return 1; } } while (0)
@@ -47,16 +46,18 @@ int main(int argc, char** argv) {
     RC(gnms_box3d_records_from_boxes7_f32(d_b7, 7, B * N, d_rec, nullptr, nullptr));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    gnms_debug_tiles_per_cta(4);
-    const int variants[4] = {4, 8, 9, 10};
+    struct V { const char* name; int kernel, tpc; };
+    const V variants[4] = {{"direct, 1 tile/CTA", GNMS_MATRIX_KERNEL_DIRECT, 4}, {"tma,    1 tile/CTA", GNMS_MATRIX_KERNEL_TMA, 4},
+                           {"direct, persistent", GNMS_MATRIX_KERNEL_DIRECT, 0}, {"tma,    persistent", GNMS_MATRIX_KERNEL_TMA, 0}};
     for (int vi = 0; vi < 4; ++vi) {
-        gnms_debug_tall_tiles(variants[vi]);
+        gnms_launch_opts o = {};
+        o.struct_size = sizeof(o); o.matrix_kernel = variants[vi].kernel; o.tiles_per_cta = variants[vi].tpc;
         float* out = vi == 0 ? d_ref : d_out;
         CK(cudaMemset(out, 0xff, mat * 4));
-        for (int i = 0; i < 2; ++i) RC(gnms_overlap3d_batched_f32(d_rec, N, B, out, 1, 1, nullptr));
+        for (int i = 0; i < 2; ++i) RC(gnms_overlap3d_batched_ex_f32(d_rec, N, B, out, 1, 1, &o, nullptr));
         CK(cudaDeviceSynchronize());
         CK(cudaEventRecord(e0));
-        for (int i = 0; i < 10; ++i) RC(gnms_overlap3d_batched_f32(d_rec, N, B, out, 1, 1, nullptr));
+        for (int i = 0; i < 10; ++i) RC(gnms_overlap3d_batched_ex_f32(d_rec, N, B, out, 1, 1, &o, nullptr));
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms = 0.f;
@@ -67,8 +68,8 @@ int main(int argc, char** argv) {
             count_diff<<<148 * 8, 256>>>(reinterpret_cast<const uint4*>(d_ref), reinterpret_cast<const uint4*>(d_out), mat / 4, d_cnt);
             CK(cudaMemcpy(&diff, d_cnt, 8, cudaMemcpyDeviceToHost));
         }
-        printf("tall=%d  %8.1f us per launch (%d images)  %7.1f GB/s of matrix  words differing from the default: %llu\n",
-               variants[vi], ms * 100.f, B, mat * 4.0 / (ms * 1e-4) / 1e9, diff);
+        printf("%s  %8.1f us per launch (%d images)  %7.1f GB/s of matrix  words differing from the first variant: %llu\n",
+               variants[vi].name, ms * 100.f, B, mat * 4.0 / (ms * 1e-4) / 1e9, diff);
         fflush(stdout);
     }
     return 0;

@@ -40,8 +40,11 @@ def main():
     ap.add_argument("--tile-queue", type=int, default=1, help="1: hits go through a shared-memory queue drained by the whole CTA; 0: inline loop")
     args = ap.parse_args()
     lib = _lib.load()
-    lib.gnms_debug_tile_queue(args.tile_queue)
-    lib.gnms_debug_rank_by_sort(args.rank_by_sort)
+    rank_method = {-1: _lib.RANK_AUTO, 0: _lib.RANK_COUNT, 1: _lib.RANK_SORT}[args.rank_by_sort]
+    base_flags = 0 if args.tile_queue else _lib.OPT_INLINE_HITS
+
+    def opts(mask=0):
+        return _lib.launch_opts(rank_method=rank_method, stage_mask=mask, flags=base_flags)
     dev = torch.device("cuda", 0)
     B, N = args.images, args.n
     params = ops.make_params()
@@ -51,8 +54,8 @@ def main():
     s = ctypes.c_void_p(st.cuda_stream)
     res = {}
     for mat in (True, False):
-        lib.gnms_debug_stage_mask(0xff)
         pl = Nms3dPlan(B, N, dev, params, materialise=mat)
+        pl.forward_opts = opts()
         pl.boxes7.copy_(torch.from_numpy(boxes)); pl.scores.copy_(torch.from_numpy(scores))
         pl.grad_prob.normal_()
         pl.stage_corners(s); pl.stage_records(s); pl.stage_forward(s)
@@ -64,11 +67,11 @@ def main():
         for m, nm in STAGES.items():
             if m in (3, 32) and mat:
                 continue
-            lib.gnms_debug_stage_mask(m)
+            pl.forward_opts = opts(m)
             us = time_call(pl.stage_forward, st)
             extra = "  -> %.0f GB/s of matrix written" % (B * 4.0 * N * N / us / 1e3) if (m == 4 and mat) else ""
             print("matrix=%d  %-14s %9.1f us%s" % (mat, nm, us, extra))
-        lib.gnms_debug_stage_mask(0xff)
+        pl.forward_opts = opts()
         del pl
     print("matrix vs matrix-free:", " ".join("%s=%s" % (k, torch.equal(res[True][k], res[False][k])) for k in ("prob", "counts", "lead")))
 
