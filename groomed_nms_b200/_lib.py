@@ -95,6 +95,9 @@ SIGNATURES = {
     "gnms_soft_nms_workspace_bytes": (sz, [i32]),
     "gnms_aploss_f32": (i32, [vp, vp, i32, vp, vp, vp, sz, vp]),
     "gnms_aploss_workspace_bytes": (sz, [i32]),
+    "gnms_score_head_workspace_bytes": (sz, [i32]),
+    "gnms_score_head_forward_f32": (i32, [vp, i64, i32, vp, vp, vp]),
+    "gnms_score_head_backward_f32": (i32, [vp, i64, i32, vp, vp, vp, vp, vp]),
     "gnms_targets_overlaps_workspace_bytes": (sz, [i32, i32]),
     "gnms_targets_overlaps_f64": (i32, [vp, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "gnms_iou3d_exact_f64": (i32, [vp, i64, i32, vp, i64, i32, vp, i32, vp, vp, vp]),

@@ -1,0 +1,111 @@
+// Score head of the batched-image configuration (BASELINE.json configs[3]): the scores that enter
+// GrooMeD-NMS come from a shared linear layer + sigmoid over per-box features, so that a real parameter gradient exists for
+// the one NCCL all-reduce of the step.  It stands for the reference's acceptance-probability head, a 1x1 convolution (= a
+// per-anchor linear map of the 512 proposal features) followed by a sigmoid
+// (models/densenet121_3d_dilate_decomp_alpha.py:112-121 builds it, :230 applies it).
+//   forward : scores[m] = sigmoid(dot(x[m, :K], wb[:K]) + wb[K])
+//   backward: grad_wb[k] = sum_m g[m] s[m] (1 - s[m]) x[m, k]   (k < K),   grad_wb[K] = sum_m g[m] s[m] (1 - s[m])
+// Both are HBM streams over x (4 K bytes per box); the reduction is two-stage and ordered, so the gradient is deterministic.
+#include "common.cuh"
+
+namespace gnms {
+
+constexpr int kHeadBlocks = 148 * 2;
+
+template <int K>
+__global__ void __launch_bounds__(256) score_head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wb,
+                                                             float* __restrict__ scores, int64_t M) {
+    constexpr int kLanes = K / 4;                         // lanes per box, one float4 each (K = 64: 16 lanes, 2 boxes per warp)
+    static_assert(kLanes >= 1 && kLanes <= 32 && (kLanes & (kLanes - 1)) == 0, "K must be 4 * a power of two <= 128");
+    const int lane = threadIdx.x & 31, sub = lane % kLanes;
+    const float4 w = __ldg(reinterpret_cast<const float4*>(wb) + sub);
+    const float bias = __ldg(wb + K);
+    const int64_t per_warp = 32 / kLanes;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t m0 = warp0 * per_warp; m0 < M; m0 += nwarps * per_warp) {
+        const int64_t m = m0 + lane / kLanes;
+        float acc = 0.f;
+        if (m < M) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(x + m * K) + sub);
+            acc = v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+        }
+#pragma unroll
+        for (int o = kLanes / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (m < M && sub == 0) scores[m] = 1.0f / (1.0f + __expf(-(acc + bias)));
+    }
+}
+
+// stage 1: block b sums its contiguous slice of boxes into part[b][K + 1]; 256 threads = (256 / K) row groups x K columns
+template <int K>
+__global__ void __launch_bounds__(256) score_head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scores,
+                                                             const float* __restrict__ g, int64_t M, float* __restrict__ part) {
+    constexpr int kGroups = 256 / K;
+    __shared__ float red[kGroups][K + 1];
+    const int c = threadIdx.x % K, rg = threadIdx.x / K;
+    const int64_t per = (M + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * per, hi = lo + per < M ? lo + per : M;
+    float acc = 0.f, accb = 0.f;
+    for (int64_t m = lo + rg; m < hi; m += kGroups) {
+        const float s = __ldg(scores + m);
+        const float coef = __ldg(g + m) * s * (1.0f - s);
+        acc += coef * __ldcs(x + m * K + c);
+        accb += coef;
+    }
+    red[rg][c] = acc;
+    if (c == 0) red[rg][K] = accb;
+    __syncthreads();
+    if (rg == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < kGroups; ++q) t += red[q][c];
+        part[(size_t)blockIdx.x * (K + 1) + c] = t;
+        if (c == 0) {
+            float tb = 0.f;
+#pragma unroll
+            for (int q = 0; q < kGroups; ++q) tb += red[q][K];
+            part[(size_t)blockIdx.x * (K + 1) + K] = tb;
+        }
+    }
+}
+// stage 2: one thread per parameter adds the block partials in block order
+__global__ void score_head_reduce_kernel(const float* __restrict__ part, int nblocks, int K1, float* __restrict__ grad_wb) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K1) return;
+    float t = 0.f;
+    for (int b = 0; b < nblocks; ++b) t += part[(size_t)b * K1 + k];
+    grad_wb[k] = t;
+}
+
+}  // namespace gnms
+
+using namespace gnms;
+
+extern "C" size_t gnms_score_head_workspace_bytes(int K) { return (size_t)kHeadBlocks * (size_t)(K + 1) * sizeof(float); }
+
+extern "C" int gnms_score_head_forward_f32(const float* x, int64_t M, int K, const float* wb, float* scores, void* stream) {
+    if (M < 0 || K != 64) return M < 0 ? GNMS_E_BADARG : GNMS_E_UNSUPPORTED;
+    if (M == 0) return 0;
+    if (!x || !wb || !scores) return GNMS_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(x) & 15u) || (reinterpret_cast<uintptr_t>(wb) & 15u)) return GNMS_E_ALIGN;
+    int64_t blocks = (M / 2 + 7) / 8;                                 // 8 warps per block, 2 boxes per warp and trip
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    score_head_fwd_kernel<64><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, wb, scores, M);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gnms_score_head_backward_f32(const float* x, int64_t M, int K, const float* scores, const float* grad_scores,
+                                            float* grad_wb, void* workspace, void* stream) {
+    if (M < 0 || K != 64) return M < 0 ? GNMS_E_BADARG : GNMS_E_UNSUPPORTED;
+    if (!grad_wb || !workspace) return GNMS_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (M == 0) { GNMS_CUDA_TRY(cudaMemsetAsync(grad_wb, 0, (size_t)(K + 1) * 4, s)); return 0; }
+    if (!x || !scores || !grad_scores) return GNMS_E_BADARG;
+    float* part = reinterpret_cast<float*>(workspace);
+    score_head_bwd_kernel<64><<<kHeadBlocks, 256, 0, s>>>(x, scores, grad_scores, M, part);
+    GNMS_LAUNCH_CHECK();
+    score_head_reduce_kernel<<<1, 128, 0, s>>>(part, kHeadBlocks, K + 1, grad_wb);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}

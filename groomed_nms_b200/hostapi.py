@@ -149,6 +149,83 @@ class Nms3dPlan(object):
         return g
 
 
+class BatchedHeadPlan(object):
+    """Allocation-free training step of the batched-image configuration (BASELINE.json configs[3], SURVEY.md section 8(d)
+    C4): this rank's `batch` images of `n` 2D boxes each.
+
+        scores = sigmoid(x . w + b)          shared 64 -> 1 head over per-box features (gnms_score_head_forward_f32)
+        prob   = GrooMeD-NMS(scores, boxes)  fused forward from the boxes (+ the [n,n] IoU matrices if materialise)
+        dL/dscores                           analytic NMS backward for the upstream gradient grad_prob
+        dL/d(w, b)                           head backward, written straight into the gradient bucket
+        all-reduce(bucket)                   ONE NCCL all-reduce (sum) per step over all ranks
+
+    Everything is enqueued on one stream; `capture()` records it (collective included) in a CUDA graph."""
+
+    FEAT = 64
+
+    def __init__(self, batch, n, device, params, materialise=True, bucket_pad_elems=0, group=None):
+        from .sharding import GradBucket
+        self.lib = _lib.load()
+        self.B, self.N, self.dev, self.params, self.materialise, self.group = batch, n, device, params, materialise, group
+        f = dict(dtype=torch.float32, device=device)
+        self.x = torch.zeros((batch, n, self.FEAT), **f)
+        self.boxes = torch.zeros((batch, n, 4), **f)
+        self.wb = torch.zeros((self.FEAT + 1,), **f)
+        self.grad_prob = torch.zeros((batch, n), **f)
+        self.scores = torch.empty((batch, n), **f)
+        self.overlap = torch.empty((batch, n, n), **f) if materialise else None
+        self.prob = torch.empty((batch, n), **f)
+        self.grad_scores = torch.empty((batch, n), **f)
+        self.valid_idx = torch.empty((batch, n), dtype=torch.int64, device=device)
+        self.invalid_idx = torch.empty((batch, n), dtype=torch.int64, device=device)
+        self.counts = torch.empty((batch, 2), dtype=torch.int32, device=device)
+        self.order = torch.empty((batch, n), dtype=torch.int32, device=device)
+        self.lead = torch.empty((batch, n), dtype=torch.int32, device=device)
+        self.fl = torch.empty((4, batch, n), **f)
+        self.ws = torch.empty((int(self.lib.gnms_workspace_bytes(n, batch)),), dtype=torch.uint8, device=device)
+        self.head_ws = torch.empty((int(self.lib.gnms_score_head_workspace_bytes(self.FEAT)),), dtype=torch.uint8, device=device)
+        self.saved = Saved(_vp(self.order), _vp(self.fl[0]), _vp(self.lead), _vp(self.fl[1]), _vp(self.fl[2]), _vp(self.fl[3]))
+        self.bucket = GradBucket({"head_wb": self.FEAT + 1}, device, pad_elems=bucket_pad_elems)
+        self.grad_wb = self.bucket.view("head_wb")
+        self.forward_opts = None
+        # head fwd, sort/rank, spatial, elect, zero_failed, list_failed, culled tiles, has_earlier_failed, chain, [matrix],
+        # NMS backward, head backward (2 launches); the all-reduce is NCCL's kernel, not counted
+        self.launches_per_step = 12 + (1 if materialise else 0)
+
+    def compute(self, s):
+        """Forward + backward of this rank's shard (no collective)."""
+        p = ctypes.byref(self.params)
+        M = self.B * self.N
+        check(self.lib.gnms_score_head_forward_f32(_vp(self.x), M, self.FEAT, _vp(self.wb), _vp(self.scores), s), "score_head_forward")
+        check(self.lib.gnms_forward_boxes_ex_f32(_vp(self.scores), _vp(self.boxes), _lib.BOX_2D, 0, 0, self.N, self.B, None, p,
+                                                 _vp(self.overlap), _vp(self.prob), _vp(self.valid_idx), _vp(self.invalid_idx),
+                                                 _vp(self.counts), self.saved, _vp(self.ws), _lib.opts_ref(self.forward_opts), s),
+              "forward_boxes")
+        check(self.lib.gnms_backward_f32(_vp(self.grad_prob), _vp(self.prob), None, 0, self.N, self.B, None, p, self.saved,
+                                         _vp(self.grad_scores), None, self.N, _vp(self.ws), s), "backward")
+        check(self.lib.gnms_score_head_backward_f32(_vp(self.x), M, self.FEAT, _vp(self.scores), _vp(self.grad_scores),
+                                                    _vp(self.grad_wb), _vp(self.head_ws), s), "score_head_backward")
+
+    def step(self, stream=None, reduce=True):
+        st = stream if stream is not None else torch.cuda.current_stream(self.dev)
+        self.compute(ctypes.c_void_p(st.cuda_stream))
+        if reduce:
+            with torch.cuda.stream(st):
+                self.bucket.all_reduce(self.group)
+
+    def capture(self, reduce=True):
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            self.step(side, reduce)                  # warm-up outside capture (function attributes, NCCL communicator)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step(torch.cuda.current_stream(self.dev), reduce)
+        return g
+
+
 class SplitPlan(object):
     """The same step over `batch` images, issued as `splits` independent sub-batches on parallel graph branches.
     Images are independent, and every stage except the tile kernel is a small-grid, latency-bound launch (one CTA

@@ -339,6 +339,46 @@ class GroomedNMSBatchFunction(torch.autograd.Function):
         return gs, None, None, None, None, None, None
 
 
+def score_head_forward(x, wb):
+    """scores[..] = sigmoid(x[.., :K] . wb[:K] + wb[K]) (K = 64): the per-box linear + sigmoid head of the batched
+    configuration (the reference's 1x1-conv acceptance head, models/densenet121_3d_dilate_decomp_alpha.py:112-121,230)."""
+    _require_cuda(x, "x")
+    x, wb = _f32c(x), _f32c(wb)
+    K = x.shape[-1]
+    M = x.numel() // K
+    out = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().gnms_score_head_forward_f32(_p(x), M, K, _p(wb), _p(out), _stream(x.device)), "gnms_score_head_forward_f32")
+    return out
+
+
+def score_head_backward(x, scores, grad_scores, out=None):
+    """-> grad_wb[K+1] = dL/d(weights, bias); `out` may be a view of a gradient bucket."""
+    x, scores, g = _f32c(x), _f32c(scores), _f32c(grad_scores)
+    K = x.shape[-1]
+    M = x.numel() // K
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((K + 1,), dtype=torch.float32, device=x.device)
+    ws = torch.empty((int(lib.gnms_score_head_workspace_bytes(K)),), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.gnms_score_head_backward_f32(_p(x), M, K, _p(scores), _p(g), _p(out), _p(ws), _stream(x.device)), "gnms_score_head_backward_f32")
+    return out
+
+
+class ScoreHeadFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, wb):
+        s = score_head_forward(x.detach(), wb.detach())
+        ctx.save_for_backward(x, s)
+        return s
+
+    @staticmethod
+    def backward(ctx, g):
+        x, s = ctx.saved_tensors
+        return None, score_head_backward(x, s, g.contiguous())
+
+
 def prune(x, nms_threshold, temperature, pruning_method):
     """Elementwise pruning function (lib/groomed_nms.py:167-189)."""
     _require_cuda(x, "iou")

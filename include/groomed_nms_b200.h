@@ -269,6 +269,17 @@ int gnms_aploss_f32(const float* logits, const float* targets, int n, float* los
                     void* workspace, size_t workspace_bytes, void* stream);
 size_t gnms_aploss_workspace_bytes(int n);
 
+/* ---------------------------------------------------------------- score head (batched-image configuration) */
+/* The head that produces the scores entering GrooMeD-NMS in the batched configuration (BASELINE.json configs[3]): the
+ * reference's acceptance-probability head is a 1x1 convolution -- a per-anchor linear map of the proposal features --
+ * followed by a sigmoid (models/densenet121_3d_dilate_decomp_alpha.py:112-121,230).  x[M,K] row-major features (K = 64),
+ * wb[K+1] = weights then bias.  forward: scores[m] = sigmoid(x[m,:].w + b).  backward: grad_wb[K+1] = dL/d(w, b) given
+ * dL/dscores (deterministic two-stage sum; this is the flat gradient bucket the step all-reduces over NCCL). */
+size_t gnms_score_head_workspace_bytes(int K);
+int gnms_score_head_forward_f32(const float* x, int64_t M, int K, const float* wb, float* scores, void* stream);
+int gnms_score_head_backward_f32(const float* x, int64_t M, int K, const float* scores, const float* grad_scores,
+                                 float* grad_wb, void* workspace, void* stream);
+
 /* ---------------------------------------------------------------- target-assignment overlaps (next to the path) */
 /* lib/rpn_util.py:439-461 compute_targets: ols = iou(rois, gts) (kind GNMS_KIND_IOU, lib/core.py:480-513 numpy branch)
  * or iou_ign(rois, gts) (kind 1, lib/core.py:535-575), float64 like numpy's promotion at the call site (rois float32,
