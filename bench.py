@@ -41,8 +41,8 @@ def algorithmic_bytes(n, d):
 
 def ncu_traffic(images):
     """DRAM bytes (read + write) of one tile-kernel launch from the committed `ncu --set full` capture of this command
-    (profiles/r1_tile_kernel_traffic.json), or None if no capture exists for this batch size."""
-    path = os.path.join(ROOT, "profiles", "r1_tile_kernel_traffic.json")
+    (profiles/r2_tile_kernel_traffic.json), or None if no capture exists for this batch size."""
+    path = os.path.join(ROOT, "profiles", "r2_tile_kernel_traffic.json")
     try:
         d = json.load(open(path))
         if int(d["images_per_launch"]) == int(images):
@@ -72,6 +72,8 @@ def _ref_init():
     """Worker initialiser: one torch thread per worker process, the UNMODIFIED reference imported under the shim."""
     global _REF
     os.environ["OMP_NUM_THREADS"] = "1"
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
     from oracle import ref_shim
     import torch
     torch.set_num_threads(1)
@@ -99,6 +101,12 @@ def _ref_one_image(seed):
                                                      return_sorted_prob=False, group_boxes=True, mask_group_boxes=True, group_size=100)
     prob.backward(up)
     return time.perf_counter() - t0, float(s.grad.sum()) + float(prob.detach().sum())
+
+
+def _port_init():
+    os.environ["OMP_NUM_THREADS"] = "1"
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
 
 
 def _port_one_image(seed):
@@ -143,8 +151,9 @@ class CpuArm(object):
         self.kind, self.workers = kind, workers
         self.fn = _ref_one_image if kind == "reference" else _port_one_image
         os.environ.setdefault("OMP_NUM_THREADS", "1")
-        ctx = mp.get_context("fork")
-        self.pool = ctx.Pool(workers, initializer=_ref_init if kind == "reference" else None)
+        # spawn, not fork: the GPU arm has used CUDA and autograd threads in this process by the time the CPU leg starts
+        ctx = mp.get_context("spawn")
+        self.pool = ctx.Pool(workers, initializer=_ref_init if kind == "reference" else _port_init)
         self.next_seed = 3
 
     def step(self, n_images):
@@ -261,6 +270,89 @@ def time_stage(torch, fn, stream, iters, warm=3):
     e1.record(stream)
     e1.synchronize()
     return e0.elapsed_time(e1) / iters
+
+
+
+def measure_latency(torch, dev, params):
+    """Single-call latency (B = 1), microseconds: what one `differentiable_nms` call of the reference's per-image loop costs.
+    `c_abi_*`: Nms3dPlan(1, 4096) -- 7-DoF boxes -> records -> forward -> backward as one CUDA graph (device time per replay
+    from CUDA events over back-to-back replays; wall time of replay + stream sync).  `python_api_*`: the reference-facing
+    lib.groomed_nms.differentiable_nms(scores, iou) on a materialised matrix + autograd backward, wall clock with the one
+    sync the variable-length index results need; overlaps through lib.core.iou / ops.overlap3d are timed separately."""
+    import numpy as np
+    from groomed_nms_b200 import ops, synthetic
+    from groomed_nms_b200.hostapi import Nms3dPlan
+    from groomed_nms_b200.lib import core as C
+    from groomed_nms_b200.lib import groomed_nms as G
+    out = {}
+
+    def wall(fn, n=40, warm=8):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        ts.sort()
+        return 1e6 * ts[len(ts) // 2]
+
+    b7, sc = synthetic.config_c3(seed=3)
+    for name, mat in (("c_abi_graph_N4096_3d_matrix_free", False), ("c_abi_graph_N4096_3d_with_matrix", True)):
+        pl = Nms3dPlan(1, N_BOXES, dev, params, materialise=mat)
+        pl.boxes7.copy_(torch.from_numpy(b7)[None]); pl.scores.copy_(torch.from_numpy(sc)[None]); pl.grad_prob.normal_()
+        g = pl.capture()
+        for _ in range(10):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(100):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = {"device_us_per_call": 1e3 * e0.elapsed_time(e1) / 100, "wall_us_per_call": wall(g.replay)}
+        del pl, g
+    rec = ops.box3d_records(ops.corners_from_boxes7(torch.from_numpy(b7).to(dev)))
+    bx2, sc2 = synthetic.config_c2()
+    bx5, sc5, _ = synthetic.clustered_boxes_2d(500, 6, seed=11, jitter=0.05)
+    cases = (("python_api_N4096_3d", torch.from_numpy(sc).to(dev), lambda: ops.overlap3d(rec, rec, False, True, generalized=True, affine=True)[1]),
+             ("python_api_N1024_2d", torch.from_numpy(sc2).to(dev), lambda b=torch.from_numpy(bx2).to(dev): C.iou(b, b)),
+             ("python_api_N500_2d", torch.from_numpy(sc5).to(dev), lambda b=torch.from_numpy(bx5).to(dev): C.iou(b, b)))
+    for name, scores, make_iou in cases:
+        iou = make_iou()
+        up = torch.randn_like(scores)
+
+        def call():
+            s = scores.clone().requires_grad_(True)
+            valid, invalid, prob = G.differentiable_nms(s, iou, nms_threshold=0.4, pruning_method="linear", temperature=0.01,
+                                                       valid_box_prob_threshold=0.3, group_boxes=True, mask_group_boxes=True, group_size=100)
+            prob.backward(up)
+        out[name] = {"wall_us_fwd_bwd": wall(call), "wall_us_overlap_matrix": wall(make_iou)}
+    return out
+
+
+def measure_sustained(torch, graph, boxes_per_step, seconds=2.5):
+    """The step's CUDA graph replayed back to back for `seconds` (the headline `value` is a ~20 ms burst): boxes/s over the
+    whole interval, with the SM clock seen meanwhile."""
+    for _ in range(5):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    n = 0
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(50):
+            graph.replay()
+        n += 50
+        torch.cuda.current_stream().synchronize() if n % 500 == 0 else None
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"steps": n, "seconds": ms * 1e-3, "ms_per_step": ms / n, "value": boxes_per_step * n / (ms * 1e-3)}
 
 
 def run_ours(args, rank, world):
@@ -395,6 +487,13 @@ def run_ours(args, rank, world):
         stages["two_kernel:overlap3d_matrix"] = time_stage(torch, tk.stage_overlap, st, it)
         stages["two_kernel:forward_from_matrix(rank+mask+chain)"] = time_stage(torch, tk.stage_forward, st, it)
         del tk
+    latency, sustained = None, None
+    if rank == 0 and not args.no_extras:
+        latency = measure_latency(torch, dev, params)
+        smp = ClockSampler(local)
+        smp.start()
+        sustained = measure_sustained(torch, head.capture(), B * N)
+        sustained["clocks"] = smp.stop()
 
     if world > 1:
         dist.barrier()
@@ -427,13 +526,15 @@ def run_ours(args, rank, world):
                     "blocking_call_api": "groomed_nms_b200.hostapi.HostRunner.run_host (one synchronous call per step)"},
             "gpu_launches": head.launches_per_step * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "gnms::tile_tall_kernel<3D records, generalized, affine, packed fp32x2> "
-                                                   "(symmetric 256x64 overlap tiles written direct + mirrored, %d images per launch)" % B,
+            "roofline": {"bound": "hbm", "kernel": ("gnms::tile_tall_kernel<3D records, generalized, affine, packed fp32x2> (symmetric 256x64 overlap tiles "
+                                                    "stored direct + mirrored straight from registers, %d images per launch)" if args.matrix_kernel == "direct" else
+                                                    "gnms::tile_tma_kernel<3D records, generalized, affine, packed fp32x2> (symmetric 256x64 overlap tiles, each 32x32 block "
+                                                    "and its mirror image staged in swizzled shared memory and written by TMA tensor stores, %d images per launch)") % B,
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k_bytes, "avg_launch_ms": k_ms, "traffic": ncu_traffic(B),
                          "timing": "CUDA events around %d back-to-back launches of this kernel alone on the launching stream" % max(10, args.steps),
-                         "note": "fp32 instruction issue / latency limits the kernel (about 37 issue slots per pair at 4 warps per "
-                                 "sub-partition), not HBM: see DESIGN.md section 5 and profiles/"},
+                         "note": "fp32 instruction issue limits the kernel (41 warp instructions per 32 pairs, 30 % of them FMNMX on the half-rate "
+                                 "ALU pipe, 4 warps per sub-partition), not HBM: see DESIGN.md section 5 and profiles/r2_ncu_tile_tma_kernel.txt"},
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "effective_GBps": step_bytes / (ms_step * 1e-3) / 1e9,
                               "frac_of_peak": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
                               "note": "section 8(d) byte model 8N^2+(4D+24)N per image over the whole fwd+bwd step"},
@@ -441,6 +542,7 @@ def run_ours(args, rank, world):
                            "value": boxes_per_step / (ms_other / args.steps * 1e-3),
                            "effective_frac_of_peak": step_bytes / (ms_other / args.steps * 1e-3) / 1e9 / peak},
             "stage_ms": stages,
+            "extra": {"latency_us": latency, "sustained": sustained},
         }
         if not args.no_cpu:
             workers = host_workers()
@@ -459,6 +561,130 @@ def run_ours(args, rank, world):
         dist.destroy_process_group()
 
 
+
+# ------------------------------------------------------------------------------------------------ C4: batched images + NCCL all-reduce
+def c4_inputs(images, n, np, synthetic):
+    """Seeded inputs of the listed global image ids: 2D boxes (16 clusters), 64 features per box, upstream gradient."""
+    boxes = np.stack([synthetic.config_c4_image(i, n=n)[0] for i in images])
+    feats = np.stack([np.random.default_rng(7000 + i).standard_normal((n, 64)).astype(np.float32) for i in images])
+    grads = np.stack([np.random.default_rng(9000 + i).standard_normal(n).astype(np.float32) for i in images])
+    wb = (np.random.default_rng(42).standard_normal(65) * 0.3).astype(np.float32)
+    return boxes, feats, grads, wb
+
+
+def run_c4(args, rank, world):
+    """BASELINE.json configs[3]: batch = 32 images x N = 2048 2D boxes, images sharded over the ranks (shard_range), scores from
+    a shared 64 -> 1 head, GrooMeD-NMS forward + backward, ONE NCCL all-reduce of the flat gradient bucket per step.
+    value = strong scaling (the 32 images divided over the ranks); extra.weak = 4 images per rank whatever the rank count."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from groomed_nms_b200 import _lib, ops, synthetic
+    from groomed_nms_b200.hostapi import BatchedHeadPlan
+    from groomed_nms_b200.sharding import shard_range
+    _lib.load()
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, TOTAL = 2048, 32
+    params = ops.make_params(nms_threshold=0.4, pruning_method="linear", temperature=0.01, valid_box_prob_threshold=0.3,
+                             group_boxes=True, mask_group_boxes=True, group_size=100)
+    pad = args.bucket_mb * (1 << 20) // 4
+
+    def make_plan(images):
+        boxes, feats, grads, wb = c4_inputs(images, N, np, synthetic)
+        pl = BatchedHeadPlan(len(images), N, dev, params, materialise=not args.c4_matrix_free, bucket_pad_elems=pad)
+        pl.boxes.copy_(torch.from_numpy(boxes)); pl.x.copy_(torch.from_numpy(feats)); pl.grad_prob.copy_(torch.from_numpy(grads))
+        pl.wb.copy_(torch.from_numpy(wb))
+        return pl
+
+    def timed(graph, steps, warmup):
+        for _ in range(warmup):
+            graph.replay()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    res = {}
+    for label, images in (("strong", list(shard_range(TOTAL, world, rank))), ("weak", [4 * rank + i for i in range(4)])):
+        pl = make_plan(images)
+        try:
+            g_full = pl.capture(reduce=True)
+            graphed = True
+        except Exception as e:                               # NCCL in a graph unavailable: time eager launches instead
+            graphed = False
+
+            class Eager(object):
+                def __init__(self, f): self.f = f
+                def replay(self): self.f()
+            g_full = Eager(lambda pl=pl: pl.step(None, True))
+        ms_full = timed(g_full, args.steps, args.warmup)
+        ms_compute = timed(pl.capture(reduce=False), args.steps, args.warmup)
+
+        class ReduceOnly(object):
+            def __init__(self, pl): self.pl = pl
+            def replay(self): self.pl.bucket.all_reduce()
+        ms_reduce = timed(ReduceOnly(pl), args.steps, args.warmup) if world > 1 else 0.0
+        res[label] = dict(images_per_rank=len(images), ms_per_step=ms_full, ms_compute_only=ms_compute, ms_allreduce_alone=ms_reduce,
+                          graphed=graphed, boxes_per_step=(TOTAL if label == "strong" else 4 * world) * N, bucket_bytes=pl.bucket.nbytes,
+                          launches=pl.launches_per_step)
+        # the reduced gradient must not depend on how the images were sharded (checked against rank 0's own full computation)
+        if label == "strong":
+            pl.step(None, True)
+            torch.cuda.synchronize()
+            got = pl.grad_wb.clone()
+            if world > 1:
+                full = make_plan(list(range(TOTAL)))
+                full.step(None, False)
+                torch.cuda.synchronize()
+                err = float((got - full.grad_wb).abs().max() / full.grad_wb.abs().max().clamp_min(1e-30))
+                res[label]["allreduced_grad_rel_err_vs_single_process"] = err
+                del full
+        del pl
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        st = res["strong"]
+        value = st["boxes_per_step"] / (st["ms_per_step"] * 1e-3)
+        bytes_step = TOTAL * algorithmic_bytes(N, 4)
+        line = {
+            "metric": "groomed_nms_fwd_bwd_boxes_per_s_batched_N2048", "value": value, "unit": "boxes/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": st["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C4: batch 32 images x N=2048 2D boxes (16 clusters each), shared 64->1 score head, group+mask linear, fwd+bwd, "
+                                   "one NCCL all-reduce of the flat gradient bucket per step", "images_total": TOTAL,
+                       "images_per_rank": st["images_per_rank"], "matrix": "materialised" if not args.c4_matrix_free else "matrix-free",
+                       "bucket_bytes": st["bucket_bytes"], "collective": "ncclAllReduce(sum, fp32) via torch.distributed (NCCL), captured in the step's CUDA graph"
+                                       if st["graphed"] else "ncclAllReduce(sum, fp32) via torch.distributed (NCCL), eager",
+                       "parallelism": "per-image shard over %d rank(s)" % world},
+            "gpu_launches": st["launches"] * args.steps, "clocks": clocks,
+            "step_roofline": {"algorithmic_bytes_per_step": bytes_step, "effective_GBps": bytes_step / (st["ms_per_step"] * 1e-3) / 1e9 / 1.0,
+                              "frac_of_peak_per_gpu": bytes_step / world / (st["ms_per_step"] * 1e-3) / 1e9 / peak, "peak": peak, "peak_source": peak_src},
+            "extra": {"strong": st, "weak": dict(res["weak"], value=res["weak"]["boxes_per_step"] / (res["weak"]["ms_per_step"] * 1e-3))},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -469,11 +695,16 @@ def main():
     ap.add_argument("--e2e-depth", type=int, default=3, help="slots of the host pipeline (copies of one call overlap the kernels of the others)")
     ap.add_argument("--path", default="materialised", choices=["materialised", "fused"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the single-call latency and sustained-throughput legs")
     ap.add_argument("--no-overlap-branch", action="store_true", help="matrix kernel and NMS kernels on one stream instead of two graph branches")
     ap.add_argument("--tiles-per-cta", type=int, default=4, help="matrix-only tile kernel on its branch: tiles per CTA (0 = persistent)")
     ap.add_argument("--packed", type=int, default=1, help="packed fp32x2 arithmetic in the matrix-only kernel (0 = scalar)")
     ap.add_argument("--matrix-kernel", default="auto", choices=["auto", "direct", "tma"],
                     help="how the overlap matrix leaves the SM: register-direct STG or shared-memory staging + TMA tensor stores")
+    ap.add_argument("--config", default="c3", choices=["c3", "c4"], help="c3 = the headline N=4096 7-DoF workload; c4 = batch 32 x N=2048 2D "
+                                                                          "images sharded over the ranks with one NCCL gradient all-reduce per step")
+    ap.add_argument("--bucket-mb", type=int, default=0, help="c4: pad the gradient bucket to this many MiB (48 = the reference model's size)")
+    ap.add_argument("--c4-matrix-free", action="store_true", help="c4: do not materialise the [N,N] IoU matrices")
     ap.add_argument("--splits", type=int, default=1, help="issue the batch as this many sub-batches on parallel graph branches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -481,6 +712,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
         run_reference(args, rank)
+    elif args.config == "c4":
+        run_c4(args, rank, world)
     else:
         run_ours(args, rank, world)
 

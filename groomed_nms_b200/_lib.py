@@ -68,6 +68,7 @@ SIGNATURES = {
     "gnms_overlap2d_list_f32": (i32, [vp, vp, i32, vp, i32, vp]),
     "gnms_iou2d_backward_f32": (i32, [vp, i32, vp, i32, vp, i32, vp, vp, vp]),
     "gnms_corners_from_boxes7_f32": (i32, [vp, i64, i32, vp, vp]),
+    "gnms_corners_from_boxes7_ex_f32": (i32, [vp, i64, i32, i32, vp, vp]),
     "gnms_project_points_f32": (i32, [vp, vp, i64, i32, vp, vp]),
     "gnms_box3d_records_f32": (i32, [vp, i32, vp, i32, vp]),
     "gnms_box3d_records_from_boxes7_f32": (i32, [vp, i64, i32, vp, vp, vp]),

@@ -70,7 +70,10 @@ __global__ void overlap2d_list_kernel(const float* __restrict__ a, const float* 
 // 7-DoF -> 8 corners.  Template corners (l on x for idx {1,3,5,6}; h on y for {2,3,6,7}; w on z for {4,5,6,7},
 // centred), rotation about y, translation                                     lib/math_3d.py:369-435
 // corners of one cuboid (lib/math_3d.py:364-435), x / y / z of the 8 corners
-__device__ __forceinline__ void corners_of(const float* __restrict__ p, float (&ox)[8], float (&oy)[8], float (&oz)[8]) {
+// kitti_order = false: the iou_3d_convention vertex order (:379-403); true: the other order of the reference (:405-426, x-high for
+// corners {1,2,3,4}, y-high for {2,3,6,7}, z-high for {3,4,5,6})
+__device__ __forceinline__ void corners_of(const float* __restrict__ p, float (&ox)[8], float (&oy)[8], float (&oz)[8],
+                                           bool kitti_order = false) {
     float x = p[0], y = p[1], z = p[2], w = p[3], h = p[4], l = p[5], ry = p[6];
     float cs = cosf(ry), sn = sinf(ry);
     float hl = __fdiv_rn(l, 2.0f), hh = __fdiv_rn(h, 2.0f), hw = __fdiv_rn(w, 2.0f);
@@ -78,7 +81,7 @@ __device__ __forceinline__ void corners_of(const float* __restrict__ p, float (&
     float cy[2] = {__fsub_rn(0.0f, hh), __fsub_rn(h, hh)};
     float cz[2] = {__fsub_rn(0.0f, hw), __fsub_rn(w, hw)};
     // corner k uses: x-high for k in {1,3,5,6}; y-high for {2,3,6,7}; z-high for {4,5,6,7}
-    const unsigned xmask = 0x6Au, ymask = 0xCCu, zmask = 0xF0u;
+    const unsigned xmask = kitti_order ? 0x1Eu : 0x6Au, ymask = 0xCCu, zmask = kitti_order ? 0x78u : 0xF0u;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         float px = cx[(xmask >> k) & 1], py = cy[(ymask >> k) & 1], pz = cz[(zmask >> k) & 1];
@@ -105,11 +108,11 @@ __device__ __forceinline__ void record_of(float4 x0, float4 x1, float4 y0, float
     o1 = make_float4(bz1, bz2, vol, abev);
 }
 
-__global__ void corners_kernel(const float* __restrict__ boxes7, int64_t ld, int N, float* __restrict__ corners) {
+__global__ void corners_kernel(const float* __restrict__ boxes7, int64_t ld, int N, float* __restrict__ corners, int kitti_order) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float ox[8], oy[8], oz[8];
-    corners_of(boxes7 + (int64_t)n * ld, ox, oy, oz);
+    corners_of(boxes7 + (int64_t)n * ld, ox, oy, oz, kitti_order != 0);
     float4* o = reinterpret_cast<float4*>(corners + (int64_t)n * 24);
     o[0] = make_float4(ox[0], ox[1], ox[2], ox[3]);
     o[1] = make_float4(ox[4], ox[5], ox[6], ox[7]);
@@ -470,11 +473,14 @@ extern "C" int gnms_overlap2d_list_f32(const float* a, const float* b, int M, fl
 }
 
 extern "C" int gnms_corners_from_boxes7_f32(const float* boxes7, int64_t ld, int N, float* corners, void* stream) {
+    return gnms_corners_from_boxes7_ex_f32(boxes7, ld, N, 1, corners, stream);
+}
+extern "C" int gnms_corners_from_boxes7_ex_f32(const float* boxes7, int64_t ld, int N, int iou_3d_convention, float* corners, void* stream) {
     if (N < 0 || ld < 7) return GNMS_E_BADARG;
     if (N == 0) return 0;
     if (!boxes7 || !corners) return GNMS_E_BADARG;
     if (!aligned16(corners)) return GNMS_E_ALIGN;
-    corners_kernel<<<gnms_div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(boxes7, ld, N, corners);
+    corners_kernel<<<gnms_div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(boxes7, ld, N, corners, iou_3d_convention ? 0 : 1);
     GNMS_LAUNCH_CHECK();
     return 0;
 }

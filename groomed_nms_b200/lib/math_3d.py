@@ -7,15 +7,17 @@ from ._util import Origin, no_autograd, to_cuda_f32
 
 
 def get_corners_of_cuboid(x3d, y3d, z3d, w3d, h3d, l3d, ry3d, iou_3d_convention=True):
-    """7-DoF boxes -> [N,3,8] corners (reference lib/math_3d.py:364-490), corner numbering of the
-    iou_3d_convention docstring (:379-398).  torch in -> torch out on the same device, numpy in -> numpy out."""
-    if not iou_3d_convention:
-        raise NotImplementedError("only iou_3d_convention=True is on the GrooMeD-NMS path")
+    """7-DoF boxes -> [N,3,8] corners (reference lib/math_3d.py:364-490).  iou_3d_convention=True: corner numbering of the
+    docstring at :379-398 (what the GrooMeD-NMS path uses); False: the other vertex order of the reference (:405-426:
+    length on x for corners {1,2,3,4}, height on y for {2,3,6,7}, width on z for {3,4,5,6}).  The reference's own False
+    branch only broadcasts for N in {1, 4} in torch (`corners[:, 0, [1,2,3,4]] = l3d`, :422-424) and is missing from its
+    numpy twin (:450-477); this gives the vertex order that branch documents, for any N and both container types.
+    torch in -> torch out on the same device, numpy in -> numpy out."""
     no_autograd("lib.math_3d.get_corners_of_cuboid", x3d, y3d, z3d, w3d, h3d, l3d, ry3d)
     origin = Origin(x3d)
     cols = [to_cuda_f32(v).reshape(-1) for v in (x3d, y3d, z3d, w3d, h3d, l3d, ry3d)]
     boxes7 = torch.stack(cols, dim=1)
-    out = ops.corners_from_boxes7(boxes7)
+    out = ops.corners_from_boxes7(boxes7, iou_3d_convention=bool(iou_3d_convention))
     return origin.back(out, keep_np_dtype=True)
 
 

@@ -101,15 +101,16 @@ def project_points(p2, pts, pad_ones):
     return out
 
 
-def corners_from_boxes7(boxes7):
-    """[N,7] (x,y,z,w,h,l,ry) -> corners [N,3,8] (lib/math_3d.py:364-435)."""
+def corners_from_boxes7(boxes7, iou_3d_convention=True):
+    """[N,7] (x,y,z,w,h,l,ry) -> corners [N,3,8] (lib/math_3d.py:364-435); iou_3d_convention selects the vertex order."""
     _require_cuda(boxes7, "boxes7")
     b = _f32c(boxes7)
     N = b.shape[0]
     out = torch.empty((N, 3, 8), dtype=torch.float32, device=b.device)
     if N:
         with torch.cuda.device(b.device):
-            check(_lib.load().gnms_corners_from_boxes7_f32(_p(b), b.stride(0), N, _p(out), _stream(b.device)), "gnms_corners_from_boxes7_f32")
+            check(_lib.load().gnms_corners_from_boxes7_ex_f32(_p(b), b.stride(0), N, int(bool(iou_3d_convention)), _p(out),
+                                                              _stream(b.device)), "gnms_corners_from_boxes7_f32")
     return out
 
 

@@ -135,6 +135,9 @@ int gnms_iou2d_backward_f32(const float* a, int M, const float* b, int N, const 
 /* boxes7[N,7] = (x3d,y3d,z3d,w3d,h3d,l3d,ry3d) row-major with row stride `ld` floats -> corners[N,3,8]
  * (lib/math_3d.py:364-435, iou_3d_convention=True). */
 int gnms_corners_from_boxes7_f32(const float* boxes7, int64_t ld, int N, float* corners, void* stream);
+/* Same with the reference's `iou_3d_convention` argument: != 0 is the order above (lib/math_3d.py:379-403), 0 the other vertex
+ * order of the reference (:405-426: length on x for corners {1,2,3,4}, height on y for {2,3,6,7}, width on z for {3,4,5,6}). */
+int gnms_corners_from_boxes7_ex_f32(const float* boxes7, int64_t ld, int N, int iou_3d_convention, float* corners, void* stream);
 
 /* lib/math_3d.py:47-72 project_3d_points_in_4D_format: out[4,n] = p2[4,4] @ [pts;1] (pts is [3,n] when
  * pad_ones!=0, else [4,n]); rows 0,1 divided by row 2 where |row 2| > 1e-2. */

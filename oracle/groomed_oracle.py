@@ -144,8 +144,9 @@ def mutated_corners(corners_3d):
 # ---------------------------------------------------------------------------------------------------------
 # 7-DoF -> corners, projection                                      reference: lib/math_3d.py:47-72,364-490
 # ---------------------------------------------------------------------------------------------------------
-def get_corners_of_cuboid(x3d, y3d, z3d, w3d, h3d, l3d, ry3d):
-    """lib/math_3d.py:364-435 (iou_3d_convention=True) -> [N,3,8] fp32.
+def get_corners_of_cuboid(x3d, y3d, z3d, w3d, h3d, l3d, ry3d, iou_3d_convention=True):
+    """lib/math_3d.py:364-435 -> [N,3,8] fp32; iou_3d_convention=False is the vertex order of :405-426 (the reference's torch
+    branch there only broadcasts for N in {1, 4}; tests/golden/corners_kitti_order.npz holds its N = 4 output).
 
     bmm row products are evaluated as (cos*cx + 0*cy) + sin*cz etc. in fp32; the reference's bmm/einsum
     accumulation order/FMA use is backend-defined, so corner parity is a 1e-6-relative check, and overlap
@@ -153,9 +154,9 @@ def get_corners_of_cuboid(x3d, y3d, z3d, w3d, h3d, l3d, ry3d):
     x3d, y3d, z3d, w3d, h3d, l3d, ry3d = [_f32(v) for v in (x3d, y3d, z3d, w3d, h3d, l3d, ry3d)]
     n = x3d.shape[0]
     c = np.zeros((n, 3, 8), dtype=F32)
-    c[:, 0, [1, 3, 5, 6]] = l3d[:, None]                               # :401
-    c[:, 1, [2, 3, 6, 7]] = h3d[:, None]                               # :402
-    c[:, 2, [4, 5, 6, 7]] = w3d[:, None]                               # :403
+    c[:, 0, [1, 3, 5, 6] if iou_3d_convention else [1, 2, 3, 4]] = l3d[:, None]   # :401 / :422
+    c[:, 1, [2, 3, 6, 7]] = h3d[:, None]                                          # :402 / :423
+    c[:, 2, [4, 5, 6, 7] if iou_3d_convention else [3, 4, 5, 6]] = w3d[:, None]   # :403 / :424
     c[:, 0] -= (l3d / F32(2))[:, None]                                 # :424-426
     c[:, 1] -= (h3d / F32(2))[:, None]
     c[:, 2] -= (w3d / F32(2))[:, None]

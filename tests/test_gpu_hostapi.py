@@ -30,8 +30,9 @@ def _reference(boxes, scores, grads, params):
 
 @pytest.mark.parametrize("B,N", [(3, 1024), (2, 1000), (5, 256)])
 @pytest.mark.parametrize("tiles_per_cta", [0, 3])
-def test_plans_match_plain_calls(B, N, tiles_per_cta):
-    from groomed_nms_b200 import ops
+@pytest.mark.parametrize("matrix_kernel", [1, 2])
+def test_plans_match_plain_calls(B, N, tiles_per_cta, matrix_kernel):
+    from groomed_nms_b200 import _lib, ops
     from groomed_nms_b200.hostapi import Nms3dPlan
     dev = torch.device("cuda", 0)
     params = ops.make_params()
@@ -39,7 +40,8 @@ def test_plans_match_plain_calls(B, N, tiles_per_cta):
     ov, st, gs = _reference(boxes, scores, grads, params)
     for mat, branch in ((True, True), (True, False), (False, False)):
         pl = Nms3dPlan(B, N, dev, params, materialise=mat, overlap_branch=branch)
-        pl.tiles_per_cta = tiles_per_cta
+        pl.matrix_opts = _lib.launch_opts(matrix_kernel=matrix_kernel, tiles_per_cta=tiles_per_cta)
+        pl.forward_opts = _lib.launch_opts(matrix_kernel=matrix_kernel)
         pl.boxes7.copy_(torch.from_numpy(boxes)); pl.scores.copy_(torch.from_numpy(scores)); pl.grad_prob.copy_(torch.from_numpy(grads))
         g = pl.capture()
         for _ in range(3):                                  # replays must be idempotent
@@ -83,3 +85,40 @@ def test_host_runner_and_pipeline_match_plain_calls():
         assert torch.equal(prob, want[j][1].prob.cpu())
         nv = int(counts[0, 0])
         assert torch.equal(valid[0, :nv], want[j][1].valid_idx[0, :nv].cpu())
+
+
+def test_benched_shape_parity_64_images_of_4096():
+    """Exactly what bench.py times: Nms3dPlan(64, 4096, materialise=True) -- the matrix kernel on its own graph branch with
+    CTAs that retire after one 256 x 64 tile, the NMS kernels on a higher-priority branch, one CUDA graph -- replayed; 4 sampled
+    images' overlap matrices bit for bit against the general (non-symmetric, non-tiled) overlap kernel, and every image's
+    rescored scores, leaders, keep lists and score gradients against per-image plain calls."""
+    from groomed_nms_b200 import _lib, ops, synthetic
+    from groomed_nms_b200.hostapi import Nms3dPlan
+    dev = torch.device("cuda", 0)
+    B, N = 64, 4096
+    params = ops.make_params(nms_threshold=0.4, pruning_method="linear", temperature=0.01, valid_box_prob_threshold=0.3,
+                             group_boxes=True, mask_group_boxes=True, group_size=100)
+    boxes = np.stack([synthetic.config_c3(seed=3 + 10 * i)[0] for i in range(B)])
+    scores = np.stack([synthetic.config_c3(seed=3 + 10 * i)[1] for i in range(B)])
+    grads = np.random.default_rng(1234).standard_normal((B, N)).astype(np.float32)
+    pl = Nms3dPlan(B, N, dev, params, materialise=True, overlap_branch=True)
+    pl.matrix_opts = _lib.launch_opts(tiles_per_cta=4)                  # bench.py's default
+    pl.boxes7.copy_(torch.from_numpy(boxes)); pl.scores.copy_(torch.from_numpy(scores)); pl.grad_prob.copy_(torch.from_numpy(grads))
+    g = pl.capture()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    rec = pl.rec.view(B, N, 8)
+    for b in (0, 21, 42, 63):
+        other = rec[b].clone()                                           # a different pointer: the general M x N kernel, not the tiles
+        _, want = ops.overlap3d(rec[b], other, False, True, generalized=True, affine=True)
+        assert torch.equal(pl.overlap[b].view(torch.int32), want.view(torch.int32)), b
+    up = torch.from_numpy(grads).to(dev)
+    for b in range(B):
+        st = ops.forward_boxes(pl.scores[b:b + 1], rec[b:b + 1], _lib.BOX_3D_REC, params, generalized=True, affine=True,
+                               opts=_lib.launch_opts(election=_lib.ELECT_MASK))     # the all-pairs route, not the direct election
+        assert torch.equal(pl.prob[b], st.prob[0]) and torch.equal(pl.lead[b], st.lead[0]) and torch.equal(pl.counts[b], st.counts[0]), b
+        nv = int(st.counts[0, 0])
+        assert torch.equal(pl.valid_idx[b, :nv], st.valid_idx[0, :nv]), b
+        gs, _ = ops.backward(st, up[b:b + 1])
+        assert torch.allclose(pl.grad_scores[b], gs[0], rtol=1e-6, atol=1e-7), b

@@ -200,3 +200,21 @@ def test_launch_opts_are_validated_and_versioned():
     short.rank_method = 99                                                            # beyond struct_size: must be ignored
     assert lib.gnms_overlap3d_batched_ex_f32(ops._p(rec), 64, 1, ops._p(out), 1, 1, ctypes.byref(short), None) == 0
     torch.cuda.synchronize()
+
+
+def test_corners_kitti_vertex_order_gpu():
+    """get_corners_of_cuboid(..., iou_3d_convention=False) (lib/math_3d.py:405-426): the reference's own output for N = 4
+    (golden), the oracle for any N, torch and numpy containers."""
+    from conftest import load_golden
+    from groomed_nms_b200.lib import math_3d as M
+    from oracle import groomed_oracle as O
+    g = load_golden("corners_kitti_order")
+    b = g["boxes7"]
+    got = M.get_corners_of_cuboid(*[cuda(b[:, i]) for i in range(7)], iou_3d_convention=False)
+    assert np.allclose(got.cpu().numpy(), g["corners"], rtol=1e-6, atol=1e-5)
+    rng = np.random.default_rng(5)
+    b = np.stack([rng.uniform(-20, 20, 333), rng.uniform(0.5, 2, 333), rng.uniform(5, 60, 333), rng.uniform(1.4, 1.9, 333),
+                  rng.uniform(1.3, 1.8, 333), rng.uniform(3, 5, 333), rng.uniform(-np.pi, np.pi, 333)], 1).astype(np.float32)
+    want = O.get_corners_of_cuboid(*[b[:, i] for i in range(7)], iou_3d_convention=False)
+    got_np = M.get_corners_of_cuboid(*[b[:, i] for i in range(7)], iou_3d_convention=False)
+    assert isinstance(got_np, np.ndarray) and np.allclose(got_np, want, rtol=1e-6, atol=1e-5)

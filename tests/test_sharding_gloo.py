@@ -1,15 +1,18 @@
-"""CPU, world_size 2 (gloo): the per-image shard of the batched config reproduces the single-process result.
-The per-image work is done by the numpy oracle here (no GPU in this tier); on the GPU box bench.py uses the same
-partition with one rank per GPU."""
+"""CPU, world_size 2 (gloo): the host-side logic of the N>1 path -- the rank -> image partition (shard_range), the gather
+of per-image results, and the product's gradient bucket (GradBucket: kernels write their gradients into views of one flat
+fp32 buffer which is all-reduced with ONE collective per step).  The per-image numbers here are stand-ins computed on the
+host (there is no GPU in this tier and the product has no CPU compute path); the same code runs over NCCL on the GPU box
+(tests/test_gpu_multi.py, bench.py --config c4)."""
 import os
 import socket
 
 import numpy as np
 import pytest
+import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from groomed_nms_b200 import sharding, synthetic
+from groomed_nms_b200 import sharding
 
 
 def test_shard_range_partitions_exactly():
@@ -23,26 +26,39 @@ def test_shard_range_partitions_exactly():
         sharding.shard_range(4, 2, 2)
 
 
-def _per_image(i):
-    from oracle import groomed_oracle as O
-    boxes, sc = synthetic.config_c4_image(i, n=192, k=6)
-    o = O.differentiable_nms(sc, O.iou(boxes, boxes), dense=False)
-    return (int(len(o["valid"])), float(o["prob"].sum()))
+def test_grad_bucket_views_alias_the_flat_buffer():
+    b = sharding.GradBucket({"head_wb": 65, "other": 3}, torch.device("cpu"), pad_elems=100)
+    assert b.flat.numel() == 68 + 4 + 100 and b.view("other").data_ptr() == b.flat[68:].data_ptr()      # 16-byte aligned views
+    b.view("head_wb").fill_(2.0)
+    b.view("other").fill_(5.0)
+    assert float(b.flat.sum()) == 65 * 2 + 3 * 5
+    assert b.all_reduce() is b.flat                                                                      # single process: no-op
+
+
+def _image_grad(i):
+    """Stand-in for one image's contribution to the shared-parameter gradient (deterministic, exactly representable)."""
+    rng = np.random.default_rng(100 + i)
+    return torch.from_numpy(rng.integers(-8, 9, 65).astype(np.float32))
 
 
 def _worker(rank, world, port, num_images, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    local = [_per_image(i) for i in sharding.shard_range(num_images, world, rank)]
-    allv = sharding.gather_per_image(local, num_images)
+    mine = sharding.shard_range(num_images, world, rank)
+    bucket = sharding.GradBucket({"head_wb": 65}, torch.device("cpu"), pad_elems=32)
+    g = bucket.view("head_wb")
+    for i in mine:                                              # what the head-backward kernel does for the local shard
+        g += _image_grad(i)
+    bucket.all_reduce()                                         # ONE collective for the whole bucket
+    per_image = sharding.gather_per_image([float(_image_grad(i).sum()) for i in mine], num_images)
     if rank == 0:
-        q.put(allv)
+        q.put((bucket.view("head_wb").clone().numpy(), float(bucket.flat[68:].abs().sum()), per_image))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_shard_equals_single_process():
+def test_two_rank_bucket_allreduce_equals_single_process():
     num_images = 5
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -52,10 +68,10 @@ def test_two_rank_shard_equals_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, num_images, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get()
+    grad, pad_sum, per_image = q.get()
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
-    want = [_per_image(i) for i in range(num_images)]
-    assert [g[0] for g in got] == [w[0] for w in want]
-    assert np.allclose([g[1] for g in got], [w[1] for w in want], rtol=0, atol=0)
+    want = sum(_image_grad(i) for i in range(num_images)).numpy()
+    assert np.array_equal(grad, want) and pad_sum == 0.0
+    assert per_image == [float(_image_grad(i).sum()) for i in range(num_images)]
