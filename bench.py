@@ -430,7 +430,10 @@ def run_ours(args, rank, world):
     # and all of its results out inside the timed region).  Two variants: one blocking call per step (run_host), and
     # the streaming pipeline (HostPipeline, 2 slots) in which the copies of one call overlap the kernels of the next.
     from groomed_nms_b200.hostapi import HostPipeline
-    runner = HostRunner(B, N, dev, params, materialise=False)   # run_host returns no matrix: fused matrix-free pipeline
+    # run_host returns no matrix (fused matrix-free pipeline).  The upstream gradient dL/dprob stays on the device, where a
+    # training step's loss kernels produce it; keep lists come back as int32 [B, 512] (+ the true counts)
+    runner = HostRunner(B, N, dev, params, materialise=False, keep_cap=512, grad_on_device=True)
+    runner.set_grad(torch.from_numpy(grads).to(dev))
     hb = torch.from_numpy(boxes).pin_memory(); hs = torch.from_numpy(scores).pin_memory(); hg = torch.from_numpy(grads).pin_memory()
     e2e_steps = max(args.steps, 200)          # ~40 ms of wall clock: short runs are at the mercy of host scheduling noise
 
@@ -453,11 +456,17 @@ def run_ours(args, rank, world):
             dt = float(t.item())
         return dt
 
-    e2e_blocking_s = time_host(lambda: runner.run_host(hb, hs, hg), lambda: None)
-    pipe = HostPipeline(B, N, dev, params, depth=args.e2e_depth)
-    e2e_s = time_host(lambda: pipe.submit(hb, hs, hg), pipe.drain)
+    e2e_blocking_s = time_host(lambda: runner.run_host(hb, hs), lambda: None)
+    pipe = HostPipeline(B, N, dev, params, depth=args.e2e_depth, keep_cap=512, grad_on_device=True)
+    pipe.set_grad(torch.from_numpy(grads).to(dev))
+    e2e_s = time_host(lambda: pipe.submit(hb, hs), pipe.drain)
     # the same calls with the kernels left out: what the PCIe link of this box allows for this call pattern
-    copies_s = time_host(lambda: pipe.submit(hb, hs, hg, copies_only=True), pipe.drain)
+    copies_s = time_host(lambda: pipe.submit(hb, hs, copies_only=True), pipe.drain)
+    # round-1 call pattern for comparison: the upstream gradient crosses PCIe too and keep lists are int64 [B, N]
+    pipe_r1 = HostPipeline(B, N, dev, params, depth=args.e2e_depth, keep_cap=0, grad_on_device=False)
+    e2e_r1_s = time_host(lambda: pipe_r1.submit(hb, hs, hg), pipe_r1.drain)
+    r1_bytes = (pipe_r1.h2d_bytes, pipe_r1.d2h_bytes)
+    del pipe_r1
     clocks = sampler.stop() if rank == 0 else None
 
     # per-kernel device times (rank 0): each stage launched back to back on its own; the working set of the N^2
@@ -518,7 +527,9 @@ def run_ours(args, rank, world):
                              if args.path == "materialised" else "matrix-free path: no N^2 HBM traffic; inputs are O(N)",
                        "parallelism": "per-image shard, %d rank(s), no data-path collective" % world},
             "e2e": {"value": boxes_per_step * e2e_steps / e2e_s, "unit": "boxes/s", "h2d_bytes_per_step": runner.h2d_bytes,
-                    "d2h_bytes_per_step": runner.d2h_bytes, "api": "groomed_nms_b200.hostapi.HostPipeline.submit/drain (pinned host buffers, %d slots: copies of one call overlap the kernels of the next; fused matrix-free pipeline: returns probabilities, score gradients and keep lists)" % args.e2e_depth,
+                    "d2h_bytes_per_step": runner.d2h_bytes, "api": "groomed_nms_b200.hostapi.HostPipeline.submit/drain (pinned host buffers, %d slots: copies of one call overlap the kernels of the next; fused matrix-free pipeline: boxes and scores in; probabilities, score gradients, int32 keep lists [B,512] and counts out; the upstream gradient dL/dprob is device-resident)" % args.e2e_depth,
+                    "h2d_GBps_per_rank": runner.h2d_bytes * e2e_steps / e2e_s / 1e9,
+                    "with_host_gradient_and_int64_keep_lists": {"value": boxes_per_step * e2e_steps / e2e_r1_s, "h2d_bytes_per_step": r1_bytes[0], "d2h_bytes_per_step": r1_bytes[1]},
                     "steps_timed": e2e_steps,
                     "copies_only_value": boxes_per_step * e2e_steps / copies_s,
                     "copies_only_note": "the same pipeline with the kernels left out (copies only): the ceiling the PCIe link of this box sets for e2e (%.1f GB/s H2D)" % (runner.h2d_bytes * e2e_steps / copies_s / 1e9),
@@ -682,7 +693,13 @@ def run_c4(args, rank, world):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that captured NCCL work are still alive here; tearing the process group down underneath them hung
+        # (observed at 2 ranks, NCCL 2.28.9 / torch 2.11): leave together and skip the destructors
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -87,6 +87,7 @@ SIGNATURES = {
     "gnms_forward_boxes_ex_f32": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, ctypes.POINTER(Params), vp, vp, vp, vp, vp,
                                         Saved, vp, ctypes.POINTER(LaunchOpts), vp]),
     "gnms_backward_f32": (i32, [vp, vp, vp, i64, i32, i32, vp, ctypes.POINTER(Params), Saved, vp, vp, i64, vp, vp]),
+    "gnms_pack_keep_i32": (i32, [vp, vp, i32, i32, i32, vp, vp]),
     "gnms_get_groups_f32": (i32, [vp, vp, i64, i32, f32, i32, vp, vp, vp, vp, vp]),
     "gnms_prune_f32": (i32, [vp, i64, i32, f32, f32, vp, vp]),
     "gnms_indices_copy_f32": (i32, [vp, i64, vp, i64, i64, vp, vp, vp, vp, i64, vp]),
@@ -96,6 +97,8 @@ SIGNATURES = {
     "gnms_soft_nms_workspace_bytes": (sz, [i32]),
     "gnms_aploss_f32": (i32, [vp, vp, i32, vp, vp, vp, sz, vp]),
     "gnms_aploss_workspace_bytes": (sz, [i32]),
+    "gnms_masked_topk_f32": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
+    "gnms_best_box_per_gt_f32": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, f32, vp, i32, vp, vp, vp, vp]),
     "gnms_score_head_workspace_bytes": (sz, [i32]),
     "gnms_score_head_forward_f32": (i32, [vp, i64, i32, vp, vp, vp]),
     "gnms_score_head_backward_f32": (i32, [vp, i64, i32, vp, vp, vp, vp, vp]),

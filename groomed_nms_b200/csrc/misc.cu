@@ -331,9 +331,28 @@ __global__ void col_finalize_kernel(const double* __restrict__ part_val, const i
     col_arg[g] = ci == INT_MAX ? 0 : ci;
 }
 
+// keep lists for the host: the first min(count, K) entries of every image's int64 valid_idx as int32 (a keep list is a few
+// dozen entries long, the [batch, N] int64 array it sits in 8 N bytes per image)
+__global__ void pack_keep_kernel(const int64_t* __restrict__ valid_idx, const int32_t* __restrict__ counts, int N, int K,
+                                 int32_t* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int n = min(counts[2 * b], K);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x)
+        out[(size_t)b * K + k] = k < n ? (int32_t)valid_idx[(size_t)b * N + k] : -1;
+}
+
 }  // namespace gnms
 
 using namespace gnms;
+
+extern "C" int gnms_pack_keep_i32(const int64_t* valid_idx, const int32_t* counts, int N, int batch, int K, int32_t* out, void* stream) {
+    if (N < 0 || batch < 0 || K <= 0) return GNMS_E_BADARG;
+    if (batch == 0) return 0;
+    if (!valid_idx || !counts || !out) return GNMS_E_BADARG;
+    pack_keep_kernel<<<dim3((K + 255) / 256, batch), 256, 0, (cudaStream_t)stream>>>(valid_idx, counts, N, K, out);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int gnms_prune_f32(const float* x, int64_t n, int pruning_method, float nms_threshold, float temperature,
                               float* out, void* stream) {

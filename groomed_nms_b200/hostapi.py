@@ -272,33 +272,78 @@ class SplitPlan(object):
 
 
 class HostRunner(object):
-    """End-to-end entry for HOST buffers: pinned staging + an Nms3dPlan.  run_host(...) returns host tensors."""
+    """End-to-end entry for HOST buffers: pinned staging + an Nms3dPlan.  run_host(...) returns host tensors.
 
-    def __init__(self, batch, n, device, params, materialise=False):
+    keep_cap: the keep lists go back as int32 [batch, keep_cap] (entries past an image's count are -1; counts[b, 0] is the
+              true length -- a keep list is a few dozen entries, the [batch, n] int64 array it lives in 8 n bytes per image).
+              keep_cap = 0 returns the full int64 [batch, n] array instead.
+    grad_on_device: the upstream gradient dL/dprob stays where training produces it -- on the device (plan.grad_prob, set by
+              the caller's loss kernels or once with set_grad) -- instead of crossing PCIe with every call."""
+
+    def __init__(self, batch, n, device, params, materialise=False, keep_cap=512, grad_on_device=False):
         self.plan = Nms3dPlan(batch, n, device, params, materialise=materialise)
+        self.keep_cap, self.grad_on_device = int(keep_cap), bool(grad_on_device)
         pin = dict(pin_memory=True)
         self.h_prob = torch.empty((batch, n), dtype=torch.float32, **pin)
         self.h_grad = torch.empty((batch, n), dtype=torch.float32, **pin)
-        self.h_valid = torch.empty((batch, n), dtype=torch.int64, **pin)
         self.h_counts = torch.empty((batch, 2), dtype=torch.int32, **pin)
-        self.h2d_bytes = batch * n * (7 + 1 + 1) * 4
-        self.d2h_bytes = batch * n * (4 + 4 + 8) + batch * 8
+        if self.keep_cap:
+            self.d_keep = torch.empty((batch, self.keep_cap), dtype=torch.int32, device=device)
+            self.h_valid = torch.empty((batch, self.keep_cap), dtype=torch.int32, **pin)
+        else:
+            self.d_keep = None
+            self.h_valid = torch.empty((batch, n), dtype=torch.int64, **pin)
+        self.h2d_bytes = batch * n * (7 + 1 + (0 if self.grad_on_device else 1)) * 4
+        self.d2h_bytes = batch * n * (4 + 4) + self.h_valid.numel() * self.h_valid.element_size() + batch * 8
         self.graph = None                        # the kernel sequence as a CUDA graph, captured on first use
 
-    def run_host(self, boxes7_host, scores_host, grad_prob_host):
-        """boxes7 [B,N,7], scores [B,N], dL/dprob [B,N] (pinned host fp32) -> (prob, grad_scores, valid_idx, counts)
-        on the host.  One H2D per input, the kernels (one graph launch), one D2H per output, one stream sync."""
+    def set_grad(self, grad_prob):
+        self.plan.grad_prob.copy_(grad_prob, non_blocking=True)
+
+    def enqueue_step(self, stream):
+        """The kernels of one call (+ the keep-list packing) on `stream`; capturable."""
         p = self.plan
-        if self.graph is None:
-            self.graph = p.capture()
+        p.step(stream)
+        if self.keep_cap:
+            check(p.lib.gnms_pack_keep_i32(_vp(p.valid_idx), _vp(p.counts), p.N, p.B, self.keep_cap, _vp(self.d_keep),
+                                           ctypes.c_void_p(stream.cuda_stream)), "pack_keep")
+
+    def capture(self, stream=None):
+        p = self.plan
+        st = stream if stream is not None else torch.cuda.Stream(p.dev)
+        st.wait_stream(torch.cuda.current_stream(p.dev))
+        with torch.cuda.stream(st):
+            self.enqueue_step(st)                # warm-up outside capture
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            self.enqueue_step(st)
+        return g
+
+    def copy_in(self, boxes7_host, scores_host, grad_prob_host):
+        p = self.plan
         p.boxes7.copy_(boxes7_host, non_blocking=True)
         p.scores.copy_(scores_host, non_blocking=True)
-        p.grad_prob.copy_(grad_prob_host, non_blocking=True)
-        self.graph.replay()
+        if not self.grad_on_device:
+            p.grad_prob.copy_(grad_prob_host, non_blocking=True)
+
+    def copy_out(self):
+        p = self.plan
         self.h_prob.copy_(p.prob, non_blocking=True)
         self.h_grad.copy_(p.grad_scores, non_blocking=True)
-        self.h_valid.copy_(p.valid_idx, non_blocking=True)
+        self.h_valid.copy_(self.d_keep if self.keep_cap else p.valid_idx, non_blocking=True)
         self.h_counts.copy_(p.counts, non_blocking=True)
+
+    def run_host(self, boxes7_host, scores_host, grad_prob_host=None):
+        """boxes7 [B,N,7], scores [B,N] (and dL/dprob [B,N] unless grad_on_device), pinned host fp32 ->
+        (prob, grad_scores, keep lists, counts) on the host.  One H2D per input, the kernels (one graph launch), one D2H per
+        output, one stream sync."""
+        p = self.plan
+        if self.graph is None:
+            self.graph = self.capture()
+        self.copy_in(boxes7_host, scores_host, grad_prob_host)
+        self.graph.replay()
+        self.copy_out()
         torch.cuda.current_stream(p.dev).synchronize()
         return self.h_prob, self.h_grad, self.h_valid, self.h_counts
 
@@ -310,38 +355,33 @@ class HostPipeline(object):
     kernels of its neighbours; wait(ticket) (or drain()) makes a call's results readable.  Every call still moves
     all of its inputs and outputs across PCIe."""
 
-    def __init__(self, batch, n, device, params, depth=2):
+    def __init__(self, batch, n, device, params, depth=2, keep_cap=512, grad_on_device=False):
         self.dev = device
         self.slots = []
         for _ in range(depth):
-            r = HostRunner(batch, n, device, params, materialise=False)
+            r = HostRunner(batch, n, device, params, materialise=False, keep_cap=keep_cap, grad_on_device=grad_on_device)
             st = torch.cuda.Stream(device)
-            with torch.cuda.stream(st):
-                r.plan.step(st)
-            st.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=st):
-                r.plan.step(st)
+            g = r.capture(st)
             self.slots.append(dict(r=r, st=st, g=g, ev=torch.cuda.Event(), busy=False))
         self.k = 0
         self.h2d_bytes, self.d2h_bytes = self.slots[0]["r"].h2d_bytes, self.slots[0]["r"].d2h_bytes
 
-    def submit(self, boxes7_host, scores_host, grad_prob_host, copies_only=False):
+    def set_grad(self, grad_prob):
+        for s in self.slots:
+            with torch.cuda.stream(s["st"]):
+                s["r"].set_grad(grad_prob)
+
+    def submit(self, boxes7_host, scores_host, grad_prob_host=None, copies_only=False):
         """copies_only: skip the kernels (measures what the PCIe link alone allows for this call pattern)."""
         s = self.slots[self.k % len(self.slots)]
         if s["busy"]:
             s["ev"].synchronize()                 # the slot's previous results must have been produced (and are now overwritten)
-        r, p = s["r"], s["r"].plan
+        r = s["r"]
         with torch.cuda.stream(s["st"]):
-            p.boxes7.copy_(boxes7_host, non_blocking=True)
-            p.scores.copy_(scores_host, non_blocking=True)
-            p.grad_prob.copy_(grad_prob_host, non_blocking=True)
+            r.copy_in(boxes7_host, scores_host, grad_prob_host)
             if not copies_only:
                 s["g"].replay()
-            r.h_prob.copy_(p.prob, non_blocking=True)
-            r.h_grad.copy_(p.grad_scores, non_blocking=True)
-            r.h_valid.copy_(p.valid_idx, non_blocking=True)
-            r.h_counts.copy_(p.counts, non_blocking=True)
+            r.copy_out()
             s["ev"].record(s["st"])
         s["busy"] = True
         self.k += 1

@@ -118,16 +118,16 @@ class GroomedNMSLossBranch(object):
         Returns (scores_after_nms [B,A] -- zero outside the boxes that went through NMS, differentiable wrt the scores --
                  targets_after_nms [B,A] float, 1 at the best box of every ground truth that clears best_target_box_beta).
         Same arithmetic as image() per image; the top-500 selection, corners, records, NMS forward and backward are single
-        launches over the batch (n_per_image carries the ragged counts on the device: no .cpu() / .item() anywhere)."""
+        launches over the batch (n_per_image carries the ragged counts on the device: no .cpu() / .item() anywhere); the
+        top-500 selection is one radix-select launch (gnms_masked_topk_f32) and the best-box assignment of all ground truths
+        of the batch one launch (gnms_best_box_per_gt_f32)."""
         dev = scores_to_nms.device
         B, A = scores_to_nms.shape
         K = min(self.max_boxes, A)
         fg_mask = fg_mask.to(dev).bool()
-        # :731-737  foreground anchors by descending score, at most 500 (stable: ties keep the lower anchor index)
-        masked = torch.where(fg_mask, scores_to_nms.detach().float(), torch.full_like(scores_to_nms, -float("inf"), dtype=torch.float32))
-        _, sorted_index = torch.sort(masked, dim=1, descending=True, stable=True)
-        top = sorted_index[:, :K].contiguous()                                                   # [B,K] anchor ids
-        n_img = torch.clamp(fg_mask.sum(dim=1), max=K).to(torch.int32)                           # live boxes per image
+        # :731-737  foreground anchors by descending score, at most 500 (stable: ties keep the lower anchor index): one
+        # radix-select launch over the batch instead of a full sort of all A scores per image
+        top, n_img = ops.masked_topk(scores_to_nms.detach(), fg_mask, K)                        # [B,K] anchor ids, [B] live counts
         live = torch.arange(K, device=dev)[None, :] < n_img[:, None]
         b7 = torch.gather(boxes7_raw.detach().float(), 1, top[:, :, None].expand(B, K, 7)).contiguous()
         box2d = torch.gather(coords_2d_512.detach().float(), 1, top[:, :, None].expand(B, K, 4)).contiguous()
@@ -157,23 +157,24 @@ class GroomedNMSLossBranch(object):
                     ov[b] = ops.overlap3d(rec[b * K:(b + 1) * K], rec[b * K:(b + 1) * K], False, True, generalized=True, affine=True, mul2d=iou2d)[1]
                 prob = ops.GroomedNMSBatchFunction.apply(scores_in, ov, None, params, False, False, n_img)[0]
             rec = ops.box3d_records(corners, mutate_input=False)                                # GT matching sees the mutated corners (:813)
-        scores_after_nms = torch.zeros((B, A), dtype=prob.dtype, device=dev).scatter(1, top, prob * live)      # :793
-        # ---- best box per ground truth (:801-825): per image, enqueued back to back (G_b is known on the host)
+        # :793 (dead slots all point at anchor 0 and add 0)
+        scores_after_nms = torch.zeros((B, A), dtype=prob.dtype, device=dev).scatter_add(1, top, prob * live)
+        # ---- best box per ground truth (:801-825): every ground truth of the batch in one launch
         targets_after_nms = torch.zeros((B, A), dtype=torch.float32, device=dev)
-        neg = torch.full((1,), -float("inf"), device=dev)
+        g3_all, g2_all, owner = [], [], []
         for b in range(B):
-            g3 = torch.as_tensor(gts_3d_list[b], device=dev).float().reshape(-1, 16)
+            g3 = np.asarray(gts_3d_list[b].cpu() if torch.is_tensor(gts_3d_list[b]) else gts_3d_list[b], dtype=np.float32).reshape(-1, 16)
             if g3.shape[0] == 0:
                 continue
-            g2 = torch.as_tensor(gts_2d_list[b], device=dev).float().reshape(g3.shape[0], -1)
+            g2 = np.asarray(gts_2d_list[b].cpu() if torch.is_tensor(gts_2d_list[b]) else gts_2d_list[b], dtype=np.float32).reshape(g3.shape[0], -1)
+            g3_all.append(g3); g2_all.append(g2[:, :4]); owner.append(np.full(g3.shape[0], b, np.int32))
+        if g3_all:
+            g3 = torch.from_numpy(np.concatenate(g3_all)).to(dev, non_blocking=True)
+            g2 = torch.from_numpy(np.ascontiguousarray(np.concatenate(g2_all))).to(dev, non_blocking=True)
+            gt_image = torch.from_numpy(np.concatenate(owner)).to(dev, non_blocking=True)
             gt7 = torch.stack([g3[:, 7], g3[:, 8], g3[:, 9], g3[:, 3], g3[:, 4], g3[:, 5], g3[:, 10]], dim=1).contiguous()
-            rec_b2 = ops.box3d_records(ops.corners_from_boxes7(gt7), mutate_input=False)
-            iou2d_gt = ops.overlap2d(box2d[b], g2[:, :4].contiguous())                          # :814
-            _, score_gt = ops.overlap3d(rec[b * K:(b + 1) * K], rec_b2, False, True, generalized=True, affine=True, mul2d=iou2d_gt)  # :813,817
-            score_gt = torch.where(live[b][:, None], score_gt, neg)                             # dead slots never win
-            best, max_idx = torch.max(score_gt, dim=0)                                          # :818
-            hit = (best > self.best_target_box_beta).float()                                    # :820-822
-            targets_after_nms[b].scatter_reduce_(0, top[b][max_idx], hit, reduce="amax")
+            rec_gt = ops.box3d_records(ops.corners_from_boxes7(gt7), mutate_input=False)
+            ops.best_box_per_gt(rec.view(B, K, 8), box2d, n_img, rec_gt, g2, gt_image, self.best_target_box_beta, top, targets_after_nms)
         return scores_after_nms, targets_after_nms
 
     # ---------------------------------------------------------------------------------------------- :1091-1137

@@ -340,6 +340,36 @@ class GroomedNMSBatchFunction(torch.autograd.Function):
         return gs, None, None, None, None, None, None
 
 
+def masked_topk(scores, mask, k):
+    """scores [B,A], mask [B,A] (bool / uint8) -> (idx int64 [B,k] anchor ids by descending score among the masked ones, stable;
+    n int32 [B] = min(#masked, k)).  One launch for the batch (lib/loss/rpn_3d.py:731-737)."""
+    _require_cuda(scores, "scores")
+    s = _f32c(scores)
+    m = mask.to(torch.uint8).contiguous() if mask.dtype != torch.uint8 else mask.contiguous()
+    B, A = s.shape
+    idx = torch.empty((B, k), dtype=torch.int64, device=s.device)
+    n = torch.empty((B,), dtype=torch.int32, device=s.device)
+    with torch.cuda.device(s.device):
+        check(_lib.load().gnms_masked_topk_f32(_p(s), _p(m), A, B, k, _p(idx), _p(n), _stream(s.device)), "gnms_masked_topk_f32")
+    return idx, n
+
+
+def best_box_per_gt(rec, box2d, n_per_image, gt_rec, gt_2d, gt_image, beta, top, targets):
+    """Marks, in targets [B,A] (fp32, modified in place), the best candidate box of every ground truth whose score
+    (0.5 (1 + GIoU3D)) * IoU2D exceeds beta (lib/loss/rpn_3d.py:813-825).  rec [B,K,8], box2d [B,K,4], top int64 [B,K],
+    gt_rec [G,8], gt_2d [G,4], gt_image int32 [G].  Returns (best_slot int32 [G], best_score fp32 [G])."""
+    B, K = rec.shape[0], rec.shape[1]
+    G = gt_rec.shape[0]
+    slot = torch.empty((G,), dtype=torch.int32, device=rec.device)
+    score = torch.empty((G,), dtype=torch.float32, device=rec.device)
+    if G and K:
+        with torch.cuda.device(rec.device):
+            check(_lib.load().gnms_best_box_per_gt_f32(_p(_f32c(rec)), _p(_f32c(box2d)), _p(n_per_image), K, _p(_f32c(gt_rec)), _p(_f32c(gt_2d)),
+                                                       _p(gt_image), G, float(beta), _p(top), targets.shape[1], _p(targets), _p(slot),
+                                                       _p(score), _stream(rec.device)), "gnms_best_box_per_gt_f32")
+    return slot, score
+
+
 def score_head_forward(x, wb):
     """scores[..] = sigmoid(x[.., :K] . wb[:K] + wb[K]) (K = 64): the per-box linear + sigmoid head of the batched
     configuration (the reference's 1x1-conv acceptance head, models/densenet121_3d_dilate_decomp_alpha.py:112-121,230)."""

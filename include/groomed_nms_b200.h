@@ -227,6 +227,11 @@ int gnms_backward_f32(const float* grad_prob, const float* prob, const float* io
                       const int32_t* n_per_image, const gnms_params* p, gnms_saved saved, float* grad_scores,
                       float* grad_iou, int64_t ld_gi, void* workspace, void* stream);
 
+/* Keep lists in transfer form: out[b, k] = (int32) valid_idx[b, k] for k < min(counts[b, 0], K), -1 beyond -- K << N entries
+ * per image instead of the [batch, N] int64 array (the reference's `valid_boxes_index`, lib/groomed_nms.py:122, is that short
+ * list; counts[b, 0] tells the caller whether K was enough). */
+int gnms_pack_keep_i32(const int64_t* valid_idx, const int32_t* counts, int N, int batch, int K, int32_t* out, void* stream);
+
 /* get_groups (lib/groomed_nms.py:208-270) from a matrix: group_id[N] int32 = index (in leader order) of the
  * group of INPUT box i or -1, group_rank[N] int32 = position inside the group (0 = leader), n_groups int32[1]. */
 int gnms_get_groups_f32(const float* scores, const float* iou, int64_t ld, int N, float group_threshold,
@@ -271,6 +276,22 @@ size_t gnms_soft_nms_workspace_bytes(int N);
 int gnms_aploss_f32(const float* logits, const float* targets, int n, float* loss, float* grad,
                     void* workspace, size_t workspace_bytes, void* stream);
 size_t gnms_aploss_workspace_bytes(int n);
+
+/* ---------------------------------------------------------------- loss-branch front / back end, batched */
+/* lib/loss/rpn_3d.py:731-737, all images of a step in one launch: the (at most) K <= 1024 highest-scoring foreground anchors
+ * of every image.  scores[batch, A] fp32, mask[batch, A] uint8 (non-zero = foreground).  out_idx int64[batch, K]: anchor ids
+ * by descending score, ties by lower anchor id (slots past out_n[b] hold 0); out_n int32[batch] = min(#foreground, K).
+ * Replaces a full sort of all A (= 69 120) scores per image and the host round trip of :739-744. */
+int gnms_masked_topk_f32(const float* scores, const uint8_t* mask, int A, int batch, int K, int64_t* out_idx, int32_t* out_n,
+                         void* stream);
+/* lib/loss/rpn_3d.py:813-825, all ground truths of a step in one launch: for ground truth g of image gt_image[g], the
+ * candidate i < n_per_image[b] maximising (0.5 * (1 + giou3d(rec[b,i], gt_rec[g]))) * iou2d(box2d[b,i], gt_2d[g]) (first maximum,
+ * NaN counts as the maximum, like torch.max); if that score is > beta, targets[b, top[b, i]] = 1.  rec[batch,K,8] records and
+ * box2d[batch,K,4] of the candidates, gt_rec[n_gt,8], gt_2d[n_gt,4], top int64[batch,K] = anchor id of candidate slot,
+ * targets fp32[batch, A] (caller-zeroed).  best_slot int32[n_gt] / best_score fp32[n_gt]: optional. */
+int gnms_best_box_per_gt_f32(const float* rec, const float* box2d, const int32_t* n_per_image, int K, const float* gt_rec,
+                             const float* gt_2d, const int32_t* gt_image, int n_gt, float beta, const int64_t* top, int A,
+                             float* targets, int32_t* best_slot, float* best_score, void* stream);
 
 /* ---------------------------------------------------------------- score head (batched-image configuration) */
 /* The head that produces the scores entering GrooMeD-NMS in the batched configuration (BASELINE.json configs[3]): the

@@ -199,6 +199,71 @@ def run_loss(arm, scene, overrides=None, fake_cuda=False, config="groumd_nms"):
     return out
 
 
+def run_train_steps(arm, scene, iters=3, overrides=None, fake_cuda=False, config="groumd_nms", seed=0):
+    """Config C5 (BASELINE.json configs[4]): the loop body of the reference's scripts/train_rpn_3d.py:131-142 -- its own
+    densenet121_3d_dilate_decomp_alpha RPN (random init: `build(conf, 'test')` then .train()), its own
+    RPN_3D_loss and its own loss_backprop (backward, clip_grad_value_, SGD step; lib/core.py:99-113) -- on synthetic
+    384 x 1280 images and the scene's ground truths, stock or with groomed_nms_b200.install() active.
+    Returns the loss of every iteration, gradient probes of the first iteration and the time per iteration."""
+    import time
+    torch, L, rec = setup(arm, fake_cuda)
+    device = "cpu" if fake_cuda else "cuda"
+    conf = build_conf(scene, overrides, config)
+    np.random.seed(conf.rng_seed)
+    torch.manual_seed(seed)
+    if not fake_cuda:
+        torch.cuda.manual_seed_all(seed)
+        torch.backends.cudnn.deterministic = True
+        torch.backends.cudnn.benchmark = False
+    model_mod = importlib.import_module("models." + conf.model)
+    core = importlib.import_module("lib.core")
+    net = model_mod.build(conf, "test")                   # 'test' = no download of pretrained weights; then train mode as the script does
+    net.train()
+    net.phase = "train"
+    if not fake_cuda:
+        net = net.cuda()
+    opt = torch.optim.SGD(net.parameters(), lr=conf.lr, momentum=conf.momentum, weight_decay=conf.weight_decay)   # lib/core.py:71-77
+    crit = L.RPN_3D_loss(conf, verbose=False)
+    H, W = scene["feat_size"]
+    B = len(scene["gts"])
+    g = torch.Generator(device="cpu").manual_seed(seed + 1)
+    images = torch.randn((B, 3, H * conf.feat_stride, W * conf.feat_stride), generator=g).to(device)
+    imobjs = build_imobjs(scene)
+    out = {"losses": [], "iter_ms": [], "loss_ms": []}
+    probes = {}
+    for it in range(iters):
+        if not fake_cuda:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cls, prob, bbox_2d, bbox_3d, feat_size, rois, rois_3d, rois_3d_cen, acc, acc_cls = net(images)          # train_rpn_3d.py:137
+        if not fake_cuda:
+            torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        loss, stats = crit(cls, prob, bbox_2d, bbox_3d, imobjs, feat_size, rois, rois_3d, rois_3d_cen, acc, acc_cls)   # :140
+        if not fake_cuda:
+            torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        if it == 0:
+            loss.backward(retain_graph=True)
+            named = dict(net.named_parameters())
+            for name in ("acceptance_prob.layer_0.weight", "cls.weight", "bbox_z3d.weight", "prop_feats.0.weight", "base.conv0.weight"):
+                probes["grad_" + name] = _np(named[name].grad).reshape(-1)[:4096].copy()
+            probes["stat_names"] = np.array([s_["name"] for s_ in stats])
+            probes["stat_vals"] = np.array([float(_np(s_["val"]).reshape(-1)[0]) for s_ in stats])
+            opt.zero_grad()
+        core.loss_backprop(loss, net, opt, conf=conf, iteration=it)                                               # :142
+        if not fake_cuda:
+            torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        out["losses"].append(float(loss.detach()))
+        out["iter_ms"].append(1e3 * (t3 - t0))
+        out["loss_ms"].append(1e3 * (t2 - t1))
+    res = dict(losses=np.array(out["losses"]), iter_ms=np.array(out["iter_ms"]), loss_ms=np.array(out["loss_ms"]),
+               n_nms=np.array([len(rec.nms)]), nms_sizes=np.array([len(d["scores_in"]) for d in rec.nms]))
+    res.update(probes)
+    return res
+
+
 def parse_overrides(items):
     ov = {}
     for it in items or []:
@@ -220,10 +285,19 @@ def main(argv=None):
     ap.add_argument("--near-iou", type=float, default=0.3)
     ap.add_argument("--set", action="append", default=[])
     ap.add_argument("--fake-cuda", action="store_true")
+    ap.add_argument("--model", action="store_true", help="config C5: the reference's model + loss + optimiser step instead of the loss alone")
+    ap.add_argument("--iters", type=int, default=3)
     a = ap.parse_args(argv)
     from groomed_nms_b200 import synthetic
     H, W = [int(x) for x in a.feat.split("x")]
     scene = synthetic.c5_scene(seed=a.seed, batch=a.batch, feat_size=(H, W), near_iou=a.near_iou)
+    if a.model:
+        out = run_train_steps(a.arm, scene, iters=a.iters, overrides=parse_overrides(a.set), fake_cuda=a.fake_cuda)
+        np.savez_compressed(a.out, **out)
+        print("ref_harness %s C5: losses %s, ms per iteration %s (loss alone %s), NMS sizes %s -> %s" % (
+            a.arm, np.round(out["losses"], 6).tolist(), np.round(out["iter_ms"], 1).tolist(), np.round(out["loss_ms"], 1).tolist(),
+            out["nms_sizes"].tolist(), a.out))
+        return
     out = run_loss(a.arm, scene, parse_overrides(a.set), fake_cuda=a.fake_cuda)
     np.savez_compressed(a.out, **out)
     print("ref_harness %s: loss %.6f, %d images through NMS, %d AP-loss calls -> %s" % (a.arm, float(out["loss"][0]), int(out["n_nms"][0]),

@@ -84,7 +84,16 @@ def test_host_runner_and_pipeline_match_plain_calls():
         prob, grad, valid, counts = pipe.wait(tickets[j])
         assert torch.equal(prob, want[j][1].prob.cpu())
         nv = int(counts[0, 0])
-        assert torch.equal(valid[0, :nv], want[j][1].valid_idx[0, :nv].cpu())
+        assert valid.dtype == torch.int32 and valid.shape == (B, 512)                    # compact keep lists (keep_cap)
+        assert torch.equal(valid[0, :nv].long(), want[j][1].valid_idx[0, :nv].cpu()) and bool((valid[0, nv:] == -1).all())
+    # the full int64 lists (keep_cap = 0) and an upstream gradient that stays on the device
+    full = HostRunner(B, N, dev, params, keep_cap=0, grad_on_device=True)
+    full.set_grad(torch.from_numpy(batches[0][2]).to(dev))
+    prob, grad, valid, counts = full.run_host(pinned[0][0], pinned[0][1])
+    assert valid.dtype == torch.int64 and valid.shape == (B, N)
+    nv = int(counts[1, 0])
+    assert torch.equal(valid[1, :nv], want[0][1].valid_idx[1, :nv].cpu()) and torch.allclose(grad, want[0][2].cpu(), rtol=1e-6, atol=1e-7)
+    assert full.h2d_bytes == B * N * 32 and runner.h2d_bytes == B * N * 36
 
 
 def test_benched_shape_parity_64_images_of_4096():
