@@ -71,8 +71,9 @@ def after_nms_rank_loss(scores_after, targets_after, weights, lam=1.0):
 
 
 def inference_site(coords_2d, scores, coords_3d, coords_3d_raw, cls_pred, tracker, use_diff, overlap_in_nms="2d", nms_thres=0.4,
-                   topn_pre=3000, temperature=1.0, valid_thr=0.3, group_size=100, max_boxes=500, corners=None):
+                   topn_pre=3000, temperature=1.0, valid_thr=0.3, group_size=100, max_boxes=500, corners=None, mask_group_boxes=True):
     """lib/rpn_util.py:1258-1341 composed from the pinned pieces -> (aboxes rows as the reference stacks them, keep_inds).
+    Pinned against the reference's own im_detect_3d by tests/golden/inference_site_ref.npz (tests/test_oracle_detect_ref.py).
     corners: optionally the CUDA path's corners of the first 500 sorted boxes (parity is defined from the corners onward)."""
     order = O.stable_sort_desc(scores.astype(F32))[:min(topn_pre, len(scores))]          # :1260-1290
     if use_diff:                                                                         # :1293-1320
@@ -89,7 +90,8 @@ def inference_site(coords_2d, scores, coords_3d, coords_3d_raw, cls_pred, tracke
             ov3 = (F32(0.5) * (F32(1) + g3)).astype(F32)
             ov = ov3 if overlap_in_nms == "3d" else (iou2d * ov3).astype(F32)
         fwd = O.differentiable_nms(scores[sel].astype(F32), ov, nms_threshold=nms_thres, temperature=temperature,
-                                   valid_box_prob_threshold=valid_thr, group_size=group_size, dense=False)
+                                   valid_box_prob_threshold=valid_thr, group_size=group_size, mask_group_boxes=mask_group_boxes,
+                                   dense=not mask_group_boxes)
         keep = fwd["valid"]
         base = sel
     else:                                                                                # :1334

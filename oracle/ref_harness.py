@@ -264,6 +264,61 @@ def run_train_steps(arm, scene, iters=3, overrides=None, fake_cuda=False, config
     return res
 
 
+def run_detect(arm, scene, overrides=None, fake_cuda=False, config="groumd_nms"):
+    """The inference call site: the reference's im_detect_3d (lib/rpn_util.py:1052-1357) on
+    one image, driven by a stand-in `net` that returns the scene's network outputs, stock or with install() active.
+    Records the detections as they enter the NMS block (:1258-1290: sorted by score, truncated to nms_topN_pre) and the
+    rows im_detect_3d returns.  The reference's gpu_nms is a Cython/CUDA extension for sm_35 that is not rebuilt here; in
+    the stock arm its place is taken by the reference's own pure-python twin, lib/nms/py_cpu_nms.py (same +1 convention
+    and `>` test, lib/nms/nms_kernel.cu:27-30,71)."""
+    import types
+    from oracle import ref_shim
+    ref_shim.install()
+    import torch
+    if fake_cuda:
+        ref_shim.fake_cuda()
+    else:
+        torch.set_default_tensor_type('torch.cuda.FloatTensor')
+    if arm == "installed":
+        import groomed_nms_b200
+        groomed_nms_b200.install()
+    else:
+        py = importlib.import_module("lib.nms.py_cpu_nms")
+        sys.modules["lib.nms.gpu_nms"].gpu_nms = lambda dets, thresh, device_id=0: py.py_cpu_nms(dets, thresh)
+    R = importlib.import_module("lib.rpn_util")
+    device = "cpu" if fake_cuda else "cuda"
+    conf = build_conf(scene, overrides, config)
+    lv, (cls, prob, bbox_2d, bbox_3d, rois, rois_3d, rois_cen, acc) = network_outputs(torch, scene, device)
+    captured = {}
+
+    def spy(fn, name):
+        def wrapped(*a, **k):
+            fr = sys._getframe(1).f_locals
+            if "aboxes" in fr and "pre" not in captured:
+                captured["pre"] = dict(aboxes=np.array(fr["aboxes"]), coords_3d=np.array(fr["coords_3d"]), coords_3d_raw=np.array(fr["coords_3d_raw"]),
+                                       cls_pred=np.array(fr["cls_pred"]), tracker=np.array(fr["tracker"]))
+            out = fn(*a, **k)
+            captured["nms_fn"] = name
+            captured["keep"] = np.asarray(out[0].numpy() if name == "differentiable_nms" else out, dtype=np.int64)
+            return out
+        return wrapped
+    R.differentiable_nms = spy(R.differentiable_nms, "differentiable_nms")
+    R.gpu_nms = spy(R.gpu_nms, "gpu_nms")
+
+    def net(im):                                   # eval-mode outputs of the model (models/...alpha.py:250)
+        with torch.no_grad():
+            return (cls[:1].detach(), prob[:1].detach(), bbox_2d[:1].detach().clone(), bbox_3d[:1].detach().clone(), list(scene["feat_size"]),
+                    rois[0].detach(), acc[:1].detach(), None)
+    H, W = scene["feat_size"]
+    im = np.zeros((H * 16, W * 16, 3), dtype=np.float32)
+    preprocess = lambda x: np.ascontiguousarray(x.transpose(2, 0, 1))
+    aboxes = R.im_detect_3d(im, net, conf, preprocess, np.array(scene["p2"], dtype=np.float64))
+    out = dict(aboxes_out=np.asarray(aboxes), keep=captured["keep"], nms_fn=np.frombuffer(captured["nms_fn"].encode(), dtype=np.uint8))
+    for k, v in captured["pre"].items():
+        out["pre_" + k] = v
+    return out, conf
+
+
 def parse_overrides(items):
     ov = {}
     for it in items or []:
@@ -286,11 +341,18 @@ def main(argv=None):
     ap.add_argument("--set", action="append", default=[])
     ap.add_argument("--fake-cuda", action="store_true")
     ap.add_argument("--model", action="store_true", help="config C5: the reference's model + loss + optimiser step instead of the loss alone")
+    ap.add_argument("--detect", action="store_true", help="the inference call site: the reference's im_detect_3d on one image of the scene")
     ap.add_argument("--iters", type=int, default=3)
     a = ap.parse_args(argv)
     from groomed_nms_b200 import synthetic
     H, W = [int(x) for x in a.feat.split("x")]
     scene = synthetic.c5_scene(seed=a.seed, batch=a.batch, feat_size=(H, W), near_iou=a.near_iou)
+    if a.detect:
+        out, _ = run_detect(a.arm, scene, parse_overrides(a.set), fake_cuda=a.fake_cuda)
+        np.savez_compressed(a.out, **out)
+        print("ref_harness %s detect: %d detections into NMS (%s), %d kept -> %s" % (a.arm, len(out["pre_aboxes"]), bytes(out["nms_fn"]).decode(),
+                                                                                  len(out["aboxes_out"]), a.out))
+        return
     if a.model:
         out = run_train_steps(a.arm, scene, iters=a.iters, overrides=parse_overrides(a.set), fake_cuda=a.fake_cuda)
         np.savez_compressed(a.out, **out)

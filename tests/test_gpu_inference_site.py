@@ -57,3 +57,22 @@ def test_no_detections():
     out, keep = nms_after_detection(z, np.zeros((0,), np.float32), np.zeros((0, 11), np.float32), np.zeros((0, 7), np.float32),
                                     np.zeros((0,), np.float32), np.zeros((0,), np.float32), dict(use_nms_in_loss=True))
     assert out.shape == (0, 18) and keep.shape == (0,)
+
+
+import detect_golden  # noqa: E402
+
+REF_CASES = detect_golden.cases()
+
+
+@pytest.mark.parametrize("name", sorted(REF_CASES))
+def test_inference_site_matches_reference_run(name):
+    """nms_after_detection against what the UNMODIFIED reference's im_detect_3d returned on the same detections
+    (tests/golden/inference_site_ref.npz, oracle/gen_golden_detect.py): kept rows and keep indices exact."""
+    from groomed_nms_b200.lib.rpn_util import nms_after_detection
+    c = REF_CASES[name]
+    n = len(c["pre_aboxes"])
+    ab = c["pre_aboxes"]
+    out, keep = nms_after_detection(ab[:, :4], ab[:, 4], c["pre_coords_3d"][:n], c["pre_coords_3d_raw"][:n], c["pre_cls_pred"][:n].astype(np.float32),
+                                    c["pre_tracker"][:n].astype(np.float32), c["conf"])
+    assert keep.tolist() == c["keep"].tolist()
+    assert np.array_equal(out, c["aboxes_out"].astype(np.float32))

@@ -73,3 +73,24 @@ def test_reference_loss_stock_vs_installed(name, tmp_path):
         a, b = stock[key], ours[key]
         assert np.allclose(a, b, rtol=1e-4, atol=1e-6 * max(1e-12, np.abs(a).max())), key
     assert np.abs(stock["grad_acc_logit"]).max() > 0
+
+
+DETECT_CONFIGS = {
+    "groomed_2d": [],
+    "groomed_product": ["--set", "overlap_in_nms=\"product\""],
+    "classical": ["--set", "use_nms_in_loss=false"],
+}
+
+
+@pytest.mark.skipif(not os.path.isfile(STAGED), reason="reference not staged (python tools/stage_reference.py in the build container)")
+@pytest.mark.parametrize("name", sorted(DETECT_CONFIGS))
+def test_reference_im_detect_3d_stock_vs_installed(name, tmp_path):
+    """The inference call site (lib/rpn_util.py:1258-1341 inside im_detect_3d): the reference's own function, stock (its numpy /
+    CPU-torch NMS; py_cpu_nms standing in for the unbuilt Cython gpu_nms) and with install() active (iou, corners,
+    iou3d_approximate, differentiable_nms and gpu_nms on the sm_100a kernels): the same detections survive, in the same order."""
+    extra = ["--detect", "--seed", "31", "--batch", "1", "--feat", "24x80"] + DETECT_CONFIGS[name]
+    stock = _run("stock", str(tmp_path / "stock.npz"), extra)
+    ours = _run("installed", str(tmp_path / "installed.npz"), extra)
+    assert np.array_equal(stock["pre_aboxes"], ours["pre_aboxes"])
+    assert np.array_equal(stock["keep"], ours["keep"]) and len(stock["keep"]) > 0
+    assert np.array_equal(stock["aboxes_out"], ours["aboxes_out"])
