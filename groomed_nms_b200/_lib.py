@@ -91,6 +91,9 @@ SIGNATURES = {
     "gnms_get_groups_f32": (i32, [vp, vp, i64, i32, f32, i32, vp, vp, vp, vp, vp]),
     "gnms_prune_f32": (i32, [vp, i64, i32, f32, f32, vp, vp]),
     "gnms_indices_copy_f32": (i32, [vp, i64, vp, i64, i64, vp, vp, vp, vp, i64, vp]),
+    "gnms_soft_sort_workspace_bytes": (sz, [i32]),
+    "gnms_soft_sort_forward_f32": (i32, [vp, i32, f32, vp, i64, vp, vp, vp, vp, vp, vp, vp]),
+    "gnms_soft_sort_backward_f32": (i32, [vp, i32, f32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "gnms_hard_nms_f32": (i32, [vp, i32, f32, f32, i32, vp, vp, vp, vp]),
     "gnms_nms_host": (i32, [vp, vp, vp, i32, i32, f32, i32]),
     "gnms_soft_nms_f64": (i32, [vp, i32, f64, f64, f64, i32, f64, vp, vp, vp, vp, vp]),

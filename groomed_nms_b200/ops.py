@@ -340,6 +340,57 @@ class GroomedNMSBatchFunction(torch.autograd.Function):
         return gs, None, None, None, None, None, None
 
 
+class SoftSortFunction(torch.autograd.Function):
+    """soft_sort (lib/groomed_nms.py:131-165) on the hand-written kernels: forward (rank, exp / row sums, permutation matrix,
+    P s, P M) and the analytic backward are one C-ABI call each.  Returns (soft_scores, P, soft_matrix or None)."""
+
+    @staticmethod
+    def forward(ctx, scores, matrix, temperature):
+        _require_cuda(scores, "scores")
+        s = _f32c(scores.detach())
+        m = _f32c(matrix.detach()) if matrix is not None else None
+        N = s.shape[0]
+        if N > MAX_BOXES:
+            raise RuntimeError("groomed_nms_b200: at most %d boxes (got %d)" % (MAX_BOXES, N))
+        dev = s.device
+        ss = torch.empty((N,), dtype=torch.float32, device=dev)
+        P = torch.empty((N, N), dtype=torch.float32, device=dev)
+        sm = torch.empty((N, N), dtype=torch.float32, device=dev) if m is not None else None
+        perm = torch.empty((N,), dtype=torch.int32, device=dev)
+        hs = torch.empty((N,), dtype=torch.float32, device=dev)
+        S = torch.empty((N,), dtype=torch.float32, device=dev)
+        if N:
+            with torch.cuda.device(dev):
+                check(_lib.load().gnms_soft_sort_forward_f32(_p(s), N, float(temperature), _p(m), m.stride(0) if m is not None else 0, _p(ss), _p(P),
+                                                             _p(sm), _p(perm), _p(hs), _p(S), _stream(dev)), "gnms_soft_sort_forward_f32")
+        ctx.save_for_backward(s, m, P, perm, hs, S)
+        ctx.temperature = float(temperature)
+        ctx.need_m = matrix is not None and matrix.requires_grad
+        if sm is None:
+            return ss, P
+        return ss, P, sm
+
+    @staticmethod
+    def backward(ctx, g_ss, g_P, g_sm=None):
+        s, m, P, perm, hs, S = ctx.saved_tensors
+        N = s.shape[0]
+        dev = s.device
+        lib = _lib.load()
+        grad_s = torch.empty((N,), dtype=torch.float32, device=dev)
+        grad_m = torch.empty((N, N), dtype=torch.float32, device=dev) if (m is not None and ctx.need_m) else None
+        if N:
+            scratch = torch.empty((N, N), dtype=torch.float32, device=dev)
+            ws = torch.empty((int(lib.gnms_soft_sort_workspace_bytes(N)),), dtype=torch.uint8, device=dev)
+            g_ss = _f32c(g_ss) if g_ss is not None else None
+            g_P = _f32c(g_P) if g_P is not None else None
+            g_sm = _f32c(g_sm) if g_sm is not None else None
+            with torch.cuda.device(dev):
+                check(lib.gnms_soft_sort_backward_f32(_p(s), N, ctx.temperature, _p(m), m.stride(0) if m is not None else 0, _p(P), _p(perm), _p(hs),
+                                                      _p(S), _p(g_ss), _p(g_P), _p(g_sm), _p(grad_s), _p(grad_m), _p(scratch), _p(ws),
+                                                      _stream(dev)), "gnms_soft_sort_backward_f32")
+        return grad_s, grad_m, None
+
+
 def masked_topk(scores, mask, k):
     """scores [B,A], mask [B,A] (bool / uint8) -> (idx int64 [B,k] anchor ids by descending score among the masked ones, stable;
     n int32 [B] = min(#masked, k)).  One launch for the batch (lib/loss/rpn_3d.py:731-737)."""

@@ -248,6 +248,21 @@ int gnms_prune_f32(const float* x, int64_t n, int pruning_method, float nms_thre
 int gnms_indices_copy_f32(float* A, int64_t colsA, const float* B, int64_t colsB, int64_t C, const int64_t* ra,
                           const int64_t* ca, const int64_t* rb, const int64_t* cb, int64_t npairs, void* stream);
 
+/* soft_sort (lib/groomed_nms.py:131-165; SoftSort, Prillo & Eisenschlos 2020), sorting_method="soft".
+ * forward: s[N], optional M[N,N] (row stride ld_m) -> soft_scores[N] = P s, P[N,N] with P[i][j] = exp(-|s_j - h_i| / T) / S[j]
+ * (h = s sorted descending, S[i] = sum_j exp(-|s_j - h_i| / T) + 1e-3; the division is column-wise by the ROW sums, as the
+ * reference's broadcast at :155 does), soft_matrix[N,N] = P M (rows only, :164).  Saved for the backward: perm int32[N] (sorted
+ * position -> input index), hsorted[N], S[N].  The N x N x N product is an fp32 FMA-pipe GEMM (1e-5 parity with the
+ * reference's fp32 matmul rules out TF32 / BF16 tensor-core inputs).
+ * backward: upstream g_scores[N], g_P[N,N], g_SM[N,N] (each optional) -> grad_s[N], grad_M[N,N] (optional); dP_scratch[N,N]
+ * is caller-allocated scratch, workspace gnms_soft_sort_workspace_bytes(N). */
+size_t gnms_soft_sort_workspace_bytes(int N);
+int gnms_soft_sort_forward_f32(const float* s, int N, float temperature, const float* M, int64_t ld_m, float* soft_scores, float* P,
+                               float* soft_matrix, int32_t* perm, float* hsorted, float* S, void* stream);
+int gnms_soft_sort_backward_f32(const float* s, int N, float temperature, const float* M, int64_t ld_m, const float* P,
+                                const int32_t* perm, const float* hsorted, const float* S, const float* g_scores, const float* g_P,
+                                const float* g_SM, float* grad_s, float* grad_M, float* dP_scratch, void* workspace, void* stream);
+
 /* ---------------------------------------------------------------- classical NMS -------------------- */
 /* dets[N,5] = (x1,y1,x2,y2,score) device.  shift = the "+1" pixel convention (1.0 for lib/nms, any for
  * girshick_nms).  cmp = GNMS_CMP_*.  keep int32[N] = kept ORIGINAL indices in descending score order,

@@ -1,10 +1,11 @@
 """TEST INFRASTRUCTURE ONLY -- small golden vectors from the UNMODIFIED reference that the other generators do not cover.
 
-    python oracle/gen_golden_misc.py          # rewrites tests/golden/corners_kitti_order.npz
+    python oracle/gen_golden_misc.py          # rewrites tests/golden/corners_kitti_order.npz and soft_sort.npz
 
 corners_kitti_order: get_corners_of_cuboid(..., iou_3d_convention=False) (lib/math_3d.py:405-426) for N = 4 boxes -- the one
 batch size besides 1 for which the reference's torch branch broadcasts (`corners[:, 0, [1,2,3,4]] = l3d`, :422)."""
 import os
+import signal
 import sys
 
 import numpy as np
@@ -15,8 +16,47 @@ sys.path.insert(0, ROOT)
 from oracle import ref_shim  # noqa: E402
 
 
+def soft_sort_cases(ref):
+    """soft_sort (lib/groomed_nms.py:131-165) forward + autograd backward, and differentiable_nms(sorting_method="soft")."""
+    from groomed_nms_b200 import synthetic
+    g = {}
+    for name, n, temp in (("a", 64, 0.05), ("b", 120, 0.01), ("c", 33, 0.5)):
+        boxes, sc, _ = synthetic.clustered_boxes_2d(n, 5, seed=40 + n, jitter=0.08)
+        iou = ref.core.iou(torch.from_numpy(boxes), torch.from_numpy(boxes)).contiguous().numpy()
+        rng = np.random.default_rng(n)
+        gs, gp, gm = rng.standard_normal(n).astype(np.float32), rng.standard_normal((n, n)).astype(np.float32), rng.standard_normal((n, n)).astype(np.float32)
+        s = torch.from_numpy(sc).clone().requires_grad_(True)
+        m = torch.from_numpy(iou).clone().requires_grad_(True)
+        ss, P, sm = ref.groomed_nms.soft_sort(s, full_matrix=m, temperature=temp)
+        ((ss * torch.from_numpy(gs)).sum() + (P * torch.from_numpy(gp)).sum() + (sm * torch.from_numpy(gm)).sum()).backward()
+        g.update({name + "_scores": sc, name + "_iou": iou, name + "_temp": np.array([temp], np.float32),       # upstream gradients: rng(n), see the tests
+                  name + "_soft_scores": ss.detach().numpy(), name + "_P": P.detach().numpy(), name + "_soft_matrix": sm.detach().numpy(),
+                  name + "_grad_s": s.grad.numpy(), name + "_grad_m": m.grad.numpy()})
+        # the whole soft path of differentiable_nms.  soft_sort permutes the ROWS of the matrix only (:164), so unless the boxes
+        # already come in descending score order the "diagonal" the grouping loop relies on is an arbitrary overlap, the leader
+        # never leaves the pool and the reference loops forever (lib/groomed_nms.py:247-262).  The only inputs on which the
+        # reference's soft path terminates are (nearly) pre-sorted ones: the fixture sorts the boxes by score first and uses a
+        # sharp sorting temperature.  (The alarm is the safety net.)
+        o = np.argsort(-sc, kind="stable")
+        sc_s, iou_s = sc[o].copy(), iou[o][:, o].copy()
+        s2 = torch.from_numpy(sc_s).clone().requires_grad_(True)
+        up = rng.standard_normal(n).astype(np.float32)
+        signal.alarm(120)
+        valid, invalid, prob = ref.groomed_nms.differentiable_nms(s2, torch.from_numpy(iou_s).clone(), nms_threshold=0.4, temperature=0.1,
+                                                                  sorting_method="soft", sorting_temperature=1e-4, group_size=20)
+        signal.alarm(0)
+        g.update({name + "_dnms_order": o.astype(np.int64)})
+        prob.backward(torch.from_numpy(up))
+        g.update({name + "_dnms_up": up, name + "_dnms_prob": prob.detach().numpy(), name + "_dnms_valid": valid.numpy().astype(np.int64),
+                  name + "_dnms_invalid": invalid.numpy().astype(np.int64), name + "_dnms_grad_s": s2.grad.numpy()})
+    path = os.path.join(ROOT, "tests", "golden", "soft_sort.npz")
+    np.savez_compressed(path, **g)
+    print("wrote", path, "%.1f KiB" % (os.path.getsize(path) / 1024.0))
+
+
 def main():
     ref = ref_shim.load()
+    soft_sort_cases(ref)
     rng = np.random.default_rng(21)
     b7 = np.stack([rng.uniform(-20, 20, 4), rng.uniform(0.5, 2, 4), rng.uniform(5, 60, 4), rng.uniform(1.4, 1.9, 4),
                    rng.uniform(1.3, 1.8, 4), rng.uniform(3, 5, 4), rng.uniform(-np.pi, np.pi, 4)], 1).astype(np.float32)

@@ -227,7 +227,7 @@ def run_train_steps(arm, scene, iters=3, overrides=None, fake_cuda=False, config
     H, W = scene["feat_size"]
     B = len(scene["gts"])
     g = torch.Generator(device="cpu").manual_seed(seed + 1)
-    images = torch.randn((B, 3, H * conf.feat_stride, W * conf.feat_stride), generator=g).to(device)
+    images = torch.randn((B, 3, H * conf.feat_stride, W * conf.feat_stride), generator=g, device="cpu").to(device)
     imobjs = build_imobjs(scene)
     out = {"losses": [], "iter_ms": [], "loss_ms": []}
     probes = {}

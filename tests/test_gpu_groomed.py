@@ -568,3 +568,47 @@ def test_config_c4_batched_2d_images_vs_oracle(G):
     for b in (1, 7, 20):
         s1 = ops.forward_boxes(cuda(sc[b:b + 1]), cuda(boxes[b:b + 1]), _lib.BOX_2D, p)
         assert torch.equal(s1.prob[0], st.prob[b]) and torch.equal(s1.lead[0], st.lead[b]) and torch.equal(s1.counts[0], st.counts[b])
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_soft_sort_kernels_match_reference(case, G):
+    """soft_sort (lib/groomed_nms.py:131-165) on the hand-written kernels (rank by counting, exp / row sums / the column-wise
+    division the reference performs, fp32 FMA GEMM for the N x N x N product) and its analytic backward, against the
+    reference's own forward and autograd (tests/golden/soft_sort.npz, oracle/gen_golden_misc.py).  1e-5 relative."""
+    from conftest import load_golden
+    g = load_golden("soft_sort")
+    sc, iou, temp = g[case + "_scores"], g[case + "_iou"], float(g[case + "_temp"][0])
+    n = len(sc)
+    rng = np.random.default_rng(n)
+    gs, gp, gm = rng.standard_normal(n).astype(np.float32), rng.standard_normal((n, n)).astype(np.float32), rng.standard_normal((n, n)).astype(np.float32)
+    s = cuda(sc).requires_grad_(True)
+    m = cuda(iou).requires_grad_(True)
+    ss, P, sm = G.soft_sort(s, full_matrix=m, temperature=temp)
+    tol = dict(rtol=1e-5, atol=1e-6)
+    assert np.allclose(ss.detach().cpu().numpy(), g[case + "_soft_scores"], **tol)
+    assert np.allclose(P.detach().cpu().numpy(), g[case + "_P"], **tol)
+    assert np.allclose(sm.detach().cpu().numpy(), g[case + "_soft_matrix"], **tol)
+    ((ss * cuda(gs)).sum() + (P * cuda(gp)).sum() + (sm * cuda(gm)).sum()).backward()
+    want_s, want_m = g[case + "_grad_s"], g[case + "_grad_m"]
+    assert np.allclose(m.grad.cpu().numpy(), want_m, rtol=1e-5, atol=1e-5 * np.abs(want_m).max())
+    assert np.allclose(s.grad.cpu().numpy(), want_s, rtol=1e-4, atol=1e-5 * np.abs(want_s).max())
+    # without a matrix: (soft scores, permutation) only
+    ss2, P2 = G.soft_sort(cuda(sc), temperature=temp)
+    assert torch.equal(ss2, ss.detach()) and torch.equal(P2, P.detach())
+    # the soft path of differentiable_nms on pre-sorted inputs (the regime in which the reference's loop terminates)
+    o = g[case + "_dnms_order"]
+    s2 = cuda(sc[o]).requires_grad_(True)
+    v, i, p = G.differentiable_nms(s2, cuda(iou[o][:, o]), nms_threshold=0.4, temperature=0.1, sorting_method="soft", sorting_temperature=1e-4,
+                                   group_size=20)
+    assert v.cpu().tolist() == g[case + "_dnms_valid"].tolist() and sorted(i.cpu().tolist()) == sorted(g[case + "_dnms_invalid"].tolist())
+    assert np.allclose(p.detach().cpu().numpy(), g[case + "_dnms_prob"], rtol=1e-5, atol=1e-6)
+    p.backward(cuda(_dnms_up(n)))
+    want = g[case + "_dnms_grad_s"]
+    assert np.allclose(s2.grad.cpu().numpy(), want, rtol=1e-4, atol=1e-5 * max(1e-9, np.abs(want).max()))
+
+
+def _dnms_up(n):
+    """The upstream gradient oracle/gen_golden_misc.py drew for the dnms-soft case: the 4th draw of rng(n)."""
+    rng = np.random.default_rng(n)
+    rng.standard_normal(n); rng.standard_normal((n, n)); rng.standard_normal((n, n))
+    return rng.standard_normal(n).astype(np.float32)
