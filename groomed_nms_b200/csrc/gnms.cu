@@ -843,11 +843,7 @@ static inline int tall_tiles_per_image(int N, int kQ) {
     return n;
 }
 
-// kPipe (EXPERIMENT, not the default; 483.8 vs 509.4 us and bit-identical in the one run of tools/exp/ab_tall.cu, partial
-// tiles and persistent launch not yet run on a device -- DESIGN.md section 8 lead (a)): the row records of the next
-// 32-row step are loaded before the stores of this one and the store pointers are advanced before, not after, the
-// stores, so that the instructions that follow the stores do not rewrite the registers the queued STG still read.
-template <int kSrc, bool kGen, bool kAffine, int kQ, bool kPacked = false, bool kPipe = false>
+template <int kSrc, bool kGen, bool kAffine, int kQ, bool kPacked = false>
 __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
     typedef typename RecOf<kSrc>::type RecT;
     constexpr int kNF = SoaOf<kSrc>::kFields;
@@ -923,17 +919,12 @@ __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
             }
         };
         RecT rr[4];
-        if constexpr (kPipe) {
-            load_rows(4 * ty, rr);
-            drow -= 32u * (size_t)row_bytes;
-            dcol -= 128;
-        }
 #pragma unroll 1
         for (int h = 0; h < h_end; ++h) {
             const int rl = 32 * h + 4 * ty;
             if (R * kRows + 32 * h >= N) break;
             const bool mirror = (h >> 1) != c;                        // the diagonal 64 x 64 quarter is not mirrored
-            if constexpr (!kPipe) load_rows(rl, rr);
+            load_rows(rl, rr);
             float v[4][4];
             bool unsafe = tile_unsafe;
             if constexpr (kPacked && kSrc == kSrcBox3d) {             // two column boxes per instruction (fp32x2)
@@ -956,11 +947,6 @@ __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) v[r][k] = RecOf<kSrc>::template exact<kGen, kAffine>(rr[r], cr[k]);
             }
-            if constexpr (kPipe) {
-                if (h + 1 < h_end) load_rows(rl + 32, rr);            // next step's rows, before this step's stores
-                drow += 32u * (size_t)row_bytes;
-                dcol += 128;
-            }
             if (full_tile) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
@@ -982,10 +968,8 @@ __global__ void __launch_bounds__(128, 4) tile_tall_kernel(TileArgs A) {
                         }
                     }
             }
-            if constexpr (!kPipe) {
-                drow += 32u * (size_t)row_bytes;
-                dcol += 128;
-            }
+            drow += 32u * (size_t)row_bytes;
+            dcol += 128;
         }
     }
 }

@@ -13,7 +13,11 @@ class backpropAPLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, targets, delta=1.0, positive_label=1, negative_label=0):
         dev_in = logits.device
-        loss, grad = ops.aploss(to_cuda_f32(logits.detach()), to_cuda_f32(targets.detach()))
+        t = to_cuda_f32(targets.detach())
+        if positive_label != 1 or negative_label != 0:
+            # the kernel knows positives as 1, negatives as 0 and everything else as "ignored" (:31,36 compare with the labels)
+            t = torch.where(t == positive_label, torch.ones_like(t), torch.where(t == negative_label, torch.zeros_like(t), -torch.ones_like(t)))
+        loss, grad = ops.aploss(to_cuda_f32(logits.detach()), t)
         ctx.grad = grad.reshape(logits.shape).to(dev_in)
         if bool((targets.max() <= 0).item()) if targets.numel() else True:
             return torch.zeros(1, device=dev_in)                    # reference returns `metric` of shape (1,) (:27-29)

@@ -90,3 +90,16 @@ def test_aploss_golden_and_autograd():
     assert np.allclose(x.grad.cpu().numpy(), g["rand_grad_x1p7"], rtol=1e-4, atol=1e-7)
     z = APLoss()(cuda(g["rand_logits"]), torch.zeros(400, device="cuda"))
     assert z.shape == (1,) and z.item() == 0.0
+
+
+def test_aploss_custom_labels():
+    """positive_label / negative_label (lib/loss/aploss.py:31,36): relabelled targets give the same loss and gradient."""
+    from groomed_nms_b200.lib.loss.aploss import APLoss
+    g = load_golden("aploss")
+    t = cuda(g["rand_targets"])
+    relabelled = torch.where(t == 1, torch.full_like(t, 5.0), torch.where(t == 0, torch.full_like(t, 2.0), torch.full_like(t, -3.0)))
+    x = cuda(g["rand_logits"]).requires_grad_(True)
+    loss = APLoss(positive_label=5, negative_label=2)(x, relabelled)
+    loss.backward()
+    assert np.allclose(loss.item(), g["rand_loss"], rtol=1e-5)
+    assert np.allclose(x.grad.cpu().numpy() * 1.7, g["rand_grad_x1p7"], rtol=1e-4, atol=1e-7)
