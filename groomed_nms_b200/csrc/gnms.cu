@@ -2489,7 +2489,7 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     // The caller wants the overlap matrix AND the leaders can be elected directly: the matrix then comes from the
     // matrix-only tile kernel (no bits, no ranks -- it does not depend on anything else in this call) and the rest of the
     // call is the matrix-free path.
-    if (overlap_out && src != kSrcMatrix && g_direct && g_split_matrix && mode == GNMS_MODE_GROUP_MASK && N <= kElectMaxBoxes &&
+    if (overlap_out && src != kSrcMatrix && g_direct && g_split_matrix && need_groups && N <= kElectMaxBoxes &&
         N <= 128 * kTT && batch < 32768 && p->nms_threshold >= 0.f &&
         (src == kSrcBox2d || !affine || p->nms_threshold >= 0.5f || (generalized && p->nms_threshold > 0.05f))) {
         if (g_stage_mask & 4) {
@@ -2507,7 +2507,8 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     }
     const bool culled = cull_c >= 0.f;
     // direct leader election first (elect_kernel): the mask kernels below then only work for the images it gave up on
-    const bool direct = g_direct && culled && mode == GNMS_MODE_GROUP_MASK && N <= kElectMaxBoxes;
+    // (modes GROUP_MASK and GROUP_NOMASK share the grouping; the per-group solves of the latter gather their overlaps on the fly)
+    const bool direct = g_direct && culled && need_groups && N <= kElectMaxBoxes;
     // rank by counting costs batch * N^2 compares over the whole chip, the per-image radix sort a constant ~10 us
     const bool by_sort = g_rank_by_sort == 1 || (g_rank_by_sort < 0 && (double)batch * N * N >= 10.0 * 4096 * 4096);
     if (g_stage_mask & 1) {

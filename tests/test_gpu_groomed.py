@@ -407,20 +407,29 @@ def test_inverse_modes_random_vs_oracle(G, mode, n, k, gs):
 
 
 @pytest.mark.parametrize("mode", [1, 2])
-def test_inverse_modes_from_boxes_equal_matrix_path(mode):
+@pytest.mark.parametrize("n,k", [(700, 5), (3000, 40)])
+def test_inverse_modes_from_boxes_equal_matrix_path(mode, n, k):
+    """Modes GROUP_NOMASK / NOGROUP from boxes: the grouping of mode B comes from the direct leader election (or, forced, from
+    the all-pairs bitmask) and the triangular solves gather their overlaps on the fly -- all must equal the matrix path; with
+    and without the overlap matrix as an extra output."""
     from groomed_nms_b200 import synthetic, ops, _lib
-    boxes, sc, _ = synthetic.clustered_boxes_2d(700, 5, seed=19, jitter=0.06)
+    boxes, sc, _ = synthetic.clustered_boxes_2d(n, k, seed=19, jitter=0.06)
     bx = cuda(boxes)
     iou = ops.overlap2d(bx, bx)
     p = ops.make_params(group_size=30, group_boxes=(mode == 1), mask_group_boxes=False)
     st1 = ops.forward_matrix(cuda(sc)[None], iou[None], p)
-    st2 = ops.forward_boxes(cuda(sc)[None], bx[None], _lib.BOX_2D, p)
-    for f in ("prob", "lead", "pre", "counts"):
-        assert torch.equal(getattr(st1, f), getattr(st2, f)), f
-    g = torch.randn(1, 700, device="cuda")
+    g = torch.randn(1, n, device="cuda")
     g1, _ = ops.backward(st1, g)
-    g2, _ = ops.backward(st2, g)
-    assert torch.equal(g1, g2)
+    for election in (_lib.ELECT_DIRECT, _lib.ELECT_MASK):
+        for want_matrix in (False, True):
+            ov = torch.empty((1, n, n), device="cuda") if want_matrix else None
+            st2 = ops.forward_boxes(cuda(sc)[None], bx[None], _lib.BOX_2D, p, overlap_out=ov, opts=_lib.launch_opts(election=election))
+            for f in ("prob", "lead", "pre", "counts"):
+                assert torch.equal(getattr(st1, f), getattr(st2, f)), (f, election, want_matrix)
+            if want_matrix:
+                assert torch.equal(ov[0].view(torch.int32), iou.view(torch.int32))
+            g2, _ = ops.backward(st2, g)
+            assert torch.equal(g1, g2)
 
 
 def test_soft_sort_path_runs_and_matches_torch_composite(G):

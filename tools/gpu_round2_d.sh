@@ -1,5 +1,5 @@
 set -x
-python -m pytest tests/test_gpu_groomed.py -x -q -k "soft_sort" 2>&1 | tail -15
+python -m pytest tests/test_gpu_groomed.py tests/test_gpu_classical.py -x -q -k "soft_sort or aploss or inverse_modes or direct" 2>&1 | tail -15
 python -m pytest tests/test_gpu_c5_train_step.py -x -q -s 2>&1 | grep -v "^$" | tail -12
 python - <<'PY'
 import torch, time
