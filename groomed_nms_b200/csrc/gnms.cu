@@ -2486,12 +2486,11 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     const bool tiles = need_groups && src != kSrcMatrix;              // fused overlap + mask tile kernel
     // matrix-free pass: spatial order + culling of tile pairs that provably hold no pair above the threshold
     float cull_c = -1.f;                                               // < 0: culling not applicable
-    // The caller wants the overlap matrix AND the leaders can be elected directly: the matrix then comes from the
-    // matrix-only tile kernel (no bits, no ranks -- it does not depend on anything else in this call) and the rest of the
-    // call is the matrix-free path.
-    if (overlap_out && src != kSrcMatrix && g_direct && g_split_matrix && need_groups && N <= kElectMaxBoxes &&
-        N <= 128 * kTT && batch < 32768 && p->nms_threshold >= 0.f &&
-        (src == kSrcBox2d || !affine || p->nms_threshold >= 0.5f || (generalized && p->nms_threshold > 0.05f))) {
+    // The caller wants the overlap matrix: it comes from the matrix-only tile kernel (no bits, no ranks -- it depends on nothing
+    // else in this call; TMA tensor stores where the matrix layout allows) and the rest of the call is the matrix-free path:
+    // direct leader election where applicable, else the (spatially culled) bits-only tile pass; mode NOGROUP needs neither.
+    // The one-pass kernel that writes matrix and bits together is kept behind GNMS_OPT_ONE_PASS for comparison.
+    if (overlap_out && src != kSrcMatrix && g_split_matrix && batch < 32768) {
         if (g_stage_mask & 4) {
             rc = gnms_launch_overlap_tiles(boxes, src, generalized, affine, N, batch, overlap_out, O, s);
             if (rc) return rc;

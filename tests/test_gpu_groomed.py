@@ -420,10 +420,10 @@ def test_inverse_modes_from_boxes_equal_matrix_path(mode, n, k):
     st1 = ops.forward_matrix(cuda(sc)[None], iou[None], p)
     g = torch.randn(1, n, device="cuda")
     g1, _ = ops.backward(st1, g)
-    for election in (_lib.ELECT_DIRECT, _lib.ELECT_MASK):
+    for election, flags in ((_lib.ELECT_DIRECT, 0), (_lib.ELECT_MASK, 0), (_lib.ELECT_MASK, _lib.OPT_ONE_PASS), (_lib.ELECT_MASK, _lib.OPT_ONE_PASS | _lib.OPT_INLINE_HITS)):
         for want_matrix in (False, True):
             ov = torch.empty((1, n, n), device="cuda") if want_matrix else None
-            st2 = ops.forward_boxes(cuda(sc)[None], bx[None], _lib.BOX_2D, p, overlap_out=ov, opts=_lib.launch_opts(election=election))
+            st2 = ops.forward_boxes(cuda(sc)[None], bx[None], _lib.BOX_2D, p, overlap_out=ov, opts=_lib.launch_opts(election=election, flags=flags))
             for f in ("prob", "lead", "pre", "counts"):
                 assert torch.equal(getattr(st1, f), getattr(st2, f)), (f, election, want_matrix)
             if want_matrix:
