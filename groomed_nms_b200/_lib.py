@@ -17,7 +17,7 @@ sz = ctypes.c_size_t
 
 MAX_BOXES = 8192
 PRUNE = {"linear": 0, "sigmoidal": 1, "soft_nms": 2}
-MODE_GROUP_MASK, MODE_GROUP_NOMASK, MODE_NOGROUP = 0, 1, 2
+MODE_GROUP_MASK, MODE_GROUP_NOMASK, MODE_NOGROUP, MODE_GROUP_MASK_INPUT_TRIL = 0, 1, 2, 3
 KIND_IOU, KIND_INTERSECT = 0, 1
 BOX_2D, BOX_3D_REC = 0, 1
 CMP_GT, CMP_GE, CMP_NLE = 0, 1, 2
@@ -69,6 +69,8 @@ SIGNATURES = {
     "gnms_iou2d_backward_f32": (i32, [vp, i32, vp, i32, vp, i32, vp, vp, vp]),
     "gnms_corners_from_boxes7_f32": (i32, [vp, i64, i32, vp, vp]),
     "gnms_corners_from_boxes7_ex_f32": (i32, [vp, i64, i32, i32, vp, vp]),
+    "gnms_corners_backward_f32": (i32, [vp, i64, i32, i32, vp, vp, vp]),
+    "gnms_iou3d_approx_backward_f32": (i32, [vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "gnms_project_points_f32": (i32, [vp, vp, i64, i32, vp, vp]),
     "gnms_box3d_records_f32": (i32, [vp, i32, vp, i32, vp]),
     "gnms_box3d_records_from_boxes7_f32": (i32, [vp, i64, i32, vp, vp, vp]),

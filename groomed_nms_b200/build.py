@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgroomed_b200.so")
-SOURCES = ["overlap.cu", "gnms.cu", "misc.cu", "head.cu", "lossbranch.cu", "softsort.cu"]
+SOURCES = ["overlap.cu", "gnms.cu", "misc.cu", "head.cu", "lossbranch.cu", "softsort.cu", "grad3d.cu"]
 DEPS = ["common.cuh", "solve.cuh", os.path.join("..", "..", "include", "groomed_nms_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

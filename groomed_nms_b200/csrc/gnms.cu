@@ -1653,6 +1653,7 @@ struct ChainArgs {
     int32_t* n_keep;
     int leaders_only;              // hard NMS: stop after leader election
     int direct;                    // leaders / first suppressors come from elect_kernel (unless it gave up for this image)
+    int tril_input;                // GNMS_MODE_GROUP_MASK_INPUT_TRIL: a member that precedes its leader in INPUT order keeps its score
     int stage;                     // 0: grouping + closed-form rescore + lists (mode GROUP_MASK)
                                    // 1: grouping only, exports the group structure (mode GROUP_NOMASK, before the solve)
                                    // 2: lists only, from pre[] / lead[] already in global memory (after the solve)
@@ -1888,7 +1889,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
             }
             if (v != v) {
                 ld_ = -1;
-            } else {
+            } else if (!(A.tril_input && order_r[pos] < order_r[ld_])) {      // (soft-sort variant: Phi is cut by INPUT position)
                 pv = prune(v, P.pruning_method, P.nms_threshold, P.temperature);
                 dpv = prune_grad(v, pv, P.pruning_method, P.temperature);
             }
@@ -2326,7 +2327,7 @@ static void launch_mask_boxes(dim3 grid, cudaStream_t s, int generalized, int af
 static int check_common(int N, int batch, const gnms_params* p) {
     if (N < 0 || batch < 0 || !p) return GNMS_E_BADARG;
     if (N > GNMS_MAX_BOXES) return GNMS_E_TOOLARGE;
-    if (p->pruning_method < 0 || p->pruning_method > 2 || p->mode < 0 || p->mode > 2 || p->group_size < 0)
+    if (p->pruning_method < 0 || p->pruning_method > 2 || p->mode < 0 || p->mode > GNMS_MODE_GROUP_MASK_INPUT_TRIL || p->group_size < 0)
         return GNMS_E_BADARG;
     return 0;
 }
@@ -2481,7 +2482,8 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     char* ws = reinterpret_cast<char*>(workspace);
     const int NW = (N + 31) / 32;
     int box_stride = src == kSrcBox2d ? 4 : 8;
-    const int mode = p->mode;
+    const bool tril_input = p->mode == GNMS_MODE_GROUP_MASK_INPUT_TRIL;
+    const int mode = tril_input ? GNMS_MODE_GROUP_MASK : p->mode;
     const bool need_groups = mode != GNMS_MODE_NOGROUP;
     const bool tiles = need_groups && src != kSrcMatrix;              // fused overlap + mask tile kernel
     // matrix-free pass: spatial order + culling of tile pairs that provably hold no pair above the threshold
@@ -2621,6 +2623,7 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     A.order = sv.order; A.sorted_scores = sv.sorted_scores; A.prob = prob; A.valid_idx = valid_idx;
     A.invalid_idx = invalid_idx; A.counts = counts; A.lead = sv.lead; A.pval = sv.pval; A.dpval = sv.dpval;
     A.pre = sv.pre; A.slot = slot; A.direct = direct ? 1 : 0;
+    A.p.mode = mode; A.tril_input = tril_input ? 1 : 0;
     if (!(g_stage_mask & 16)) return 0;
     if (mode == GNMS_MODE_GROUP_MASK) {
         A.stage = 0;
@@ -2702,7 +2705,7 @@ extern "C" int gnms_backward_f32(const float* grad_prob, const float* prob, cons
     if (p->sorted_output && !workspace) return GNMS_E_BADARG;
     rc = configure_once();
     if (rc) return rc;
-    if (p->mode != GNMS_MODE_GROUP_MASK) {
+    if (p->mode != GNMS_MODE_GROUP_MASK && p->mode != GNMS_MODE_GROUP_MASK_INPUT_TRIL) {      // (the latter saved pval = 0 where Phi is cut)
         if (!workspace) return GNMS_E_BADARG;                          // holds the group structure / box records
         const WsLayout L = ws_layout(N);
         GNMS_CUDA_TRY(cudaMemsetAsync(grad_scores, 0, (size_t)batch * N * sizeof(float), (cudaStream_t)stream));

@@ -19,12 +19,11 @@ def _needs_autograd(args, kwargs):
 
 
 def _grad_aware(mine, original):
-    """The kernel-backed mirrors of get_corners_of_cuboid / project_3d_points_in_4D_format / iou3d_approximate / intersect /
-    get_volume return plain tensors (no grad_fn); only `iou` and `differentiable_nms` carry an analytic backward.  The
-    reference's composites are differentiable, and its loss does differentiate them when the acceptance-probability
-    target is not detached (lib/loss/rpn_3d.py:663-679 with :1060).  So a call whose inputs require grad goes to the
-    reference's own function (same results, autograd intact); everything else -- in particular every call on the
-    GrooMeD-NMS path, whose overlaps are detached at lib/loss/rpn_3d.py:791 -- goes to the kernels."""
+    """`iou`, `iou3d_approximate`, `get_corners_of_cuboid` and `differentiable_nms` carry an analytic backward of their own (the
+    loss differentiates the first three when the acceptance-probability target is not detached, lib/loss/rpn_3d.py:620,
+    :663-679 with :1060).  The remaining kernel-backed mirrors -- project_3d_points_in_4D_format / intersect / get_volume, which
+    nothing in the reference differentiates directly -- return plain tensors (no grad_fn): a call of those whose inputs require
+    grad goes to the reference's own composite (same results, autograd intact), every other call goes to the kernels."""
     @functools.wraps(original)
     def dispatch(*args, **kwargs):
         if _needs_autograd(args, kwargs):
@@ -35,7 +34,7 @@ def _grad_aware(mine, original):
     return dispatch
 
 
-_HAS_BACKWARD = {"iou"}                 # mirrors that are torch.autograd.Functions themselves
+_HAS_BACKWARD = {"iou", "iou3d_approximate", "get_corners_of_cuboid"}   # mirrors that carry their own analytic backward
 
 
 def install(patch_core=True):

@@ -128,12 +128,21 @@ def iou3d_approximate(corners_3d_b1, corners_3d_b2, mode="list", method="normal"
     they are contiguous fp32 CUDA tensors -- the training loss relies on that quirk (lib/loss/rpn_3d.py:813)."""
     if mode not in ("list", "combinations"):
         raise ValueError('unknown mode {}'.format(mode))
-    no_autograd("lib.core.iou3d_approximate", corners_3d_b1, corners_3d_b2)
     origin = Origin(corners_3d_b1)
     c1, c2 = to_cuda_f32(corners_3d_b1), to_cuda_f32(corners_3d_b2)
     if c1.dim() == 2:
         c1, c2 = c1.unsqueeze(0), c2.unsqueeze(0)
     gen = method == "generalized"
+    if torch.is_grad_enabled() and (c1.requires_grad or c2.requires_grad):
+        # differentiable call (lib/loss/rpn_3d.py:663-679): analytic backward from private copies of the corners, then the
+        # reference's own in-place Y <- Z write as a torch op, so that autograd sees the mutation exactly as in the reference
+        # (and refuses a leaf that requires grad with torch's own error, as the reference does)
+        bev, i3d = ops.Iou3dApproxFunction.apply(c1, c2, mode == "list", gen)
+        for c in ((corners_3d_b1,) if corners_3d_b1 is corners_3d_b2 else (corners_3d_b1, corners_3d_b2)):
+            if isinstance(c, torch.Tensor):
+                v = c.unsqueeze(0) if c.dim() == 2 else c
+                v[:, 1, :] = v[:, 2, :]
+        return origin.back(bev), origin.back(i3d)
 
     def records(c, orig):
         inplace = isinstance(orig, torch.Tensor) and orig.is_cuda and orig.dtype == torch.float32 and c.is_contiguous() \

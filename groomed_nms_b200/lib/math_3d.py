@@ -12,12 +12,16 @@ def get_corners_of_cuboid(x3d, y3d, z3d, w3d, h3d, l3d, ry3d, iou_3d_convention=
     length on x for corners {1,2,3,4}, height on y for {2,3,6,7}, width on z for {3,4,5,6}).  The reference's own False
     branch only broadcasts for N in {1, 4} in torch (`corners[:, 0, [1,2,3,4]] = l3d`, :422-424) and is missing from its
     numpy twin (:450-477); this gives the vertex order that branch documents, for any N and both container types.
-    torch in -> torch out on the same device, numpy in -> numpy out."""
-    no_autograd("lib.math_3d.get_corners_of_cuboid", x3d, y3d, z3d, w3d, h3d, l3d, ry3d)
+    torch in -> torch out on the same device, numpy in -> numpy out.  Differentiable like the reference's composite."""
     origin = Origin(x3d)
     cols = [to_cuda_f32(v).reshape(-1) for v in (x3d, y3d, z3d, w3d, h3d, l3d, ry3d)]
     boxes7 = torch.stack(cols, dim=1)
-    out = ops.corners_from_boxes7(boxes7, iou_3d_convention=bool(iou_3d_convention))
+    if torch.is_grad_enabled() and boxes7.requires_grad:
+        # analytic backward wrt all seven parameters (the acceptance-probability target differentiates this call,
+        # lib/loss/rpn_3d.py:663-679)
+        out = ops.CornersFunction.apply(boxes7, bool(iou_3d_convention))
+    else:
+        out = ops.corners_from_boxes7(boxes7, iou_3d_convention=bool(iou_3d_convention))
     return origin.back(out, keep_np_dtype=True)
 
 

@@ -155,13 +155,87 @@ def overlap3d_list(rec_a, rec_b, generalized=False, affine=False):
     return bev, o3d
 
 
+class CornersFunction(torch.autograd.Function):
+    """get_corners_of_cuboid with its analytic backward (the reference's composite of cos / sin / bmm is differentiable, and
+    the acceptance-probability target differentiates it: lib/loss/rpn_3d.py:663-679)."""
+
+    @staticmethod
+    def forward(ctx, boxes7, iou_3d_convention):
+        ctx.convention = bool(iou_3d_convention)
+        b = _f32c(boxes7)
+        ctx.save_for_backward(b)
+        return corners_from_boxes7(b, ctx.convention)
+
+    @staticmethod
+    def backward(ctx, g):
+        (b,) = ctx.saved_tensors
+        return corners_backward(b, g, ctx.convention), None
+
+
+def corners_backward(boxes7, grad_corners, iou_3d_convention=True):
+    """dL/d(x, y, z, w, h, l, ry) [N,7] from dL/dcorners [N,3,8]."""
+    b, g = _f32c(boxes7), _f32c(grad_corners)
+    N = b.shape[0]
+    gb = torch.empty((N, 7), dtype=torch.float32, device=b.device)
+    if N:
+        with torch.cuda.device(b.device):
+            check(_lib.load().gnms_corners_backward_f32(_p(b), b.stride(0), N, int(bool(iou_3d_convention)), _p(g), _p(gb),
+                                                        _stream(b.device)), "gnms_corners_backward_f32")
+    return gb
+
+
+class Iou3dApproxFunction(torch.autograd.Function):
+    """iou3d_approximate (lib/core.py:305-421) -> (iou_bev, iou_3d) with the analytic backward wrt both corner sets.
+    Works on private copies of the corners: the reference's in-place Y<-Z write (:379-380) is replayed by the caller as an
+    ordinary torch op so that autograd records it exactly as it does in the reference."""
+
+    @staticmethod
+    def forward(ctx, corners_a, corners_b, list_mode, generalized):
+        a, b = _f32c(corners_a.detach()).clone(), _f32c(corners_b.detach()).clone()
+        ctx.list_mode, ctx.generalized = bool(list_mode), bool(generalized)
+        ctx.save_for_backward(a, b)
+        ra, rb = box3d_records(a), box3d_records(b)
+        if list_mode:
+            bev, o3d = overlap3d_list(ra, rb, generalized=generalized)
+        else:
+            bev, o3d = overlap3d(ra, rb, True, True, generalized=generalized)
+        return bev, o3d
+
+    @staticmethod
+    def backward(ctx, g_bev, g_3d):
+        a, b = ctx.saved_tensors
+        ga, gb = iou3d_approx_backward(a, b, g_bev, g_3d, ctx.list_mode, ctx.generalized)
+        return ga, gb, None, None
+
+
+def iou3d_approx_backward(corners_a, corners_b, g_bev, g_3d, list_mode, generalized):
+    """(dL/dcorners_a [M,3,8], dL/dcorners_b [N,3,8]) from dL/diou_bev and / or dL/diou_3d ([M,N], or [M] in list mode)."""
+    a, b = _f32c(corners_a), _f32c(corners_b)
+    M, N = a.shape[0], b.shape[0]
+    ga, gb = torch.zeros_like(a), torch.zeros_like(b)
+    if g_bev is None and g_3d is None:
+        return ga, gb
+    g_bev = _f32c(g_bev) if g_bev is not None else None
+    g_3d = _f32c(g_3d) if g_3d is not None else None
+    if M and N:
+        with torch.cuda.device(a.device):
+            check(_lib.load().gnms_iou3d_approx_backward_f32(_p(a), M, _p(b), N, int(bool(list_mode)), int(bool(generalized)),
+                                                             _p(g_bev), _p(g_3d), _p(ga), _p(gb), _stream(a.device)),
+                  "gnms_iou3d_approx_backward_f32")
+    return ga, gb
+
+
 # ------------------------------------------------------------------------------------------------ GrooMeD-NMS
 def make_params(nms_threshold=0.4, pruning_method="linear", temperature=0.01, valid_box_prob_threshold=0.3,
-                return_sorted_prob=False, group_boxes=True, mask_group_boxes=True, group_size=100):
+                return_sorted_prob=False, group_boxes=True, mask_group_boxes=True, group_size=100, tril_in_input_order=False):
     if pruning_method not in _lib.PRUNE:
         raise NotImplementedError("Pruning method not implemented!")      # lib/groomed_nms.py:177
     mode = _lib.MODE_GROUP_MASK if (group_boxes and mask_group_boxes) else (
         _lib.MODE_GROUP_NOMASK if group_boxes else _lib.MODE_NOGROUP)
+    if tril_in_input_order:
+        if mode != _lib.MODE_GROUP_MASK:
+            raise NotImplementedError("tril_in_input_order exists for group_boxes=True, mask_group_boxes=True only")
+        mode = _lib.MODE_GROUP_MASK_INPUT_TRIL
     p = Params()
     p.nms_threshold = float(nms_threshold)
     p.temperature = float(temperature)
@@ -229,7 +303,7 @@ def forward_matrix(scores, iou, params, n_per_image=None, private_ws=None, opts=
         raise RuntimeError("groomed_nms_b200: at most %d boxes per image (got %d)" % (MAX_BOXES, N))
     dev = scores.device
     if private_ws is None:
-        private_ws = bool(params.sorted_output) or params.mode != _lib.MODE_GROUP_MASK
+        private_ws = bool(params.sorted_output) or params.mode in (_lib.MODE_GROUP_NOMASK, _lib.MODE_NOGROUP)
     st = _alloc_state(dev, B, N, params, n_per_image, private_ws)
     st.iou = iou
     if B and N:
@@ -254,7 +328,7 @@ def forward_boxes(scores, boxes, box_kind, params, generalized=False, affine=Fal
         raise RuntimeError("groomed_nms_b200: at most %d boxes per image (got %d)" % (MAX_BOXES, N))
     dev = scores.device
     if private_ws is None:
-        private_ws = bool(params.sorted_output) or params.mode != _lib.MODE_GROUP_MASK
+        private_ws = bool(params.sorted_output) or params.mode in (_lib.MODE_GROUP_NOMASK, _lib.MODE_NOGROUP)
     st = _alloc_state(dev, B, N, params, n_per_image, private_ws)
     if B and N:
         with torch.cuda.device(dev):
@@ -299,6 +373,31 @@ class GroomedNMSFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_prob, g_valid, g_invalid, g_counts):
         gs, gi = backward(ctx.st, g_prob.unsqueeze(0), need_grad_iou=ctx.need_gi)
+        return gs[0], (gi[0] if gi is not None else None), None
+
+
+class GroomedNMSInputOrderFunction(torch.autograd.Function):
+    """GroomedNMSFunction whose probabilities come back in INPUT order (prob[i] belongs to input box i) instead of score-rank
+    order: the form the reference's sorting_method="soft" path returns (its rows are never re-sorted, lib/groomed_nms.py:42-45).
+    With return_sorted_prob the vector is sorted by value and the two coincide."""
+
+    @staticmethod
+    def forward(ctx, scores, iou, params):
+        st = forward_matrix(scores.detach().unsqueeze(0), iou.detach().unsqueeze(0), params)
+        ctx.st = st
+        ctx.need_gi = iou.requires_grad
+        ctx.mark_non_differentiable(st.valid_idx, st.invalid_idx, st.counts)
+        if params.sorted_output:
+            return st.prob[0], st.valid_idx[0], st.invalid_idx[0], st.counts[0]
+        prob_in = torch.empty_like(st.prob[0])
+        prob_in[st.order[0].long()] = st.prob[0]
+        return prob_in, st.valid_idx[0], st.invalid_idx[0], st.counts[0]
+
+    @staticmethod
+    def backward(ctx, g_prob, g_valid, g_invalid, g_counts):
+        st = ctx.st
+        g = g_prob if st.params.sorted_output else g_prob[st.order[0].long()]
+        gs, gi = backward(st, g.unsqueeze(0), need_grad_iou=ctx.need_gi)
         return gs[0], (gi[0] if gi is not None else None), None
 
 

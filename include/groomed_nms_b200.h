@@ -9,9 +9,9 @@
  * Reference interfaces replaced (paths relative to abhi1kumar/groomed_nms @ ad10dbb):
  *   lib/core.py:178-243   intersect            -> gnms_overlap2d_f32 / gnms_overlap2d_list_f32 (kind = INTERSECT)
  *   lib/core.py:480-532   iou                  -> gnms_overlap2d_f32 / gnms_overlap2d_list_f32 (kind = IOU)
- *   lib/math_3d.py:364-435 get_corners_of_cuboid -> gnms_corners_from_boxes7_f32
+ *   lib/math_3d.py:364-435 get_corners_of_cuboid -> gnms_corners_from_boxes7_f32 (+ gnms_corners_backward_f32 for its autograd)
  *   lib/core.py:354-388,434-477 get_volume / remove_rotation_in_boxes / per-box min-max -> gnms_box3d_records_f32
- *   lib/core.py:305-421   iou3d_approximate    -> gnms_overlap3d_f32 / gnms_overlap3d_list_f32
+ *   lib/core.py:305-421   iou3d_approximate    -> gnms_overlap3d_f32 / gnms_overlap3d_list_f32 (+ gnms_iou3d_approx_backward_f32)
  *   lib/groomed_nms.py:10-129 differentiable_nms (+ :167-189 pruning_function, :208-270 get_groups,
  *                         :272-336 indices_copy folded away) -> gnms_forward_f32 / gnms_backward_f32 and the
  *                         matrix-free gnms_forward_boxes_f32
@@ -52,6 +52,11 @@ extern "C" {
 #define GNMS_MODE_GROUP_MASK   0   /* group_boxes=True,  mask_group_boxes=True  (shipped default) */
 #define GNMS_MODE_GROUP_NOMASK 1   /* group_boxes=True,  mask_group_boxes=False: per-group (I+Phi_g)^-1 */
 #define GNMS_MODE_NOGROUP      2   /* group_boxes=False: full (I+Phi)^-1 */
+/* Mode GROUP_MASK with the lower-triangular cut of Phi (torch.tril, lib/groomed_nms.py:72) taken by INPUT position instead of by
+ * score rank: a member that comes before its leader in the input keeps its score.  This is what the reference computes on its
+ * sorting_method="soft" path (:42-45), where the scores it groups by (re-sorted inside get_groups, :213) need not be in the
+ * order of the rows of the soft-sorted matrix.  `prob` is still returned in score-rank order. */
+#define GNMS_MODE_GROUP_MASK_INPUT_TRIL 3
 
 /* 2D overlap kinds */
 #define GNMS_KIND_IOU       0      /* lib/core.py:480 */
@@ -139,6 +144,11 @@ int gnms_corners_from_boxes7_f32(const float* boxes7, int64_t ld, int N, float* 
  * order of the reference (:405-426: length on x for corners {1,2,3,4}, height on y for {2,3,6,7}, width on z for {3,4,5,6}). */
 int gnms_corners_from_boxes7_ex_f32(const float* boxes7, int64_t ld, int N, int iou_3d_convention, float* corners, void* stream);
 
+/* Backward of the corners above (the reference's composite of cos / sin / bmm is differentiable and the acceptance-probability
+ * target differentiates it, lib/loss/rpn_3d.py:663-679): grad_corners[N,3,8] -> grad_boxes7[N,7] (x,y,z,w,h,l,ry), fully written. */
+int gnms_corners_backward_f32(const float* boxes7, int64_t ld, int N, int iou_3d_convention, const float* grad_corners,
+                              float* grad_boxes7, void* stream);
+
 /* lib/math_3d.py:47-72 project_3d_points_in_4D_format: out[4,n] = p2[4,4] @ [pts;1] (pts is [3,n] when
  * pad_ones!=0, else [4,n]); rows 0,1 divided by row 2 where |row 2| > 1e-2. */
 int gnms_project_points_f32(const float* p2, const float* pts, int64_t n, int pad_ones, float* out, void* stream);
@@ -162,6 +172,16 @@ int gnms_overlap3d_batched_f32(const float* rec, int N, int batch, float* out_3d
                                void* stream);
 int gnms_overlap3d_list_f32(const float* rec_a, const float* rec_b, int M, float* out_bev, float* out_3d,
                             int generalized, int affine, void* stream);
+
+/* Backward of iou3d_approximate (lib/core.py:305-421) wrt both corner sets, from the UNMUTATED corners the forward read:
+ * corners_a[M,3,8], corners_b[N,3,8]; g_bev / g_3d are dL/diou_bev and dL/diou_3d, [M,N] row-major (combinations) or [M]
+ * (list_mode != 0, M == N), either may be NULL; grad_corners_a[M,3,8] / grad_corners_b[N,3,8] are fully written.
+ * Sub-gradients follow torch: clamp(x, 0) passes on x >= 0, binary min / max and max(0, x) split ties evenly, the min / max
+ * over the corners of one box send the gradient to the first extremal corner. */
+int gnms_iou3d_approx_backward_f32(const float* corners_a, int M, const float* corners_b, int N, int list_mode, int generalized,
+                                   const float* g_bev, const float* g_3d, float* grad_corners_a, float* grad_corners_b,
+                                   void* stream);
+
 /* The batched self-overlaps with per-call launch options (matrix_kernel, tiles_per_cta, flags). */
 int gnms_overlap2d_batched_ex_f32(const float* boxes, int N, int batch, float* out, const gnms_launch_opts* opts, void* stream);
 int gnms_overlap3d_batched_ex_f32(const float* rec, int N, int batch, float* out_3d, int generalized, int affine,

@@ -171,6 +171,111 @@ def get_corners_of_cuboid(x3d, y3d, z3d, w3d, h3d, l3d, ry3d, iou_3d_convention=
     return out
 
 
+def get_corners_of_cuboid_backward(boxes7, grad_corners, iou_3d_convention=True):
+    """Vector-Jacobian product of get_corners_of_cuboid (lib/math_3d.py:364-435): dL/dcorners [N,3,8] -> dL/d(x,y,z,w,h,l,ry)
+    [N,7].  Pinned by tests/golden/grad3d.npz (the reference's autograd)."""
+    b, g = _f32(boxes7).astype(np.float64), _f32(grad_corners).astype(np.float64)
+    hx = np.full(8, -0.5); hx[[1, 3, 5, 6] if iou_3d_convention else [1, 2, 3, 4]] = 0.5
+    hy = np.full(8, -0.5); hy[[2, 3, 6, 7]] = 0.5
+    hz = np.full(8, -0.5); hz[[4, 5, 6, 7] if iou_3d_convention else [3, 4, 5, 6]] = 0.5
+    w, h, l, ry = b[:, 3], b[:, 4], b[:, 5], b[:, 6]
+    cs, sn = np.cos(ry)[:, None], np.sin(ry)[:, None]
+    px, pz = hx[None] * l[:, None], hz[None] * w[:, None]
+    ga, gb_, gc = g[:, 0], g[:, 1], g[:, 2]
+    out = np.empty((b.shape[0], 7))
+    out[:, 0], out[:, 1], out[:, 2] = ga.sum(1), gb_.sum(1), gc.sum(1)
+    out[:, 3] = (hz[None] * (sn * ga + cs * gc)).sum(1)
+    out[:, 4] = (hy[None] * gb_).sum(1)
+    out[:, 5] = (hx[None] * (cs * ga - sn * gc)).sum(1)
+    out[:, 6] = (ga * (-sn * px + cs * pz) + gc * (-cs * px - sn * pz)).sum(1)
+    return out.astype(F32)
+
+
+def iou3d_approximate_backward(corners_3d_b1, corners_3d_b2, g_bev, g_3d, mode="list", method="normal"):
+    """Vector-Jacobian product of iou3d_approximate (lib/core.py:305-421) wrt both (unmutated) corner sets, with torch's
+    sub-gradients: clamp(x, 0) of intersect (:210-218) passes on x >= 0; binary min / max and max(zeros, x) (:376, :430) split
+    ties evenly; the min / max over the corners of a box go to the first extremal corner.  Pinned by tests/golden/grad3d.npz."""
+    ca, cb = _f32(corners_3d_b1).astype(np.float64), _f32(corners_3d_b2).astype(np.float64)
+    comb = mode == "combinations"
+    M, N = ca.shape[0], cb.shape[0]
+    shape = (M, N) if comb else (M,)
+    gbev = np.zeros(shape) if g_bev is None else np.asarray(g_bev, np.float64)
+    g3 = np.zeros(shape) if g_3d is None else np.asarray(g_3d, np.float64)
+
+    def ext(c):
+        e = {}
+        for name, row, idx in (("x8", 0, slice(None)), ("y", 1, slice(None)), ("z8", 2, slice(None)), ("bx", 0, BEV_CORNERS), ("bz", 2, BEV_CORNERS)):
+            v = c[:, row, :][:, idx]
+            ids = np.arange(8)[idx]
+            e[name + "lo"], e[name + "hi"] = v.min(1), v.max(1)
+            e["i" + name + "lo"], e["i" + name + "hi"] = (row, ids[v.argmin(1)]), (row, ids[v.argmax(1)])
+        return e
+    ea, eb = ext(ca), ext(cb)
+    A = (lambda v: v[:, None]) if comb else (lambda v: v)
+    B = (lambda v: v[None, :]) if comb else (lambda v: v)
+    names = ["x8lo", "x8hi", "ylo", "yhi", "z8lo", "z8hi", "bxlo", "bxhi", "bzlo", "bzhi"]
+    Ga, Gb = {k: np.zeros(shape) for k in names}, {k: np.zeros(shape) for k in names}
+
+    def d_min(ka, kb, g):
+        a, b = np.broadcast_arrays(A(ea[ka]), B(eb[kb]))
+        Ga[ka] += g * np.where(a < b, 1.0, np.where(a == b, 0.5, 0.0)); Gb[kb] += g * np.where(b < a, 1.0, np.where(a == b, 0.5, 0.0))
+
+    def d_max(ka, kb, g):
+        a, b = np.broadcast_arrays(A(ea[ka]), B(eb[kb]))
+        Ga[ka] += g * np.where(a > b, 1.0, np.where(a == b, 0.5, 0.0)); Gb[kb] += g * np.where(b > a, 1.0, np.where(a == b, 0.5, 0.0))
+    relu_b = lambda x: np.where(x > 0, 1.0, np.where(x == 0, 0.5, 0.0))
+    relu_c = lambda x: (x >= 0).astype(np.float64)
+    dw = np.minimum(A(ea["bxhi"]), B(eb["bxhi"])) - np.maximum(A(ea["bxlo"]), B(eb["bxlo"]))
+    dh = np.minimum(A(ea["bzhi"]), B(eb["bzhi"])) - np.maximum(A(ea["bzlo"]), B(eb["bzlo"]))
+    iw, ih = np.maximum(dw, 0), np.maximum(dh, 0)
+    ibev = iw * ih
+    area = lambda e: (e["bxhi"] - e["bxlo"]) * (e["bzhi"] - e["bzlo"])
+    U2 = A(area(ea)) + B(area(eb)) - ibev
+    dy = np.minimum(A(ea["yhi"]), B(eb["yhi"])) - np.maximum(A(ea["ylo"]), B(eb["ylo"]))
+    yint = np.maximum(dy, 0)
+    vol = lambda e: (e["x8hi"] - e["x8lo"]) * (e["yhi"] - e["ylo"]) * (e["z8hi"] - e["z8lo"])
+    V = A(vol(ea)) + B(vol(eb))
+    i3 = ibev * yint
+    un = V - i3
+    with np.errstate(divide="ignore", invalid="ignore"):
+        g_un, g_i3 = -g3 * i3 / (un * un), g3 / un
+        if method == "generalized":
+            hx = np.maximum(A(ea["bxhi"]), B(eb["bxhi"])) - np.minimum(A(ea["bxlo"]), B(eb["bxlo"]))
+            hy = np.maximum(A(ea["yhi"]), B(eb["yhi"])) - np.minimum(A(ea["ylo"]), B(eb["ylo"]))
+            hz = np.maximum(A(ea["bzhi"]), B(eb["bzhi"])) - np.minimum(A(ea["bzlo"]), B(eb["bzlo"]))
+            xh, yh, zh = np.maximum(hx, 0), np.maximum(hy, 0), np.maximum(hz, 0)
+            vh = xh * yh * zh
+            g_vh = -g3 * un / (vh * vh)
+            g_un = g_un + g3 / vh
+        g_V = g_un
+        g_i3 = g_i3 - g_un
+        g_ibev = g_i3 * yint + gbev / U2
+        g_U2 = -gbev * ibev / (U2 * U2)
+    g_ibev = g_ibev - g_U2
+    g_dw, g_dh = g_ibev * ih * relu_c(dw), g_ibev * iw * relu_c(dh)
+    d_min("bxhi", "bxhi", g_dw); d_max("bxlo", "bxlo", -g_dw); d_min("bzhi", "bzhi", g_dh); d_max("bzlo", "bzlo", -g_dh)
+    for G, e, S in ((Ga, ea, A), (Gb, eb, B)):
+        G["bxhi"] += g_U2 * S(e["bzhi"] - e["bzlo"]); G["bxlo"] -= g_U2 * S(e["bzhi"] - e["bzlo"])
+        G["bzhi"] += g_U2 * S(e["bxhi"] - e["bxlo"]); G["bzlo"] -= g_U2 * S(e["bxhi"] - e["bxlo"])
+        dx_, dy_, dz_ = S(e["x8hi"] - e["x8lo"]), S(e["yhi"] - e["ylo"]), S(e["z8hi"] - e["z8lo"])
+        G["x8hi"] += g_V * dy_ * dz_; G["x8lo"] -= g_V * dy_ * dz_
+        G["yhi"] += g_V * dx_ * dz_; G["ylo"] -= g_V * dx_ * dz_
+        G["z8hi"] += g_V * dx_ * dy_; G["z8lo"] -= g_V * dx_ * dy_
+    g_dy = g_i3 * ibev * relu_b(dy)
+    d_min("yhi", "yhi", g_dy); d_max("ylo", "ylo", -g_dy)
+    if method == "generalized":
+        gx, gy, gz = g_vh * yh * zh * relu_b(hx), g_vh * xh * zh * relu_b(hy), g_vh * xh * yh * relu_b(hz)
+        d_max("bxhi", "bxhi", gx); d_min("bxlo", "bxlo", -gx); d_max("yhi", "yhi", gy); d_min("ylo", "ylo", -gy)
+        d_max("bzhi", "bzhi", gz); d_min("bzlo", "bzlo", -gz)
+    out_a, out_b = np.zeros_like(ca), np.zeros_like(cb)
+    for out, G, e, axis in ((out_a, Ga, ea, 1), (out_b, Gb, eb, 0)):
+        for k in names:
+            row, idx = e["i" + k]
+            tot = G[k].sum(axis=axis) if comb else G[k]
+            np.add.at(out, (np.arange(out.shape[0]), row, idx), tot)
+    return out_a.astype(F32), out_b.astype(F32)
+
+
 def project_3d_points_in_4D_format(p2, points, pad_ones=False):
     """lib/math_3d.py:47-72: p2[4,4] @ [pts;1], x,y divided by z where |z| > 1e-2."""
     p2 = _f32(p2)

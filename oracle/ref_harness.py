@@ -215,6 +215,10 @@ def run_train_steps(arm, scene, iters=3, overrides=None, fake_cuda=False, config
         torch.cuda.manual_seed_all(seed)
         torch.backends.cudnn.deterministic = True
         torch.backends.cudnn.benchmark = False
+        # true fp32 in both arms: with TF32 convolutions (torch's default) a 1e-7 difference in the gradient that enters the
+        # backbone is re-rounded to 10 mantissa bits layer after layer and the two arms drift apart by 1e-4 of the largest entry
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
     model_mod = importlib.import_module("models." + conf.model)
     core = importlib.import_module("lib.core")
     net = model_mod.build(conf, "test")                   # 'test' = no download of pretrained weights; then train mode as the script does

@@ -218,3 +218,65 @@ def test_corners_kitti_vertex_order_gpu():
     want = O.get_corners_of_cuboid(*[b[:, i] for i in range(7)], iou_3d_convention=False)
     got_np = M.get_corners_of_cuboid(*[b[:, i] for i in range(7)], iou_3d_convention=False)
     assert isinstance(got_np, np.ndarray) and np.allclose(got_np, want, rtol=1e-6, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ autograd of the 3D feeders
+def _rel(a, b):
+    return np.abs(a - b).max() / max(1e-12, np.abs(b).max())
+
+
+def test_corners_autograd_matches_reference(L):
+    """get_corners_of_cuboid backward (gnms_corners_backward_f32) vs the reference's autograd (golden grad3d.npz)."""
+    _, m3d = L
+    g = load_golden("grad3d")
+    t = [cuda(g["corners_boxes7"][:, i].copy()).requires_grad_(True) for i in range(7)]
+    c = m3d.get_corners_of_cuboid(*t)
+    assert c.requires_grad and np.allclose(c.detach().cpu().numpy(), g["corners_out"], rtol=1e-6, atol=1e-5)
+    (c * cuda(g["corners_up"])).sum().backward()
+    got = np.stack([v.grad.cpu().numpy() for v in t], 1)
+    assert _rel(got, g["corners_grad"]) < 1e-6
+    # the other vertex order: same kernel, other sign table -- against the oracle's VJP
+    from oracle import groomed_oracle as O
+    t = [cuda(g["corners_boxes7"][:, i].copy()).requires_grad_(True) for i in range(7)]
+    (m3d.get_corners_of_cuboid(*t, iou_3d_convention=False) * cuda(g["corners_up"])).sum().backward()
+    want = O.get_corners_of_cuboid_backward(g["corners_boxes7"], g["corners_up"], iou_3d_convention=False)
+    assert _rel(np.stack([v.grad.cpu().numpy() for v in t], 1), want) < 1e-6
+
+
+@pytest.mark.parametrize("mode", ["list", "combinations"])
+@pytest.mark.parametrize("method", ["normal", "generalized"])
+def test_iou3d_approximate_autograd_matches_reference(L, mode, method):
+    """iou3d_approximate backward (gnms_iou3d_approx_backward_f32) wrt both corner sets vs the reference's autograd."""
+    core, _ = L
+    g = load_golden("grad3d")
+    k = "pairs_%s_%s_" % (mode, method)
+    la = cuda(g["pairs_a"]).requires_grad_(True)
+    lb = cuda(g["pairs_b"][:64 if mode == "combinations" else 96]).requires_grad_(True)
+    with pytest.raises(RuntimeError):                                       # a leaf that requires grad: torch refuses the in-place
+        core.iou3d_approximate(la, lb, mode=mode, method=method)            # Y <- Z write, exactly as under the reference
+    ca, cb = la * 1.0, lb * 1.0
+    bev, i3d = core.iou3d_approximate(ca, cb, mode=mode, method=method)
+    assert bits_equal(bev.detach().cpu().numpy(), g[k + "bev"]) and bits_equal(i3d.detach().cpu().numpy(), g[k + "3d"])
+    assert torch.equal(ca[:, 1], ca[:, 2]) and torch.equal(cb[:, 1], cb[:, 2])            # the reference's mutation (lib/core.py:379-380)
+    ((bev * cuda(g[k + "up_bev"])).sum() + (i3d * cuda(g[k + "up_3d"])).sum()).backward()
+    assert _rel(la.grad.cpu().numpy(), g[k + "grad_a"]) < 1e-5 and _rel(lb.grad.cpu().numpy(), g[k + "grad_b"]) < 1e-5
+
+
+def test_acceptance_target_chain_autograd_matches_reference(L):
+    """parameters -> corners -> iou3d_approximate(list) as lib/loss/rpn_3d.py:663-679 differentiates it, real cuboids (every
+    per-box min / max is a tie), and the NMS-style self call whose mutated corners are used afterwards."""
+    core, m3d = L
+    g = load_golden("grad3d")
+    ta = [cuda(g["chain_a"][:, i].copy()).requires_grad_(True) for i in range(7)]
+    tb = [cuda(g["chain_b"][:, i].copy()).requires_grad_(True) for i in range(7)]
+    _, i3d = core.iou3d_approximate(m3d.get_corners_of_cuboid(*ta), m3d.get_corners_of_cuboid(*tb))
+    assert np.allclose(i3d.detach().cpu().numpy(), g["chain_3d"], rtol=1e-4, atol=1e-6)
+    (i3d * cuda(g["chain_up"])).sum().backward()
+    assert _rel(np.stack([v.grad.cpu().numpy() for v in ta], 1), g["chain_grad_a"]) < 1e-4
+    assert _rel(np.stack([v.grad.cpu().numpy() for v in tb], 1), g["chain_grad_b"]) < 1e-4
+    ts = [cuda(g["corners_boxes7"][:, i].copy()).requires_grad_(True) for i in range(7)]
+    cs = m3d.get_corners_of_cuboid(*ts)
+    bev, i3d = core.iou3d_approximate(cs, cs, mode="combinations", method="generalized")
+    assert np.allclose(cs.detach().cpu().numpy(), g["self_corners_after"], rtol=1e-6, atol=1e-5)
+    ((bev * cuda(g["self_up_bev"])).sum() + (i3d * cuda(g["self_up_3d"])).sum() + (cs * cuda(g["corners_up"])).sum()).backward()
+    assert _rel(np.stack([v.grad.cpu().numpy() for v in ts], 1), g["self_grad"]) < 1e-4
