@@ -480,8 +480,7 @@ def run_ours(args, rank, world):
         stages["forward_boxes+matrix_out(all kernels, one stream)"] = time_stage(torch, pl.stage_forward, st, it)
         # the kernels of that forward one by one (debug stage mask of the library: the same launches, in isolation)
         keep = pl.forward_opts
-        for bit, name in ((_lib.STAGE_RANK, "sort_kernel+rank_kernel"), (_lib.STAGE_SPATIAL, "spatial_kernel"),
-                          (_lib.STAGE_ELECT, "elect_kernel(+zero/list of failed images)"),
+        for bit, name in ((_lib.STAGE_RANK, "sort_kernel+rank_kernel"), (_lib.STAGE_ELECT, "elect2_kernel(batched leader election)"),
                           (_lib.STAGE_TILES, "tile_kernel(matrix only)"), (_lib.STAGE_CHAIN, "chain_kernel")):
             # the same launches one at a time: a per-call stage mask (gnms_launch_opts), tiles_per_cta as in the step
             pl.forward_opts = _lib.launch_opts(matrix_kernel=matrix_kernel, stage_mask=bit, flags=keep.flags,

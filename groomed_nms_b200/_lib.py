@@ -38,7 +38,7 @@ class LaunchOpts(ctypes.Structure):
 
 MATRIX_KERNEL_AUTO, MATRIX_KERNEL_DIRECT, MATRIX_KERNEL_TMA = 0, 1, 2
 RANK_AUTO, RANK_COUNT, RANK_SORT = 0, 1, 2
-ELECT_AUTO, ELECT_DIRECT, ELECT_MASK = 0, 1, 2
+ELECT_AUTO, ELECT_DIRECT, ELECT_MASK, ELECT_BATCHED = 0, 1, 2, 3
 STAGE_RANK, STAGE_SPATIAL, STAGE_TILES, STAGE_EARLIER, STAGE_CHAIN, STAGE_ELECT = 1, 2, 4, 8, 16, 32
 OPT_SCALAR_MATH, OPT_INLINE_HITS, OPT_ONE_PASS = 1, 2, 4
 

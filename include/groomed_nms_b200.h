@@ -97,8 +97,9 @@ const char* gnms_error_string(int rc);
 #define GNMS_RANK_COUNT  1            /* rank by counting (small batches) */
 #define GNMS_RANK_SORT   2            /* per-image radix sort in shared memory */
 #define GNMS_ELECT_AUTO   0
-#define GNMS_ELECT_DIRECT 1           /* leaders elected directly from the boxes where applicable (default) */
+#define GNMS_ELECT_DIRECT 1           /* leaders elected directly from the boxes, one per step (round-1 kernel, kept for comparison) */
 #define GNMS_ELECT_MASK   2           /* always through the all-pairs suppression bitmask */
+#define GNMS_ELECT_BATCHED 3          /* leaders elected from the boxes, up to 32 per step (what AUTO picks where applicable) */
 /* stage bits of gnms_launch_opts.stage_mask (profiling: run only some kernels of a forward) */
 #define GNMS_STAGE_RANK     1u
 #define GNMS_STAGE_SPATIAL  2u

@@ -420,7 +420,8 @@ def test_inverse_modes_from_boxes_equal_matrix_path(mode, n, k):
     st1 = ops.forward_matrix(cuda(sc)[None], iou[None], p)
     g = torch.randn(1, n, device="cuda")
     g1, _ = ops.backward(st1, g)
-    for election, flags in ((_lib.ELECT_DIRECT, 0), (_lib.ELECT_MASK, 0), (_lib.ELECT_MASK, _lib.OPT_ONE_PASS), (_lib.ELECT_MASK, _lib.OPT_ONE_PASS | _lib.OPT_INLINE_HITS)):
+    for election, flags in ((_lib.ELECT_BATCHED, 0), (_lib.ELECT_DIRECT, 0), (_lib.ELECT_MASK, 0), (_lib.ELECT_MASK, _lib.OPT_ONE_PASS),
+                            (_lib.ELECT_MASK, _lib.OPT_ONE_PASS | _lib.OPT_INLINE_HITS)):
         for want_matrix in (False, True):
             ov = torch.empty((1, n, n), device="cuda") if want_matrix else None
             st2 = ops.forward_boxes(cuda(sc)[None], bx[None], _lib.BOX_2D, p, overlap_out=ov, opts=_lib.launch_opts(election=election, flags=flags))
@@ -537,7 +538,7 @@ def test_direct_election_mixed_batch_and_fallback(kind):
     ref = ops.forward_matrix(cuda(sc), iou, p, n_per_image=npi)
     n_lead = [(int((ref.lead[b, :n] == torch.arange(n, device="cuda")).sum())) for b, n in enumerate(ns)]
     assert n_lead[0] < 100 and n_lead[1] > 384 and n_lead[5] > 384      # both routes are really exercised
-    for direct in (_lib.ELECT_DIRECT, _lib.ELECT_MASK):
+    for direct in (_lib.ELECT_BATCHED, _lib.ELECT_DIRECT, _lib.ELECT_MASK):
         st = ops.forward_boxes(cuda(sc), dev_data, kw["box_kind"], p, kw.get("generalized", False), kw.get("affine", False),
                                n_per_image=npi, opts=_lib.launch_opts(election=direct))
         torch.cuda.synchronize()
@@ -550,6 +551,50 @@ def test_direct_election_mixed_batch_and_fallback(kind):
         g1, _ = ops.backward(ref, up)
         g2, _ = ops.backward(st, up)
         assert torch.allclose(g1, g2, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("kind", ["2d", "3d"])
+def test_batched_election_queue_overflow_and_odd_sizes(kind):
+    """elect2_kernel (up to 32 leaders per step) on inputs built to break its bookkeeping: boxes piled on one spot so that
+    nearly every (box, leader) pair passes the gap bound but few exceed the threshold -- the pair queue overflows and steps are
+    redone with fewer leaders -- at sizes that are not multiples of 32 / 1024, ragged, against the matrix path bit for bit."""
+    from groomed_nms_b200 import _lib, ops
+    rng = np.random.default_rng(5)
+    N = 4096
+    ns = [4096, 3001, 1025, 33, 4095]
+    sc = np.zeros((len(ns), N), np.float32)
+    if kind == "2d":
+        data = np.zeros((len(ns), N, 4), np.float32)
+        for b in range(len(ns)):
+            c = rng.uniform(0, 260 + 60 * b, (N, 2)); wh = rng.uniform(60, 140, (N, 2))
+            data[b] = np.concatenate([c - wh / 2, c + wh / 2], 1)
+            sc[b] = (rng.uniform(0.05, 1.0, N) + np.arange(N) * 1e-7).astype(np.float32)
+        dev = cuda(data)
+        iou = torch.stack([ops.overlap2d(dev[b], dev[b]) for b in range(len(ns))])
+        kw = dict(box_kind=_lib.BOX_2D, generalized=False, affine=False)
+    else:
+        recs = []
+        for b in range(len(ns)):
+            b7 = np.stack([rng.uniform(-4, 4 + b, N), 1.6 + 0.3 * rng.standard_normal(N), rng.uniform(10, 18 + b, N),
+                           1.6 + 0.2 * rng.standard_normal(N), 1.5 + 0.1 * rng.standard_normal(N), 4 + 0.5 * rng.standard_normal(N),
+                           rng.uniform(-np.pi, np.pi, N)], 1).astype(np.float32)
+            sc[b] = (rng.uniform(0.05, 1.0, N) + np.arange(N) * 1e-7).astype(np.float32)
+            recs.append(ops.box3d_records(ops.corners_from_boxes7(cuda(b7))))
+        dev = torch.stack(recs)
+        iou = torch.stack([ops.overlap3d(r, r, False, True, generalized=True, affine=True)[1] for r in recs])
+        kw = dict(box_kind=_lib.BOX_3D_REC, generalized=True, affine=True)
+    npi = torch.tensor(ns, dtype=torch.int32, device="cuda")
+    for thr, gs in ((0.4, 100), (0.7, 3)):
+        p = ops.make_params(nms_threshold=thr, group_size=gs)
+        ref = ops.forward_matrix(cuda(sc), iou, p, n_per_image=npi)
+        st = ops.forward_boxes(cuda(sc), dev, kw["box_kind"], p, kw["generalized"], kw["affine"], n_per_image=npi,
+                               opts=_lib.launch_opts(election=_lib.ELECT_BATCHED))
+        torch.cuda.synchronize()
+        for f in ("order", "lead", "prob", "pre", "counts"):
+            assert torch.equal(getattr(ref, f), getattr(st, f)), (thr, f)
+        for b in range(len(ns)):
+            nv = int(ref.counts[b, 0])
+            assert torch.equal(ref.valid_idx[b, :nv], st.valid_idx[b, :nv])
 
 
 def test_config_c4_batched_2d_images_vs_oracle(G):

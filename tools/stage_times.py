@@ -38,13 +38,14 @@ def main():
     ap.add_argument("--n", type=int, default=4096)
     ap.add_argument("--rank-by-sort", type=int, default=-1, help="-1 library heuristic, 0 counting kernel, 1 per-image radix sort")
     ap.add_argument("--tile-queue", type=int, default=1, help="1: hits go through a shared-memory queue drained by the whole CTA; 0: inline loop")
+    ap.add_argument("--election", type=int, default=0, help="0 library heuristic, 1 direct leader election, 2 suppression-bit route")
     args = ap.parse_args()
     lib = _lib.load()
     rank_method = {-1: _lib.RANK_AUTO, 0: _lib.RANK_COUNT, 1: _lib.RANK_SORT}[args.rank_by_sort]
     base_flags = 0 if args.tile_queue else _lib.OPT_INLINE_HITS
 
     def opts(mask=0):
-        return _lib.launch_opts(rank_method=rank_method, stage_mask=mask, flags=base_flags)
+        return _lib.launch_opts(rank_method=rank_method, election=args.election, stage_mask=mask, flags=base_flags)
     dev = torch.device("cuda", 0)
     B, N = args.images, args.n
     params = ops.make_params()
