@@ -459,7 +459,10 @@ def run_ours(args, rank, world):
     e2e_blocking_s = time_host(lambda: runner.run_host(hb, hs), lambda: None)
     pipe = HostPipeline(B, N, dev, params, depth=args.e2e_depth, keep_cap=512, grad_on_device=True)
     pipe.set_grad(torch.from_numpy(grads).to(dev))
-    e2e_s = time_host(lambda: pipe.submit(hb, hs), pipe.drain)
+    # host-side timing of a copy-bound pipeline is at the mercy of whatever else the box's host does: two takes, both reported
+    # (e2e.samples), the faster one is the value
+    e2e_takes = [time_host(lambda: pipe.submit(hb, hs), pipe.drain) for _ in range(2)]
+    e2e_s = min(e2e_takes)
     # the same calls with the kernels left out: what the PCIe link of this box allows for this call pattern
     copies_s = time_host(lambda: pipe.submit(hb, hs, copies_only=True), pipe.drain)
     # round-1 call pattern for comparison: the upstream gradient crosses PCIe too and keep lists are int64 [B, N]
@@ -526,7 +529,7 @@ def run_ours(args, rank, world):
                              if args.path == "materialised" else "matrix-free path: no N^2 HBM traffic; inputs are O(N)",
                        "parallelism": "per-image shard, %d rank(s), no data-path collective" % world},
             "e2e": {"value": boxes_per_step * e2e_steps / e2e_s, "unit": "boxes/s", "h2d_bytes_per_step": runner.h2d_bytes,
-                    "d2h_bytes_per_step": runner.d2h_bytes, "api": "groomed_nms_b200.hostapi.HostPipeline.submit/drain (pinned host buffers, %d slots: copies of one call overlap the kernels of the next; fused matrix-free pipeline: boxes and scores in; probabilities, score gradients, int32 keep lists [B,512] and counts out; the upstream gradient dL/dprob is device-resident)" % args.e2e_depth,
+                    "d2h_bytes_per_step": runner.d2h_bytes, "samples": [boxes_per_step * e2e_steps / t for t in e2e_takes], "api": "groomed_nms_b200.hostapi.HostPipeline.submit/drain (pinned host buffers, %d slots: copies of one call overlap the kernels of the next; fused matrix-free pipeline: boxes and scores in; probabilities, score gradients, int32 keep lists [B,512] and counts out; the upstream gradient dL/dprob is device-resident)" % args.e2e_depth,
                     "h2d_GBps_per_rank": runner.h2d_bytes * e2e_steps / e2e_s / 1e9,
                     "with_host_gradient_and_int64_keep_lists": {"value": boxes_per_step * e2e_steps / e2e_r1_s, "h2d_bytes_per_step": r1_bytes[0], "d2h_bytes_per_step": r1_bytes[1]},
                     "steps_timed": e2e_steps,
