@@ -66,6 +66,7 @@ SIGNATURES = {
     "gnms_error_string": (ctypes.c_char_p, [i32]),
     "gnms_overlap2d_f32": (i32, [vp, i32, vp, i32, vp, i64, i32, vp]),
     "gnms_overlap2d_list_f32": (i32, [vp, vp, i32, vp, i32, vp]),
+    "gnms_overlap2d_f64": (i32, [vp, i64, i32, vp, i64, i32, i32, i32, i32, vp, vp]),
     "gnms_iou2d_backward_f32": (i32, [vp, i32, vp, i32, vp, i32, vp, vp, vp]),
     "gnms_corners_from_boxes7_f32": (i32, [vp, i64, i32, vp, vp]),
     "gnms_corners_from_boxes7_ex_f32": (i32, [vp, i64, i32, i32, vp, vp]),

@@ -422,6 +422,43 @@ extern "C" int gnms_aploss_f32(const float* logits, const float* targets, int n,
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- 2D overlaps in fp64
+// The reference's iou / intersect keep the dtype of their inputs: float64 numpy arrays (the detections of the inference
+// path, lib/rpn_util.py:1295) are compared with the NMS threshold in float64.  One thread per output, the numpy branch's
+// operation order (lib/core.py:196-206, 498-515), separately rounded.
+__global__ void __launch_bounds__(256) overlap2d_f64_kernel(const double* __restrict__ a, int64_t ld_a, int M, const double* __restrict__ b,
+                                                            int64_t ld_b, int N, int kind, int list_mode, int area_f32, double* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = list_mode ? M : (int64_t)M * N;
+    if (t >= total) return;
+    const int i = list_mode ? (int)t : (int)(t / N), j = list_mode ? (int)t : (int)(t % N);
+    const double* pa = a + (int64_t)i * ld_a;
+    const double* pb = b + (int64_t)j * ld_b;
+    const double iw = fmax(__dsub_rn(fmin(pa[2], pb[2]), fmax(pa[0], pb[0])), 0.0);
+    const double ih = fmax(__dsub_rn(fmin(pa[3], pb[3]), fmax(pa[1], pb[1])), 0.0);
+    const double inter = __dmul_rn(iw, ih);
+    if (kind == GNMS_KIND_INTERSECT) { out[t] = inter; return; }
+    // a side that was float32 in the caller's hands has its area computed in float32 (numpy / torch keep float32 for
+    // float32 x float32 and promote only where the two sides meet; the coordinates are exact in both types)
+    const double aa = (area_f32 & 1) ? (double)__fmul_rn(__fsub_rn((float)pa[2], (float)pa[0]), __fsub_rn((float)pa[3], (float)pa[1]))
+                                     : __dmul_rn(__dsub_rn(pa[2], pa[0]), __dsub_rn(pa[3], pa[1]));
+    const double ab = (area_f32 & 2) ? (double)__fmul_rn(__fsub_rn((float)pb[2], (float)pb[0]), __fsub_rn((float)pb[3], (float)pb[1]))
+                                     : __dmul_rn(__dsub_rn(pb[2], pb[0]), __dsub_rn(pb[3], pb[1]));
+    out[t] = __ddiv_rn(inter, __dsub_rn(__dadd_rn(aa, ab), inter));
+}
+
+extern "C" int gnms_overlap2d_f64(const double* a, int64_t ld_a, int M, const double* b, int64_t ld_b, int N, int kind, int list_mode,
+                                  int area_f32, double* out, void* stream) {
+    if (M < 0 || N < 0 || ld_a < 4 || ld_b < 4 || (kind != GNMS_KIND_IOU && kind != GNMS_KIND_INTERSECT) || (list_mode && M != N))
+        return GNMS_E_BADARG;
+    if (M == 0 || N == 0) return 0;
+    if (!a || !b || !out) return GNMS_E_BADARG;
+    const int64_t total = list_mode ? M : (int64_t)M * N;
+    overlap2d_f64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, ld_a, M, b, ld_b, N, kind, list_mode, area_f32, out);
+    GNMS_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" size_t gnms_targets_overlaps_workspace_bytes(int M, int G) {
     if (M <= 0 || G <= 0) return 256;
     const size_t nb = (size_t)((M + kTgtThreads - 1) / kTgtThreads);

@@ -40,6 +40,21 @@ def to_cuda_f32(x):
     return x.float() if x.dtype != torch.float32 else x
 
 
+def is_f64(x):
+    """float64 numpy array or tensor: the reference's functions compute in the dtype they are given."""
+    return (isinstance(x, np.ndarray) and x.dtype == np.float64) or (isinstance(x, torch.Tensor) and x.dtype == torch.float64)
+
+
+def to_cuda_f64(x):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(x)
+    if not x.is_cuda:
+        x = x.to(device())
+    return x.double() if x.dtype != torch.float64 else x
+
+
 def no_autograd(name, *tensors):
     """The kernel behind `name` has no backward: refuse inputs that require grad instead of silently dropping it."""
     if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):

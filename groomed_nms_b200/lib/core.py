@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from .. import _lib, ops
-from ._util import Origin, no_autograd, to_cuda_f32
+from ._util import Origin, is_f64, no_autograd, to_cuda_f32, to_cuda_f64
 from ._util import device as _device
 
 
@@ -24,6 +24,13 @@ def intersect(box_a, box_b, mode='combinations', data_type=None):
     _check_type(data_type, box_a)
     no_autograd("lib.core.intersect", box_a, box_b)
     origin = Origin(box_a)
+    if mode not in ('combinations', 'list'):
+        raise ValueError('unknown mode {}'.format(mode))                       # lib/core.py:243
+    if is_f64(box_a) or is_f64(box_b):                                        # float64 on either side: float64 arithmetic (type promotion, as the reference)
+        a, b = to_cuda_f64(box_a), to_cuda_f64(box_b)
+        if mode == 'combinations':
+            return origin.back(ops.overlap2d_f64(b, a, _lib.KIND_INTERSECT))
+        return origin.back(ops.overlap2d_f64(a, b, _lib.KIND_INTERSECT, list_mode=True))
     a, b = to_cuda_f32(box_a), to_cuda_f32(box_b)
     if mode == 'combinations':
         out = ops.overlap2d(b[:, :4], a[:, :4], _lib.KIND_INTERSECT)
@@ -40,6 +47,14 @@ def iou(box_a, box_b, mode='combinations', data_type=None):
     as a transposed view (:508); this returns the same values contiguous."""
     _check_type(data_type, box_a)
     origin = Origin(box_a)
+    if mode not in ('combinations', 'list'):
+        raise ValueError('unknown mode {}'.format(mode))                       # lib/core.py:532
+    if (is_f64(box_a) or is_f64(box_b)) and not (torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in (box_a, box_b))):
+        # float64 in, float64 arithmetic (as the reference: lib/rpn_util.py:1295 thresholds float64 IoUs); the analytic backward
+        # exists in fp32 only, so double tensors that require grad take the fp32 route below
+        a, b = to_cuda_f64(box_a), to_cuda_f64(box_b)
+        af32 = (0 if is_f64(box_a) else 1) | (0 if is_f64(box_b) else 2)     # a float32 side keeps float32 areas (type promotion)
+        return origin.back(ops.overlap2d_f64(a, b, _lib.KIND_IOU, list_mode=(mode == 'list'), area_f32=af32))
     a, b = to_cuda_f32(box_a), to_cuda_f32(box_b)
     if mode == 'combinations':
         out = ops.Overlap2dFunction.apply(a[:, :4], b[:, :4], False)

@@ -35,6 +35,11 @@ def nms_after_detection(coords_2d, scores, coords_3d, coords_3d_raw, cls_pred, t
     dev = scores.device if torch.is_tensor(scores) and scores.is_cuda else device()
     use_diff = bool(get('use_nms_in_loss', False)) if use_differentiable_nms is None else bool(use_differentiable_nms)
     overlap_in_nms = get('overlap_in_nms', "2d")
+    # the reference's detections are float64 numpy arrays here: it orders them by their float64 scores and thresholds float64
+    # 2D IoUs rounded to float32 (differentiable_nms converts its inputs, lib/groomed_nms.py:34-36).  Same here when given float64.
+    f64_in = (coords_2d.dtype == torch.float64) if torch.is_tensor(coords_2d) else (np.asarray(coords_2d).dtype == np.float64)
+    sc_key = _to_dev(scores, dev, torch.float64).reshape(-1) if f64_in else None
+    c2_64 = _to_dev(coords_2d, dev, torch.float64) if f64_in else None
     c2 = _to_dev(coords_2d, dev); sc = _to_dev(scores, dev).reshape(-1)
     c3 = _to_dev(coords_3d, dev); c3r = _to_dev(coords_3d_raw, dev)
     cls = _to_dev(cls_pred, dev).reshape(-1, 1); trk = _to_dev(tracker, dev).reshape(-1, 1)
@@ -44,7 +49,7 @@ def nms_after_detection(coords_2d, scores, coords_3d, coords_3d_raw, cls_pred, t
         keep = torch.zeros((0,), dtype=torch.int64, device=dev)
         return (out.cpu().numpy(), keep.cpu().numpy()) if as_numpy else (out, keep)
     # :1260-1266  descending score order (numpy's argsort on -score is not stable; ties keep the lower index here)
-    sorted_inds = torch.sort(sc, descending=True, stable=True)[1]
+    sorted_inds = torch.sort(sc_key if f64_in else sc, descending=True, stable=True)[1]
     n_pre = min(int(get('nms_topN_pre', 3000)), A)                                              # :1286-1290
     sorted_inds = sorted_inds[:n_pre]
     if use_diff:                                                                                # :1293-1320
@@ -55,13 +60,22 @@ def nms_after_detection(coords_2d, scores, coords_3d, coords_3d_raw, cls_pred, t
                                  bool(get('diff_nms_mask_group_boxes', True)), get('diff_nms_group_size', 100))
         s_in = sc[sel].contiguous()[None]
         box2d = c2[sel].contiguous()
-        if overlap_in_nms == "2d":                                                              # :1297-1298
+        iou2d_64 = None
+        if f64_in and overlap_in_nms in ("2d", "product"):                                      # :1295 in float64
+            b64 = c2_64[sel].contiguous()
+            iou2d_64 = ops.overlap2d_f64(b64, b64)
+        if overlap_in_nms == "2d" and iou2d_64 is not None:
+            st = ops.forward_matrix(s_in, iou2d_64.float()[None], params)
+        elif overlap_in_nms == "2d":                                                            # :1297-1298
             st = ops.forward_boxes(s_in, box2d[None], _lib.BOX_2D, params)
         else:
             rec = ops.box3d_records(ops.corners_from_boxes7(c3r[sel][:, :7].contiguous()), mutate_input=False)   # :1303-1311
             if overlap_in_nms == "3d":                                                          # :1314-1315
                 st = ops.forward_boxes(s_in, rec[None], _lib.BOX_3D_REC, params, generalized=True, affine=True)
-            else:                                                                               # product :1316-1317
+            elif iou2d_64 is not None:                                                          # product :1316-1317, float64 x float32
+                ov3 = ops.overlap3d(rec, rec, False, True, generalized=True, affine=True)[1]
+                st = ops.forward_matrix(s_in, (iou2d_64 * ov3.double()).float()[None], params)
+            else:
                 iou2d = ops.overlap2d(box2d, box2d)
                 ov = ops.overlap3d(rec, rec, False, True, generalized=True, affine=True, mul2d=iou2d)[1]
                 st = ops.forward_matrix(s_in, ov[None], params)
@@ -73,7 +87,12 @@ def nms_after_detection(coords_2d, scores, coords_3d, coords_3d_raw, cls_pred, t
         keep = k[:int(nk.item())].long()
         num_boxes = n_pre
     rows = sorted_inds[:num_boxes][keep]                                                        # :1337-1340
-    out = torch.cat([c2[rows], sc[rows, None], cls[rows], c3[rows], trk[rows]], dim=1)
+    if f64_in:                                                                                  # float64 detections stay float64 (np.hstack promotes)
+        d = torch.float64
+        out = torch.cat([c2_64[rows], sc_key[rows, None], _to_dev(cls_pred, dev, d).reshape(-1, 1)[rows], _to_dev(coords_3d, dev, d)[rows],
+                         _to_dev(tracker, dev, d).reshape(-1, 1)[rows]], dim=1)
+    else:
+        out = torch.cat([c2[rows], sc[rows, None], cls[rows], c3[rows], trk[rows]], dim=1)
     return (out.cpu().numpy(), keep.cpu().numpy()) if as_numpy else (out, keep)
 
 

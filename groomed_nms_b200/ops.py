@@ -59,6 +59,23 @@ def overlap2d_list(box_a, box_b, kind=_lib.KIND_IOU):
     return out
 
 
+def overlap2d_f64(box_a, box_b, kind=_lib.KIND_IOU, list_mode=False, area_f32=0):
+    """fp64 IoU / intersection of float64 CUDA boxes ([M, >=4] x [N, >=4], unit column stride) -> [M,N] or [M] float64.
+    area_f32: bit 0 / 1 = side a / b was float32 before promotion (its areas are rounded to float32)."""
+    _require_cuda(box_a, "box_a")
+    a = box_a if box_a.stride(-1) == 1 else box_a.contiguous()
+    b = box_b if box_b.stride(-1) == 1 else box_b.contiguous()
+    M, N = a.shape[0], b.shape[0]
+    if list_mode and M != N:
+        raise ValueError("list mode needs the same number of boxes")
+    out = torch.empty((M,) if list_mode else (M, N), dtype=torch.float64, device=a.device)
+    if M and N:
+        with torch.cuda.device(a.device):
+            check(_lib.load().gnms_overlap2d_f64(_p(a), a.stride(0), M, _p(b), b.stride(0), N, kind, int(bool(list_mode)), int(area_f32), _p(out),
+                                                 _stream(a.device)), "gnms_overlap2d_f64")
+    return out
+
+
 class Overlap2dFunction(torch.autograd.Function):
     """iou() with autograd (the reference's iou is a differentiable torch composite; the detection loss
     back-propagates through the list mode, lib/loss/rpn_3d.py:620)."""

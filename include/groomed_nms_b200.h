@@ -131,6 +131,14 @@ int gnms_overlap2d_f32(const float* a, int M, const float* b, int N, float* out,
 /* "list" mode: out[i] = overlap(a_i, b_i). */
 int gnms_overlap2d_list_f32(const float* a, const float* b, int M, float* out, int kind, void* stream);
 
+/* The same in fp64 for float64 inputs (the reference's functions keep the dtype of their inputs; its inference path compares
+ * float64 IoUs with the NMS threshold, lib/rpn_util.py:1295): a[M,*] / b[N,*] with row strides ld_a / ld_b >= 4 doubles;
+ * out is [M,N] row-major (combinations: out[i,j] = overlap(a_i, b_j)) or [M] (list_mode != 0, M == N).
+ * area_f32: bit 0 / bit 1 set = side a / b was float32 in the caller's hands (mixed calls such as lib/rpn_util.py:448): its box
+ * areas are then rounded to float32 as numpy / torch type promotion does, everything else is float64. */
+int gnms_overlap2d_f64(const double* a, int64_t ld_a, int M, const double* b, int64_t ld_b, int N, int kind, int list_mode,
+                       int area_f32, double* out, void* stream);
+
 /* Backward of the IoU above (the reference's iou is a differentiable torch composite, lib/core.py:480-532, and
  * the detection loss differentiates its list mode, lib/loss/rpn_3d.py:620).  g is [M,N] (combinations, ld = N)
  * or [M] (list_mode!=0, then N must equal M); grad_a[M,4] / grad_b[N,4] are fully written.  min/max ties split the

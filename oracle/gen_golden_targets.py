@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/targets_overlaps.npz by running the UNMODIFIED reference
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/targets_overlaps.npz and iou2d_f64.npz by running the UNMODIFIED reference
 (lib/core.py iou / iou_ign, numpy branch, exactly as lib/rpn_util.py:439-461 compute_targets calls them) on CPU in the
 build container.  Inputs mirror the call site's dtypes: rois float32 (network anchors), ground truths float64.
 
@@ -43,6 +43,23 @@ def main():
         print(tag, ols.dtype, ols.shape, ols_ign.dtype)
     path = os.path.join(ROOT, "tests", "golden", "targets_overlaps.npz")
     np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+    # iou / intersect on float64 and mixed float32 / float64 numpy inputs (the dtypes of lib/rpn_util.py:448 and :1295)
+    rng = np.random.default_rng(64)
+
+    def boxes(m, dt):
+        c = rng.uniform(0, 500, (m, 2)); wh = rng.uniform(5, 200, (m, 2))
+        return np.concatenate([c - wh / 2, c + wh / 2], 1).astype(dt)
+    g = {"a64": boxes(57, np.float64), "b64": boxes(57, np.float64), "a32": boxes(57, np.float32), "b32": boxes(57, np.float32)}
+    g["a64"][3] = g["b64"][5]                                                      # an exact match and a zero-area pair (0 / 0)
+    g["a64"][7, 2:] = g["a64"][7, :2]; g["b64"][7] = g["a64"][7]
+    for ka, kb in (("a64", "b64"), ("a32", "b64"), ("a64", "b32")):
+        for mode in ("combinations", "list"):
+            with np.errstate(invalid="ignore", divide="ignore"):
+                g["iou_%s_%s_%s" % (ka, kb, mode)] = ref.core.iou(g[ka], g[kb], mode=mode)
+                g["inter_%s_%s_%s" % (ka, kb, mode)] = ref.core.intersect(g[ka], g[kb], mode=mode)
+    path = os.path.join(ROOT, "tests", "golden", "iou2d_f64.npz")
+    np.savez_compressed(path, **g)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 

@@ -69,6 +69,31 @@ def iou(box_a, box_b, mode="combinations"):
 BEV_CORNERS = [2, 3, 6, 7]                                             # lib/core.py:383-384
 
 
+def overlap2d_f64(box_a, box_b, mode="combinations", kind="iou"):
+    """iou / intersect on float64 or mixed float32 / float64 inputs (lib/core.py:196-206, 498-515, numpy branch): everything in
+    float64 except the box areas of a float32 side, which numpy / torch type promotion keep in float32.  Returns [M,N] for iou
+    and [N,M] for intersect in combinations mode, like the reference; [M] in list mode."""
+    a, b = np.asarray(box_a), np.asarray(box_b)
+    A, B = a.astype(np.float64), b.astype(np.float64)
+    if mode == "combinations":
+        A_, B_ = A[:, None, :], B[None, :, :]
+    elif mode == "list":
+        A_, B_ = A, B
+    else:
+        raise ValueError("unknown mode {}".format(mode))
+    iw = np.maximum(np.minimum(A_[..., 2], B_[..., 2]) - np.maximum(A_[..., 0], B_[..., 0]), 0.0)
+    ih = np.maximum(np.minimum(A_[..., 3], B_[..., 3]) - np.maximum(A_[..., 1], B_[..., 1]), 0.0)
+    inter = iw * ih
+    if kind == "intersect":
+        return inter.T if mode == "combinations" else inter
+    area = lambda x: ((x[:, 2] - x[:, 0]) * (x[:, 3] - x[:, 1])).astype(np.float64)      # in x's own dtype, then promoted
+    aa, ab = area(a), area(b)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if mode == "combinations":
+            return inter / ((aa[:, None] + ab[None, :]) - inter)
+        return inter / ((aa + ab) - inter)
+
+
 def get_volume(corners_3d):
     """lib/core.py:434-451: prod over (x,y,z) of max-min over the 8 corners, ((dx*dy)*dz)."""
     c = _f32(corners_3d)

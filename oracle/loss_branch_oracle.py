@@ -75,13 +75,15 @@ def inference_site(coords_2d, scores, coords_3d, coords_3d_raw, cls_pred, tracke
     """lib/rpn_util.py:1258-1341 composed from the pinned pieces -> (aboxes rows as the reference stacks them, keep_inds).
     Pinned against the reference's own im_detect_3d by tests/golden/inference_site_ref.npz (tests/test_oracle_detect_ref.py).
     corners: optionally the CUDA path's corners of the first 500 sorted boxes (parity is defined from the corners onward)."""
-    order = O.stable_sort_desc(scores.astype(F32))[:min(topn_pre, len(scores))]          # :1260-1290
+    f64 = coords_2d.dtype == np.float64              # float64 detections: float64 score order and float64 2D IoUs, rounded to float32
+    #                                                  only where differentiable_nms converts its inputs (lib/groomed_nms.py:34-36)
+    order = (np.argsort(-scores, kind="stable") if f64 else O.stable_sort_desc(scores.astype(F32)))[:min(topn_pre, len(scores))]   # :1260-1290
     if use_diff:                                                                         # :1293-1320
         sel = order[:max_boxes]
         box2d = coords_2d[sel].astype(F32)
-        iou2d = O.iou(box2d, box2d)
+        iou2d = O.overlap2d_f64(coords_2d[sel], coords_2d[sel]) if f64 else O.iou(box2d, box2d)
         if overlap_in_nms == "2d":
-            ov = iou2d
+            ov = iou2d.astype(F32)
         else:
             if corners is None:
                 r = coords_3d_raw[sel].astype(F32)
@@ -100,4 +102,4 @@ def inference_site(coords_2d, scores, coords_3d, coords_3d_raw, cls_pred, tracke
         base = order
     rows = base[keep]
     out = np.concatenate([coords_2d[rows], scores[rows, None], cls_pred[rows, None], coords_3d[rows], tracker[rows, None]], 1)
-    return out.astype(F32), keep
+    return out.astype(np.float64 if f64 else F32), keep

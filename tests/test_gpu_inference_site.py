@@ -76,3 +76,21 @@ def test_inference_site_matches_reference_run(name):
                                     c["pre_tracker"][:n].astype(np.float32), c["conf"])
     assert keep.tolist() == c["keep"].tolist()
     assert np.array_equal(out, c["aboxes_out"].astype(np.float32))
+
+
+@pytest.mark.parametrize("overlap", ["2d", "product"])
+def test_float64_detections_follow_the_reference_dtypes(overlap):
+    """float64 detections (what numpy promotion hands the reference at lib/rpn_util.py:1295): float64 score order, 2D IoUs in
+    float64 rounded to float32 where differentiable_nms converts its inputs, float64 rows out."""
+    from groomed_nms_b200 import ops
+    from groomed_nms_b200.lib.rpn_util import nms_after_detection
+    from oracle import loss_branch_oracle as LO
+    c2, scores, c3, raw, cls_pred, trk = _detections(23, 1500)
+    c2 = c2.astype(np.float64) * (1.0 + 1e-9); scores = scores.astype(np.float64)
+    scores[40] = scores[41] * (1.0 + 1e-12)                                  # equal in float32, ordered in float64
+    conf = dict(use_nms_in_loss=True, overlap_in_nms=overlap, nms_thres=0.4, nms_topN_pre=3000, diff_nms_temperature=0.1)
+    out, keep = nms_after_detection(c2, scores, c3, raw, cls_pred, trk, conf)
+    order = np.argsort(-scores, kind="stable")[:500]
+    corners = ops.corners_from_boxes7(cuda(raw[order])).cpu().numpy()
+    want, want_keep = LO.inference_site(c2, scores, c3, raw, cls_pred, trk, True, overlap_in_nms=overlap, temperature=0.1, corners=corners)
+    assert out.dtype == np.float64 and keep.tolist() == want_keep.tolist() and np.array_equal(out, want)

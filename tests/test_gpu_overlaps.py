@@ -280,3 +280,24 @@ def test_acceptance_target_chain_autograd_matches_reference(L):
     assert np.allclose(cs.detach().cpu().numpy(), g["self_corners_after"], rtol=1e-6, atol=1e-5)
     ((bev * cuda(g["self_up_bev"])).sum() + (i3d * cuda(g["self_up_3d"])).sum() + (cs * cuda(g["corners_up"])).sum()).backward()
     assert _rel(np.stack([v.grad.cpu().numpy() for v in ts], 1), g["self_grad"]) < 1e-4
+
+
+def test_iou2d_float64_and_mixed_dtypes_match_reference(L):
+    """float64 (and mixed float32 / float64) inputs are computed in float64 like the reference's type promotion does
+    (lib/rpn_util.py:448, :1295): bit-exact against golden iou2d_f64.npz, numpy and torch containers."""
+    core, _ = L
+    g = load_golden("iou2d_f64")
+
+    def same(got, want):
+        got = got.cpu().numpy() if isinstance(got, torch.Tensor) else got
+        return got.dtype == np.float64 and got.shape == want.shape and np.array_equal(np.isnan(got), np.isnan(want)) \
+            and np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])
+    for ka, kb in (("a64", "b64"), ("a32", "b64"), ("a64", "b32")):
+        for mode in ("combinations", "list"):
+            assert same(core.iou(g[ka], g[kb], mode=mode), g["iou_%s_%s_%s" % (ka, kb, mode)]), (ka, kb, mode)
+            assert same(core.intersect(g[ka], g[kb], mode=mode), g["inter_%s_%s_%s" % (ka, kb, mode)]), (ka, kb, mode)
+            ta, tb = torch.from_numpy(g[ka]).cuda(), torch.from_numpy(g[kb]).cuda()
+            assert same(core.iou(ta, tb, mode=mode), g["iou_%s_%s_%s" % (ka, kb, mode)])
+    # a [N,5] detections array sliced like lib/rpn_util.py:1295 (non-contiguous rows)
+    dets = np.concatenate([g["a64"], np.ones((57, 1))], 1)
+    assert same(core.iou(dets[:, 0:4], dets[:, 0:4]), core.iou(g["a64"], g["a64"]))
