@@ -1975,6 +1975,7 @@ __global__ void __launch_bounds__(kE2Threads) elect2_kernel(Elect2Args A) {
                         if (was_leader) atomicAnd(&leaderb[c >> 5], ~(1u << (c & 31)));
                     }
                 }
+                __syncwarp();                                                  // (every lane has read s_leaders)
                 if (lane == 0) { s_m = keep; s_leaders = kept; s_K = icut; s_qn = 0; s_over = 0; }
             }
             __syncthreads();
@@ -2016,6 +2017,7 @@ __global__ void __launch_bounds__(kE2Threads) elect2_kernel(Elect2Args A) {
             const int pos = k * kE2Threads + tid;
             const bool a = ((alive[k * 32 + warp] >> lane) & 1u) && fsup[pos] == INT_MAX;
             const unsigned bal = __ballot_sync(0xffffffffu, a);
+            __syncwarp();                                                      // (every lane has read the word lane 0 rewrites)
             if (lane == 0) alive[k * 32 + warp] = bal;
         }
         __syncthreads(); GNMS_E2_T(6);
