@@ -272,6 +272,39 @@ class SplitPlan(object):
         return g
 
 
+def bind_host_to_gpu(device_index):
+    """Pin this process (and the pinned buffers it allocates afterwards: first touch) to the CPUs of the NUMA node the GPU hangs
+    off, read from sysfs (/sys/bus/pci/devices/<bdf>/numa_node, local_cpulist).  Returns a small report; does nothing -- and says
+    so -- where the platform exposes no locality (numa_node -1, as in most VMs) or the files are missing."""
+    import os
+    rep = {"device": int(device_index), "bound": False}
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read().strip())
+        cpulist = open(base + "/local_cpulist").read().strip()
+        rep.update(pci=bdf, numa_node=node, local_cpulist=cpulist)
+        if node < 0 or not cpulist:
+            rep["why"] = "the platform reports no NUMA locality for this GPU"
+            return rep
+        cpus = set()
+        for part in cpulist.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            rep["why"] = "already confined to (or not allowed on) the GPU's local CPUs"
+            return rep
+        os.sched_setaffinity(0, cpus)
+        rep["bound"] = True
+        rep["cpus"] = len(cpus)
+    except Exception as e:                                   # no sysfs, no permission: leave the process where it is
+        rep["why"] = "%s: %s" % (type(e).__name__, e)
+    return rep
+
+
 class HostRunner(object):
     """End-to-end entry for HOST buffers: pinned staging + an Nms3dPlan.  run_host(...) returns host tensors.
 
