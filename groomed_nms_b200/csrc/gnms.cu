@@ -2327,6 +2327,103 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
     //  loaded before any is used)
     int32_t* grank = list;
     int32_t* llist = reinterpret_cast<int32_t*>(wcol);
+    bool cap_done = false;
+    if (!(A.group_id || A.stage == 1) && N >= 1024) {
+        // Plain forward: only WHICH boxes exceed the cap matters, and only groups of more than group_size + 1 boxes have any.
+        // Position-parallel, no mask columns: (1) group sizes -- the lanes of a 32-position word that share a leader add once;
+        // (2) the big leaders get dense slots; (3) warp w walks ITS run of consecutive words in order and keeps, per slot, how
+        // many boxes of the group precede each word inside the run; (4) an exclusive prefix over the 32 runs per slot;
+        // (5) rank = boxes of the group before this one (the leader is entry 0): beyond group_size -> no group.
+        constexpr int kCapSlots = 64, kCapW = GNMS_MAX_BOXES / 32 / 32;
+        int32_t* gcount = grank;
+        int32_t* bigpref = reinterpret_cast<int32_t*>(wcol);                       // [NW]
+        uint16_t* tbl = reinterpret_cast<uint16_t*>(bigpref + NWa);                // [32 runs][kCapSlots]
+        const int WPW = (nw + 31) / 32, gs1 = P.group_size;
+        for (int pos = tid; pos < n; pos += kChainThreads) gcount[pos] = 0;
+        for (int i = tid; i < 32 * kCapSlots; i += kChainThreads) tbl[i] = 0;
+        __syncthreads();
+        int ldr[kCapW];
+        uint32_t cls[kCapW];
+#pragma unroll
+        for (int u = 0; u < kCapW; ++u) {
+            ldr[u] = -1; cls[u] = 0u;
+            const int wd = warp * WPW + u;
+            if (u < WPW && wd < nw) {                                              // (warp-uniform)
+                const int pos = wd * 32 + lane;
+                const int l = pos < n ? lead[pos] : -1;
+                const uint32_t mm = __match_any_sync(0xffffffffu, l);
+                ldr[u] = l; cls[u] = mm;
+                if (l >= 0 && lane == __ffs(mm) - 1) atomicAdd(&gcount[l], __popc(mm));
+            }
+        }
+        __syncthreads();
+        for (int base = 0; base < nw * 32; base += kChainThreads) {
+            const int pos = base + tid;
+            const bool big = pos < n && lead[pos] == pos && gcount[pos] > gs1 + 1;
+            const uint32_t bal = __ballot_sync(0xffffffffu, big);
+            if (lane == 0 && (pos >> 5) < nw) tmpbits[pos >> 5] = bal;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int run = 0;
+            for (int base = 0; base < nw; base += 32) {
+                const int wi = base + lane;
+                const int c = wi < nw ? __popc(tmpbits[wi]) : 0;
+                int incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (wi < nw) bigpref[wi] = run + incl - c;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) s_cnt = run;
+        }
+        __syncthreads();
+        const int nbig = s_cnt;
+        if (nbig <= kCapSlots) {
+            cap_done = true;
+            if (nbig > 0) {
+                int slot[kCapW], pre[kCapW];
+#pragma unroll
+                for (int u = 0; u < kCapW; ++u) {
+                    slot[u] = -1; pre[u] = 0;
+                    const int wd = warp * WPW + u;
+                    if (u < WPW && wd < nw) {
+                        const int l = ldr[u];
+                        if (l >= 0 && ((tmpbits[l >> 5] >> (l & 31)) & 1u))
+                            slot[u] = bigpref[l >> 5] + __popc(tmpbits[l >> 5] & ((1u << (l & 31)) - 1u));
+                        if (slot[u] >= 0) pre[u] = tbl[warp * kCapSlots + slot[u]];
+                        __syncwarp();
+                        if (slot[u] >= 0 && lane == __ffs(cls[u]) - 1) tbl[warp * kCapSlots + slot[u]] += (uint16_t)__popc(cls[u]);
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();
+                for (int sl = warp; sl < nbig; sl += kChainThreads / 32) {         // lane = run
+                    const int v = tbl[lane * kCapSlots + sl];
+                    int incl = v;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += t;
+                    }
+                    tbl[lane * kCapSlots + sl] = (uint16_t)(incl - v);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < kCapW; ++u) {
+                    if (slot[u] >= 0) {
+                        const int rk = (int)tbl[warp * kCapSlots + slot[u]] + pre[u] + __popc(cls[u] & ((1u << lane) - 1u));
+                        if (rk > gs1) lead[(warp * WPW + u) * 32 + lane] = -1;
+                    }
+                }
+            }
+            __syncthreads(); GNMS_PHASE(17);
+        }
+    }
+    if (!cap_done) {
     // member count per leader (shared-memory atomics); ranks are only needed where the cap can bite
     // (count > group_size) or when the caller wants the groups themselves
     for (int pos = tid; pos < n; pos += kChainThreads) grank[pos] = 0;
@@ -2470,6 +2567,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
     for (int pos = tid; pos < n; pos += kChainThreads) {
         if (lead[pos] >= 0 && lead[pos] != pos && grank[pos] > gs) lead[pos] = -1;
     }
+    }   // !cap_done
     __syncthreads(); GNMS_PHASE(18);
 
     // ---- get_groups outputs
@@ -2997,16 +3095,15 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
     // rank by counting costs batch * N^2 compares over the whole chip, the per-image radix sort a constant ~10 us
     const bool by_sort = g_rank_by_sort == 1 || (g_rank_by_sort < 0 && (double)batch * N * N >= 10.0 * 4096 * 4096);
     if (g_stage_mask & 1) {
+        const int zm = ((tiles && !direct && !direct2) || (src != kSrcMatrix && overlap_out)) ? 1 : 0;
         if (by_sort) {
-            const int zm = ((tiles && !direct && !direct2) || (src != kSrcMatrix && overlap_out)) ? 1 : 0;
             sort_kernel<<<batch + (zm ? 4 * batch : 1), kSortThreads, sort_smem_bytes(N), s>>>(scores, N, N, batch, npi, sv.order,
                                                                                               sv.sorted_scores, ws, L.total, zm);
             GNMS_LAUNCH_CHECK();
         }
         rank_kernel<<<dim3(gnms_div_up(N, kRankElems), batch), 256, by_sort ? 0 : rank_smem_bytes(N), s>>>(
             scores, 1, N, N, npi, sv.order, sv.sorted_scores, ws, L.total, src == kSrcMatrix ? nullptr : boxes, src,
-            (int64_t)N * box_stride, 0.f, by_sort ? 2 : 0, ((tiles && !direct && !direct2) || (src != kSrcMatrix && overlap_out)) ? 1 : 0,
-            tile_list_ptr(workspace, N, batch));
+            (int64_t)N * box_stride, 0.f, by_sort ? 2 : 0, zm, tile_list_ptr(workspace, N, batch));
     }
     GNMS_LAUNCH_CHECK();
     if (src != kSrcMatrix && !boxes) return GNMS_E_BADARG;

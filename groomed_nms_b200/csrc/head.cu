@@ -67,13 +67,17 @@ __global__ void __launch_bounds__(256) score_head_bwd_kernel(const float* __rest
         }
     }
 }
-// stage 2: one thread per parameter adds the block partials in block order
-__global__ void score_head_reduce_kernel(const float* __restrict__ part, int nblocks, int K1, float* __restrict__ grad_wb) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= K1) return;
-    float t = 0.f;
-    for (int b = 0; b < nblocks; ++b) t += part[(size_t)b * K1 + k];
-    grad_wb[k] = t;
+// stage 2: one warp per parameter; lane l adds the partials of blocks l, l + 32, ... in block order, then a fixed shuffle tree
+// (the same association every run: deterministic, like stage 1)
+__global__ void __launch_bounds__(1024) score_head_reduce_kernel(const float* __restrict__ part, int nblocks, int K1, float* __restrict__ grad_wb) {
+    const int lane = threadIdx.x & 31;
+    for (int k = threadIdx.x >> 5; k < K1; k += blockDim.x >> 5) {
+        float t = 0.f;
+        for (int b = lane; b < nblocks; b += 32) t += part[(size_t)b * K1 + k];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+        if (lane == 0) grad_wb[k] = t;
+    }
 }
 
 }  // namespace gnms
@@ -105,7 +109,7 @@ extern "C" int gnms_score_head_backward_f32(const float* x, int64_t M, int K, co
     float* part = reinterpret_cast<float*>(workspace);
     score_head_bwd_kernel<64><<<kHeadBlocks, 256, 0, s>>>(x, scores, grad_scores, M, part);
     GNMS_LAUNCH_CHECK();
-    score_head_reduce_kernel<<<1, 128, 0, s>>>(part, kHeadBlocks, K + 1, grad_wb);
+    score_head_reduce_kernel<<<1, 1024, 0, s>>>(part, kHeadBlocks, K + 1, grad_wb);
     GNMS_LAUNCH_CHECK();
     return 0;
 }
