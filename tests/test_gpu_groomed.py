@@ -668,3 +668,49 @@ def _dnms_up(n):
     rng = np.random.default_rng(n)
     rng.standard_normal(n); rng.standard_normal((n, n)); rng.standard_normal((n, n))
     return rng.standard_normal(n).astype(np.float32)
+
+
+@pytest.mark.parametrize("kind", ["2d", "3d"])
+def test_batched_election_with_degenerate_boxes(kind):
+    """Boxes the straight-line division and the gap bound must not be trusted on -- zero-area, inverted, denormal-size, huge,
+    infinite and NaN coordinates -- take the exact path inside elect2_kernel and are never culled: everything still equals the
+    matrix path (where a NaN overlap makes the box leave the pool without a group, lib/groomed_nms.py:249-250)."""
+    from groomed_nms_b200 import _lib, ops, synthetic
+    rng = np.random.default_rng(11)
+    N = 1500
+    if kind == "2d":
+        boxes, sc, _ = synthetic.clustered_boxes_2d(N, 6, seed=31, jitter=0.07)
+        bad = rng.choice(N, 60, replace=False)
+        boxes[bad[0:10], 2] = boxes[bad[0:10], 0]                               # zero width
+        boxes[bad[10:20], 2:] = boxes[bad[10:20], :2] - 5.0                     # inverted
+        boxes[bad[20:30], 2:] = boxes[bad[20:30], :2] + 1e-30                   # denormal-size
+        boxes[bad[30:40]] *= 1e30                                               # huge
+        boxes[bad[40:50], 3] = np.inf
+        boxes[bad[50:60], 1] = np.nan
+        dev = cuda(boxes)
+        iou = ops.overlap2d(dev, dev)
+        kw = dict(box_kind=_lib.BOX_2D, generalized=False, affine=False)
+        data = dev
+    else:
+        b7, sc = synthetic.config_c3(seed=8, n=N, k=10)
+        bad = rng.choice(N, 50, replace=False)
+        b7[bad[0:10], 3:6] = 0.0                                                # zero volume
+        b7[bad[10:20], 3:6] = 1e-25
+        b7[bad[20:30], :3] *= 1e12
+        b7[bad[30:40], 2] = np.inf
+        b7[bad[40:50], 0] = np.nan
+        rec = ops.box3d_records(ops.corners_from_boxes7(cuda(b7)))
+        iou = ops.overlap3d(rec, rec, False, True, generalized=True, affine=True)[1]
+        kw = dict(box_kind=_lib.BOX_3D_REC, generalized=True, affine=True)
+        data = rec
+    assert bool(torch.isnan(iou).any())
+    for thr in (0.4, 0.6):
+        p = ops.make_params(nms_threshold=thr, group_size=30)
+        ref = ops.forward_matrix(cuda(sc)[None], iou[None], p)
+        for election in (_lib.ELECT_BATCHED, _lib.ELECT_DIRECT, _lib.ELECT_MASK):
+            st = ops.forward_boxes(cuda(sc)[None], data[None], kw["box_kind"], p, kw["generalized"], kw["affine"],
+                                   opts=_lib.launch_opts(election=election))
+            torch.cuda.synchronize()
+            for f in ("order", "lead", "counts"):
+                assert torch.equal(getattr(ref, f), getattr(st, f)), (thr, election, f)
+            assert torch.equal(ref.prob.view(torch.int32), st.prob.view(torch.int32)), (thr, election)
