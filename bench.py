@@ -552,7 +552,7 @@ def run_ours(args, rank, world):
                          "algorithmic_bytes_per_launch": k_bytes, "avg_launch_ms": k_ms, "traffic": ncu_traffic(B),
                          "timing": "CUDA events around %d back-to-back launches of this kernel alone on the launching stream" % max(10, args.steps),
                          "note": "fp32 instruction issue limits the kernel (41 warp instructions per 32 pairs, 30 % of them FMNMX on the half-rate "
-                                 "ALU pipe, 4 warps per sub-partition), not HBM: see DESIGN.md section 5 and profiles/r2_ncu_tile_tma_kernel.txt"},
+                                 "ALU pipe, 4 warps per sub-partition), not HBM: see DESIGN.md section 5 and profiles/r2_ncu_tile_tma_kernel_b64.txt"},
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "effective_GBps": step_bytes / (ms_step * 1e-3) / 1e9,
                               "frac_of_peak": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
                               "note": "section 8(d) byte model 8N^2+(4D+24)N per image over the whole fwd+bwd step"},
