@@ -488,7 +488,7 @@ def run_ours(args, rank, world):
         # the kernels of that forward one by one (debug stage mask of the library: the same launches, in isolation)
         keep = pl.forward_opts
         for bit, name in ((_lib.STAGE_RANK, "sort_kernel+rank_kernel"), (_lib.STAGE_ELECT, "elect2_kernel(batched leader election)"),
-                          (_lib.STAGE_TILES, "tile_kernel(matrix only)"), (_lib.STAGE_CHAIN, "chain_kernel")):
+                          (_lib.STAGE_TILES, "tile_kernel(matrix only)"), (_lib.STAGE_CHAIN, "chain_kernel(on its own; the step runs it at the end of elect2_kernel)")):
             # the same launches one at a time: a per-call stage mask (gnms_launch_opts), tiles_per_cta as in the step
             pl.forward_opts = _lib.launch_opts(matrix_kernel=matrix_kernel, stage_mask=bit, flags=keep.flags,
                                                tiles_per_cta=args.tiles_per_cta if pl.overlap_branch else 0)

@@ -40,7 +40,7 @@ MATRIX_KERNEL_AUTO, MATRIX_KERNEL_DIRECT, MATRIX_KERNEL_TMA = 0, 1, 2
 RANK_AUTO, RANK_COUNT, RANK_SORT = 0, 1, 2
 ELECT_AUTO, ELECT_DIRECT, ELECT_MASK, ELECT_BATCHED = 0, 1, 2, 3
 STAGE_RANK, STAGE_SPATIAL, STAGE_TILES, STAGE_EARLIER, STAGE_CHAIN, STAGE_ELECT = 1, 2, 4, 8, 16, 32
-OPT_SCALAR_MATH, OPT_INLINE_HITS, OPT_ONE_PASS = 1, 2, 4
+OPT_SCALAR_MATH, OPT_INLINE_HITS, OPT_ONE_PASS, OPT_SPLIT_CHAIN = 1, 2, 4, 8
 
 
 def launch_opts(matrix_kernel=0, tiles_per_cta=0, rank_method=0, election=0, stage_mask=0, flags=0):

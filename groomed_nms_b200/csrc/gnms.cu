@@ -1611,425 +1611,6 @@ __global__ void __launch_bounds__(256) zero_failed_kernel(int N, int batch, char
     }
 }
 
-// ------------------------------------------------------------------------------------------ 2f. batched leader election
-// The per-leader loop above pays one barrier-bound step per leader.  The greedy election is exact under batching: take the
-// first K <= 32 boxes still in the pool (score order).  Everything ahead of them has been decided, so among themselves they
-// are resolved by the K x K overlap bits alone (a candidate is a leader iff every earlier candidate that overlaps it is itself
-// suppressed); and every other box of the pool then leaves with the LOWEST new leader it overlaps -- exactly the leader the
-// one-at-a-time loop (lib/groomed_nms.py:247-262) would have reached first.  A detector image needs 2-5 such steps instead of
-// one per leader.  One CTA per image, 1024 threads, the image's sorted records in shared memory (N <= 4096):
-//   A  warp 0 lists the first K pool positions
-//   B  warp i evaluates candidate i against candidates j < i
-//   C  warp 0 resolves the K x K bits and publishes the new leaders: their records, and for the two widest axes a table
-//      "which of this step's leaders can reach a box whose lower edge falls in bin b" (64 bins per axis, conservative)
-//   D  every pool box: two table look-ups name the few leaders that can reach it; for those the conservative gap bound of the
-//      tile culling on every axis (gap > c * (sum of the two extents) => overlap <= thr; exact zeros when c == 0); the pairs
-//      that survive go to a shared-memory queue
-//   E  the queue is evaluated densely, one pair per thread, atomicMin of the leader position per box; the overlap of a box
-//      with the leader that won is written out (it is the Phi entry the rescore needs: chain_kernel does not evaluate it again)
-//   F  boxes with a suppressor leave the pool (one ballot per 32 positions)
-// If the queue overflows the step is redone with the first quarter of its leaders (the rest of the candidates go back to the
-// pool): with one leader it always fits, so the kernel never gives up -- no fallback kernels follow it.
-__device__ int warp_list_bits(const uint32_t* bits, int nw, int limit, int32_t* out);     // (defined with chain_kernel below)
-constexpr int kE2Threads = 1024;
-constexpr int kE2Queue = 8192;
-constexpr int kE2PerThread = kE2Queue / kE2Threads;
-constexpr int kE2Bins = 64;
-struct Elect2Args {
-    int N, batch;
-    const int32_t* n_per_image;
-    char* ws;
-    size_t ws_img_stride;
-    float thr, cull_c;
-    float* vout;                   // [batch, N] by sorted position: overlap with the first suppressor (members only)
-};
-static size_t elect2_smem_bytes(int N) {
-    const size_t Np = ((size_t)N + kE2Threads - 1) / kE2Threads * kE2Threads;
-    return Np * 32 + Np * 4 + (size_t)kE2Queue * 4 + 4 * 128 * 4 + 32 * 3 * 16 + 5 * 32 * 4 + 32 * 32 * 4 + 2 * kE2Bins * 4 + Np * 2 + 64;
-}
-
-template <int kSrc> struct AxesOf;
-template <> struct AxesOf<kSrcBox3d> {          // depth first: detector outputs spread most along z, then x
-    static constexpr int kAxes = 3;
-    static __device__ __forceinline__ void get(const Rec3& r, float (&lo)[3], float (&hi)[3]) {
-        lo[0] = r.bz1; hi[0] = r.bz2; lo[1] = r.bx1; hi[1] = r.bx2; lo[2] = r.ymin; hi[2] = r.ymax;
-    }
-};
-template <> struct AxesOf<kSrcBox2d> {
-    static constexpr int kAxes = 2;
-    static __device__ __forceinline__ void get(const Box2& r, float (&lo)[3], float (&hi)[3]) {
-        lo[0] = r.x1; hi[0] = r.x2; lo[1] = r.y1; hi[1] = r.y2; lo[2] = 0.f; hi[2] = 0.f;
-    }
-};
-// bin of a lower edge: monotone in x for fixed (origin, scale >= 0), which is all the reach tables rely on
-__device__ __forceinline__ int e2_bin(float x, float origin, float scale) {
-    const float t = __fmul_rn(__fsub_rn(x, origin), scale);
-    return t >= (float)(kE2Bins - 1) ? kE2Bins - 1 : (t > 0.f ? (int)t : 0);         // (NaN -> 0; such boxes never use the tables)
-}
-
-#ifdef GNMS_DEBUG
-__device__ long long g_e2_clk[16];          // [0..7] cycles per phase (load, A, B, C, D, E, F, store), [8] steps, [9] leaders, [10] queued pairs, [11] redone steps
-#define GNMS_E2_T(k) do { if (tid == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_e2_clk[k] += t_ - e2_t; e2_t = t_; } } while (0)
-#define GNMS_E2_C(k, v) do { if (tid == 0 && blockIdx.x == 0) g_e2_clk[k] += (v); } while (0)
-#else
-#define GNMS_E2_T(k) do { } while (0)
-#define GNMS_E2_C(k, v) do { } while (0)
-#endif
-template <int kSrc, bool kGen, bool kAffine>
-__global__ void __launch_bounds__(kE2Threads) elect2_kernel(Elect2Args A) {
-    typedef typename RecOf<kSrc>::type RecT;
-    constexpr int kAxes = AxesOf<kSrc>::kAxes;
-    extern __shared__ __align__(16) unsigned char s_e2[];
-    const int b = blockIdx.x, N = A.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#ifdef GNMS_DEBUG
-    long long e2_t = clock64();
-#endif
-    const int n = A.n_per_image ? min(A.n_per_image[b], N) : N;
-    const int nw = (n + 31) / 32;
-    const int Np = (N + kE2Threads - 1) / kE2Threads * kE2Threads, KK = Np / kE2Threads;
-    const WsLayout L = ws_layout(N);
-    char* w = A.ws + (size_t)b * A.ws_img_stride;
-    float* vout = A.vout + (size_t)b * N;
-    float4* rec4 = reinterpret_cast<float4*>(s_e2);                                  // [Np][2] sorted records
-    int32_t* fsup = reinterpret_cast<int32_t*>(rec4 + (size_t)Np * 2);              // [Np] first suppressor (sorted position)
-    uint32_t* queue = reinterpret_cast<uint32_t*>(fsup + Np);                        // [kE2Queue] (position << 5) | leader slot
-    uint32_t* alive = queue + kE2Queue;                                              // [128] the pool, by sorted position
-    uint32_t* leaderb = alive + 128;
-    uint32_t* badb = leaderb + 128;                                                  // record outside div_rn_fast's proven range
-    float4* ltab = reinterpret_cast<float4*>(badb + 128);                            // [32][3]: (lo, hi, extent, bad) per axis
-    int32_t* cand = reinterpret_cast<int32_t*>(ltab + 32 * 3);                       // [32] candidate positions
-    uint32_t* covm = reinterpret_cast<uint32_t*>(cand + 32);                         // [32] bit j of row i: !(overlap(i, j) <= thr)
-    int32_t* lpos = reinterpret_cast<int32_t*>(covm + 32);                           // [32] position of leader slot q
-    int32_t* lcidx = lpos + 32;                                                      // [32] candidate index of leader slot q
-    float* covv = reinterpret_cast<float*>(lcidx + 32);                              // [32][32] overlap(candidate i, candidate j < i)
-    uint32_t* reach = reinterpret_cast<uint32_t*>(covv + 32 * 32);                   // [2][kE2Bins] leader slots that reach a bin
-    uint32_t* lbins = reach + 2 * kE2Bins;                                           // [32] leader slot q: first / last bin on axes 0, 1 (4 bytes)
-    uint32_t* apref = lbins + 32;                                                    // [128] pool bits before each word
-    uint16_t* bins = reinterpret_cast<uint16_t*>(apref + 128);                       // [Np] bin on axis 0 | bin on axis 1 << 8 (0xffff: bad box)
-    __shared__ int s_K, s_m, s_qn, s_over;
-    __shared__ uint32_t s_leaders;
-    __shared__ float s_red[32][8];
-    __shared__ float s_binp[8];               // per axis a in {0, 1}: origin, scale, largest extent, absolute margin
-    {
-        const char* src = w + L.sbox;
-        for (int i = tid; i < 2 * n; i += kE2Threads) cp_async16(rec4 + i, src + (size_t)i * 16);
-    }
-    if (tid < 128) { alive[tid] = tid < nw ? valid_word(tid, n) : 0u; leaderb[tid] = 0u; }
-    auto record = [&](int pos) -> RecT {
-        const float4 u = rec4[2 * pos], v = rec4[2 * pos + 1];
-        if constexpr (kSrc == kSrcBox3d) return Rec3{u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
-        else return Box2{u.x, u.y, u.z, u.w, v.x};
-    };
-    auto is_bad = [&](int pos) -> bool { return (badb[pos >> 5] >> (pos & 31)) & 1u; };
-    cp_async_wait_all();
-    __syncthreads();
-    {
-        // bad flags; per axis (0, 1): range of the lower edges, largest extent, largest magnitude -- over the sane boxes
-        float mn0 = INFINITY, mx0 = -INFINITY, mn1 = INFINITY, mx1 = -INFINITY, ex0 = 0.f, ex1 = 0.f, mg = 0.f;
-        for (int k = 0; k < KK; ++k) {
-            const int pos = k * kE2Threads + tid;
-            fsup[pos] = INT_MAX;
-            bool bad = false;
-            if (pos < n) {
-                const RecT r = record(pos);
-                if constexpr (kSrc == kSrcBox3d) bad = !rec3_sane(r);
-                else bad = !box2_sane(r);
-                if (!bad) {
-                    float lo[3], hi[3];
-                    AxesOf<kSrc>::get(r, lo, hi);
-                    mn0 = fminf(mn0, lo[0]); mx0 = fmaxf(mx0, lo[0]); ex0 = fmaxf(ex0, __fsub_rn(hi[0], lo[0]));
-                    mn1 = fminf(mn1, lo[1]); mx1 = fmaxf(mx1, lo[1]); ex1 = fmaxf(ex1, __fsub_rn(hi[1], lo[1]));
-                    mg = fmaxf(mg, fmaxf(fmaxf(fabsf(lo[0]), fabsf(hi[0])), fmaxf(fabsf(lo[1]), fabsf(hi[1]))));
-                }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, bad);
-            if (lane == 0) badb[k * 32 + warp] = bal;
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            mn0 = fminf(mn0, __shfl_xor_sync(0xffffffffu, mn0, d)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, d));
-            mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, d)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, d));
-            ex0 = fmaxf(ex0, __shfl_xor_sync(0xffffffffu, ex0, d)); ex1 = fmaxf(ex1, __shfl_xor_sync(0xffffffffu, ex1, d));
-            mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, d));
-        }
-        if (lane == 0) { s_red[warp][0] = mn0; s_red[warp][1] = mx0; s_red[warp][2] = mn1; s_red[warp][3] = mx1; s_red[warp][4] = ex0; s_red[warp][5] = ex1; s_red[warp][6] = mg; }
-        __syncthreads();
-        if (warp == 0) {
-            mn0 = s_red[lane][0]; mx0 = s_red[lane][1]; mn1 = s_red[lane][2]; mx1 = s_red[lane][3]; ex0 = s_red[lane][4]; ex1 = s_red[lane][5]; mg = s_red[lane][6];
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                mn0 = fminf(mn0, __shfl_xor_sync(0xffffffffu, mn0, d)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, d));
-                mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, d)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, d));
-                ex0 = fmaxf(ex0, __shfl_xor_sync(0xffffffffu, ex0, d)); ex1 = fmaxf(ex1, __shfl_xor_sync(0xffffffffu, ex1, d));
-                mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, d));
-            }
-            if (lane == 0) {
-                // scale = bins / range (0 when the range is empty, not finite or absurd: then every box sits in bin 0 and the
-                // tables cull nothing); margin: a few ulps of the largest coordinate, it absorbs the rounding of the reach edges
-                const float r0 = __fsub_rn(mx0, mn0), r1 = __fsub_rn(mx1, mn1);
-                s_binp[0] = mn0; s_binp[1] = (r0 > 0.f && r0 < 1e30f) ? __fdiv_rn((float)kE2Bins, r0) : 0.f; s_binp[2] = ex0;
-                s_binp[4] = mn1; s_binp[5] = (r1 > 0.f && r1 < 1e30f) ? __fdiv_rn((float)kE2Bins, r1) : 0.f; s_binp[6] = ex1;
-                s_binp[3] = s_binp[7] = __fmul_rn(__fadd_rn(mg, fmaxf(ex0, ex1)), 1.9073486e-6f);                    // 2^-19
-            }
-        }
-    }
-    const float thr = A.thr, cc = A.cull_c;
-    __syncthreads();
-    {
-        const float bo0 = s_binp[0], bs0 = s_binp[1], bo1 = s_binp[4], bs1 = s_binp[5];
-        for (int k = 0; k < KK; ++k) {
-            const int pos = k * kE2Threads + tid;
-            uint16_t bb = 0xffffu;
-            if (pos < n && !is_bad(pos)) {
-                float lo[3], hi[3];
-                AxesOf<kSrc>::get(record(pos), lo, hi);
-                bb = (uint16_t)(e2_bin(lo[0], bo0, bs0) | (e2_bin(lo[1], bo1, bs1) << 8));
-            }
-            bins[pos] = bb;
-        }
-    }
-    GNMS_E2_T(0);
-    while (true) {
-        // ---- A: the first <= 32 positions of the pool.  Lane i counts words 4i .. 4i+3, a warp scan gives the number of pool
-        //      bits before every word, and output slot o (lane o) finds its word by bisection and its bit with __fns.
-        if (warp == 0) {
-            const uint4 wv = reinterpret_cast<const uint4*>(alive)[lane];
-            const int c0 = __popc(wv.x), c1 = __popc(wv.y), c2 = __popc(wv.z), c3 = __popc(wv.w);
-            int incl = c0 + c1 + c2 + c3;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            const int before = incl - (c0 + c1 + c2 + c3);
-            reinterpret_cast<uint4*>(apref)[lane] = make_uint4(before, before + c0, before + c0 + c1, before + c0 + c1 + c2);
-            __syncwarp();
-            const int K0 = min(total, 32);
-            if (lane < K0) {
-                int lo_ = 0, hi_ = 127;                                       // last word whose prefix is <= lane
-                while (lo_ < hi_) {
-                    const int mid = (lo_ + hi_ + 1) >> 1;
-                    if ((int)apref[mid] <= lane) lo_ = mid; else hi_ = mid - 1;
-                }
-                cand[lane] = lo_ * 32 + __fns(alive[lo_], 0, lane - (int)apref[lo_] + 1);
-            }
-            covm[lane] = 0u;
-            if (lane == 0) s_K = K0;
-        }
-        __syncthreads(); GNMS_E2_T(1);
-        int K = s_K;
-        if (K == 0) break;
-        GNMS_E2_C(8, 1);
-        // ---- B: candidate x earlier candidate
-        if (warp < K) {
-            bool hit = false;
-            if (lane < warp) {
-                const int pi = cand[warp], pj = cand[lane];
-                const RecT mine = record(pi), other = record(pj);
-                bool unsafe = is_bad(pi) || is_bad(pj);
-                float v = RecOf<kSrc>::template fast<kGen, kAffine>(mine, other, unsafe);
-                if (__builtin_expect(unsafe, 0)) v = RecOf<kSrc>::template exact<kGen, kAffine>(mine, other);
-                hit = !(v <= thr);                                             // NaN leaves the pool too (:249-250)
-                covv[warp * 32 + lane] = v;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            if (lane == 0) covm[warp] = bal;
-        }
-        __syncthreads(); GNMS_E2_T(2);
-        // ---- C: resolve the candidates in score order (dependency rounds, usually 2-3)
-        if (warp == 0) {
-            const uint32_t row = lane < K ? covm[lane] : 0u;
-            uint32_t undecided = K == 32 ? 0xffffffffu : ((1u << K) - 1u), leaders = 0u;
-            while (undecided) {
-                const bool mine = (undecided >> lane) & 1u;
-                const bool isl = mine && (row & (undecided | leaders)) == 0u;
-                const bool iss = mine && (row & leaders) != 0u;
-                const uint32_t nl = __ballot_sync(0xffffffffu, isl), ns = __ballot_sync(0xffffffffu, iss);
-                leaders |= nl;
-                undecided &= ~(nl | ns);
-            }
-            if (lane < K) {
-                const int c = cand[lane];
-                if ((leaders >> lane) & 1u) {
-                    const int q = __popc(leaders & ((1u << lane) - 1u));
-                    lpos[q] = c; lcidx[q] = lane;
-                    float lo[3], hi[3];
-                    AxesOf<kSrc>::get(record(c), lo, hi);
-                    const bool lbad = is_bad(c);
-#pragma unroll
-                    for (int ax = 0; ax < kAxes; ++ax) ltab[q * 3 + ax] = make_float4(lo[ax], hi[ax], __fsub_rn(hi[ax], lo[ax]), lbad ? 1.f : 0.f);
-                    // reach tables: a box can pass the gap test on axis a only if its lower edge lies in
-                    // [lo - R - emax - margin, hi + R + margin], R = c (extent + emax); bins of those two edges, inclusive
-                    uint32_t lb = 0u;
-#pragma unroll
-                    for (int a = 0; a < 2; ++a) {
-                        int b0 = 0, b1 = kE2Bins - 1;
-                        if (!lbad) {
-                            const float emax = s_binp[a * 4 + 2], mgn = s_binp[a * 4 + 3];
-                            const float R = __fmul_rn(cc, __fadd_rn(__fsub_rn(hi[a], lo[a]), emax));
-                            b0 = e2_bin(__fsub_rn(__fsub_rn(__fsub_rn(lo[a], R), emax), mgn), s_binp[a * 4], s_binp[a * 4 + 1]);
-                            b1 = e2_bin(__fadd_rn(__fadd_rn(hi[a], R), mgn), s_binp[a * 4], s_binp[a * 4 + 1]);
-                        }
-                        lb |= (uint32_t)(b0 | (b1 << 8)) << (16 * a);
-                    }
-                    lbins[q] = lb;
-                    atomicOr(&leaderb[c >> 5], 1u << (c & 31));
-                } else {
-                    const int jf = __ffs(row & leaders) - 1;
-                    fsup[c] = cand[jf];
-                    vout[c] = covv[lane * 32 + jf];
-                }
-                atomicAnd(&alive[c >> 5], ~(1u << (c & 31)));
-            }
-            if (lane == 0) { s_m = __popc(leaders); s_leaders = leaders; s_qn = 0; s_over = 0; }
-        }
-        __syncthreads();
-        {
-            // reach tables: 8 threads per (axis, bin), 4 leader slots each, OR-reduced over the 8 neighbouring lanes
-            const int a = tid >> 9, bin = (tid >> 3) & (kE2Bins - 1), part = tid & 7, m0 = s_m;
-            uint32_t bits = 0u;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int q = part * 4 + u;
-                if (q < m0) {
-                    const uint32_t lb = lbins[q] >> (16 * a);
-                    if (bin >= (int)(lb & 0xffu) && bin <= (int)((lb >> 8) & 0xffu)) bits |= 1u << q;
-                }
-            }
-            bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
-            bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
-            bits |= __shfl_xor_sync(0xffffffffu, bits, 4);
-            if (part == 0) reach[a * kE2Bins + bin] = bits;
-        }
-        __syncthreads(); GNMS_E2_T(3);
-        GNMS_E2_C(9, s_m);
-        // ---- D: pool x the leaders that can reach it
-        while (true) {
-            const int m = s_m;
-            const uint32_t mall = m == 32 ? 0xffffffffu : ((1u << m) - 1u);
-            for (int k = 0; k < KK; ++k) {
-                const int pos = k * kE2Threads + tid;
-                uint32_t nearm = 0u;
-                if ((alive[k * 32 + warp] >> lane) & 1u) {
-                    const uint32_t bb = bins[pos];
-                    const bool mybad = bb == 0xffffu;
-                    uint32_t cm = mall;
-                    if (!mybad) cm &= reach[bb & 0xffu] & reach[kE2Bins + (bb >> 8)];
-                    float lo[3], hi[3];
-                    if (cm) AxesOf<kSrc>::get(record(pos), lo, hi);
-                    while (cm) {
-                        const int q = __ffs(cm) - 1;
-                        cm &= cm - 1u;
-                        bool nr = true;
-                        if (ltab[q * 3].w == 0.f && !mybad) {
-#pragma unroll
-                            for (int ax = 0; ax < kAxes; ++ax) {
-                                const float4 t = ltab[q * 3 + ax];
-                                if (fmaxf(__fsub_rn(lo[ax], t.y), __fsub_rn(t.x, hi[ax])) > __fmul_rn(cc, __fadd_rn(t.z, __fsub_rn(hi[ax], lo[ax])))) nr = false;
-                            }
-                        }
-                        nearm |= (uint32_t)nr << q;
-                    }
-                }
-                // warp-aggregated push
-                const int cnt = __popc(nearm);
-                int incl = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += t;
-                }
-                const int tot = __shfl_sync(0xffffffffu, incl, 31);
-                if (tot == 0) continue;
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_qn, tot);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base + tot > kE2Queue) { if (lane == 0) s_over = 1; continue; }
-                int at = base + incl - cnt;
-                while (nearm) {
-                    const int q = __ffs(nearm) - 1;
-                    nearm &= nearm - 1u;
-                    queue[at++] = ((uint32_t)pos << 5) | (uint32_t)q;
-                }
-            }
-            __syncthreads();
-            if (!s_over) break;
-            GNMS_E2_C(11, 1);
-            __syncthreads();                                                   // (everybody has seen the flag)
-            if (warp == 0) {
-                // keep the first quarter of this step's leaders; later candidates go back to the pool unless one of the kept
-                // leaders suppresses them (then their first suppressor is already right: it is the lowest leader of their row)
-                const uint32_t leaders = s_leaders;
-                const int keep = max(1, m >> 2);
-                uint32_t rest = leaders;
-                for (int t = 0; t < keep; ++t) rest &= rest - 1u;
-                const int icut = __ffs(rest) - 1;                              // candidate index of the first dropped leader
-                const uint32_t kept = leaders & ((1u << icut) - 1u);
-                if (lane >= icut && lane < K) {
-                    const int c = cand[lane];
-                    const bool was_leader = (leaders >> lane) & 1u;
-                    if (was_leader || (covm[lane] & kept) == 0u) {
-                        atomicOr(&alive[c >> 5], 1u << (c & 31));
-                        fsup[c] = INT_MAX;
-                        if (was_leader) atomicAnd(&leaderb[c >> 5], ~(1u << (c & 31)));
-                    }
-                }
-                __syncwarp();                                                  // (every lane has read s_leaders)
-                if (lane == 0) { s_m = keep; s_leaders = kept; s_K = icut; s_qn = 0; s_over = 0; }
-            }
-            __syncthreads();
-            K = s_K;
-        }
-        // ---- E: the queued pairs, one per thread and round
-        GNMS_E2_T(4);
-        const int qn = s_qn;
-        GNMS_E2_C(10, qn);
-        float vreg[kE2PerThread];
-#pragma unroll
-        for (int i = 0; i < kE2PerThread; ++i) {
-            const int e = i * kE2Threads + tid;
-            vreg[i] = 0.f;
-            if (e < qn) {
-                const uint32_t ent = queue[e];
-                const int pos = (int)(ent >> 5), l = lpos[ent & 31u];
-                const RecT mine = record(pos), ldr = record(l);
-                bool unsafe = is_bad(pos) || is_bad(l);
-                float v = RecOf<kSrc>::template fast<kGen, kAffine>(mine, ldr, unsafe);
-                if (__builtin_expect(unsafe, 0)) v = RecOf<kSrc>::template exact<kGen, kAffine>(mine, ldr);
-                if (!(v <= thr)) atomicMin(&fsup[pos], l);
-                vreg[i] = v;
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < kE2PerThread; ++i) {
-            const int e = i * kE2Threads + tid;
-            if (e < qn) {
-                const uint32_t ent = queue[e];
-                const int pos = (int)(ent >> 5);
-                if (fsup[pos] == lpos[ent & 31u] && !(vreg[i] <= thr)) vout[pos] = vreg[i];
-            }
-        }
-        GNMS_E2_T(5);
-        // ---- F: boxes with a suppressor leave the pool
-        for (int k = 0; k < KK; ++k) {
-            const int pos = k * kE2Threads + tid;
-            const bool a = ((alive[k * 32 + warp] >> lane) & 1u) && fsup[pos] == INT_MAX;
-            const unsigned bal = __ballot_sync(0xffffffffu, a);
-            __syncwarp();                                                      // (every lane has read the word lane 0 rewrites)
-            if (lane == 0) alive[k * 32 + warp] = bal;
-        }
-        __syncthreads(); GNMS_E2_T(6);
-    }
-    int32_t* dfsup = reinterpret_cast<int32_t*>(w + L.dfsup);
-    uint32_t* dleader = reinterpret_cast<uint32_t*>(w + L.dleader);
-    for (int pos = tid; pos < n; pos += kE2Threads) dfsup[pos] = fsup[pos];
-    GNMS_E2_T(7);
-    if (tid < (N + 31) / 32) dleader[tid] = tid < 128 ? leaderb[tid] : 0u;
-    if (tid == 0) *reinterpret_cast<int32_t*>(w + L.dflag) = 0;
-}
-
 // ------------------------------------------------------------------------------------------ 3. chain
 // shared-memory carve-up of chain_kernel (host and device agree through these two functions)
 __host__ __device__ inline size_t chain_wcol_end(int N) {
@@ -2115,10 +1696,21 @@ __device__ int g_chain_clk_on = 0;
 #define GNMS_PHASE(k) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
+// The sections of shared memory the chain works in.  chain_kernel carves them out of its own dynamic shared memory; the batched
+// election (elect2_kernel) hands over its own leader bitset and first-suppressor array and carves the rest out of the record
+// area it no longer needs, so that the election's result never leaves the SM.
+struct ChainSmem {
+    uint32_t* removed;             // NW
+    uint32_t* leader;              // NW
+    uint32_t* tmpbits;             // NW
+    int32_t* fsup;                 // N   (later: lead[])
+    int32_t* list;                 // N   (leader / candidate lists, later grank)
+    uint32_t* wcol;                // max(kWin * NW words, P * 8 bytes)  (later: sort keys)
+    float* ss_s;                   // N   sorted scores staged once
+};
+// state_in_smem: S.leader / S.fsup already hold the election's result (elect2_kernel calls this at its end)
+__device__ __forceinline__ void chain_body(const ChainArgs& A, const int b, const ChainSmem S, const bool state_in_smem) {
     GNMS_PHASE(0);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int b = blockIdx.x;
     const int N = A.N;
     const int n = A.n_per_image ? min(A.n_per_image[b], N) : N;
     const int NW = (N + 31) / 32;
@@ -2132,15 +1724,14 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
     const int32_t* order = A.order + (size_t)b * N;
     const float* ss = A.sorted_scores + (size_t)b * N;
 
-    // shared memory carve-up
     const int NWa = (NW + 3) & ~3, Na = (N + 3) & ~3;                     // keep every section 16-byte aligned
-    uint32_t* removed = reinterpret_cast<uint32_t*>(smem_raw);            // NW
-    uint32_t* leader = removed + NWa;                                     // NW
-    uint32_t* tmpbits = leader + NWa;                                     // NW
-    int32_t* fsup = reinterpret_cast<int32_t*>(tmpbits + NWa);            // N   (later: lead[])
-    int32_t* list = fsup + Na;                                            // N   (leader / candidate lists, later grank)
-    uint32_t* wcol = reinterpret_cast<uint32_t*>(list + Na);              // kWin * NW (later: sort keys)
-    float* ss_s = reinterpret_cast<float*>(smem_raw + chain_wcol_end(N)); // N   sorted scores staged once
+    uint32_t* removed = S.removed;
+    uint32_t* leader = S.leader;
+    uint32_t* tmpbits = S.tmpbits;
+    int32_t* fsup = S.fsup;
+    int32_t* list = S.list;
+    uint32_t* wcol = S.wcol;
+    float* ss_s = S.ss_s;
     __shared__ int s_cnt;
     for (int pos = tid; pos < n; pos += kChainThreads) ss_s[pos] = ss[pos];   // consumed after several barriers
 
@@ -2156,8 +1747,10 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
         }
         __syncthreads(); GNMS_PHASE(1);
     } else {
-    const bool direct = A.direct && *reinterpret_cast<const int32_t*>(w + L.dflag) == 0;
-    if (direct) {
+    const bool direct = state_in_smem || (A.direct && *reinterpret_cast<const int32_t*>(w + L.dflag) == 0);
+    if (state_in_smem) {
+        for (int i = tid; i < NW; i += kChainThreads) removed[i] = 0u;
+    } else if (direct) {
         const uint32_t* dleader = reinterpret_cast<const uint32_t*>(w + L.dleader);
         const int32_t* dfsup = reinterpret_cast<const int32_t*>(w + L.dfsup);
         for (int i = tid; i < NW; i += kChainThreads) { removed[i] = 0u; leader[i] = i < nw ? dleader[i] : 0u; }
@@ -2781,6 +2374,466 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
     }
 }
 
+__global__ void __launch_bounds__(kChainThreads) chain_kernel(ChainArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = A.N, NW = (N + 31) / 32;
+    const int NWa = (NW + 3) & ~3, Na = (N + 3) & ~3;
+    ChainSmem S;
+    S.removed = reinterpret_cast<uint32_t*>(smem_raw);
+    S.leader = S.removed + NWa;
+    S.tmpbits = S.leader + NWa;
+    S.fsup = reinterpret_cast<int32_t*>(S.tmpbits + NWa);
+    S.list = S.fsup + Na;
+    S.wcol = reinterpret_cast<uint32_t*>(S.list + Na);
+    S.ss_s = reinterpret_cast<float*>(smem_raw + chain_wcol_end(N));
+    chain_body(A, blockIdx.x, S, false);
+}
+
+// ------------------------------------------------------------------------------------------ 2f. batched leader election
+// The per-leader loop above pays one barrier-bound step per leader.  The greedy election is exact under batching: take the
+// first K <= 32 boxes still in the pool (score order).  Everything ahead of them has been decided, so among themselves they
+// are resolved by the K x K overlap bits alone (a candidate is a leader iff every earlier candidate that overlaps it is itself
+// suppressed); and every other box of the pool then leaves with the LOWEST new leader it overlaps -- exactly the leader the
+// one-at-a-time loop (lib/groomed_nms.py:247-262) would have reached first.  A detector image needs 2-5 such steps instead of
+// one per leader.  One CTA per image, 1024 threads, the image's sorted records in shared memory (N <= 4096):
+//   A  warp 0 lists the first K pool positions
+//   B  warp i evaluates candidate i against candidates j < i
+//   C  warp 0 resolves the K x K bits and publishes the new leaders: their records, and for the two widest axes a table
+//      "which of this step's leaders can reach a box whose lower edge falls in bin b" (64 bins per axis, conservative)
+//   D  every pool box: two table look-ups name the few leaders that can reach it; for those the conservative gap bound of the
+//      tile culling on every axis (gap > c * (sum of the two extents) => overlap <= thr; exact zeros when c == 0); the pairs
+//      that survive go to a shared-memory queue
+//   E  the queue is evaluated densely, one pair per thread, atomicMin of the leader position per box; the overlap of a box
+//      with the leader that won is written out (it is the Phi entry the rescore needs: chain_kernel does not evaluate it again)
+//   F  boxes with a suppressor leave the pool (one ballot per 32 positions)
+// If the queue overflows the step is redone with the first quarter of its leaders (the rest of the candidates go back to the
+// pool): with one leader it always fits, so the kernel never gives up -- no fallback kernels follow it.
+__device__ int warp_list_bits(const uint32_t* bits, int nw, int limit, int32_t* out);     // (defined with chain_kernel below)
+constexpr int kE2Threads = 1024;
+constexpr int kE2Queue = 8192;
+constexpr int kE2PerThread = kE2Queue / kE2Threads;
+constexpr int kE2Bins = 64;
+struct Elect2Args {
+    int N, batch;
+    const int32_t* n_per_image;
+    char* ws;
+    size_t ws_img_stride;
+    float thr, cull_c;
+    float* vout;                   // [batch, N] by sorted position: overlap with the first suppressor (members only)
+    int fuse_chain;                // != 0: run the chain (grouping cap, rescore, lists) right here, from shared memory
+    ChainArgs chain;
+};
+static size_t elect2_smem_bytes(int N) {
+    const size_t Np = ((size_t)N + kE2Threads - 1) / kE2Threads * kE2Threads;
+    return Np * 32 + Np * 4 + (size_t)kE2Queue * 4 + 4 * 128 * 4 + 32 * 3 * 16 + 5 * 32 * 4 + 32 * 32 * 4 + 2 * kE2Bins * 4 + Np * 2 + 64;
+}
+
+template <int kSrc> struct AxesOf;
+template <> struct AxesOf<kSrcBox3d> {          // depth first: detector outputs spread most along z, then x
+    static constexpr int kAxes = 3;
+    static __device__ __forceinline__ void get(const Rec3& r, float (&lo)[3], float (&hi)[3]) {
+        lo[0] = r.bz1; hi[0] = r.bz2; lo[1] = r.bx1; hi[1] = r.bx2; lo[2] = r.ymin; hi[2] = r.ymax;
+    }
+};
+template <> struct AxesOf<kSrcBox2d> {
+    static constexpr int kAxes = 2;
+    static __device__ __forceinline__ void get(const Box2& r, float (&lo)[3], float (&hi)[3]) {
+        lo[0] = r.x1; hi[0] = r.x2; lo[1] = r.y1; hi[1] = r.y2; lo[2] = 0.f; hi[2] = 0.f;
+    }
+};
+// bin of a lower edge: monotone in x for fixed (origin, scale >= 0), which is all the reach tables rely on
+__device__ __forceinline__ int e2_bin(float x, float origin, float scale) {
+    const float t = __fmul_rn(__fsub_rn(x, origin), scale);
+    return t >= (float)(kE2Bins - 1) ? kE2Bins - 1 : (t > 0.f ? (int)t : 0);         // (NaN -> 0; such boxes never use the tables)
+}
+
+#ifdef GNMS_DEBUG
+__device__ long long g_e2_clk[16];          // [0..7] cycles per phase (load, A, B, C, D, E, F, store), [8] steps, [9] leaders, [10] queued pairs, [11] redone steps
+#define GNMS_E2_T(k) do { if (tid == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_e2_clk[k] += t_ - e2_t; e2_t = t_; } } while (0)
+#define GNMS_E2_C(k, v) do { if (tid == 0 && blockIdx.x == 0) g_e2_clk[k] += (v); } while (0)
+#else
+#define GNMS_E2_T(k) do { } while (0)
+#define GNMS_E2_C(k, v) do { } while (0)
+#endif
+template <int kSrc, bool kGen, bool kAffine>
+__global__ void __launch_bounds__(kE2Threads) elect2_kernel(Elect2Args A) {
+    typedef typename RecOf<kSrc>::type RecT;
+    constexpr int kAxes = AxesOf<kSrc>::kAxes;
+    extern __shared__ __align__(16) unsigned char s_e2[];
+    const int b = blockIdx.x, N = A.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef GNMS_DEBUG
+    long long e2_t = clock64();
+#endif
+    const int n = A.n_per_image ? min(A.n_per_image[b], N) : N;
+    const int nw = (n + 31) / 32;
+    const int Np = (N + kE2Threads - 1) / kE2Threads * kE2Threads, KK = Np / kE2Threads;
+    const WsLayout L = ws_layout(N);
+    char* w = A.ws + (size_t)b * A.ws_img_stride;
+    float* vout = A.vout + (size_t)b * N;
+    float4* rec4 = reinterpret_cast<float4*>(s_e2);                                  // [Np][2] sorted records
+    int32_t* fsup = reinterpret_cast<int32_t*>(rec4 + (size_t)Np * 2);              // [Np] first suppressor (sorted position)
+    uint32_t* queue = reinterpret_cast<uint32_t*>(fsup + Np);                        // [kE2Queue] (position << 5) | leader slot
+    uint32_t* alive = queue + kE2Queue;                                              // [128] the pool, by sorted position
+    uint32_t* leaderb = alive + 128;
+    uint32_t* badb = leaderb + 128;                                                  // record outside div_rn_fast's proven range
+    float4* ltab = reinterpret_cast<float4*>(badb + 128);                            // [32][3]: (lo, hi, extent, bad) per axis
+    int32_t* cand = reinterpret_cast<int32_t*>(ltab + 32 * 3);                       // [32] candidate positions
+    uint32_t* covm = reinterpret_cast<uint32_t*>(cand + 32);                         // [32] bit j of row i: !(overlap(i, j) <= thr)
+    int32_t* lpos = reinterpret_cast<int32_t*>(covm + 32);                           // [32] position of leader slot q
+    int32_t* lcidx = lpos + 32;                                                      // [32] candidate index of leader slot q
+    float* covv = reinterpret_cast<float*>(lcidx + 32);                              // [32][32] overlap(candidate i, candidate j < i)
+    uint32_t* reach = reinterpret_cast<uint32_t*>(covv + 32 * 32);                   // [2][kE2Bins] leader slots that reach a bin
+    uint32_t* lbins = reach + 2 * kE2Bins;                                           // [32] leader slot q: first / last bin on axes 0, 1 (4 bytes)
+    uint32_t* apref = lbins + 32;                                                    // [128] pool bits before each word
+    uint16_t* bins = reinterpret_cast<uint16_t*>(apref + 128);                       // [Np] bin on axis 0 | bin on axis 1 << 8 (0xffff: bad box)
+    __shared__ int s_K, s_m, s_qn, s_over;
+    __shared__ uint32_t s_leaders;
+    __shared__ float s_red[32][8];
+    __shared__ float s_binp[8];               // per axis a in {0, 1}: origin, scale, largest extent, absolute margin
+    {
+        const char* src = w + L.sbox;
+        for (int i = tid; i < 2 * n; i += kE2Threads) cp_async16(rec4 + i, src + (size_t)i * 16);
+    }
+    if (tid < 128) { alive[tid] = tid < nw ? valid_word(tid, n) : 0u; leaderb[tid] = 0u; }
+    auto record = [&](int pos) -> RecT {
+        const float4 u = rec4[2 * pos], v = rec4[2 * pos + 1];
+        if constexpr (kSrc == kSrcBox3d) return Rec3{u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+        else return Box2{u.x, u.y, u.z, u.w, v.x};
+    };
+    auto is_bad = [&](int pos) -> bool { return (badb[pos >> 5] >> (pos & 31)) & 1u; };
+    cp_async_wait_all();
+    __syncthreads();
+    {
+        // bad flags; per axis (0, 1): range of the lower edges, largest extent, largest magnitude -- over the sane boxes
+        float mn0 = INFINITY, mx0 = -INFINITY, mn1 = INFINITY, mx1 = -INFINITY, ex0 = 0.f, ex1 = 0.f, mg = 0.f;
+        for (int k = 0; k < KK; ++k) {
+            const int pos = k * kE2Threads + tid;
+            fsup[pos] = INT_MAX;
+            bool bad = false;
+            if (pos < n) {
+                const RecT r = record(pos);
+                if constexpr (kSrc == kSrcBox3d) bad = !rec3_sane(r);
+                else bad = !box2_sane(r);
+                if (!bad) {
+                    float lo[3], hi[3];
+                    AxesOf<kSrc>::get(r, lo, hi);
+                    mn0 = fminf(mn0, lo[0]); mx0 = fmaxf(mx0, lo[0]); ex0 = fmaxf(ex0, __fsub_rn(hi[0], lo[0]));
+                    mn1 = fminf(mn1, lo[1]); mx1 = fmaxf(mx1, lo[1]); ex1 = fmaxf(ex1, __fsub_rn(hi[1], lo[1]));
+                    mg = fmaxf(mg, fmaxf(fmaxf(fabsf(lo[0]), fabsf(hi[0])), fmaxf(fabsf(lo[1]), fabsf(hi[1]))));
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, bad);
+            if (lane == 0) badb[k * 32 + warp] = bal;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            mn0 = fminf(mn0, __shfl_xor_sync(0xffffffffu, mn0, d)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, d));
+            mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, d)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, d));
+            ex0 = fmaxf(ex0, __shfl_xor_sync(0xffffffffu, ex0, d)); ex1 = fmaxf(ex1, __shfl_xor_sync(0xffffffffu, ex1, d));
+            mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, d));
+        }
+        if (lane == 0) { s_red[warp][0] = mn0; s_red[warp][1] = mx0; s_red[warp][2] = mn1; s_red[warp][3] = mx1; s_red[warp][4] = ex0; s_red[warp][5] = ex1; s_red[warp][6] = mg; }
+        __syncthreads();
+        if (warp == 0) {
+            mn0 = s_red[lane][0]; mx0 = s_red[lane][1]; mn1 = s_red[lane][2]; mx1 = s_red[lane][3]; ex0 = s_red[lane][4]; ex1 = s_red[lane][5]; mg = s_red[lane][6];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                mn0 = fminf(mn0, __shfl_xor_sync(0xffffffffu, mn0, d)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, d));
+                mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, d)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, d));
+                ex0 = fmaxf(ex0, __shfl_xor_sync(0xffffffffu, ex0, d)); ex1 = fmaxf(ex1, __shfl_xor_sync(0xffffffffu, ex1, d));
+                mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, d));
+            }
+            if (lane == 0) {
+                // scale = bins / range (0 when the range is empty, not finite or absurd: then every box sits in bin 0 and the
+                // tables cull nothing); margin: a few ulps of the largest coordinate, it absorbs the rounding of the reach edges
+                const float r0 = __fsub_rn(mx0, mn0), r1 = __fsub_rn(mx1, mn1);
+                s_binp[0] = mn0; s_binp[1] = (r0 > 0.f && r0 < 1e30f) ? __fdiv_rn((float)kE2Bins, r0) : 0.f; s_binp[2] = ex0;
+                s_binp[4] = mn1; s_binp[5] = (r1 > 0.f && r1 < 1e30f) ? __fdiv_rn((float)kE2Bins, r1) : 0.f; s_binp[6] = ex1;
+                s_binp[3] = s_binp[7] = __fmul_rn(__fadd_rn(mg, fmaxf(ex0, ex1)), 1.9073486e-6f);                    // 2^-19
+            }
+        }
+    }
+    const float thr = A.thr, cc = A.cull_c;
+    __syncthreads();
+    {
+        const float bo0 = s_binp[0], bs0 = s_binp[1], bo1 = s_binp[4], bs1 = s_binp[5];
+        for (int k = 0; k < KK; ++k) {
+            const int pos = k * kE2Threads + tid;
+            uint16_t bb = 0xffffu;
+            if (pos < n && !is_bad(pos)) {
+                float lo[3], hi[3];
+                AxesOf<kSrc>::get(record(pos), lo, hi);
+                bb = (uint16_t)(e2_bin(lo[0], bo0, bs0) | (e2_bin(lo[1], bo1, bs1) << 8));
+            }
+            bins[pos] = bb;
+        }
+    }
+    GNMS_E2_T(0);
+    while (true) {
+        // ---- A: the first <= 32 positions of the pool.  Lane i counts words 4i .. 4i+3, a warp scan gives the number of pool
+        //      bits before every word, and output slot o (lane o) finds its word by bisection and its bit with __fns.
+        if (warp == 0) {
+            const uint4 wv = reinterpret_cast<const uint4*>(alive)[lane];
+            const int c0 = __popc(wv.x), c1 = __popc(wv.y), c2 = __popc(wv.z), c3 = __popc(wv.w);
+            int incl = c0 + c1 + c2 + c3;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int before = incl - (c0 + c1 + c2 + c3);
+            reinterpret_cast<uint4*>(apref)[lane] = make_uint4(before, before + c0, before + c0 + c1, before + c0 + c1 + c2);
+            __syncwarp();
+            const int K0 = min(total, 32);
+            if (lane < K0) {
+                int lo_ = 0, hi_ = 127;                                       // last word whose prefix is <= lane
+                while (lo_ < hi_) {
+                    const int mid = (lo_ + hi_ + 1) >> 1;
+                    if ((int)apref[mid] <= lane) lo_ = mid; else hi_ = mid - 1;
+                }
+                cand[lane] = lo_ * 32 + __fns(alive[lo_], 0, lane - (int)apref[lo_] + 1);
+            }
+            covm[lane] = 0u;
+            if (lane == 0) s_K = K0;
+        }
+        __syncthreads(); GNMS_E2_T(1);
+        int K = s_K;
+        if (K == 0) break;
+        GNMS_E2_C(8, 1);
+        // ---- B: candidate x earlier candidate
+        if (warp < K) {
+            bool hit = false;
+            if (lane < warp) {
+                const int pi = cand[warp], pj = cand[lane];
+                const RecT mine = record(pi), other = record(pj);
+                bool unsafe = is_bad(pi) || is_bad(pj);
+                float v = RecOf<kSrc>::template fast<kGen, kAffine>(mine, other, unsafe);
+                if (__builtin_expect(unsafe, 0)) v = RecOf<kSrc>::template exact<kGen, kAffine>(mine, other);
+                hit = !(v <= thr);                                             // NaN leaves the pool too (:249-250)
+                covv[warp * 32 + lane] = v;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) covm[warp] = bal;
+        }
+        __syncthreads(); GNMS_E2_T(2);
+        // ---- C: resolve the candidates in score order (dependency rounds, usually 2-3)
+        if (warp == 0) {
+            const uint32_t row = lane < K ? covm[lane] : 0u;
+            uint32_t undecided = K == 32 ? 0xffffffffu : ((1u << K) - 1u), leaders = 0u;
+            while (undecided) {
+                const bool mine = (undecided >> lane) & 1u;
+                const bool isl = mine && (row & (undecided | leaders)) == 0u;
+                const bool iss = mine && (row & leaders) != 0u;
+                const uint32_t nl = __ballot_sync(0xffffffffu, isl), ns = __ballot_sync(0xffffffffu, iss);
+                leaders |= nl;
+                undecided &= ~(nl | ns);
+            }
+            if (lane < K) {
+                const int c = cand[lane];
+                if ((leaders >> lane) & 1u) {
+                    const int q = __popc(leaders & ((1u << lane) - 1u));
+                    lpos[q] = c; lcidx[q] = lane;
+                    float lo[3], hi[3];
+                    AxesOf<kSrc>::get(record(c), lo, hi);
+                    const bool lbad = is_bad(c);
+#pragma unroll
+                    for (int ax = 0; ax < kAxes; ++ax) ltab[q * 3 + ax] = make_float4(lo[ax], hi[ax], __fsub_rn(hi[ax], lo[ax]), lbad ? 1.f : 0.f);
+                    // reach tables: a box can pass the gap test on axis a only if its lower edge lies in
+                    // [lo - R - emax - margin, hi + R + margin], R = c (extent + emax); bins of those two edges, inclusive
+                    uint32_t lb = 0u;
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        int b0 = 0, b1 = kE2Bins - 1;
+                        if (!lbad) {
+                            const float emax = s_binp[a * 4 + 2], mgn = s_binp[a * 4 + 3];
+                            const float R = __fmul_rn(cc, __fadd_rn(__fsub_rn(hi[a], lo[a]), emax));
+                            b0 = e2_bin(__fsub_rn(__fsub_rn(__fsub_rn(lo[a], R), emax), mgn), s_binp[a * 4], s_binp[a * 4 + 1]);
+                            b1 = e2_bin(__fadd_rn(__fadd_rn(hi[a], R), mgn), s_binp[a * 4], s_binp[a * 4 + 1]);
+                        }
+                        lb |= (uint32_t)(b0 | (b1 << 8)) << (16 * a);
+                    }
+                    lbins[q] = lb;
+                    atomicOr(&leaderb[c >> 5], 1u << (c & 31));
+                } else {
+                    const int jf = __ffs(row & leaders) - 1;
+                    fsup[c] = cand[jf];
+                    vout[c] = covv[lane * 32 + jf];
+                }
+                atomicAnd(&alive[c >> 5], ~(1u << (c & 31)));
+            }
+            if (lane == 0) { s_m = __popc(leaders); s_leaders = leaders; s_qn = 0; s_over = 0; }
+        }
+        __syncthreads();
+        {
+            // reach tables: 8 threads per (axis, bin), 4 leader slots each, OR-reduced over the 8 neighbouring lanes
+            const int a = tid >> 9, bin = (tid >> 3) & (kE2Bins - 1), part = tid & 7, m0 = s_m;
+            uint32_t bits = 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = part * 4 + u;
+                if (q < m0) {
+                    const uint32_t lb = lbins[q] >> (16 * a);
+                    if (bin >= (int)(lb & 0xffu) && bin <= (int)((lb >> 8) & 0xffu)) bits |= 1u << q;
+                }
+            }
+            bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+            bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+            bits |= __shfl_xor_sync(0xffffffffu, bits, 4);
+            if (part == 0) reach[a * kE2Bins + bin] = bits;
+        }
+        __syncthreads(); GNMS_E2_T(3);
+        GNMS_E2_C(9, s_m);
+        // ---- D: pool x the leaders that can reach it
+        while (true) {
+            const int m = s_m;
+            const uint32_t mall = m == 32 ? 0xffffffffu : ((1u << m) - 1u);
+            for (int k = 0; k < KK; ++k) {
+                const int pos = k * kE2Threads + tid;
+                uint32_t nearm = 0u;
+                if ((alive[k * 32 + warp] >> lane) & 1u) {
+                    const uint32_t bb = bins[pos];
+                    const bool mybad = bb == 0xffffu;
+                    uint32_t cm = mall;
+                    if (!mybad) cm &= reach[bb & 0xffu] & reach[kE2Bins + (bb >> 8)];
+                    float lo[3], hi[3];
+                    if (cm) AxesOf<kSrc>::get(record(pos), lo, hi);
+                    while (cm) {
+                        const int q = __ffs(cm) - 1;
+                        cm &= cm - 1u;
+                        bool nr = true;
+                        if (ltab[q * 3].w == 0.f && !mybad) {
+#pragma unroll
+                            for (int ax = 0; ax < kAxes; ++ax) {
+                                const float4 t = ltab[q * 3 + ax];
+                                if (fmaxf(__fsub_rn(lo[ax], t.y), __fsub_rn(t.x, hi[ax])) > __fmul_rn(cc, __fadd_rn(t.z, __fsub_rn(hi[ax], lo[ax])))) nr = false;
+                            }
+                        }
+                        nearm |= (uint32_t)nr << q;
+                    }
+                }
+                // warp-aggregated push
+                const int cnt = __popc(nearm);
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                if (tot == 0) continue;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_qn, tot);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base + tot > kE2Queue) { if (lane == 0) s_over = 1; continue; }
+                int at = base + incl - cnt;
+                while (nearm) {
+                    const int q = __ffs(nearm) - 1;
+                    nearm &= nearm - 1u;
+                    queue[at++] = ((uint32_t)pos << 5) | (uint32_t)q;
+                }
+            }
+            __syncthreads();
+            if (!s_over) break;
+            GNMS_E2_C(11, 1);
+            __syncthreads();                                                   // (everybody has seen the flag)
+            if (warp == 0) {
+                // keep the first quarter of this step's leaders; later candidates go back to the pool unless one of the kept
+                // leaders suppresses them (then their first suppressor is already right: it is the lowest leader of their row)
+                const uint32_t leaders = s_leaders;
+                const int keep = max(1, m >> 2);
+                uint32_t rest = leaders;
+                for (int t = 0; t < keep; ++t) rest &= rest - 1u;
+                const int icut = __ffs(rest) - 1;                              // candidate index of the first dropped leader
+                const uint32_t kept = leaders & ((1u << icut) - 1u);
+                if (lane >= icut && lane < K) {
+                    const int c = cand[lane];
+                    const bool was_leader = (leaders >> lane) & 1u;
+                    if (was_leader || (covm[lane] & kept) == 0u) {
+                        atomicOr(&alive[c >> 5], 1u << (c & 31));
+                        fsup[c] = INT_MAX;
+                        if (was_leader) atomicAnd(&leaderb[c >> 5], ~(1u << (c & 31)));
+                    }
+                }
+                __syncwarp();                                                  // (every lane has read s_leaders)
+                if (lane == 0) { s_m = keep; s_leaders = kept; s_K = icut; s_qn = 0; s_over = 0; }
+            }
+            __syncthreads();
+            K = s_K;
+        }
+        // ---- E: the queued pairs, one per thread and round
+        GNMS_E2_T(4);
+        const int qn = s_qn;
+        GNMS_E2_C(10, qn);
+        float vreg[kE2PerThread];
+#pragma unroll
+        for (int i = 0; i < kE2PerThread; ++i) {
+            const int e = i * kE2Threads + tid;
+            vreg[i] = 0.f;
+            if (e < qn) {
+                const uint32_t ent = queue[e];
+                const int pos = (int)(ent >> 5), l = lpos[ent & 31u];
+                const RecT mine = record(pos), ldr = record(l);
+                bool unsafe = is_bad(pos) || is_bad(l);
+                float v = RecOf<kSrc>::template fast<kGen, kAffine>(mine, ldr, unsafe);
+                if (__builtin_expect(unsafe, 0)) v = RecOf<kSrc>::template exact<kGen, kAffine>(mine, ldr);
+                if (!(v <= thr)) atomicMin(&fsup[pos], l);
+                vreg[i] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kE2PerThread; ++i) {
+            const int e = i * kE2Threads + tid;
+            if (e < qn) {
+                const uint32_t ent = queue[e];
+                const int pos = (int)(ent >> 5);
+                if (fsup[pos] == lpos[ent & 31u] && !(vreg[i] <= thr)) vout[pos] = vreg[i];
+            }
+        }
+        GNMS_E2_T(5);
+        // ---- F: boxes with a suppressor leave the pool
+        for (int k = 0; k < KK; ++k) {
+            const int pos = k * kE2Threads + tid;
+            const bool a = ((alive[k * 32 + warp] >> lane) & 1u) && fsup[pos] == INT_MAX;
+            const unsigned bal = __ballot_sync(0xffffffffu, a);
+            __syncwarp();                                                      // (every lane has read the word lane 0 rewrites)
+            if (lane == 0) alive[k * 32 + warp] = bal;
+        }
+        __syncthreads(); GNMS_E2_T(6);
+    }
+    if (A.fuse_chain) {
+        // the chain continues in place: leader bitset and first suppressors stay where they are, everything else it needs is
+        // carved out of the record area (dead now).  vout[] (global, written above) is read back by the same CTA: the barrier
+        // that ended the loop ordered those writes.
+        static_assert(kE2Threads == kChainThreads, "the chain runs with the election's thread block");
+        const int NWc = (N + 31) / 32, NWa = (NWc + 3) & ~3, Na = (N + 3) & ~3;
+        unsigned char* base = s_e2;
+        ChainSmem S;
+        S.removed = reinterpret_cast<uint32_t*>(base);
+        S.tmpbits = S.removed + NWa;
+        S.list = reinterpret_cast<int32_t*>(S.tmpbits + NWa);
+        S.wcol = reinterpret_cast<uint32_t*>(S.list + Na);
+        size_t P2 = 1;
+        while ((int)P2 < N) P2 <<= 1;
+        const size_t wbytes = P2 * 8 > (size_t)kWin * NWc * 4 ? P2 * 8 : (size_t)kWin * NWc * 4;
+        S.ss_s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(S.wcol) + wbytes);
+        S.leader = leaderb;
+        S.fsup = fsup;
+        for (int pos = n + tid; pos < N; pos += kE2Threads) fsup[pos] = INT_MAX;      // (dead tail, as the chain's own loader leaves it)
+        __syncthreads();
+        chain_body(A.chain, b, S, true);
+        return;
+    }
+    int32_t* dfsup = reinterpret_cast<int32_t*>(w + L.dfsup);
+    uint32_t* dleader = reinterpret_cast<uint32_t*>(w + L.dleader);
+    for (int pos = tid; pos < n; pos += kE2Threads) dfsup[pos] = fsup[pos];
+    GNMS_E2_T(7);
+    if (tid < (N + 31) / 32) dleader[tid] = tid < 128 ? leaderb[tid] : 0u;
+    if (tid == 0) *reinterpret_cast<int32_t*>(w + L.dflag) = 0;
+}
+
+
 }  // namespace gnms
 #include "solve.cuh"
 namespace gnms {
@@ -3114,9 +3167,22 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
         if (g_stage_mask & 2) spatial_kernel<<<batch, 1024, 0, s>>>(SA);     // spatial order + group table, no tile list yet
         GNMS_LAUNCH_CHECK();
     }
+    ChainArgs A = {};
+    A.N = N; A.batch = batch; A.n_per_image = npi; A.ws = ws; A.ws_img_stride = L.total;
+    A.src = src; A.iou = iou; A.ld = ld; A.iou_img_stride = (int64_t)N * ld;
+    A.generalized = generalized; A.affine = affine; A.p = *p;
+    A.order = sv.order; A.sorted_scores = sv.sorted_scores; A.prob = prob; A.valid_idx = valid_idx;
+    A.invalid_idx = invalid_idx; A.counts = counts; A.lead = sv.lead; A.pval = sv.pval; A.dpval = sv.dpval;
+    A.pre = sv.pre; A.slot = slot; A.direct = (direct || direct2) ? 1 : 0; A.have_v = (direct2 && (g_stage_mask & 32)) ? 1 : 0;
+    A.p.mode = mode; A.tril_input = tril_input ? 1 : 0;
+    // mode GROUP_MASK after the batched election: the chain runs at the end of elect2_kernel, out of the same shared memory
+    // (one launch; the election's result never goes through global memory).  A stage mask that asks for one of the two alone
+    // keeps them apart.
+    const bool chain_fused = direct2 && mode == GNMS_MODE_GROUP_MASK && (g_stage_mask & 32) && (g_stage_mask & 16) && !(O.flags & GNMS_OPT_SPLIT_CHAIN);
     if (direct2 && (g_stage_mask & 32)) {
         Elect2Args E = {};
         E.N = N; E.batch = batch; E.n_per_image = npi; E.ws = ws; E.ws_img_stride = L.total; E.thr = p->nms_threshold; E.cull_c = cull_c; E.vout = sv.pval;
+        E.fuse_chain = chain_fused ? 1 : 0; E.chain = A; E.chain.stage = 0;
         const size_t esm = elect2_smem_bytes(N);
 #define GNMS_ELECT2(SRC, G, AF)                                                                                       \
     do {                                                                                                              \
@@ -3223,15 +3289,7 @@ static int run_forward(const float* scores, int src, const float* iou, int64_t l
             GNMS_LAUNCH_CHECK();
         }
     }
-    ChainArgs A = {};
-    A.N = N; A.batch = batch; A.n_per_image = npi; A.ws = ws; A.ws_img_stride = L.total;
-    A.src = src; A.iou = iou; A.ld = ld; A.iou_img_stride = (int64_t)N * ld;
-    A.generalized = generalized; A.affine = affine; A.p = *p;
-    A.order = sv.order; A.sorted_scores = sv.sorted_scores; A.prob = prob; A.valid_idx = valid_idx;
-    A.invalid_idx = invalid_idx; A.counts = counts; A.lead = sv.lead; A.pval = sv.pval; A.dpval = sv.dpval;
-    A.pre = sv.pre; A.slot = slot; A.direct = (direct || direct2) ? 1 : 0; A.have_v = (direct2 && (g_stage_mask & 32)) ? 1 : 0;
-    A.p.mode = mode; A.tril_input = tril_input ? 1 : 0;
-    if (!(g_stage_mask & 16)) return 0;
+    if (!(g_stage_mask & 16) || chain_fused) return 0;
     if (mode == GNMS_MODE_GROUP_MASK) {
         A.stage = 0;
         chain_kernel<<<batch, kChainThreads, chain_smem_bytes(N), s>>>(A);

@@ -62,11 +62,11 @@ class Nms3dPlan(object):
         self.fl = torch.empty((4, batch, n), **f)
         self.ws = torch.empty((int(self.lib.gnms_workspace_bytes(n, batch)),), dtype=torch.uint8, device=device)
         self.saved = Saved(_vp(self.order), _vp(self.fl[0]), _vp(self.lead), _vp(self.fl[1]), _vp(self.fl[2]), _vp(self.fl[3]))
-        # matrix-free:     records (from the 7-DoF boxes), sort, rank, elect2 (batched leader election), chain, backward
+        # matrix-free:     records (from the 7-DoF boxes), sort, rank, elect2 (batched leader election with the chain at its end), backward
         # matrix produced: the same plus the matrix-only tile kernel
-        # (batches below ~10 images of N = 4096 rank by counting: one launch fewer; two_kernel: overlap + mask + chain instead)
+        # (batches below ~10 images of N = 4096 rank by counting: one launch fewer; two_kernel: overlap, rank, mask, chain, backward)
         by_sort = float(batch) * n * n >= 10.0 * 4096 * 4096
-        self.launches_per_step = (5 if by_sort else 4) + 1 + (1 if materialise else 0)
+        self.launches_per_step = (6 if by_sort else 5) if two_kernel else (4 if by_sort else 3) + 1 + (1 if materialise else 0)
 
     # -- individual stages (each is one C-ABI call = one kernel launch unless noted)
     def stage_corners(self, s):
@@ -188,10 +188,10 @@ class BatchedHeadPlan(object):
         self.bucket = GradBucket({"head_wb": self.FEAT + 1}, device, pad_elems=bucket_pad_elems)
         self.grad_wb = self.bucket.view("head_wb")
         self.forward_opts = None
-        # head fwd, [sort,] rank, elect2, chain, [matrix], NMS backward, head backward (2 launches); the all-reduce is NCCL's
+        # head fwd, [sort,] rank, elect2 (+ chain), [matrix], NMS backward, head backward (2 launches); the all-reduce is NCCL's
         # kernel, not counted
         by_sort = float(batch) * n * n >= 10.0 * 4096 * 4096
-        self.launches_per_step = 7 + (1 if by_sort else 0) + (1 if materialise else 0)
+        self.launches_per_step = 6 + (1 if by_sort else 0) + (1 if materialise else 0)
 
     def compute(self, s):
         """Forward + backward of this rank's shard (no collective)."""

@@ -110,6 +110,7 @@ const char* gnms_error_string(int rc);
 #define GNMS_OPT_SCALAR_MATH   1u     /* flags: scalar fp32 instead of packed fp32x2 arithmetic in the matrix-only kernel */
 #define GNMS_OPT_INLINE_HITS   2u     /* flags: threshold hits handled inline instead of through the CTA-drained queue */
 #define GNMS_OPT_ONE_PASS      4u     /* flags: matrix + suppression bits from one all-pairs pass (no separate matrix-only kernel) */
+#define GNMS_OPT_SPLIT_CHAIN   8u     /* flags: batched election and chain as two launches (default: the chain runs at the end of the election kernel) */
 typedef struct gnms_launch_opts {
     uint32_t struct_size;          /* sizeof(gnms_launch_opts) */
     int32_t  matrix_kernel;        /* GNMS_MATRIX_KERNEL_* : how the [N,N] overlap matrix is written */

@@ -538,9 +538,9 @@ def test_direct_election_mixed_batch_and_fallback(kind):
     ref = ops.forward_matrix(cuda(sc), iou, p, n_per_image=npi)
     n_lead = [(int((ref.lead[b, :n] == torch.arange(n, device="cuda")).sum())) for b, n in enumerate(ns)]
     assert n_lead[0] < 100 and n_lead[1] > 384 and n_lead[5] > 384      # both routes are really exercised
-    for direct in (_lib.ELECT_BATCHED, _lib.ELECT_DIRECT, _lib.ELECT_MASK):
+    for direct, flags in ((_lib.ELECT_BATCHED, 0), (_lib.ELECT_BATCHED, _lib.OPT_SPLIT_CHAIN), (_lib.ELECT_DIRECT, 0), (_lib.ELECT_MASK, 0)):
         st = ops.forward_boxes(cuda(sc), dev_data, kw["box_kind"], p, kw.get("generalized", False), kw.get("affine", False),
-                               n_per_image=npi, opts=_lib.launch_opts(election=direct))
+                               n_per_image=npi, opts=_lib.launch_opts(election=direct, flags=flags))
         torch.cuda.synchronize()
         for f in ("order", "lead", "prob", "pre", "counts"):
             assert torch.equal(getattr(ref, f), getattr(st, f)), (direct, f)
