@@ -2412,6 +2412,7 @@ __device__ int warp_list_bits(const uint32_t* bits, int nw, int limit, int32_t* 
 constexpr int kE2Threads = 1024;
 constexpr int kE2Queue = 8192;
 constexpr int kE2PerThread = kE2Queue / kE2Threads;
+constexpr int kE2MaxK = kElectMaxBoxes / kE2Threads;        // pool positions per thread
 constexpr int kE2Bins = 64;
 struct Elect2Args {
     int N, batch;
@@ -2688,10 +2689,13 @@ __global__ void __launch_bounds__(kE2Threads) elect2_kernel(Elect2Args A) {
         while (true) {
             const int m = s_m;
             const uint32_t mall = m == 32 ? 0xffffffffu : ((1u << m) - 1u);
-            for (int k = 0; k < KK; ++k) {
-                const int pos = k * kE2Threads + tid;
-                uint32_t nearm = 0u;
-                if ((alive[k * 32 + warp] >> lane) & 1u) {
+            // (the positions of a thread are swept first, all of them, then pushed with ONE warp scan and one atomic)
+            uint32_t nearm[kE2MaxK];
+#pragma unroll
+            for (int k = 0; k < kE2MaxK; ++k) {
+                nearm[k] = 0u;
+                if (k < KK && ((alive[k * 32 + warp] >> lane) & 1u)) {
+                    const int pos = k * kE2Threads + tid;
                     const uint32_t bb = bins[pos];
                     const bool mybad = bb == 0xffffu;
                     uint32_t cm = mall;
@@ -2709,28 +2713,44 @@ __global__ void __launch_bounds__(kE2Threads) elect2_kernel(Elect2Args A) {
                                 if (fmaxf(__fsub_rn(lo[ax], t.y), __fsub_rn(t.x, hi[ax])) > __fmul_rn(cc, __fadd_rn(t.z, __fsub_rn(hi[ax], lo[ax])))) nr = false;
                             }
                         }
-                        nearm |= (uint32_t)nr << q;
+                        nearm[k] |= (uint32_t)nr << q;
                     }
                 }
-                // warp-aggregated push
-                const int cnt = __popc(nearm);
-                int incl = cnt;
+            }
+            {
+                // one scan for the (up to four) positions of every lane: their counts travel as 16-bit fields of one word, so
+                // that the queue keeps the pairs of 32 consecutive positions together (the evaluation reads their records)
+                unsigned long long packed = 0ull;
+#pragma unroll
+                for (int k = 0; k < kE2MaxK; ++k) packed |= (unsigned long long)__popc(nearm[k]) << (16 * k);
+                unsigned long long incl = packed;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
                     if (lane >= d) incl += t;
                 }
-                const int tot = __shfl_sync(0xffffffffu, incl, 31);
-                if (tot == 0) continue;
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_qn, tot);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base + tot > kE2Queue) { if (lane == 0) s_over = 1; continue; }
-                int at = base + incl - cnt;
-                while (nearm) {
-                    const int q = __ffs(nearm) - 1;
-                    nearm &= nearm - 1u;
-                    queue[at++] = ((uint32_t)pos << 5) | (uint32_t)q;
+                const unsigned long long totp = __shfl_sync(0xffffffffu, incl, 31);
+                const int tot = (int)((totp & 0xffffu) + ((totp >> 16) & 0xffffu) + ((totp >> 32) & 0xffffu) + (totp >> 48));
+                if (tot != 0) {                                                // (warp-uniform)
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_qn, tot);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base + tot > kE2Queue) {
+                        if (lane == 0) s_over = 1;
+                    } else {
+                        const unsigned long long excl = incl - packed;
+#pragma unroll
+                        for (int k = 0; k < kE2MaxK; ++k) {
+                            int at = base + (int)((excl >> (16 * k)) & 0xffffu);
+                            uint32_t nm = nearm[k];
+                            while (nm) {
+                                const int q = __ffs(nm) - 1;
+                                nm &= nm - 1u;
+                                queue[at++] = ((uint32_t)(k * kE2Threads + tid) << 5) | (uint32_t)q;
+                            }
+                            base += (int)((totp >> (16 * k)) & 0xffffu);
+                        }
+                    }
                 }
             }
             __syncthreads();
