@@ -2491,9 +2491,25 @@ __global__ void __launch_bounds__(kE2Threads) elect2_kernel(Elect2Args A) {
     __shared__ uint32_t s_leaders;
     __shared__ float s_red[32][8];
     __shared__ float s_binp[8];               // per axis a in {0, 1}: origin, scale, largest extent, absolute margin
-    {
+    // the image's sorted records (32 n bytes, contiguous): 1-D bulk copies by the copy engine, one thread issues them and an
+    // mbarrier counts the bytes in -- no load instructions, no registers, the other threads set up the pool meanwhile
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)n * 32u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
         const char* src = w + L.sbox;
-        for (int i = tid; i < 2 * n; i += kE2Threads) cp_async16(rec4 + i, src + (size_t)i * 16);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(rec4);
+        for (uint32_t off = 0; off < bytes; off += 16384u) {
+            const uint32_t sz = bytes - off < 16384u ? bytes - off : 16384u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst + off), "l"(src + off), "r"(sz), "r"(mbar) : "memory");
+        }
     }
     if (tid < 128) { alive[tid] = tid < nw ? valid_word(tid, n) : 0u; leaderb[tid] = 0u; }
     auto record = [&](int pos) -> RecT {
@@ -2502,7 +2518,13 @@ __global__ void __launch_bounds__(kE2Threads) elect2_kernel(Elect2Args A) {
         else return Box2{u.x, u.y, u.z, u.w, v.x};
     };
     auto is_bad = [&](int pos) -> bool { return (badb[pos >> 5] >> (pos & 31)) & 1u; };
-    cp_async_wait_all();
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mbar) : "memory");
+        }
+    }
     __syncthreads();
     {
         // bad flags; per axis (0, 1): range of the lower edges, largest extent, largest magnitude -- over the sane boxes
