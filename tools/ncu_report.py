@@ -32,7 +32,10 @@ def main():
     rows = page(rep, "raw")
     hdr, units = rows[0], rows[1]
     ki = hdr.index("Kernel Name")
-    row = next(r for r in rows[2:] if want in r[ki])
+    row = next((r for r in rows[2:] if want in r[ki]), None)
+    if row is None:
+        print("(no launch of a kernel matching '%s' in %s)" % (want, rep))
+        return
     print("kernel: %s" % row[ki])
     print()
     for m in METRICS:

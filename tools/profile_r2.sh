@@ -8,9 +8,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/r2_bench_under_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"tile_tma_kernel" -s 6 -c 1 -f -o gpurun_out/r2_tile_tma_b64 \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/r2_bench_under_ncu2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"sort_kernel|rank_kernel|elect2_kernel|chain_kernel|backward_mask_kernel|records7" \
-    -s 12 -c 6 -f -o gpurun_out/r2_small_kernels python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/r2_bench_under_ncu3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"elect2_kernel|chain_kernel" -s 4 -c 2 -f -o gpurun_out/r2_b1_kernels \
+ncu --set full --clock-control none --import-source on -k regex:"sort_kernel|rank_kernel|elect2_kernel|backward_mask_kernel|records7" \
+    -s 10 -c 5 -f -o gpurun_out/r2_small_kernels python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/r2_bench_under_ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"elect2_kernel" -s 2 -c 1 -f -o gpurun_out/r2_b1_kernels \
     python tools/run_c3_once.py 1 4 > gpurun_out/r2_b1_under_ncu.log 2>&1
 python bench.py > gpurun_out/r2_bench_b64.json 2> gpurun_out/r2_bench_b64.err
 tail -c 600 gpurun_out/r2_bench_b64.json

@@ -9,10 +9,10 @@ python tools/ncu_report.py gpurun_out/r2_tile_tma_b64.ncu-rep tile_tma_kernel \
   "ncu --set full --clock-control none --import-source on -k regex:tile_tma_kernel -s 6 -c 1 python bench.py --steps 2 --warmup 3 --no-cpu --no-extras" \
   "the launch bench.py times: 64 images of N=4096, one 256 x 64 tile per CTA x 4 tiles per CTA; build = $HEAD + working tree of that run (tools/profile_r2.sh)" \
   > profiles/r2_ncu_tile_tma_kernel_b64.txt
-for k in sort_kernel rank_kernel elect2_kernel chain_kernel backward_mask_kernel records7; do
+for k in sort_kernel rank_kernel elect2_kernel backward_mask_kernel records7; do
   python tools/ncu_report.py gpurun_out/r2_small_kernels.ncu-rep $k "ncu --set full, bench.py step (64 images of N=4096 per launch), build $HEAD" ; echo; echo "=================================================================="; echo
 done > profiles/r2_ncu_small_kernels.txt
-for k in elect2_kernel chain_kernel; do
+for k in elect2_kernel; do
   python tools/ncu_report.py gpurun_out/r2_b1_kernels.ncu-rep $k "ncu --set full, ONE image of N=4096 (tools/run_c3_once.py 1 4), build $HEAD" ; echo; echo "=================================================================="; echo
 done > profiles/r2_ncu_b1_kernels.txt
 python - <<'PY'
