@@ -2917,18 +2917,51 @@ __global__ void __launch_bounds__(kChainThreads) backward_mask_kernel(BwdArgs A)
         ds[pos] = pass ? g : 0.f;
     }
     __syncthreads();
-    // leaders: ds_l = g~_l - sum_m p_ml g~_m.  Members add their fp32 product into an fp64 shared-memory
-    // accumulator: the fp64 sum of fp32 terms is exact unless the terms span > 2^29 in magnitude, so the result
-    // does not depend on the order in which the atomics land (deterministic run to run), and is rounded once.
-    double* acc = reinterpret_cast<double*>(ds + ((N + 1) & ~1));
-    for (int pos = tid; pos < n; pos += kChainThreads) acc[pos] = 0.0;
+    // leaders: ds_l = g~_l - sum_m p_ml g~_m.  The sum must not depend on the order in which the members' atomics land
+    // (deterministic run to run).  Shared-memory atomics on doubles (and on floats, and on 64-bit integers) are compare-and-swap
+    // loops on this part -- a hundred members fighting over their leader's word took most of the kernel -- only 32-bit integer
+    // adds are native.  So the products are accumulated in FIXED POINT: scaled by a power of two taken from the image's largest
+    // product (|term| < 2^47), rounded to an integer and added as four 16-bit digits into four 32-bit counters per leader
+    // (up to 2^13 members cannot overflow them; integer adds commute, so the sum is exact and order-free).  Terms keep 47 bits
+    // below the largest one: the same guarantee as an fp64 sum up to a span of 2^23.  Infinite / NaN products take the fp64 path.
+    float* red = reinterpret_cast<float*>(ds + ((N + 3) & ~3));                    // [32] block reduction
+    uint32_t* dig = reinterpret_cast<uint32_t*>(red + 32);                         // [4][N]
+    double* acc = reinterpret_cast<double*>(dig);                                  // (fp64 path: [N], aliases the digits)
+    float mx = 0.f;
+    for (int pos = tid; pos < n; pos += kChainThreads) {
+        const int ld_ = A.lead[o + pos];
+        if (ld_ >= 0 && ld_ != pos && ds[pos] != 0.f) {
+            const float pr = fabsf(__fmul_rn(A.pval[o + pos], ds[pos]));
+            mx = pr > mx || pr != pr ? pr : mx;                                    // (NaN sticks)
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const float t = __shfl_xor_sync(0xffffffffu, mx, d); mx = (t > mx || t != t) ? t : mx; }
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    for (int i = tid; i < 4 * N; i += kChainThreads) dig[i] = 0u;
     __syncthreads();
+    mx = red[tid & 31];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const float t = __shfl_xor_sync(0xffffffffu, mx, d); mx = (t > mx || t != t) ? t : mx; }
+    const bool fixed = mx < INFINITY;                                              // (false for inf and NaN; block-uniform)
+    int ex = 0;
+    if (fixed && mx > 0.f) (void)frexpf(mx, &ex);                                  // mx < 2^ex
+    const int sh = 47 - ex;
     for (int pos = tid; pos < n; pos += kChainThreads) {
         const int ld_ = A.lead[o + pos];
         if (ld_ >= 0 && ld_ != pos) {
             const float gt = ds[pos];
             if (gt != 0.f) {
-                atomicAdd(&acc[ld_], (double)__fmul_rn(A.pval[o + pos], gt));
+                const float pr = __fmul_rn(A.pval[o + pos], gt);
+                if (fixed) {
+                    const long long t = __double2ll_rn(ldexp((double)pr, sh));
+                    atomicAdd(&dig[ld_], (uint32_t)(t & 0xffff));
+                    atomicAdd(&dig[N + ld_], (uint32_t)((t >> 16) & 0xffff));
+                    atomicAdd(&dig[2 * N + ld_], (uint32_t)((t >> 32) & 0xffff));
+                    atomicAdd(&dig[3 * N + ld_], (uint32_t)(int32_t)(t >> 48));    // signed top digit
+                } else {
+                    atomicAdd(&acc[ld_], (double)pr);
+                }
                 if (A.grad_iou) {
                     const int64_t gi = (int64_t)b * N * A.ld_gi + (int64_t)A.order[o + pos] * A.ld_gi + A.order[o + ld_];
                     A.grad_iou[gi] = __fmul_rn(-__fmul_rn(A.sorted_scores[o + ld_], gt), A.dpval[o + pos]);
@@ -2937,8 +2970,17 @@ __global__ void __launch_bounds__(kChainThreads) backward_mask_kernel(BwdArgs A)
         }
     }
     __syncthreads();
-    for (int pos = tid; pos < n; pos += kChainThreads)
-        A.grad_scores[o + A.order[o + pos]] = __fsub_rn(ds[pos], (float)acc[pos]);
+    for (int pos = tid; pos < n; pos += kChainThreads) {
+        double sum;
+        if (fixed) {
+            const long long v = (long long)dig[pos] + ((long long)dig[N + pos] << 16) + ((long long)dig[2 * N + pos] << 32) +
+                                (long long)((unsigned long long)(long long)(int32_t)dig[3 * N + pos] << 48);
+            sum = ldexp((double)v, -sh);
+        } else {
+            sum = acc[pos];
+        }
+        A.grad_scores[o + A.order[o + pos]] = __fsub_rn(ds[pos], (float)sum);
+    }
     if (n < N) {
         // padded boxes (n_per_image < N): their input slots get zero gradient
         for (int i = tid; i < N; i += kChainThreads) {
@@ -2960,7 +3002,7 @@ static int configure_once() {
     if (done.load(std::memory_order_acquire)) return 0;
     GNMS_CUDA_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)chain_smem_bytes(GNMS_MAX_BOXES)));
-    GNMS_CUDA_TRY(cudaFuncSetAttribute(backward_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * GNMS_MAX_BOXES + 64));
+    GNMS_CUDA_TRY(cudaFuncSetAttribute(backward_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 20 * GNMS_MAX_BOXES + 256));
     GNMS_CUDA_TRY(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(GNMS_MAX_BOXES)));
     done.store(true, std::memory_order_release);
     return 0;
@@ -3433,7 +3475,7 @@ extern "C" int gnms_backward_f32(const float* grad_prob, const float* prob, cons
     A.sorted_scores = sv.sorted_scores; A.lead = sv.lead; A.pval = sv.pval; A.dpval = sv.dpval; A.pre = sv.pre;
     A.slot = workspace ? slot_ptr(workspace, N, batch) : nullptr;
     A.grad_scores = grad_scores; A.grad_iou = grad_iou; A.ld_gi = ld_gi;
-    backward_mask_kernel<<<batch, kChainThreads, (size_t)N * 12 + 16, (cudaStream_t)stream>>>(A);
+    backward_mask_kernel<<<batch, kChainThreads, (size_t)N * 20 + 256, (cudaStream_t)stream>>>(A);
     GNMS_LAUNCH_CHECK();
     return 0;
 }

@@ -1,4 +1,6 @@
 set -x
-mkdir -p gpurun_out
-ncu --set full --clock-control none --import-source on -k regex:"elect2_kernel" -s 2 -c 1 -f -o gpurun_out/r2_b1_kernels python tools/run_c3_once.py 1 4 > gpurun_out/r2_b1_under_ncu.log 2>&1
-tail -3 gpurun_out/r2_b1_under_ncu.log
+timeout 600 python -m pytest tests/test_gpu_groomed.py tests/test_gpu_hostapi.py tests/test_gpu_loss_branch.py tests/test_gpu_loss_ref.py tests/test_gpu_head.py tests/test_gpu_lossbranch_kernels.py -x -q -m gpu 2>&1 | tail -6
+timeout 300 python bench.py --no-cpu 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); e=d['e2e']
+print('value %.1f M  ms/step %.4f  other_path %.4f ms (%.2f G)  e2e %.1f M' % (d['value']/1e6, d['ms_per_step'], d['other_path']['ms_per_step'], d['other_path']['value']/1e9, e['value']/1e6))
+print('backward', d['stage_ms']['backward'], json.dumps(d['extra']['latency_us']['c_abi_graph_N4096_3d_matrix_free']))"
