@@ -1,6 +1,6 @@
 set -x
-timeout 600 python -m pytest tests/test_gpu_groomed.py tests/test_gpu_hostapi.py tests/test_gpu_loss_branch.py tests/test_gpu_loss_ref.py tests/test_gpu_head.py tests/test_gpu_lossbranch_kernels.py -x -q -m gpu 2>&1 | tail -6
-timeout 300 python bench.py --no-cpu 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); e=d['e2e']
-print('value %.1f M  ms/step %.4f  other_path %.4f ms (%.2f G)  e2e %.1f M' % (d['value']/1e6, d['ms_per_step'], d['other_path']['ms_per_step'], d['other_path']['value']/1e9, e['value']/1e6))
-print('backward', d['stage_ms']['backward'], json.dumps(d['extra']['latency_us']['c_abi_graph_N4096_3d_matrix_free']))"
+mkdir -p gpurun_out
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_groomed.py tests/test_gpu_overlaps.py tests/test_gpu_inference_site.py tests/test_gpu_hostapi.py tests/test_gpu_head.py -q -m gpu -x 2>&1 | tail -8 > gpurun_out/r2_memcheck.txt
+cat gpurun_out/r2_memcheck.txt
+timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/run_c3_once.py 2 1 2>&1 | tail -12 > gpurun_out/r2_racecheck.txt
+cat gpurun_out/r2_racecheck.txt
