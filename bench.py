@@ -613,7 +613,7 @@ def run_c4(args, rank, world):
 
     def make_plan(images):
         boxes, feats, grads, wb = c4_inputs(images, N, np, synthetic)
-        pl = BatchedHeadPlan(len(images), N, dev, params, materialise=not args.c4_matrix_free, bucket_pad_elems=pad)
+        pl = BatchedHeadPlan(len(images), N, dev, params, materialise=not args.c4_matrix_free, bucket_pad_elems=pad, collective=args.c4_collective)
         pl.boxes.copy_(torch.from_numpy(boxes)); pl.x.copy_(torch.from_numpy(feats)); pl.grad_prob.copy_(torch.from_numpy(grads))
         pl.wb.copy_(torch.from_numpy(wb))
         return pl
@@ -661,7 +661,8 @@ def run_c4(args, rank, world):
             def __init__(self, pl): self.pl = pl
             def replay(self): self.pl.bucket.all_reduce()
         ms_reduce = timed(ReduceOnly(pl), args.steps, args.warmup) if world > 1 else 0.0
-        res[label] = dict(images_per_rank=len(images), ms_per_step=ms_full, ms_compute_only=ms_compute, ms_allreduce_alone=ms_reduce,
+        res[label] = dict(images_per_rank=len(images), ms_per_step=ms_full, ms_compute_only=ms_compute, ms_nccl_allreduce_alone=ms_reduce,
+                          collective=pl.collective, peer_exchange_ok=(int(pl.exchange.status.item()) == 0) if pl.exchange is not None else None,
                           graphed=graphed, boxes_per_step=(TOTAL if label == "strong" else 4 * world) * N, bucket_bytes=pl.bucket.nbytes,
                           launches=pl.launches_per_step)
         # the reduced gradient must not depend on how the images were sharded (checked against rank 0's own full computation)
@@ -688,10 +689,14 @@ def run_c4(args, rank, world):
             "warmup": args.warmup, "ms_per_step": st["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C4: batch 32 images x N=2048 2D boxes (16 clusters each), shared 64->1 score head, group+mask linear, fwd+bwd, "
-                                   "one NCCL all-reduce of the flat gradient bucket per step", "images_total": TOTAL,
+                                   "one all-reduce of the gradient bucket per step", "images_total": TOTAL,
                        "images_per_rank": st["images_per_rank"], "matrix": "materialised" if not args.c4_matrix_free else "matrix-free",
-                       "bucket_bytes": st["bucket_bytes"], "collective": "ncclAllReduce(sum, fp32) via torch.distributed (NCCL), captured in the step's CUDA graph"
-                                       if st["graphed"] else "ncclAllReduce(sum, fp32) via torch.distributed (NCCL), eager",
+                       "bucket_bytes": st["bucket_bytes"],
+                       "collective": ("all-reduce inside the head-gradient kernel over NVLink peer memory (gnms_score_head_backward_allreduce_f32: CUDA IPC buffers, "
+                                      "release / acquire flags, rank-ordered sum), captured in the step's CUDA graph; ncclAllReduce on the same bucket timed beside it "
+                                      "(extra.*.ms_nccl_allreduce_alone)") if st["collective"] == "peer" else
+                                     ("ncclAllReduce(sum, fp32) via torch.distributed (NCCL), captured in the step's CUDA graph"
+                                      if st["graphed"] else "ncclAllReduce(sum, fp32) via torch.distributed (NCCL), eager"),
                        "parallelism": "per-image shard over %d rank(s)" % world},
             "gpu_launches": st["launches"] * args.steps, "clocks": clocks,
             "step_roofline": {"algorithmic_bytes_per_step": bytes_step, "effective_GBps": bytes_step / (st["ms_per_step"] * 1e-3) / 1e9 / 1.0,
@@ -729,6 +734,8 @@ def main():
                                                                           "images sharded over the ranks with one NCCL gradient all-reduce per step")
     ap.add_argument("--bucket-mb", type=int, default=0, help="c4: pad the gradient bucket to this many MiB (48 = the reference model's size)")
     ap.add_argument("--c4-matrix-free", action="store_true", help="c4: do not materialise the [N,N] IoU matrices")
+    ap.add_argument("--c4-collective", default="auto", choices=["auto", "peer", "nccl"],
+                    help="c4: all-reduce inside the head-gradient kernel over NVLink peer memory (auto: when the bucket is not padded) or NCCL")
     ap.add_argument("--splits", type=int, default=1, help="issue the batch as this many sub-batches on parallel graph branches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

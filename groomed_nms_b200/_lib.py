@@ -56,6 +56,11 @@ def opts_ref(o):
     return ctypes.byref(o) if o is not None else None
 
 
+class Peers(ctypes.Structure):
+    """gnms_peers: the exchange buffers of all ranks (device pointers, this rank's own included)."""
+    _fields_ = [("buf", vp * 16), ("rank", ctypes.c_int32), ("world", ctypes.c_int32)]
+
+
 class Saved(ctypes.Structure):
     _fields_ = [("order", vp), ("sorted_scores", vp), ("lead", vp), ("pval", vp), ("dpval", vp), ("pre", vp)]
 
@@ -108,6 +113,10 @@ SIGNATURES = {
     "gnms_score_head_workspace_bytes": (sz, [i32]),
     "gnms_score_head_forward_f32": (i32, [vp, i64, i32, vp, vp, vp]),
     "gnms_score_head_backward_f32": (i32, [vp, i64, i32, vp, vp, vp, vp, vp]),
+    "gnms_peer_buffer_create": (i32, [ctypes.POINTER(vp), ctypes.c_char_p]),
+    "gnms_peer_buffer_open": (i32, [ctypes.c_char_p, ctypes.POINTER(vp)]),
+    "gnms_peer_buffer_close": (i32, [vp, i32]),
+    "gnms_score_head_backward_allreduce_f32": (i32, [vp, i64, i32, vp, vp, vp, vp, ctypes.POINTER(Peers), vp, vp]),
     "gnms_targets_overlaps_workspace_bytes": (sz, [i32, i32]),
     "gnms_targets_overlaps_f64": (i32, [vp, i64, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "gnms_iou3d_exact_f64": (i32, [vp, i64, i32, vp, i64, i32, vp, i32, vp, vp, vp]),

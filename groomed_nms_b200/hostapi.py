@@ -157,14 +157,16 @@ class BatchedHeadPlan(object):
         prob   = GrooMeD-NMS(scores, boxes)  fused forward from the boxes (+ the [n,n] IoU matrices if materialise)
         dL/dscores                           analytic NMS backward for the upstream gradient grad_prob
         dL/d(w, b)                           head backward, written straight into the gradient bucket
-        all-reduce(bucket)                   ONE NCCL all-reduce (sum) per step over all ranks
+        all-reduce(bucket)                   ONE all-reduce (sum) per step over all ranks: inside the head-gradient kernel over
+                                             NVLink peer memory (collective="peer": gnms_score_head_backward_allreduce_f32), or
+                                             NCCL on the flat bucket (collective="nccl"; what a padded bucket needs)
 
     Everything is enqueued on one stream; `capture()` records it (collective included) in a CUDA graph."""
 
     FEAT = 64
 
-    def __init__(self, batch, n, device, params, materialise=True, bucket_pad_elems=0, group=None):
-        from .sharding import GradBucket
+    def __init__(self, batch, n, device, params, materialise=True, bucket_pad_elems=0, group=None, collective="auto"):
+        from .sharding import GradBucket, PeerExchange
         self.lib = _lib.load()
         self.B, self.N, self.dev, self.params, self.materialise, self.group = batch, n, device, params, materialise, group
         f = dict(dtype=torch.float32, device=device)
@@ -188,12 +190,19 @@ class BatchedHeadPlan(object):
         self.bucket = GradBucket({"head_wb": self.FEAT + 1}, device, pad_elems=bucket_pad_elems)
         self.grad_wb = self.bucket.view("head_wb")
         self.forward_opts = None
-        # head fwd, [sort,] rank, elect2 (+ chain), [matrix], NMS backward, head backward (2 launches); the all-reduce is NCCL's
-        # kernel, not counted
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if collective not in ("auto", "peer", "nccl"):
+            raise ValueError("collective must be auto, peer or nccl")
+        # the gradient of this head alone is 260 bytes: it travels inside the kernel; a padded bucket (a whole model) is NCCL's job
+        self.exchange = PeerExchange(device, group) if multi and (collective == "peer" or (collective == "auto" and bucket_pad_elems == 0)) else None
+        self.collective = "peer" if self.exchange is not None else ("nccl" if multi else "none")
+        # head fwd, [sort,] rank, elect2 (+ chain), [matrix], NMS backward, head backward (2 launches; the second one carries the
+        # all-reduce in peer mode, otherwise NCCL's kernel follows, not counted)
         by_sort = float(batch) * n * n >= 10.0 * 4096 * 4096
         self.launches_per_step = 6 + (1 if by_sort else 0) + (1 if materialise else 0)
 
-    def compute(self, s):
+    def compute(self, s, head_backward=True):
         """Forward + backward of this rank's shard (no collective)."""
         p = ctypes.byref(self.params)
         M = self.B * self.N
@@ -204,12 +213,21 @@ class BatchedHeadPlan(object):
               "forward_boxes")
         check(self.lib.gnms_backward_f32(_vp(self.grad_prob), _vp(self.prob), None, 0, self.N, self.B, None, p, self.saved,
                                          _vp(self.grad_scores), None, self.N, _vp(self.ws), s), "backward")
-        check(self.lib.gnms_score_head_backward_f32(_vp(self.x), M, self.FEAT, _vp(self.scores), _vp(self.grad_scores),
-                                                    _vp(self.grad_wb), _vp(self.head_ws), s), "score_head_backward")
+        if head_backward:
+            check(self.lib.gnms_score_head_backward_f32(_vp(self.x), M, self.FEAT, _vp(self.scores), _vp(self.grad_scores),
+                                                        _vp(self.grad_wb), _vp(self.head_ws), s), "score_head_backward")
 
     def step(self, stream=None, reduce=True):
+        """One training step.  reduce=True on EVERY rank of the group (it is a collective), or on none."""
         st = stream if stream is not None else torch.cuda.current_stream(self.dev)
-        self.compute(ctypes.c_void_p(st.cuda_stream))
+        s = ctypes.c_void_p(st.cuda_stream)
+        if reduce and self.exchange is not None:
+            self.compute(s, head_backward=False)
+            check(self.lib.gnms_score_head_backward_allreduce_f32(_vp(self.x), self.B * self.N, self.FEAT, _vp(self.scores), _vp(self.grad_scores),
+                                                                  _vp(self.grad_wb), _vp(self.head_ws), ctypes.byref(self.exchange.peers),
+                                                                  _vp(self.exchange.status), s), "score_head_backward_allreduce")
+            return
+        self.compute(s)
         if reduce:
             with torch.cuda.stream(st):
                 self.bucket.all_reduce(self.group)

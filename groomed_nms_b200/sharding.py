@@ -62,3 +62,46 @@ class GradBucket(object):
         if average:
             self.flat.div_(dist.get_world_size(group))
         return self.flat
+
+
+class PeerExchange(object):
+    """The exchange buffers behind gnms_score_head_backward_allreduce_f32: this rank allocates a small device buffer, the ranks
+    of `group` swap its CUDA IPC handle (one all_gather_object on the host, once) and map each other's buffers; the kernel then
+    moves the gradient over NVLink itself.  torch.distributed is only the channel the 64-byte handles travel through."""
+
+    def __init__(self, device, group=None):
+        import ctypes
+        import torch.distributed as dist
+        from . import _lib
+        self.lib = _lib.load()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 16:
+            raise ValueError("at most 16 ranks per exchange")
+        with torch.cuda.device(device):
+            own = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            _lib.check(self.lib.gnms_peer_buffer_create(ctypes.byref(own), handle), "gnms_peer_buffer_create")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self.ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    self.ptrs.append(own.value)
+                else:
+                    p = ctypes.c_void_p()
+                    _lib.check(self.lib.gnms_peer_buffer_open(handles[r], ctypes.byref(p)), "gnms_peer_buffer_open")
+                    self.ptrs.append(p.value)
+        self.device = device
+        self.peers = _lib.Peers()
+        for r in range(self.world):
+            self.peers.buf[r] = self.ptrs[r]
+        self.peers.rank, self.peers.world = self.rank, self.world
+        self.status = torch.zeros((1,), dtype=torch.int32, device=device)
+        dist.barrier(group)                                   # every buffer is mapped everywhere before the first step
+
+    def close(self):
+        if getattr(self, "ptrs", None):
+            with torch.cuda.device(self.device):
+                for r, p in enumerate(self.ptrs):
+                    self.lib.gnms_peer_buffer_close(p, 1 if r == self.rank else 0)
+            self.ptrs = None

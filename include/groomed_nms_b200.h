@@ -349,6 +349,23 @@ int gnms_score_head_forward_f32(const float* x, int64_t M, int K, const float* w
 int gnms_score_head_backward_f32(const float* x, int64_t M, int K, const float* scores, const float* grad_scores,
                                  float* grad_wb, void* workspace, void* stream);
 
+/* The same with the data-parallel all-reduce of the gradient inside the second launch (replaces the reference's nn.DataParallel
+ * gradient reduction, lib/core.py:68, for this head): every rank owns a small exchange buffer that all peers map over NVLink
+ * (CUDA IPC; gnms_peer_buffer_create on the owner, the 64-byte handle travels through any host channel, gnms_peer_buffer_open
+ * on the peers); the kernel reduces this rank's block partials into its buffer, releases a flag into every peer's buffer, waits
+ * for the flags of this step and sums the W ranks' 65 values in rank order.  grad_wb[K + 1] holds the ALL-REDUCED gradient on
+ * return, bitwise the same on every rank.  All ranks must call it once per step; status (device int32, may be NULL) is set to 1
+ * -- and grad_wb to NaN -- if a peer did not show up within ~2 s. */
+typedef struct gnms_peers {
+    void* buf[16];                 /* exchange buffer of every rank (buf[rank] is this rank's own), device pointers */
+    int32_t rank, world;
+} gnms_peers;
+int gnms_peer_buffer_create(void** dev_ptr, unsigned char handle_out[64]);
+int gnms_peer_buffer_open(const unsigned char handle[64], void** dev_ptr);
+int gnms_peer_buffer_close(void* dev_ptr, int owned);
+int gnms_score_head_backward_allreduce_f32(const float* x, int64_t M, int K, const float* scores, const float* grad_scores,
+                                           float* grad_wb, void* workspace, const gnms_peers* peers, int32_t* status, void* stream);
+
 /* ---------------------------------------------------------------- target-assignment overlaps (next to the path) */
 /* lib/rpn_util.py:439-461 compute_targets: ols = iou(rois, gts) (kind GNMS_KIND_IOU, lib/core.py:480-513 numpy branch)
  * or iou_ign(rois, gts) (kind 1, lib/core.py:535-575), float64 like numpy's promotion at the call site (rois float32,
