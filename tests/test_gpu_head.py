@@ -53,3 +53,39 @@ def test_batched_head_plan_matches_autograd_composition(materialise):
     if materialise:
         want = ops.overlap2d(pl.boxes[1], pl.boxes[1])
         assert torch.equal(pl.overlap[1], want)
+
+
+def test_head_backward_with_in_kernel_allreduce_single_rank():
+    """gnms_score_head_backward_allreduce_f32 with a one-rank exchange (the 2-GPU form is tests/test_gpu_multi.py): the exchange
+    buffer life cycle through the C-ABI, step parity over several calls (the counter lives in the buffer), an empty shard, and
+    the result -- with one rank the rank-ordered sum is the rank's own gradient, bit for bit the plain backward."""
+    import ctypes
+    from groomed_nms_b200 import _lib, ops
+    lib = _lib.load()
+    own = ctypes.c_void_p()
+    handle = ctypes.create_string_buffer(64)
+    _lib.check(lib.gnms_peer_buffer_create(ctypes.byref(own), handle), "create")
+    assert own.value and any(handle.raw)
+    peers = _lib.Peers()
+    peers.buf[0] = own.value
+    peers.rank, peers.world = 0, 1
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ws = torch.empty(int(lib.gnms_score_head_workspace_bytes(64)), dtype=torch.uint8, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator("cuda").manual_seed(5)
+    for step, m in enumerate([3000, 17, 0, 5000]):
+        x = torch.randn(m, 64, device="cuda", generator=g)
+        s = torch.rand(m, device="cuda", generator=g)
+        up = torch.randn(m, device="cuda", generator=g)
+        out = torch.full((65,), 7.0, device="cuda")
+        _lib.check(lib.gnms_score_head_backward_allreduce_f32(ops._p(x), m, 64, ops._p(s), ops._p(up), ops._p(out), ops._p(ws),
+                                                              ctypes.byref(peers), ops._p(status), st), "allreduce")
+        want = ops.score_head_backward(x, s, up) if m else torch.zeros(65, device="cuda")
+        assert torch.equal(out, want), step
+    assert int(status.item()) == 0
+    bad = _lib.Peers()
+    bad.rank, bad.world = 0, 1                                                 # no buffer
+    assert lib.gnms_score_head_backward_allreduce_f32(ops._p(x), 1, 64, ops._p(s), ops._p(up), ops._p(out), ops._p(ws),
+                                                      ctypes.byref(bad), None, st) != 0
+    torch.cuda.synchronize()
+    assert lib.gnms_peer_buffer_close(own, 1) == 0
