@@ -1,6 +1,5 @@
 set -x
-timeout 600 python -m pytest tests/test_gpu_multi.py tests/test_gpu_head.py -q -x 2>&1 | tail -15
-for c in peer nccl; do
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29650 bench.py --config c4 --gpus 2 --steps 200 --warmup 10 --c4-collective $c 2>/tmp/err_$c.txt | grep '^{' | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('C4 n=%d %s ms/step %.4f'%(d['n_gpus'], d['extra']['strong']['collective'], d['ms_per_step']), json.dumps(d['extra']))"
-tail -3 /tmp/err_$c.txt
-done
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -8 > gpurun_out/r2_final_pytest.log; cat gpurun_out/r2_final_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 600 python bench.py > gpurun_out/r2_bench_b64.json 2> gpurun_out/r2_bench_b64.err; tail -c 300 gpurun_out/r2_bench_b64.json; tail -3 gpurun_out/r2_bench_b64.err
