@@ -1932,8 +1932,70 @@ __device__ __forceinline__ void chain_body(const ChainArgs& A, const int b, cons
         int32_t* bigpref = reinterpret_cast<int32_t*>(wcol);                       // [NW]
         uint16_t* tbl = reinterpret_cast<uint16_t*>(bigpref + NWa);                // [32 runs][kCapSlots]
         const int WPW = (nw + 31) / 32, gs1 = P.group_size;
-        for (int pos = tid; pos < n; pos += kChainThreads) gcount[pos] = 0;
+        // Few leaders (a detector image): every leader gets a slot, so sizes and ranks come out of the same per-run pass and
+        // no atomics are needed at all.
+        __shared__ int s_gsize[kCapSlots];
+        if (warp == 0) {
+            int run = 0;
+            for (int base = 0; base < nw; base += 32) {
+                const int wi = base + lane;
+                const int c = wi < nw ? __popc(leader[wi]) : 0;
+                int incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (wi < nw) bigpref[wi] = run + incl - c;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) s_cnt = run;
+        }
         for (int i = tid; i < 32 * kCapSlots; i += kChainThreads) tbl[i] = 0;
+        __syncthreads();
+        if (s_cnt <= kCapSlots) {
+            cap_done = true;
+            int slot[kCapW], pre[kCapW];
+            uint32_t cls[kCapW];
+#pragma unroll
+            for (int u = 0; u < kCapW; ++u) {
+                slot[u] = -1; pre[u] = 0; cls[u] = 0u;
+                const int wd = warp * WPW + u;
+                if (u < WPW && wd < nw) {                                          // (warp-uniform)
+                    const int pos = wd * 32 + lane;
+                    const int l = pos < n ? lead[pos] : -1;
+                    if (l >= 0) slot[u] = bigpref[l >> 5] + __popc(leader[l >> 5] & ((1u << (l & 31)) - 1u));
+                    cls[u] = __match_any_sync(0xffffffffu, slot[u]);
+                    if (slot[u] >= 0) pre[u] = tbl[warp * kCapSlots + slot[u]];
+                    __syncwarp();
+                    if (slot[u] >= 0 && lane == __ffs(cls[u]) - 1) tbl[warp * kCapSlots + slot[u]] += (uint16_t)__popc(cls[u]);
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            for (int sl = warp; sl < s_cnt; sl += kChainThreads / 32) {            // lane = run
+                const int v = tbl[lane * kCapSlots + sl];
+                int incl = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                tbl[lane * kCapSlots + sl] = (uint16_t)(incl - v);
+                if (lane == 31) s_gsize[sl] = incl;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < kCapW; ++u) {
+                if (slot[u] >= 0 && s_gsize[slot[u]] > gs1 + 1) {
+                    const int rk = (int)tbl[warp * kCapSlots + slot[u]] + pre[u] + __popc(cls[u] & ((1u << lane) - 1u));
+                    if (rk > gs1) lead[(warp * WPW + u) * 32 + lane] = -1;
+                }
+            }
+            __syncthreads(); GNMS_PHASE(17);
+        }
+        if (!cap_done) {
+        for (int pos = tid; pos < n; pos += kChainThreads) gcount[pos] = 0;
         __syncthreads();
         int ldr[kCapW];
         uint32_t cls[kCapW];
@@ -2015,6 +2077,7 @@ __device__ __forceinline__ void chain_body(const ChainArgs& A, const int b, cons
             }
             __syncthreads(); GNMS_PHASE(17);
         }
+        }   // more than kCapSlots leaders
     }
     if (!cap_done) {
     // member count per leader (shared-memory atomics); ranks are only needed where the cap can bite
