@@ -677,6 +677,7 @@ def run_c4(args, rank, world):
                 err = float((got - full.grad_wb).abs().max() / full.grad_wb.abs().max().clamp_min(1e-30))
                 res[label]["allreduced_grad_rel_err_vs_single_process"] = err
                 del full
+        pl.close()
         del pl
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:

@@ -232,6 +232,15 @@ class BatchedHeadPlan(object):
             with torch.cuda.stream(st):
                 self.bucket.all_reduce(self.group)
 
+    def close(self):
+        """Release the peer exchange buffers (a collective: every rank calls it, after its last step)."""
+        if self.exchange is not None:
+            import torch.distributed as dist
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(self.group)                 # nobody is still reading this rank's buffer
+            self.exchange.close()
+            self.exchange = None
+
     def capture(self, reduce=True):
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
