@@ -9,6 +9,7 @@
  * Reference interfaces replaced (paths relative to abhi1kumar/groomed_nms @ ad10dbb):
  *   lib/core.py:178-243   intersect            -> gnms_overlap2d_f32 / gnms_overlap2d_list_f32 (kind = INTERSECT)
  *   lib/core.py:480-532   iou                  -> gnms_overlap2d_f32 / gnms_overlap2d_list_f32 (kind = IOU)
+ *                         (float64 / mixed-dtype inputs of either: gnms_overlap2d_f64; autograd of iou: gnms_iou2d_backward_f32)
  *   lib/math_3d.py:364-435 get_corners_of_cuboid -> gnms_corners_from_boxes7_f32 (+ gnms_corners_backward_f32 for its autograd)
  *   lib/core.py:354-388,434-477 get_volume / remove_rotation_in_boxes / per-box min-max -> gnms_box3d_records_f32
  *   lib/core.py:305-421   iou3d_approximate    -> gnms_overlap3d_f32 / gnms_overlap3d_list_f32 (+ gnms_iou3d_approx_backward_f32)
@@ -22,6 +23,10 @@
  *   lib/loss/aploss.py:14-97 backpropAPLoss    -> gnms_aploss_f32
  *   lib/rpn_util.py:439-461 compute_targets overlaps (lib/core.py iou / iou_ign, numpy branch) -> gnms_targets_overlaps_f64
  *   lib/core.py:246-302   iou3d (exact polygon overlap, shapely in the reference) -> gnms_iou3d_exact_f64
+ *   lib/groomed_nms.py:131-165 soft_sort        -> gnms_soft_sort_forward_f32 / gnms_soft_sort_backward_f32
+ *   lib/loss/rpn_3d.py:722-768,801-825 (top-500 selection, best box per ground truth) -> gnms_masked_topk_f32 / gnms_best_box_per_gt_f32
+ *   lib/core.py:68        nn.DataParallel gradient reduction of the acceptance head (models/...alpha.py:112-121,230)
+ *                                              -> gnms_score_head_*_f32, gnms_score_head_backward_allreduce_f32 (+ gnms_peer_buffer_*)
  */
 #ifndef GROOMED_NMS_B200_H_
 #define GROOMED_NMS_B200_H_
