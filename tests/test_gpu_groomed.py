@@ -714,3 +714,56 @@ def test_batched_election_with_degenerate_boxes(kind):
             for f in ("order", "lead", "counts"):
                 assert torch.equal(getattr(ref, f), getattr(st, f)), (thr, election, f)
             assert torch.equal(ref.prob.view(torch.int32), st.prob.view(torch.int32)), (thr, election)
+
+
+@pytest.mark.parametrize("seed", list(range(40)))
+def test_batched_election_fuzz_against_the_bitmask_route(seed):
+    """Randomised differential test: ragged batches of random size, cluster structure, threshold and group size through the batched
+    election (with the chain at its end, and as two launches) and through the all-pairs bitmask route -- every saved tensor and
+    list must agree bit for bit, forward and backward."""
+    from groomed_nms_b200 import _lib, ops, synthetic
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.choice([1, 31, 32, 33, 500, 1024, 1500, 2048, 3000, 4096]))
+    B = int(rng.integers(1, 5))
+    thr = float(rng.choice([0.1, 0.4, 0.55, 0.7]))
+    gs = int(rng.choice([0, 1, 5, 30, 100, 5000]))
+    kind = "3d" if seed % 2 else "2d"
+    ns = [int(rng.integers(0, N + 1)) for _ in range(B)]
+    ns[0] = N
+    sc = np.zeros((B, N), np.float32)
+    if kind == "2d":
+        data = np.zeros((B, N, 4), np.float32)
+        for b in range(B):
+            k = int(rng.integers(1, max(2, N // 20 + 1)))
+            bx, s, _ = synthetic.clustered_boxes_2d(N, k, seed=seed * 10 + b, jitter=float(rng.choice([0.03, 0.1, 0.3])))
+            data[b], sc[b] = bx, s
+        dev = cuda(data)
+        kw = dict(box_kind=_lib.BOX_2D, generalized=False, affine=False)
+    else:
+        recs = []
+        for b in range(B):
+            b7, s = synthetic.config_c3(seed=seed * 10 + b, n=N, k=int(rng.integers(1, max(2, N // 16 + 1))))
+            sc[b] = s
+            recs.append(ops.box3d_records(ops.corners_from_boxes7(cuda(b7))))
+        dev = torch.stack(recs)
+        kw = dict(box_kind=_lib.BOX_3D_REC, generalized=True, affine=True)
+    npi = torch.tensor(ns, dtype=torch.int32, device="cuda")
+    p = ops.make_params(nms_threshold=thr, group_size=gs, pruning_method=str(rng.choice(["linear", "sigmoidal", "soft_nms"])), temperature=0.1)
+    up = torch.randn(B, N, device="cuda", generator=torch.Generator("cuda").manual_seed(seed))
+    outs = []
+    for election, flags in ((_lib.ELECT_MASK, 0), (_lib.ELECT_BATCHED, 0), (_lib.ELECT_BATCHED, _lib.OPT_SPLIT_CHAIN)):
+        st = ops.forward_boxes(cuda(sc), dev, kw["box_kind"], p, kw["generalized"], kw["affine"], n_per_image=npi,
+                               opts=_lib.launch_opts(election=election, flags=flags))
+        g, _ = ops.backward(st, up)
+        torch.cuda.synchronize()
+        outs.append((st, g))
+    ref, gref = outs[0]
+    for st, g in outs[1:]:
+        for f in ("order", "lead", "counts", "pval", "dpval"):
+            assert torch.equal(getattr(ref, f), getattr(st, f)), (f, N, ns, thr, gs, kind)
+        assert torch.equal(ref.prob.view(torch.int32), st.prob.view(torch.int32)) and torch.equal(ref.pre.view(torch.int32), st.pre.view(torch.int32))
+        for b in range(B):
+            nv = int(ref.counts[b, 0])
+            assert torch.equal(ref.valid_idx[b, :nv], st.valid_idx[b, :nv])
+            assert torch.equal(ref.invalid_idx[b, :ns[b] - nv], st.invalid_idx[b, :ns[b] - nv])
+        assert torch.equal(gref, g)

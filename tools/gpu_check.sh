@@ -1,2 +1,2 @@
 set -x
-timeout 600 python -m pytest tests/test_gpu_multi.py -q -x 2>&1 | tail -8
+timeout 600 python -m pytest tests/test_gpu_groomed.py -x -q -m gpu -k "fuzz" 2>&1 | tail -25
