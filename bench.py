@@ -276,7 +276,8 @@ def time_stage(torch, fn, stream, iters, warm=3):
 def measure_latency(torch, dev, params):
     """Single-call latency (B = 1), microseconds: what one `differentiable_nms` call of the reference's per-image loop costs.
     `c_abi_*`: Nms3dPlan(1, 4096) -- 7-DoF boxes -> records -> forward -> backward as one CUDA graph (device time per replay
-    from CUDA events over back-to-back replays; wall time of replay + stream sync).  `python_api_*`: the reference-facing
+    from CUDA events over back-to-back replays; wall time of replay + stream sync); the 2D sizes (N = 1024: config C2, N = 500: what
+    the reference's loss passes per image) the same way from boxes and from a materialised IoU matrix.  `python_api_*`: the reference-facing
     lib.groomed_nms.differentiable_nms(scores, iou) on a materialised matrix + autograd backward, wall clock with the one
     sync the variable-length index results need; overlaps through lib.core.iou / ops.overlap3d are timed separately."""
     import numpy as np
@@ -318,6 +319,42 @@ def measure_latency(torch, dev, params):
     rec = ops.box3d_records(ops.corners_from_boxes7(torch.from_numpy(b7).to(dev)))
     bx2, sc2 = synthetic.config_c2()
     bx5, sc5, _ = synthetic.clustered_boxes_2d(500, 6, seed=11, jitter=0.05)
+    # the 2D sizes through the C-ABI as one CUDA graph: forward from the boxes (fused) or from a materialised matrix (the
+    # reference's call form), + backward
+    from groomed_nms_b200 import _lib as L_
+    for tag, bx, scv in (("N1024_2d", bx2, sc2), ("N500_2d", bx5, sc5)):
+        for form in ("from_boxes", "from_matrix"):
+            try:
+                tb, ts_ = torch.from_numpy(bx).to(dev)[None].contiguous(), torch.from_numpy(scv).to(dev)[None].contiguous()
+                up2 = torch.randn_like(ts_)
+                iou2 = ops.overlap2d(tb[0], tb[0])[None].contiguous() if form == "from_matrix" else None
+
+                def step2():
+                    st2 = ops.forward_matrix(ts_, iou2, params) if iou2 is not None else ops.forward_boxes(ts_, tb, L_.BOX_2D, params)
+                    ops.backward(st2, up2)
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        step2()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize()
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2):
+                    step2()
+                for _ in range(10):
+                    g2.replay()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(100):
+                    g2.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                out["c_abi_graph_%s_%s" % (tag, form)] = {"device_us_per_call": 1e3 * e0.elapsed_time(e1) / 100, "wall_us_per_call": wall(g2.replay)}
+                del g2
+            except Exception as e:                                    # (never let an extra take the bench line down)
+                out["c_abi_graph_%s_%s" % (tag, form)] = {"error": "%s: %s" % (type(e).__name__, e)}
     cases = (("python_api_N4096_3d", torch.from_numpy(sc).to(dev), lambda: ops.overlap3d(rec, rec, False, True, generalized=True, affine=True)[1]),
              ("python_api_N1024_2d", torch.from_numpy(sc2).to(dev), lambda b=torch.from_numpy(bx2).to(dev): C.iou(b, b)),
              ("python_api_N500_2d", torch.from_numpy(sc5).to(dev), lambda b=torch.from_numpy(bx5).to(dev): C.iou(b, b)))
