@@ -599,7 +599,7 @@ def run_ours(args, rank, world):
             "stage_ms": stages,
             "extra": {"latency_us": latency, "sustained": sustained},
         }
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:                      # (the CPU baseline is an N = 1 figure: the other ranks' processes share these cores)
             workers = host_workers()
             kind = "reference" if reference_staged() else "port"
             v, dt = cpu_throughput(kind, workers, workers, warm_images=workers)       # one warm image + one timed image per worker
